@@ -1,0 +1,205 @@
+/*
+ * agarcl_b200.h — C-ABI of the B200-native batched AgarCL simulator.
+ *
+ * This is the drop-in boundary for ONE hot path of machado-research/AgarCL:
+ *   N lockstep instances of  BaseEnvironment::step  (environment/envs/BaseEnvironment.hpp:89-122)
+ *     = ticks_per_step x Engine::tick (agario/engine/Engine.hpp:208-240), built-in bots
+ *       (agario/bots/*.hpp), regen/respawn, rewards, dones,
+ *   + GridObservation::add_frame (environment/envs/GridEnvironment.hpp:91-123).
+ *
+ * Every entry point below replaces what the reference's pybind11 module `agarcl`
+ * (environment/bindings.cpp:94-135) binds for that path; the cited line is the
+ * reference interface it stands in for.  Plain pointers and sizes only: no C++
+ * or torch types cross this boundary.  All functions return 0 on success and a
+ * negative agarcl_status on failure; agarcl_last_error() gives the text.
+ *
+ * The same header also fixes the per-instance STATE BLOB layout that is shared by
+ *   - the CUDA library (device state = N blobs, `stride` bytes apart),
+ *   - oracle/oracle.c (CPU restatement, test infrastructure only),
+ *   - oracle/ref_harness.cpp (the compiled reference, dumps into the same blob).
+ */
+#ifndef AGARCL_B200_H
+#define AGARCL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- constants
+ * agario/core/settings.hpp, agario/core/Entities.hpp.     */
+#define AGARCL_CELL_MIN_SIZE 25u
+#define AGARCL_CELL_SPLIT_MINIMUM 50u
+#define AGARCL_PLAYER_CELL_LIMIT 14
+#define AGARCL_FOOD_MASS 10u
+#define AGARCL_PELLET_MASS 1u
+#define AGARCL_VIRUS_INITIAL_MASS 100u
+#define AGARCL_MAX_MASS_IN_THE_GAME 22500u
+#define AGARCL_NEW_MASS_IF_NO_SPLIT 22000u
+#define AGARCL_RECOMBINE_TICKS 300u /* RECOMBINE_TIMER_SEC(10) * 30 ticks/s, sim-time */
+
+#define AGARCL_MAX_CELLS 32   /* cell slots per player (reference limit 14, Engine.hpp:592-601 can overshoot) */
+#define AGARCL_VET_CAP 16     /* remembered virus_eaten_ticks per player (Player.hpp:31) */
+#define AGARCL_MAX_PLAYERS 64 /* agents + bots per instance */
+#define AGARCL_LUT_SIZE 65536 /* integer-mass lookup tables (radius, max_speed, split_speed) */
+
+/* hdr.flags bits: set by the simulator when a fixed capacity was hit or a
+ * non-replayable reference path was taken.  Parity is only claimed while 0.  */
+#define AGARCL_FLAG_FOOD_OVERFLOW 0x001u
+#define AGARCL_FLAG_VIRUS_OVERFLOW 0x002u
+#define AGARCL_FLAG_CELL_OVERFLOW 0x004u
+#define AGARCL_FLAG_VET_OVERFLOW 0x008u
+#define AGARCL_FLAG_EATER_OVERFLOW 0x010u
+#define AGARCL_FLAG_REPLAY_EXHAUSTED 0x020u
+#define AGARCL_FLAG_PCD_TIE 0x040u     /* >16 cells in one PCD strip with equal y: std::sort order unspecified */
+#define AGARCL_FLAG_RAND_SITE 0x080u   /* a libc rand() site was reached (Bot.hpp:93-96,121-126) */
+#define AGARCL_FLAG_MASS_LUT 0x100u    /* a cell mass exceeded AGARCL_LUT_SIZE */
+#define AGARCL_FLAG_REMOVE_OVERFLOW 0x200u
+
+typedef enum agarcl_status {
+  AGARCL_OK = 0,
+  AGARCL_ERR_INVALID = -1,   /* bad argument / config (EnvironmentException in the reference) */
+  AGARCL_ERR_CUDA = -2,      /* CUDA runtime failure */
+  AGARCL_ERR_NOMEM = -3,
+  AGARCL_ERR_STATE = -4      /* call order (e.g. step before reset) */
+} agarcl_status;
+
+typedef enum agarcl_rng_mode {
+  AGARCL_RNG_PHILOX = 0,  /* counter-based per-instance Philox4x32-10 on device */
+  AGARCL_RNG_REPLAY = 1,  /* draws come from a per-instance stream uploaded with agarcl_batch_set_replay */
+  AGARCL_RNG_MT19937 = 2  /* host fills the replay stream from std::mt19937_64(seed) exactly as
+                             Engine::seed + random_location do (Engine.hpp:143-148,242-245) */
+} agarcl_rng_mode;
+
+typedef enum agarcl_obs_dtype { AGARCL_OBS_I32 = 0, AGARCL_OBS_I16 = 1 } agarcl_obs_dtype;
+
+/* ------------------------------------------------------------------- config
+ * Fields 2..11 are the positional arguments of agarcl.GridEnvironment
+ * (environment/bindings.cpp:102, BaseEnvironment.hpp:39-51); fields 12..17 are
+ * the keys of configure_observation (bindings.cpp:104-114).                   */
+typedef struct agarcl_cfg {
+  int32_t n_instances;
+  int32_t num_agents, ticks_per_step, arena_size, pellet_regen, num_pellets, num_viruses, num_bots;
+  int32_t reward_type, c_death, mode_number;
+  int32_t num_frames, grid_size, observe_cells, observe_others, observe_viruses, observe_pellets;
+  int32_t obs_dtype;        /* agarcl_obs_dtype; int32 is the reference's */
+  int32_t strict_reference; /* 1: keep quirk Q11 (frame index) exactly; 0: always render the last frame(s) */
+  int32_t rng_mode;         /* agarcl_rng_mode */
+  int32_t cap_viruses, cap_foods, cap_replay; /* 0 = defaults */
+  int32_t device;           /* CUDA device ordinal */
+  int32_t instance_base;    /* global index of local instance 0 (multi-GPU sharding; keys the RNG) */
+  int32_t reserved[3];
+} agarcl_cfg;
+
+/* ------------------------------------------------------------- state records */
+typedef struct agarcl_cell { /* 48 B; agario/core/Entities.hpp:118-212 */
+  float x, y, vx, vy;
+  float svx, svy;        /* splitting_velocity */
+  uint32_t mass;
+  uint32_t id;           /* creation order inside the instance (Ball.hpp:15,18; only relative order is used) */
+  uint32_t recomb_tick;  /* engine tick from which can_recombine() holds (Entities.hpp:183-193, sim-time) */
+  uint32_t pad[3];
+} agarcl_cell;
+
+typedef struct agarcl_virus { /* 32 B; Entities.hpp:82-114 */
+  float x, y;
+  uint32_t mass;
+  int32_t hits;          /* _num_food_hits */
+  float vx, vy;
+  uint32_t pad[2];
+} agarcl_virus;
+
+typedef struct agarcl_food { float x, y, vx, vy; } agarcl_food; /* 16 B; Entities.hpp:41-55 */
+typedef struct agarcl_pellet { float x, y; } agarcl_pellet;     /* 8 B;  Entities.hpp:22-38 */
+
+typedef struct agarcl_player { /* 128 B; agario/core/Player.hpp:25-41,211-215 */
+  int32_t n_cells;
+  float target_x, target_y;
+  int32_t action;          /* 0 none, 1 feed, 2 split (core/types.hpp:59-61) */
+  int32_t split_cd, feed_cd;
+  float anti_team_decay;
+  int32_t elapsed_ticks, last_decay_tick;
+  int32_t bot_type;        /* -1 agent; 0 Hungry, 1 HungryShy, 2 Aggressive, 3 AggressiveShy */
+  uint32_t min_mass_cell;
+  int32_t food_eaten;
+  uint32_t highest_mass;
+  int32_t cells_eaten, viruses_eaten;
+  int32_t vet_count;       /* virus_eaten_ticks.size() */
+  int32_t vet_ticks[AGARCL_VET_CAP];
+} agarcl_player;
+
+typedef struct agarcl_inst_hdr { /* 64 B */
+  uint32_t tick;           /* GameState::ticks */
+  uint32_t next_cell_id;
+  int32_t n_pellets, n_viruses, n_foods;
+  uint32_t rng_cursor;     /* uniform draws consumed so far */
+  uint32_t flags;          /* AGARCL_FLAG_* */
+  uint32_t seed_lo, seed_hi;
+  uint32_t done_sticky;    /* mode 3 sticky done (BaseEnvironment.hpp:132-135) */
+  uint32_t pad[6];
+} agarcl_inst_hdr;
+
+/* Byte offsets of one instance's arrays inside its blob. */
+typedef struct agarcl_layout {
+  int32_t P, A;            /* players (agents + bots), agents */
+  int32_t cap_cells, cap_pellets, cap_viruses, cap_foods, cap_replay;
+  uint32_t off_hdr, off_players, off_cells, off_viruses, off_foods, off_pellets;
+  uint32_t stride;         /* bytes per instance, multiple of 128 */
+  /* engine mode flags, Engine::set_mode (Engine.hpp:367-416) */
+  int32_t mass_decay, squared_pellets, regen, agent_mass;
+  int32_t obs_channels;    /* per frame: 1 + cells + 2*others + 2*viruses + 2*pellets (GridEnvironment.hpp:188-195) */
+  int32_t order[AGARCL_MAX_PLAYERS];    /* player index processed k-th (libstdc++ unordered_map order) */
+  int32_t bot_type[AGARCL_MAX_PLAYERS];
+} agarcl_layout;
+
+/* Fills `L` from `c` (host side; uses the same libstdc++ unordered_map the reference
+ * iterates, GameState.hpp:44).  Returns AGARCL_ERR_INVALID on a bad config.  */
+int agarcl_make_layout(const agarcl_cfg* c, agarcl_layout* L);
+
+/* ---------------------------------------------------------------- batch API */
+typedef struct agarcl_batch agarcl_batch;
+
+/* GridEnvironment ctor + configure_observation (bindings.cpp:102-114). Allocates all device memory. */
+int agarcl_batch_create(const agarcl_cfg* cfg, agarcl_batch** out);
+int agarcl_batch_destroy(agarcl_batch* b);
+int agarcl_batch_get_layout(const agarcl_batch* b, agarcl_layout* out);
+
+/* BaseEnvironment::seed (BaseEnvironment.hpp:211): seeds[i] for instance i (host pointer, N entries). */
+int agarcl_batch_seed(agarcl_batch* b, const uint64_t* seeds);
+/* BaseEnvironment::reset (BaseEnvironment.hpp:179-204) for instances with mask[i]!=0 (NULL = all). */
+int agarcl_batch_reset(agarcl_batch* b, const uint8_t* mask, void* stream);
+/* BaseEnvironment::take_actions (BaseEnvironment.hpp:141-176): dxdy[N*A*2], act[N*A].
+ * on_device!=0: device pointers, read by the next step without a copy. */
+int agarcl_batch_set_actions(agarcl_batch* b, const float* dxdy, const int32_t* act, int on_device, void* stream);
+/* BaseEnvironment::step + GridObservation::add_frame for every agent, enqueued on `stream` (cudaStream_t). */
+int agarcl_batch_step(agarcl_batch* b, void* stream);
+/* get_state (bindings.cpp:67-91) without the copy: device pointer to obs [N*A, C*num_frames, G, G]. */
+int agarcl_batch_obs(agarcl_batch* b, void** dev_ptr, int64_t shape[4], int32_t* dtype);
+int agarcl_batch_rewards(agarcl_batch* b, double** dev_ptr); /* step() return value, f64[N*A] */
+int agarcl_batch_dones(agarcl_batch* b, uint8_t** dev_ptr);  /* dones(), u8[N*A] */
+/* The reference-facing call with HOST buffers: copies actions in, steps, copies obs/rewards/dones
+ * out (any of the out pointers may be NULL) and synchronises.  This is what `e2e` in bench.py times. */
+int agarcl_batch_step_host(agarcl_batch* b, const float* dxdy, const int32_t* act,
+                           void* obs_out, double* rewards_out, uint8_t* dones_out);
+
+/* Parity / snapshot transport: one instance's blob (layout.stride bytes) to / from host memory. */
+int agarcl_batch_download_state(agarcl_batch* b, int32_t instance, void* blob);
+int agarcl_batch_upload_state(agarcl_batch* b, int32_t instance, const void* blob);
+/* Recorded uniform draws in [0,1) for instance i (replay of the reference's mt19937_64). */
+int agarcl_batch_set_replay(agarcl_batch* b, int32_t instance, const float* draws, int32_t n);
+/* Run only the observation kernel on the current state (tests; add_frame on a cleared buffer). */
+int agarcl_batch_render(agarcl_batch* b, void* stream);
+/* Number of kernel launches issued by the last agarcl_batch_step. */
+int agarcl_batch_launches_per_step(const agarcl_batch* b);
+/* Host helper: first n canonical floats of std::mt19937_64(seed) as uniform_real_distribution<float>
+ * draws them (random.hpp:6-20). */
+int agarcl_mt19937_draws(uint64_t seed, float* out, int32_t n);
+
+const char* agarcl_last_error(void);
+const char* agarcl_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGARCL_B200_H */

@@ -1,0 +1,373 @@
+/*
+ * ref_harness.cpp — TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * Thin C-ABI wrapper around the UNMODIFIED reference engine compiled from the sources where
+ * they lie under /root/reference (see oracle/Makefile).  It drives the reference's own
+ * agario::env::GridEnvironment<int,false> (environment/envs/GridEnvironment.hpp:350-491)
+ * and dumps its state into the agarcl_b200 state blob so tests can compare the oracle port
+ * (oracle/oracle.c) and the CUDA path against the real thing.
+ *
+ * Declared deviations from the shipped reference (DESIGN.md "Oracle"):
+ *  1. GridEnvironment.hpp:374 initialises an OpenGL member that only exists under RENDERABLE;
+ *     the Makefile drops that one mem-initialiser in a scratch copy (no behavioural effect).
+ *  2. The recombine timer reads std::chrono::steady_clock (Entities.hpp:127,185,190), i.e. WALL
+ *     time.  Here `steady_clock` is re-pointed (preprocessor, no source edit) at a simulation
+ *     clock that counts engine ticks at 30 ticks/s, so RECOMBINE_TIMER_SEC = 10 s = 300 ticks.
+ *  3. Each reset starts from a fresh player map and pid 0 ("fresh Engine per episode").
+ */
+#include <algorithm>
+#include <any>
+#include <array>
+#include <bitset>
+#include <cctype>
+#include <cerrno>
+#include <cinttypes>
+#include <ciso646>
+#include <clocale>
+#include <cstddef>
+#include <cstdio>
+#include <deque>
+#include <exception>
+#include <filesystem>
+#include <forward_list>
+#include <initializer_list>
+#include <iosfwd>
+#include <istream>
+#include <iterator>
+#include <list>
+#include <map>
+#include <optional>
+#include <ostream>
+#include <queue>
+#include <string_view>
+#include <type_traits>
+#include <typeinfo>
+#include <utility>
+#include <valarray>
+#include <variant>
+#include <version>
+#include <cassert>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <memory>
+#include <numeric>
+#include <random>
+#include <set>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+#include <mutex>
+#include <condition_variable>
+#include <functional>
+#include <atomic>
+
+#include "../include/agarcl_b200.h"
+#include <utils/thread-pool.h> /* the reference's own pool (utils/thread-pool.h:21), CPU baseline only */
+
+/* ---- deviation 2: simulation clock standing in for steady_clock ------------------------- */
+namespace std { namespace chrono {
+struct agarcl_sim_clock {
+  typedef std::chrono::duration<long long, std::ratio<1, 30>> duration; /* one engine tick */
+  typedef duration::rep rep;
+  typedef duration::period period;
+  typedef std::chrono::time_point<agarcl_sim_clock, duration> time_point;
+  static constexpr bool is_steady = true;
+  static thread_local const unsigned long* tick_ptr;
+  static time_point now() noexcept { return time_point(duration(tick_ptr ? (long long)*tick_ptr : 0LL)); }
+};
+thread_local const unsigned long* agarcl_sim_clock::tick_ptr = nullptr;
+}}
+
+typedef int screen_len;
+class FBOException : public std::runtime_error { using runtime_error::runtime_error; };
+
+#define steady_clock agarcl_sim_clock
+#define private public
+#define protected public
+#include <environment/envs/GridEnvironment.hpp> /* scratch copy in oracle/_ref/gen shadows line 374 */
+#undef private
+#undef protected
+#undef steady_clock
+
+using RefEnvT = agario::env::GridEnvironment<int, false>;
+using RefObsT = agario::env::GridObservation<int, false>;
+using SimClock = std::chrono::agarcl_sim_clock;
+
+struct RefEnv {
+  std::unique_ptr<RefEnvT> env;
+  std::unique_ptr<RefObsT> forced; /* add_frame(...,0) target, see Q11 */
+  int num_agents, grid, channels;
+  void bind_clock() { SimClock::tick_ptr = &env->engine_.state.ticks; }
+};
+
+struct CoutSilencer {
+  std::streambuf* old;
+  std::ostringstream sink;
+  CoutSilencer() : old(std::cout.rdbuf(sink.rdbuf())) {}
+  ~CoutSilencer() { std::cout.rdbuf(old); }
+};
+
+static void fresh_reset(RefEnv* r) {
+  /* deviation 3: fresh player map + pid 0 so that map iteration order is that of a new Engine */
+  auto& st = r->env->engine_.state;
+  st.players = decltype(st.players)();
+  st.next_pid = 0;
+  r->env->reset();
+}
+
+extern "C" {
+
+void* ref_create(const agarcl_cfg* c) {
+  auto* r = new RefEnv();
+  {
+    CoutSilencer quiet;
+    SimClock::tick_ptr = nullptr;
+    r->env.reset(new RefEnvT(c->num_agents, c->ticks_per_step, c->arena_size, c->pellet_regen != 0, c->num_pellets,
+                             c->num_viruses, c->num_bots, c->reward_type, c->c_death, c->mode_number));
+  }
+  r->bind_clock();
+  r->env->configure_observation(c->num_frames, c->grid_size, c->observe_cells != 0, c->observe_others != 0,
+                                c->observe_viruses != 0, c->observe_pellets != 0);
+  r->forced.reset(new RefObsT(1, c->grid_size, c->observe_cells != 0, c->observe_others != 0,
+                              c->observe_viruses != 0, c->observe_pellets != 0));
+  r->num_agents = c->num_agents;
+  r->grid = c->grid_size;
+  r->channels = std::get<0>(r->forced->shape());
+  return r;
+}
+
+void ref_destroy(void* h) {
+  SimClock::tick_ptr = nullptr;
+  delete static_cast<RefEnv*>(h);
+}
+
+void ref_seed(void* h, unsigned s) { static_cast<RefEnv*>(h)->env->seed((int)s); }
+
+void ref_reset(void* h) {
+  auto* r = static_cast<RefEnv*>(h);
+  r->bind_clock();
+  fresh_reset(r);
+}
+
+void ref_take_actions(void* h, const float* dxdy, const int32_t* act) {
+  auto* r = static_cast<RefEnv*>(h);
+  r->bind_clock();
+  std::vector<agario::env::Action> a;
+  for (int i = 0; i < r->num_agents; i++)
+    a.emplace_back(dxdy[2 * i], dxdy[2 * i + 1], static_cast<agario::action>(act[i]));
+  r->env->take_actions(a);
+}
+
+/* rewards in the reference's own return order (map order of non-bot players, quirk Q15) */
+void ref_step(void* h, double* rewards) {
+  auto* r = static_cast<RefEnv*>(h);
+  r->bind_clock();
+  auto rw = r->env->step();
+  for (size_t i = 0; i < rw.size(); i++) rewards[i] = rw[i];
+}
+
+void ref_dones(void* h, uint8_t* out) {
+  auto* r = static_cast<RefEnv*>(h);
+  auto d = r->env->dones();
+  for (size_t i = 0; i < d.size(); i++) out[i] = d[i] ? 1 : 0;
+}
+
+/* GridObservation::add_frame(player, state, 0) on a cleared buffer (GridEnvironment.hpp:91-123) */
+void ref_obs(void* h, int agent, int32_t* out) {
+  auto* r = static_cast<RefEnv*>(h);
+  r->bind_clock();
+  auto& player = r->env->engine_.player(r->env->pids_[agent]);
+  r->forced->clear_data();
+  r->forced->add_frame(player, r->env->engine_.game_state(), 0);
+  std::memcpy(out, r->forced->data(), sizeof(int32_t) * (size_t)r->forced->length());
+}
+
+/* what the reference's own step()/get_state() left in its buffer (quirk Q11) */
+void ref_obs_native(void* h, int agent, int32_t* out) {
+  auto* r = static_cast<RefEnv*>(h);
+  auto& obs = r->env->get_observations()[agent];
+  std::memcpy(out, obs.data(), sizeof(int32_t) * (size_t)obs.length());
+}
+int ref_obs_native_len(void* h) { return static_cast<RefEnv*>(h)->env->get_observations()[0].length(); }
+
+/* map iteration order of players (GameState.hpp:44) as pids */
+int ref_player_order(void* h, int32_t* out) {
+  auto* r = static_cast<RefEnv*>(h);
+  int k = 0;
+  for (auto& pr : r->env->engine_.state.players) out[k++] = pr.first;
+  return k;
+}
+
+/* next n canonical draws the engine's rng will produce, from a COPY of it (GameState.hpp:51;
+ * uniform_real_distribution<float>(0,1) consumes exactly one 64-bit word per draw) */
+void ref_rng_peek(void* h, float* out, int n) {
+  auto* r = static_cast<RefEnv*>(h);
+  std::mt19937_64 copy = r->env->engine_.state.rng;
+  for (int i = 0; i < n; i++) {
+    std::uniform_real_distribution<float> d(0.0f, 1.0f);
+    out[i] = d(copy);
+  }
+}
+
+void ref_set_cell_mass(void* h, int pid, int cell, unsigned mass) {
+  auto* r = static_cast<RefEnv*>(h);
+  r->env->engine_.player((agario::pid)pid).cells.at(cell).set_mass(mass);
+}
+void ref_set_cell_pos(void* h, int pid, int cell, float x, float y) {
+  auto* r = static_cast<RefEnv*>(h);
+  auto& c = r->env->engine_.player((agario::pid)pid).cells.at(cell);
+  c.x = x;
+  c.y = y;
+}
+void ref_set_virus(void* h, int idx, float x, float y) {
+  auto* r = static_cast<RefEnv*>(h);
+  auto& v = r->env->engine_.state.viruses.at(idx);
+  v.x = x;
+  v.y = y;
+}
+
+/* Dump the whole GameState into one agarcl blob.  Returns 0, or a negative count of capacity misses. */
+int ref_dump_state(void* h, const agarcl_layout* L, void* blob_) {
+  auto* r = static_cast<RefEnv*>(h);
+  auto& eng = r->env->engine_;
+  auto& st = eng.state;
+  auto* blob = static_cast<uint8_t*>(blob_);
+  std::memset(blob, 0, L->stride);
+  int miss = 0;
+  auto* hdr = reinterpret_cast<agarcl_inst_hdr*>(blob + L->off_hdr);
+  hdr->tick = (uint32_t)st.ticks;
+  hdr->n_pellets = (int32_t)st.pellets.size();
+  hdr->n_viruses = (int32_t)st.viruses.size();
+  hdr->n_foods = (int32_t)st.foods.size();
+  hdr->done_sticky = r->env->dones_[0] ? 1u : 0u;
+  auto* pel = reinterpret_cast<agarcl_pellet*>(blob + L->off_pellets);
+  for (size_t i = 0; i < st.pellets.size(); i++) {
+    if ((int)i >= L->cap_pellets) { miss--; break; }
+    pel[i].x = st.pellets[i].x;
+    pel[i].y = st.pellets[i].y;
+  }
+  auto* vir = reinterpret_cast<agarcl_virus*>(blob + L->off_viruses);
+  for (size_t i = 0; i < st.viruses.size(); i++) {
+    if ((int)i >= L->cap_viruses) { miss--; break; }
+    vir[i].x = st.viruses[i].x;
+    vir[i].y = st.viruses[i].y;
+    vir[i].vx = st.viruses[i].velocity.dx;
+    vir[i].vy = st.viruses[i].velocity.dy;
+    vir[i].mass = st.viruses[i].mass();
+    vir[i].hits = st.viruses[i].get_num_food_hits();
+  }
+  auto* foo = reinterpret_cast<agarcl_food*>(blob + L->off_foods);
+  for (size_t i = 0; i < st.foods.size(); i++) {
+    if ((int)i >= L->cap_foods) { miss--; break; }
+    foo[i].x = st.foods[i].x;
+    foo[i].y = st.foods[i].y;
+    foo[i].vx = st.foods[i].velocity.dx;
+    foo[i].vy = st.foods[i].velocity.dy;
+  }
+  auto* pls = reinterpret_cast<agarcl_player*>(blob + L->off_players);
+  auto* cells = reinterpret_cast<agarcl_cell*>(blob + L->off_cells);
+  uint32_t max_id = 0;
+  for (auto& pr : st.players) {
+    int p = pr.first;
+    if (p >= L->P) { miss--; continue; }
+    auto& pl = *pr.second;
+    agarcl_player& o = pls[p];
+    o.n_cells = (int32_t)pl.cells.size();
+    o.target_x = pl.target.x;
+    o.target_y = pl.target.y;
+    o.action = (int32_t)pl.action;
+    o.split_cd = (int32_t)pl.split_cooldown;
+    o.feed_cd = (int32_t)pl.feed_cooldown;
+    o.anti_team_decay = pl.anti_team_decay;
+    o.elapsed_ticks = pl.elapsed_ticks;
+    o.last_decay_tick = pl.last_decay_tick;
+    o.bot_type = L->bot_type[p];
+    o.min_mass_cell = pl._minMassCell;
+    o.food_eaten = pl.food_eaten;
+    o.highest_mass = pl.highest_mass;
+    o.cells_eaten = pl.cells_eaten;
+    o.viruses_eaten = pl.viruses_eaten;
+    o.vet_count = (int32_t)pl.virus_eaten_ticks.size();
+    for (size_t k = 0; k < pl.virus_eaten_ticks.size() && k < AGARCL_VET_CAP; k++) o.vet_ticks[k] = pl.virus_eaten_ticks[k];
+    if (pl.virus_eaten_ticks.size() > AGARCL_VET_CAP) miss--;
+    for (size_t k = 0; k < pl.cells.size(); k++) {
+      if ((int)k >= L->cap_cells) { miss--; break; }
+      auto& c = pl.cells[k];
+      agarcl_cell& oc = cells[(size_t)p * L->cap_cells + k];
+      oc.x = c.x;
+      oc.y = c.y;
+      oc.vx = c.velocity.dx;
+      oc.vy = c.velocity.dy;
+      oc.svx = c.splitting_velocity.dx;
+      oc.svy = c.splitting_velocity.dy;
+      oc.mass = c.mass();
+      oc.id = (uint32_t)c.id;
+      long long rt = c._recombine_timer.time_since_epoch().count();
+      oc.recomb_tick = rt < 0 ? 0u : (uint32_t)rt;
+      max_id = std::max(max_id, (uint32_t)c.id);
+    }
+  }
+  hdr->next_cell_id = max_id + 1;
+  return miss;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * CPU baseline: M independent GridEnvironment instances over a pool of worker threads, the
+ * pattern of BotEvaluator::run (agario/bots/benchmark.cpp:146-168).  Each work item builds an
+ * env, seeds it, and runs `steps` env-steps of (random actions, step(), forced add_frame).
+ * Returns env-steps per second over the stepping loops only (construction excluded by a
+ * barrier), `threads` workers.
+ * ------------------------------------------------------------------------------------------ */
+double ref_bench(const agarcl_cfg* c, int instances, int threads, int steps, int with_obs, unsigned base_seed) {
+  std::vector<std::unique_ptr<RefEnv>> envs((size_t)instances);
+  {
+    CoutSilencer quiet;
+    for (int i = 0; i < instances; i++) {
+      envs[i].reset(static_cast<RefEnv*>(ref_create(c)));
+      ref_seed(envs[i].get(), base_seed + (unsigned)i);
+      ref_reset(envs[i].get());
+    }
+  }
+  auto work = [&](int i) {
+    std::vector<float> dxdy((size_t)c->num_agents * 2);
+    std::vector<int32_t> act((size_t)c->num_agents);
+    std::vector<double> rew((size_t)c->num_agents);
+    RefEnv* r = envs[i].get();
+    std::vector<int32_t> obs((size_t)r->forced->length());
+    std::mt19937 arng(base_seed * 7919u + (unsigned)i);
+    std::uniform_real_distribution<float> u(-1.0f, 1.0f);
+    for (int s = 0; s < steps; s++) {
+      for (int a = 0; a < c->num_agents; a++) {
+        dxdy[2 * a] = u(arng);
+        dxdy[2 * a + 1] = u(arng);
+        act[a] = (int)(arng() % 3u);
+      }
+      ref_take_actions(r, dxdy.data(), act.data());
+      ref_step(r, rew.data());
+      if (with_obs)
+        for (int a = 0; a < c->num_agents; a++) ref_obs(r, a, obs.data());
+    }
+  };
+  auto t0 = std::chrono::high_resolution_clock::now();
+  {
+    ThreadPool pool((size_t)threads);
+    for (int i = 0; i < instances; i++) pool.schedule([&work, i]() { work(i); });
+    pool.wait();
+  }
+  auto t1 = std::chrono::high_resolution_clock::now();
+  double sec = std::chrono::duration<double>(t1 - t0).count();
+  return (double)instances * (double)steps / sec;
+}
+
+} /* extern "C" */
