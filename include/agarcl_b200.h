@@ -4,7 +4,7 @@
  * This is the drop-in boundary for ONE hot path of machado-research/AgarCL:
  *   N lockstep instances of  BaseEnvironment::step  (environment/envs/BaseEnvironment.hpp:89-122)
  *     = ticks_per_step x Engine::tick (agario/engine/Engine.hpp:208-240), built-in bots
- *       (agario/bots/*.hpp), regen/respawn, rewards, dones,
+ *       (agario/bots/ headers), regen/respawn, rewards, dones,
  *   + GridObservation::add_frame (environment/envs/GridEnvironment.hpp:91-123).
  *
  * Every entry point below replaces what the reference's pybind11 module `agarcl`
