@@ -55,7 +55,8 @@ PLAYER_DT = np.dtype([("n_cells", "<i4"), ("target_x", "<f4"), ("target_y", "<f4
                       ("vet_ticks", "<i4", (VET_CAP,))])
 HDR_DT = np.dtype([("tick", "<u4"), ("next_cell_id", "<u4"), ("n_pellets", "<i4"), ("n_viruses", "<i4"),
                    ("n_foods", "<i4"), ("rng_cursor", "<u4"), ("flags", "<u4"), ("seed_lo", "<u4"),
-                   ("seed_hi", "<u4"), ("done_sticky", "<u4"), ("pad", "<u4", (6,))])
+                   ("seed_hi", "<u4"), ("done_sticky", "<u4"), ("respawned_lo", "<u4"), ("respawned_hi", "<u4"),
+                   ("pad", "<u4", (4,))])
 
 assert CELL_DT.itemsize == 48 and VIRUS_DT.itemsize == 32 and FOOD_DT.itemsize == 16
 assert PELLET_DT.itemsize == 8 and PLAYER_DT.itemsize == 128 and HDR_DT.itemsize == 64

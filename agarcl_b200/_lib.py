@@ -1,0 +1,67 @@
+"""ctypes binding of libagarcl_b200.so (include/agarcl_b200.h).  Fails loudly when the library is
+missing or a call fails: there is no CPU path in this package."""
+import ctypes as C
+import os
+
+from ._abi import Cfg, Layout
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libagarcl_b200.so")
+
+_vp = C.c_void_p
+_lib = None
+
+SYMBOLS = [
+    "agarcl_make_layout", "agarcl_batch_create", "agarcl_batch_destroy", "agarcl_batch_get_layout",
+    "agarcl_batch_seed", "agarcl_batch_reset", "agarcl_batch_set_actions", "agarcl_batch_step",
+    "agarcl_batch_obs", "agarcl_batch_rewards", "agarcl_batch_dones", "agarcl_batch_step_host",
+    "agarcl_batch_download_state", "agarcl_batch_upload_state", "agarcl_batch_set_replay",
+    "agarcl_batch_render", "agarcl_batch_launches_per_step", "agarcl_mt19937_draws",
+    "agarcl_last_error", "agarcl_version",
+]
+
+
+class AgarclError(RuntimeError):
+    """C-ABI call failed (the reference raises EnvironmentException -> RuntimeError, bindings.cpp)."""
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is not built: run `python -m agarcl_b200.build` "
+                              "(agarcl_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.agarcl_last_error.restype = C.c_char_p
+        L.agarcl_version.restype = C.c_char_p
+        L.agarcl_make_layout.argtypes = [C.POINTER(Cfg), C.POINTER(Layout)]
+        L.agarcl_batch_create.argtypes = [C.POINTER(Cfg), C.POINTER(_vp)]
+        L.agarcl_batch_destroy.argtypes = [_vp]
+        L.agarcl_batch_get_layout.argtypes = [_vp, C.POINTER(Layout)]
+        L.agarcl_batch_seed.argtypes = [_vp, _vp]
+        L.agarcl_batch_reset.argtypes = [_vp, _vp, _vp]
+        L.agarcl_batch_set_actions.argtypes = [_vp, _vp, _vp, C.c_int, _vp]
+        L.agarcl_batch_step.argtypes = [_vp, _vp]
+        L.agarcl_batch_obs.argtypes = [_vp, C.POINTER(_vp), C.POINTER(C.c_int64 * 4), C.POINTER(C.c_int32)]
+        L.agarcl_batch_rewards.argtypes = [_vp, C.POINTER(_vp)]
+        L.agarcl_batch_dones.argtypes = [_vp, C.POINTER(_vp)]
+        L.agarcl_batch_step_host.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
+        L.agarcl_batch_download_state.argtypes = [_vp, C.c_int32, _vp]
+        L.agarcl_batch_upload_state.argtypes = [_vp, C.c_int32, _vp]
+        L.agarcl_batch_set_replay.argtypes = [_vp, C.c_int32, _vp, C.c_int32]
+        L.agarcl_batch_render.argtypes = [_vp, _vp]
+        L.agarcl_batch_launches_per_step.argtypes = [_vp]
+        L.agarcl_mt19937_draws.argtypes = [C.c_uint64, _vp, C.c_int32]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise AgarclError(lib().agarcl_last_error().decode() or f"agarcl error {rc}")
+
+
+def make_layout(cfg):
+    L = Layout()
+    check(lib().agarcl_make_layout(C.byref(cfg), C.byref(L)))
+    return L

@@ -1,0 +1,126 @@
+"""Batch handle: thin Python owner of an `agarcl_batch*` (include/agarcl_b200.h).
+
+This is the host-side mirror of the batched hot path.  Device buffers are owned by the C library;
+`obs_tensor()/rewards_tensor()/dones_tensor()` expose them to PyTorch without a copy through
+`__cuda_array_interface__` (torch is plumbing here: device memory views and streams only).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._abi import OBS_I16, Layout, StateView
+
+_vp = C.c_void_p
+
+
+class _CudaView:
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2}
+        self._owner = owner
+
+
+class Batch:
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self._h = _vp()
+        _lib.check(_lib.lib().agarcl_batch_create(C.byref(cfg), C.byref(self._h)))
+        self.layout = Layout()
+        _lib.check(_lib.lib().agarcl_batch_get_layout(self._h, C.byref(self.layout)))
+        self.N = cfg.n_instances
+        self.A = self.layout.A
+        shape = (C.c_int64 * 4)()
+        ptr = _vp()
+        dt = C.c_int32()
+        _lib.check(_lib.lib().agarcl_batch_obs(self._h, C.byref(ptr), C.byref(shape), C.byref(dt)))
+        self.obs_shape = tuple(int(x) for x in shape)
+        self.obs_dtype = np.int16 if dt.value == OBS_I16 else np.int32
+        self._obs_ptr = ptr.value
+        p = _vp()
+        _lib.check(_lib.lib().agarcl_batch_rewards(self._h, C.byref(p)))
+        self._rew_ptr = p.value
+        p = _vp()
+        _lib.check(_lib.lib().agarcl_batch_dones(self._h, C.byref(p)))
+        self._done_ptr = p.value
+
+    def close(self):
+        if self._h:
+            _lib.lib().agarcl_batch_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- reference-shaped calls
+    def seed(self, seeds):
+        s = np.ascontiguousarray(np.broadcast_to(np.asarray(seeds, dtype=np.uint64), (self.N,)) if np.ndim(seeds) else
+                                 np.arange(self.N, dtype=np.uint64) + np.uint64(seeds))
+        _lib.check(_lib.lib().agarcl_batch_seed(self._h, s.ctypes.data_as(_vp)))
+
+    def reset(self, mask=None, stream=0):
+        m = None
+        if mask is not None:
+            m = np.ascontiguousarray(mask, dtype=np.uint8)
+            assert m.size == self.N
+        _lib.check(_lib.lib().agarcl_batch_reset(self._h, m.ctypes.data_as(_vp) if m is not None else None, _vp(stream)))
+
+    def set_actions(self, dxdy, act, stream=0):
+        dxdy = np.ascontiguousarray(dxdy, dtype=np.float32)
+        act = np.ascontiguousarray(act, dtype=np.int32)
+        assert dxdy.size == self.N * self.A * 2 and act.size == self.N * self.A, "Number of actions does not match number of agents"
+        _lib.check(_lib.lib().agarcl_batch_set_actions(self._h, dxdy.ctypes.data_as(_vp), act.ctypes.data_as(_vp), 0, _vp(stream)))
+
+    def set_actions_device(self, dxdy_ptr, act_ptr, stream=0):
+        _lib.check(_lib.lib().agarcl_batch_set_actions(self._h, _vp(dxdy_ptr), _vp(act_ptr), 1, _vp(stream)))
+
+    def step(self, stream=0):
+        _lib.check(_lib.lib().agarcl_batch_step(self._h, _vp(stream)))
+
+    def render(self, stream=0):
+        _lib.check(_lib.lib().agarcl_batch_render(self._h, _vp(stream)))
+
+    def step_host(self, dxdy, act, obs_out=None, rewards_out=None, dones_out=None):
+        f = lambda a: a.ctypes.data_as(_vp) if a is not None else None
+        _lib.check(_lib.lib().agarcl_batch_step_host(self._h, f(dxdy), f(act), f(obs_out), f(rewards_out), f(dones_out)))
+
+    def launches_per_step(self):
+        return _lib.lib().agarcl_batch_launches_per_step(self._h)
+
+    # ---- parity / snapshot transport
+    def download_state(self, i):
+        sv = StateView(self.layout)
+        _lib.check(_lib.lib().agarcl_batch_download_state(self._h, i, sv.ptr))
+        return sv
+
+    def upload_state(self, i, sv):
+        _lib.check(_lib.lib().agarcl_batch_upload_state(self._h, i, sv.ptr))
+
+    def set_replay(self, i, draws):
+        d = np.ascontiguousarray(draws, dtype=np.float32)
+        _lib.check(_lib.lib().agarcl_batch_set_replay(self._h, i, d.ctypes.data_as(_vp), d.size))
+
+    # ---- zero-copy device views
+    def obs_view(self):
+        return _CudaView(self._obs_ptr, self.obs_shape, "<i2" if self.obs_dtype == np.int16 else "<i4", self)
+
+    def rewards_view(self):
+        return _CudaView(self._rew_ptr, (self.N * self.A,), "<f8", self)
+
+    def dones_view(self):
+        return _CudaView(self._done_ptr, (self.N * self.A,), "|u1", self)
+
+    def obs_tensor(self):
+        import torch
+        return torch.as_tensor(self.obs_view(), device=f"cuda:{self.cfg.device}")
+
+    def rewards_tensor(self):
+        import torch
+        return torch.as_tensor(self.rewards_view(), device=f"cuda:{self.cfg.device}")
+
+    def dones_tensor(self):
+        import torch
+        return torch.as_tensor(self.dones_view(), device=f"cuda:{self.cfg.device}")

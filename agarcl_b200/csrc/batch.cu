@@ -1,0 +1,388 @@
+// batch.cu — host side of the C ABI (include/agarcl_b200.h): owns the device memory of a batch of
+// N lockstep instances and enqueues the kernels.  Mirrors, for the batched path, what
+// environment/bindings.cpp:99-135 binds on agario::env::GridEnvironment (ctor, seed,
+// configure_observation, take_actions, step, get_state, dones, reset).
+//
+// There is NO CPU fallback: every entry point that computes needs a CUDA device and fails with
+// AGARCL_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "host_util.h"
+#include "sim_params.h"
+#include "sim_shared.cuh"
+
+namespace ag {
+cudaError_t launch_step(const SimParams& P, cudaStream_t stream);
+cudaError_t launch_obs(const ObsParams& P, cudaStream_t stream);
+cudaError_t launch_reset(const ResetParams& P, cudaStream_t stream);
+}  // namespace ag
+
+struct agarcl_batch {
+  agarcl_cfg cfg;
+  agarcl_layout L;
+  int N, A, G, C, frames;
+  size_t obs_elems, obs_bytes;
+  uint8_t* d_state = nullptr;
+  void* d_obs = nullptr;
+  double* d_rewards = nullptr;
+  uint8_t* d_dones = nullptr;
+  float* d_before = nullptr;
+  float* d_dxdy = nullptr;
+  int32_t* d_act = nullptr;
+  const float* cur_dxdy = nullptr;  // what the next step reads (own buffers or caller's device pointers)
+  const int32_t* cur_act = nullptr;
+  float* d_replay = nullptr;
+  uint64_t* d_seeds = nullptr;
+  uint8_t* d_mask = nullptr;
+  float *d_lut_radius = nullptr, *d_lut_speed = nullptr, *d_lut_split = nullptr;
+  std::vector<uint64_t> seeds;
+  ag::Luts T;
+  int HG;
+  uint32_t smem_per_warp;
+  bool was_reset = false;
+  int launches_last_step = 0;
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return agarcl_set_error(AGARCL_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));   \
+  } while (0)
+
+static void fill_sim_params(const agarcl_batch* b, ag::SimParams& P) {
+  P.L = b->L;
+  P.T = b->T;
+  P.state = b->d_state;
+  P.dxdy = b->cur_dxdy;
+  P.act = b->cur_act;
+  P.rewards = b->d_rewards;
+  P.dones = b->d_dones;
+  P.before = b->d_before;
+  P.replay = b->d_replay;
+  P.N = b->N;
+  P.instance_base = b->cfg.instance_base;
+  P.mode = b->cfg.mode_number;
+  P.reward_type = b->cfg.reward_type;
+  P.rng_mode = b->cfg.rng_mode;
+  P.target_pellets = b->cfg.num_pellets;
+  P.target_viruses = b->cfg.num_viruses;
+  P.HG = b->HG;
+  P.W = (float)b->cfg.arena_size;
+  P.hash_scale = (float)b->HG / (float)b->cfg.arena_size;
+  // initialize_pellet_grid / initialize_virus_grid: int((W + size - 1) / size) in fp32 (Engine.hpp:962-965,1207-1211)
+  P.gw_pellet = (int)(((float)b->cfg.arena_size + 510.0f - 1.0f) / 510.0f);
+  P.gw_virus = (int)(((float)b->cfg.arena_size + 25.0f - 1.0f) / 25.0f);
+  P.smem_per_warp = b->smem_per_warp;
+}
+
+static void fill_obs_params(const agarcl_batch* b, ag::ObsParams& P, int frame, int pre_respawn) {
+  P.pre_respawn = pre_respawn;
+  P.L = b->L;
+  P.state = b->d_state;
+  P.obs = b->d_obs;
+  P.N = b->N;
+  P.G = b->G;
+  P.C = b->C;
+  P.frames = b->frames;
+  P.frame = frame;
+  P.observe_cells = b->cfg.observe_cells;
+  P.observe_others = b->cfg.observe_others;
+  P.observe_viruses = b->cfg.observe_viruses;
+  P.observe_pellets = b->cfg.observe_pellets;
+  P.obs_dtype = b->cfg.obs_dtype;
+  P.W = (float)b->cfg.arena_size;
+}
+
+extern "C" int agarcl_batch_destroy(agarcl_batch* b) {
+  if (!b) return AGARCL_OK;
+  cudaFree(b->d_state); cudaFree(b->d_obs); cudaFree(b->d_rewards); cudaFree(b->d_dones); cudaFree(b->d_before);
+  cudaFree(b->d_dxdy); cudaFree(b->d_act); cudaFree(b->d_replay); cudaFree(b->d_seeds); cudaFree(b->d_mask);
+  cudaFree(b->d_lut_radius); cudaFree(b->d_lut_speed); cudaFree(b->d_lut_split);
+  delete b;
+  return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_create(const agarcl_cfg* cfg, agarcl_batch** out) {
+  if (!cfg || !out) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->n_instances < 1) return agarcl_set_error(AGARCL_ERR_INVALID, "n_instances must be >= 1");
+  agarcl_layout L;
+  int rc = agarcl_make_layout(cfg, &L);
+  if (rc != AGARCL_OK) return rc;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return agarcl_set_error(AGARCL_ERR_CUDA, "no CUDA device: agarcl_b200 has no CPU path (%s)", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return agarcl_set_error(AGARCL_ERR_INVALID, "device %d out of range", cfg->device);
+  CK(cudaSetDevice(cfg->device));
+  agarcl_batch* b = new (std::nothrow) agarcl_batch();
+  if (!b) return agarcl_set_error(AGARCL_ERR_NOMEM, "out of host memory");
+  b->cfg = *cfg;
+  b->L = L;
+  b->N = cfg->n_instances;
+  b->A = L.A;
+  b->G = cfg->grid_size;
+  b->C = L.obs_channels;
+  b->frames = cfg->num_frames;
+  b->obs_elems = (size_t)b->N * b->A * b->frames * b->C * b->G * b->G;
+  b->obs_bytes = b->obs_elems * (cfg->obs_dtype == AGARCL_OBS_I16 ? 2 : 4);
+  // spatial hash resolution: about 3 pellets per hash cell, 4..64 cells per side
+  int hg = (int)std::floor(std::sqrt((double)L.cap_pellets / 3.0));
+  b->HG = hg < 4 ? 4 : (hg > 64 ? 64 : hg);
+  b->smem_per_warp = ag::warp_smem_bytes(L, b->HG);
+  if ((size_t)b->smem_per_warp * ag::kWarpsPerCta > 200 * 1024) {
+    delete b;
+    return agarcl_set_error(AGARCL_ERR_INVALID, "configuration needs %u B of shared memory per instance (too many pellets/viruses)", b->smem_per_warp);
+  }
+#define ALLOC(ptr, bytes)                                                                           \
+  do {                                                                                              \
+    cudaError_t e__ = cudaMalloc((void**)&(ptr), (bytes));                                          \
+    if (e__ != cudaSuccess) {                                                                       \
+      agarcl_batch_destroy(b);                                                                      \
+      return agarcl_set_error(AGARCL_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(e__)); \
+    }                                                                                               \
+  } while (0)
+  const size_t NA = (size_t)b->N * b->A;
+  ALLOC(b->d_state, (size_t)b->N * L.stride);
+  ALLOC(b->d_obs, b->obs_bytes);
+  ALLOC(b->d_rewards, NA * sizeof(double));
+  ALLOC(b->d_dones, NA);
+  ALLOC(b->d_before, NA * sizeof(float));
+  ALLOC(b->d_dxdy, NA * 2 * sizeof(float));
+  ALLOC(b->d_act, NA * sizeof(int32_t));
+  ALLOC(b->d_seeds, (size_t)b->N * sizeof(uint64_t));
+  ALLOC(b->d_mask, (size_t)b->N);
+  if (L.cap_replay > 0) ALLOC(b->d_replay, (size_t)b->N * L.cap_replay * sizeof(float));
+  ALLOC(b->d_lut_radius, AGARCL_LUT_SIZE * sizeof(float));
+  ALLOC(b->d_lut_speed, AGARCL_LUT_SIZE * sizeof(float));
+  ALLOC(b->d_lut_split, AGARCL_LUT_SIZE * sizeof(float));
+#undef ALLOC
+  cudaMemset(b->d_state, 0, (size_t)b->N * L.stride);
+  cudaMemset(b->d_obs, 0, b->obs_bytes);
+  cudaMemset(b->d_rewards, 0, NA * sizeof(double));
+  cudaMemset(b->d_dones, 0, NA);
+  cudaMemset(b->d_dxdy, 0, NA * 2 * sizeof(float));
+  cudaMemset(b->d_act, 0, NA * sizeof(int32_t));
+  if (b->d_replay) cudaMemset(b->d_replay, 0, (size_t)b->N * L.cap_replay * sizeof(float));
+  b->cur_dxdy = b->d_dxdy;
+  b->cur_act = b->d_act;
+  // lookup tables of functions of an integer mass, computed with the host libm the reference uses
+  {
+    std::vector<float> rad(AGARCL_LUT_SIZE), spd(AGARCL_LUT_SIZE), spl(AGARCL_LUT_SIZE);
+    for (uint32_t m = 0; m < AGARCL_LUT_SIZE; m++) {
+      rad[m] = (float)std::sqrt((double)m / 1.0 / M_PI);                  // radius_conversion, core/utils.hpp:8-11
+      spd[m] = (float)(300 / std::pow((double)m, 0.439));                 // max_speed, Engine.hpp:1300-1302
+      double v = 3 * std::pow((double)spd[m], 1.2);                       // split_speed, Engine.hpp:1296-1298
+      v = (130.0 < v) ? 130.0 : v;
+      v = (v < 20.0) ? 20.0 : v;
+      spl[m] = (float)v;
+    }
+    cudaMemcpy(b->d_lut_radius, rad.data(), rad.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(b->d_lut_speed, spd.data(), spd.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(b->d_lut_split, spl.data(), spl.size() * 4, cudaMemcpyHostToDevice);
+    b->T.radius = b->d_lut_radius;
+    b->T.max_speed = b->d_lut_speed;
+    b->T.split_speed = b->d_lut_split;
+    b->T.anti_team[0] = 1.0f;
+    for (int n = 1; n <= AGARCL_VET_CAP; n++) b->T.anti_team[n] = (float)std::pow(1.1, (double)(n - 1));  // Engine.hpp:567
+  }
+  b->seeds.resize(b->N);
+  for (int i = 0; i < b->N; i++) b->seeds[i] = (uint64_t)(cfg->instance_base + i);
+  cudaMemcpy(b->d_seeds, b->seeds.data(), b->N * sizeof(uint64_t), cudaMemcpyHostToDevice);
+  CK(cudaDeviceSynchronize());
+  *out = b;
+  return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_get_layout(const agarcl_batch* b, agarcl_layout* out) {
+  if (!b || !out) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  *out = b->L;
+  return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_seed(agarcl_batch* b, const uint64_t* seeds) {
+  if (!b || !seeds) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(b->cfg.device));
+  for (int i = 0; i < b->N; i++) b->seeds[i] = seeds[i];
+  CK(cudaMemcpy(b->d_seeds, b->seeds.data(), b->N * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  if (b->cfg.rng_mode == AGARCL_RNG_MT19937) {
+    std::vector<float> draws(b->L.cap_replay);
+    for (int i = 0; i < b->N; i++) {
+      agarcl_mt19937_draws(seeds[i], draws.data(), b->L.cap_replay);
+      CK(cudaMemcpy(b->d_replay + (size_t)i * b->L.cap_replay, draws.data(), draws.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+  }
+  return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_set_replay(agarcl_batch* b, int32_t instance, const float* draws, int32_t n) {
+  if (!b || !draws) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  if (instance < 0 || instance >= b->N) return agarcl_set_error(AGARCL_ERR_INVALID, "instance out of range");
+  if (!b->d_replay) return agarcl_set_error(AGARCL_ERR_STATE, "batch was not created with a replay rng_mode");
+  if (n > b->L.cap_replay) n = b->L.cap_replay;
+  CK(cudaSetDevice(b->cfg.device));
+  CK(cudaMemcpy(b->d_replay + (size_t)instance * b->L.cap_replay, draws, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+  return AGARCL_OK;
+}
+
+static int render_frame(agarcl_batch* b, int frame, cudaStream_t s, int pre_respawn) {
+  ag::ObsParams P;
+  fill_obs_params(b, P, frame, pre_respawn);
+  CK(ag::launch_obs(P, s));
+  return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_render(agarcl_batch* b, void* stream) {
+  if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");
+  CK(cudaSetDevice(b->cfg.device));
+  return render_frame(b, b->frames - 1, (cudaStream_t)stream, 0);
+}
+
+extern "C" int agarcl_batch_reset(agarcl_batch* b, const uint8_t* mask, void* stream) {
+  if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");
+  CK(cudaSetDevice(b->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  ag::ResetParams P;
+  P.L = b->L;
+  P.T = b->T;
+  P.state = b->d_state;
+  P.mask = nullptr;
+  if (mask) {
+    CK(cudaMemcpyAsync(b->d_mask, mask, b->N, cudaMemcpyHostToDevice, s));
+    P.mask = b->d_mask;
+  }
+  P.seeds = b->d_seeds;
+  P.replay = b->d_replay;
+  P.dones = b->d_dones;
+  P.N = b->N;
+  P.instance_base = b->cfg.instance_base;
+  P.rng_mode = b->cfg.rng_mode;
+  P.num_pellets = b->cfg.num_pellets;
+  P.num_viruses = b->cfg.num_viruses;
+  P.W = (float)b->cfg.arena_size;
+  CK(ag::launch_reset(P, s));
+  b->was_reset = true;
+  // the reference ends reset() with _partial_observation (BaseEnvironment.hpp:202-203)
+  if (b->cfg.strict_reference) {
+    CK(cudaMemsetAsync(b->d_obs, 0, b->obs_bytes, s));
+    int frame = 0 - (b->cfg.ticks_per_step - b->frames);
+    if (frame >= 0) return render_frame(b, frame, s, 0);
+    return AGARCL_OK;
+  }
+  if (b->frames > 1) CK(cudaMemsetAsync(b->d_obs, 0, b->obs_bytes, s));
+  return render_frame(b, b->frames - 1, s, 0);
+}
+
+extern "C" int agarcl_batch_set_actions(agarcl_batch* b, const float* dxdy, const int32_t* act, int on_device, void* stream) {
+  if (!b || !dxdy || !act) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(b->cfg.device));
+  const size_t NA = (size_t)b->N * b->A;
+  if (on_device) {
+    b->cur_dxdy = dxdy;
+    b->cur_act = act;
+  } else {
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(b->d_dxdy, dxdy, NA * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b->d_act, act, NA * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    b->cur_dxdy = b->d_dxdy;
+    b->cur_act = b->d_act;
+  }
+  return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_step(agarcl_batch* b, void* stream) {
+  if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");
+  if (!b->was_reset) return agarcl_set_error(AGARCL_ERR_STATE, "step() before reset()");
+  CK(cudaSetDevice(b->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  ag::SimParams P;
+  fill_sim_params(b, P);
+  const int tps = b->cfg.ticks_per_step;
+  int launches = 0;
+  if (b->cfg.strict_reference) {
+    // quirk Q11: one _partial_observation(agent, 0) after all ticks, frame_index = -(tps - num_frames)
+    P.n_ticks = tps; P.do_begin = 1; P.do_end = 1;
+    CK(cudaMemsetAsync(b->d_obs, 0, b->obs_bytes, s));  // _step_hook: clear_data
+    CK(ag::launch_step(P, s)); launches++;
+    int frame = 0 - (tps - b->frames);
+    if (frame >= 0) { int rc = render_frame(b, frame, s, 1); if (rc) return rc; launches++; }
+  } else if (b->frames == 1) {
+    P.n_ticks = tps; P.do_begin = 1; P.do_end = 1;
+    CK(ag::launch_step(P, s)); launches++;
+    int rc = render_frame(b, 0, s, 1); if (rc) return rc; launches++;
+  } else {
+    // the last num_frames ticks of the step each contribute one frame (the documented intent of
+    // GridEnvironment::_partial_observation, GridEnvironment.hpp:413-433)
+    if (b->frames > tps) CK(cudaMemsetAsync(b->d_obs, 0, b->obs_bytes, s));
+    for (int t = 0; t < tps; t++) {
+      P.n_ticks = 1; P.do_begin = (t == 0); P.do_end = 0;
+      CK(ag::launch_step(P, s)); launches++;
+      int frame = t - (tps - b->frames);
+      if (frame >= 0) { int rc = render_frame(b, frame, s, 1); if (rc) return rc; launches++; }
+    }
+    P.n_ticks = 0; P.do_begin = 0; P.do_end = 1;
+    CK(ag::launch_step(P, s)); launches++;
+  }
+  b->launches_last_step = launches;
+  return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_launches_per_step(const agarcl_batch* b) { return b ? b->launches_last_step : 0; }
+
+extern "C" int agarcl_batch_obs(agarcl_batch* b, void** dev_ptr, int64_t shape[4], int32_t* dtype) {
+  if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");
+  if (dev_ptr) *dev_ptr = b->d_obs;
+  if (shape) { shape[0] = (int64_t)b->N * b->A; shape[1] = (int64_t)b->frames * b->C; shape[2] = b->G; shape[3] = b->G; }
+  if (dtype) *dtype = b->cfg.obs_dtype;
+  return AGARCL_OK;
+}
+extern "C" int agarcl_batch_rewards(agarcl_batch* b, double** dev_ptr) {
+  if (!b || !dev_ptr) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  *dev_ptr = b->d_rewards;
+  return AGARCL_OK;
+}
+extern "C" int agarcl_batch_dones(agarcl_batch* b, uint8_t** dev_ptr) {
+  if (!b || !dev_ptr) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  *dev_ptr = b->d_dones;
+  return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_step_host(agarcl_batch* b, const float* dxdy, const int32_t* act, void* obs_out,
+                                      double* rewards_out, uint8_t* dones_out) {
+  if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");
+  int rc = agarcl_batch_set_actions(b, dxdy, act, 0, nullptr);
+  if (rc) return rc;
+  rc = agarcl_batch_step(b, nullptr);
+  if (rc) return rc;
+  const size_t NA = (size_t)b->N * b->A;
+  if (obs_out) CK(cudaMemcpyAsync(obs_out, b->d_obs, b->obs_bytes, cudaMemcpyDeviceToHost, nullptr));
+  if (rewards_out) CK(cudaMemcpyAsync(rewards_out, b->d_rewards, NA * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+  if (dones_out) CK(cudaMemcpyAsync(dones_out, b->d_dones, NA, cudaMemcpyDeviceToHost, nullptr));
+  CK(cudaStreamSynchronize(nullptr));
+  return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_download_state(agarcl_batch* b, int32_t instance, void* blob) {
+  if (!b || !blob) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  if (instance < 0 || instance >= b->N) return agarcl_set_error(AGARCL_ERR_INVALID, "instance out of range");
+  CK(cudaSetDevice(b->cfg.device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(blob, b->d_state + (size_t)instance * b->L.stride, b->L.stride, cudaMemcpyDeviceToHost));
+  return AGARCL_OK;
+}
+extern "C" int agarcl_batch_upload_state(agarcl_batch* b, int32_t instance, const void* blob) {
+  if (!b || !blob) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  if (instance < 0 || instance >= b->N) return agarcl_set_error(AGARCL_ERR_INVALID, "instance out of range");
+  CK(cudaSetDevice(b->cfg.device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(b->d_state + (size_t)instance * b->L.stride, blob, b->L.stride, cudaMemcpyHostToDevice));
+  b->was_reset = true;
+  return AGARCL_OK;
+}

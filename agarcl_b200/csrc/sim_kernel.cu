@@ -1,0 +1,1436 @@
+// sim_kernel.cu — the engine tick for N lockstep instances, hand-written for sm_100a.
+//
+// Mapping: ONE WARP OWNS ONE GAME INSTANCE for a whole env-step (ticks_per_step ticks); a CTA is
+// kWarpsPerCta independent warps (no block barriers at all — only __syncwarp / shuffles / ballots).
+//   * a player's cells live in REGISTERS, one cell per lane (<= 32 cells), for the whole of its
+//     Engine::tick_player; order-dependent reference semantics (Gauss-Seidel self-collision,
+//     swap-pop recombine, eat order) are replayed with ballots + shuffles instead of loops over memory;
+//   * per-tick uniform-grid spatial hash of the pellets built by a warp-level counting sort in
+//     shared memory (count -> warp scan -> scatter), used to FIND pellet candidates; hits are then
+//     re-ordered and applied in the reference's order (510-unit buckets, ascending index,
+//     Engine.hpp:976-1000) so that events are bit-exact;
+//   * everything of an instance is one contiguous blob in HBM (include/agarcl_b200.h), read with
+//     16-byte vector loads; the instance stays L1/L2 resident for the 4 ticks of a step.
+// Control flow is warp-uniform everywhere a shuffle/ballot is issued.
+//
+// Reference functions restated here (agario/engine/Engine.hpp unless noted): tick 208-240,
+// tick_player 495-542, move_player 609-630, check_player_self_collisions 763-794, prevent_overlap
+// 857-888, elastic_collision_between_balls 893-938, avoid_static_overlap 701-749, separate_cells
+// 803-848, optimized_check_virus_collisions 1223-1252, disrupt 1263-1294,
+// get_pellets_to_remove_and_increment_cells 976-1000, remove_pellets 1002-1009, remove_viruses
+// 1253-1260, may_be_auto_split 592-601, cell_split 1067-1093, eat_food 1011-1025, emit_foods
+// 1027-1044, maybe_split/player_split 1056-1107, recombine_cells 1160-1179,
+// maybe_activate_anti_team/mass_decay 550-584, players_collision 150-200 with
+// PrecisionCollisionDetection::solve (agario/utils/collision_detection.hpp:11-64), move_foods /
+// maybe_hit_virus 632-687, add_pellets/add_viruses 418-424,480-485, respawn 119-137; bots
+// (agario/bots/Bot.hpp:31-129, HungryBot.hpp:19-22, HungryShyBot.hpp:23-44, AggressiveBot.hpp:28-52,
+// AggressiveShyBot.hpp:28-68); BaseEnvironment::step / take_action (environment/envs/
+// BaseEnvironment.hpp:89-122,164-176).
+#include <cuda_runtime.h>
+
+#include "sim_params.h"
+#include "sim_shared.cuh"
+
+namespace ag {
+
+// ------------------------------------------------------------------------------------------------
+// per-lane cell (registers) and shuffles
+// ------------------------------------------------------------------------------------------------
+struct Cell {
+  float x, y, vx, vy, svx, svy;
+  uint32_t mass, id, rec;
+};
+
+__device__ __forceinline__ Cell cell_load(const agarcl_cell* g) {
+  const float4* p = reinterpret_cast<const float4*>(g);
+  float4 a = p[0];
+  float4 b = p[1];
+  Cell c;
+  c.x = a.x; c.y = a.y; c.vx = a.z; c.vy = a.w;
+  c.svx = b.x; c.svy = b.y;
+  c.mass = __float_as_uint(b.z); c.id = __float_as_uint(b.w);
+  c.rec = reinterpret_cast<const uint32_t*>(g)[8];
+  return c;
+}
+__device__ __forceinline__ void cell_store(agarcl_cell* g, const Cell& c) {
+  float4* p = reinterpret_cast<float4*>(g);
+  p[0] = make_float4(c.x, c.y, c.vx, c.vy);
+  p[1] = make_float4(c.svx, c.svy, __uint_as_float(c.mass), __uint_as_float(c.id));
+  reinterpret_cast<uint4*>(g)[2] = make_uint4(c.rec, 0u, 0u, 0u);
+}
+__device__ __forceinline__ Cell cell_bcast(const Cell& c, int src) {
+  Cell r;
+  r.x = __shfl_sync(AG_FULL, c.x, src); r.y = __shfl_sync(AG_FULL, c.y, src);
+  r.vx = __shfl_sync(AG_FULL, c.vx, src); r.vy = __shfl_sync(AG_FULL, c.vy, src);
+  r.svx = __shfl_sync(AG_FULL, c.svx, src); r.svy = __shfl_sync(AG_FULL, c.svy, src);
+  r.mass = __shfl_sync(AG_FULL, c.mass, src); r.id = __shfl_sync(AG_FULL, c.id, src);
+  r.rec = __shfl_sync(AG_FULL, c.rec, src);
+  return r;
+}
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(AG_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(AG_FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(AG_FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
+
+// ------------------------------------------------------------------------------------------------
+// per-warp context: uniform registers + pointers
+// ------------------------------------------------------------------------------------------------
+struct Ctx {
+  const SimParams& P;
+  int lane;
+  uint8_t* blob;
+  agarcl_player* players;
+  agarcl_cell* cells;
+  agarcl_virus* vir;
+  agarcl_food* food;
+  agarcl_pellet* pel;
+  WarpSmem sm;
+  // header, kept in registers for the whole launch
+  uint32_t tick, next_id, cursor, flags, seed_lo, seed_hi, done_sticky;
+  int n_pellets, n_viruses, n_foods;
+  int nprem, nvrem;
+  uint32_t inst_global;
+  int inst_local;
+  float W, dt;
+  __device__ Ctx(const SimParams& p) : P(p) {}
+  __device__ __forceinline__ agarcl_cell* pcells(int p) const { return cells + (size_t)p * AGARCL_MAX_CELLS; }
+};
+
+// one uniform draw in [0,1): k-th draw of this instance (Engine::random<T>, Engine.hpp:1304-1311)
+__device__ __forceinline__ float draw_at(Ctx& c, uint32_t k) {
+  if (c.P.rng_mode == AGARCL_RNG_PHILOX) return philox_uniform(c.seed_lo, c.seed_hi, c.inst_global, k);
+  if ((int)k < c.P.L.cap_replay && c.P.replay) return c.P.replay[(size_t)c.inst_local * c.P.L.cap_replay + k];
+  c.flags |= AGARCL_FLAG_REPLAY_EXHAUSTED;
+  return 0.5f;
+}
+// Engine::random_location(radius), Engine.hpp:143-148, for the draw pair starting at k
+__device__ __forceinline__ void random_location_at(Ctx& c, uint32_t k, float radius, float& x, float& y) {
+  float span = c.W - 2.0f * radius;
+  float ux = draw_at(c, k);
+  x = (ux * span + 0.0f) + radius;
+  float uy = draw_at(c, k + 1);
+  y = (uy * span + 0.0f) + radius;
+}
+
+// Ball::touches, Ball.hpp:36-43
+__device__ __forceinline__ bool touches(const Luts& T, float ax, float ay, uint32_t am, float bx, float by, uint32_t bm) {
+  float s = radius_of(T, am) + radius_of(T, bm);
+  return s * s >= sqr_dist(ax, ay, bx, by) + 0.0f;
+}
+__device__ __forceinline__ void bound_cell(const Ctx& c, Cell& k) {
+  float r = radius_of(c.P.T, k.mass);
+  k.x = bound_axis(k.x, r, c.W);
+  k.y = bound_axis(k.y, r, c.W);
+}
+__device__ __forceinline__ void cell_move(Cell& k, float dt) {  // Cell::move, Entities.hpp:161-164
+  k.x += (k.vx + k.svx) * dt;
+  k.y += (k.vy + k.svy) * dt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair routines of the self-collision solver; operate on broadcast copies (uniform in all lanes)
+// ------------------------------------------------------------------------------------------------
+__device__ void avoid_static_overlap(const Ctx& c, Cell& a, Cell& b) {  // Engine.hpp:701-749
+  float dx = b.x - a.x, dy = b.y - a.y;
+  float dist = sqrtf(dx * dx + dy * dy);
+  float ra = radius_of(c.P.T, a.mass), rb = radius_of(c.P.T, b.mass);
+  float target = ra + rb;
+  if (dist > target) return;
+  float xr = dx / (fabsf(dx) + fabsf(dy));
+  float yr = dy / (fabsf(dx) + fabsf(dy));
+  float depth = target - dist;
+  float arx = 0.5f, ary = 0.5f, brx = 0.5f, bry = 0.5f;
+  if (a.x == ra || a.x == c.W - ra) { arx = 1.0f; a.vx = 0.0f; }
+  if (a.y == ra || a.y == c.W - ra) { ary = 1.0f; a.vy = 0.0f; }
+  if (b.x == rb || b.x == c.W - rb) { brx = 1.0f; b.vx = 0.0f; }
+  if (b.y == rb || b.y == c.W - rb) { bry = 1.0f; b.vy = 0.0f; }
+  a.x -= xr * depth * arx;
+  a.y -= yr * depth * ary;
+  b.x += xr * depth * brx;
+  b.y += yr * depth * bry;
+  bound_cell(c, a);
+  bound_cell(c, b);
+}
+
+__device__ void separate_cells(const Ctx& c, Cell& a, Cell& b, float tx, float ty) {  // Engine.hpp:803-848
+  float dx = b.x - a.x, dy = b.y - a.y;
+  float dist = sqrtf(dx * dx + dy * dy);
+  float target = radius_of(c.P.T, a.mass) + radius_of(c.P.T, b.mass);
+  if (dist > target) return;
+  float xr = dx / (fabsf(dx) + fabsf(dy));
+  float yr = dy / (fabsf(dx) + fabsf(dy));
+  float diff_a = sqr_dist(tx, ty, a.x, a.y);
+  float diff_b = sqr_dist(tx, ty, b.x, b.y);
+  float depth = target - dist;
+  int s1 = (a.mass < b.mass) ? 1 : -1;
+  int s2 = (diff_a >= diff_b) ? 1 : -1;
+  float fs = (float)((s1 == s2) ? s2 : 0);
+  bool move_a = a.mass < b.mass;
+  float tx_ = move_a ? a.x : b.x, ty_ = move_a ? a.y : b.y;
+  if (dx >= 0) {
+    tx_ -= xr * depth * fs;
+    if (dy >= 0) ty_ -= yr * depth * fs; else ty_ += yr * depth * fs;
+  } else {
+    tx_ += xr * depth * fs;
+    if (dy >= 0) ty_ -= yr * depth * fs; else ty_ += yr * depth * fs;
+  }
+  if (move_a) { a.x = tx_; a.y = ty_; } else { b.x = tx_; b.y = ty_; }
+}
+
+__device__ void elastic(Cell& a, Cell& b, float dx, float dy, float dist) {  // Engine.hpp:893-938
+  float nx = dx / dist, ny = dy / dist;
+  float tx = -ny, ty = nx;
+  float dpn1 = a.vx * nx + a.vy * ny;
+  float dpn2 = b.vx * nx + b.vy * ny;
+  float dpt1 = a.vx * tx + a.vy * ty;
+  float dpt2 = b.vx * tx + b.vy * ty;
+  int m1 = (int)a.mass, m2 = (int)b.mass;
+  float v1 = (dpn1 * (float)(m1 - m2) + 2.0f * (float)m2 * dpn2) / (float)(m1 + m2);
+  float v2 = (dpn2 * (float)(m2 - m1) + 2.0f * (float)m1 * dpn1) / (float)(m1 + m2);
+  if (a.mass < b.mass) {
+    a.vx = tx * dpt1 + nx * v1; a.vy = ty * dpt1 + ny * v1;
+  } else if (a.mass > b.mass) {
+    b.vx = tx * dpt2 + nx * v2; b.vy = ty * dpt2 + ny * v2;
+  } else {
+    a.vx = tx * dpt1 + nx * v1; a.vy = ty * dpt1 + ny * v1;
+    b.vx = tx * dpt2 + nx * v2; b.vy = ty * dpt2 + ny * v2;
+  }
+}
+
+__device__ void prevent_overlap(const Ctx& c, Cell& a, Cell& b, float tx, float ty) {  // Engine.hpp:857-888
+  float dx = b.x - a.x, dy = b.y - a.y;
+  float dist = sqrtf(dx * dx + dy * dy);
+  float target = radius_of(c.P.T, a.mass) + radius_of(c.P.T, b.mass);
+  if (dist > target) return;
+  float dt = c.dt;
+  a.x -= (a.vx + a.svx) * dt;
+  a.y -= (a.vy + a.svy) * dt;
+  b.x -= (b.vx + b.svx) * dt;
+  b.y -= (b.vy + b.svy) * dt;
+  elastic(a, b, dx, dy, dist);
+  cell_move(a, dt);
+  cell_move(b, dt);
+  if (touches(c.P.T, a.x, a.y, a.mass, b.x, b.y, b.mass)) {
+    int diff = (int)(a.mass - b.mass);
+    if (abs(diff) <= 10) avoid_static_overlap(c, a, b);
+    else separate_cells(c, a, b, tx, ty);
+  }
+  bound_cell(c, a);
+  bound_cell(c, b);
+}
+
+// Engine::check_player_self_collisions, Engine.hpp:763-794.  The reference walks pairs (a<b) in
+// index order and resolves the touching ones; here, for a fixed `a`, one ballot finds the next
+// touching b, the pair is resolved on broadcast copies, and the ballot is re-issued (a has moved).
+__device__ void self_collisions(const Ctx& c, Cell& me, int n, float tx, float ty) {
+  bool overlap = false;
+  for (int iter = 0; iter < 5; iter++) {
+    overlap = false;
+    for (int a = 0; a + 1 < n; a++) {
+      int b_last = a;
+      while (true) {
+        float ax = __shfl_sync(AG_FULL, me.x, a), ay = __shfl_sync(AG_FULL, me.y, a);
+        uint32_t am = __shfl_sync(AG_FULL, me.mass, a);
+        bool t = c.lane > b_last && c.lane < n && touches(c.P.T, ax, ay, am, me.x, me.y, me.mass);
+        unsigned m = __ballot_sync(AG_FULL, t);
+        if (!m) break;
+        int b = __ffs(m) - 1;
+        overlap = true;
+        Cell A = cell_bcast(me, a), B = cell_bcast(me, b);
+        prevent_overlap(c, A, B, tx, ty);
+        if (c.lane == a) me = A;
+        if (c.lane == b) me = B;
+        b_last = b;
+      }
+    }
+    if (!overlap) break;
+  }
+  if (overlap) {
+    for (int a = 0; a + 1 < n; a++) {
+      int b_last = a;
+      while (true) {
+        float ax = __shfl_sync(AG_FULL, me.x, a), ay = __shfl_sync(AG_FULL, me.y, a);
+        uint32_t am = __shfl_sync(AG_FULL, me.mass, a);
+        bool t = c.lane > b_last && c.lane < n && touches(c.P.T, ax, ay, am, me.x, me.y, me.mass);
+        unsigned m = __ballot_sync(AG_FULL, t);
+        if (!m) break;
+        int b = __ffs(m) - 1;
+        Cell A = cell_bcast(me, a), B = cell_bcast(me, b);
+        avoid_static_overlap(c, A, B);
+        if (c.lane == a) me = A;
+        if (c.lane == b) me = B;
+        b_last = b;
+      }
+    }
+  }
+}
+
+// Player::x / y / mass (Player.hpp:102-126): sequential fp32 accumulation in cell order
+__device__ __forceinline__ float4 centroid_of(const Cell& me, int n) {
+  float xs = 0.0f, ys = 0.0f;
+  uint32_t tot = 0;
+  for (int i = 0; i < n; i++) {
+    float x = __shfl_sync(AG_FULL, me.x, i), y = __shfl_sync(AG_FULL, me.y, i);
+    uint32_t m = __shfl_sync(AG_FULL, me.mass, i);
+    xs += x * (float)m;
+    ys += y * (float)m;
+    tot += m;
+  }
+  float fm = (float)tot;
+  return make_float4(xs / fm, ys / fm, __uint_as_float(tot), __int_as_float(n));
+}
+// same thing straight from global memory, by one lane (divergent trip counts allowed: no shuffles)
+__device__ float4 centroid_from_global(const agarcl_cell* g, int n) {
+  float xs = 0.0f, ys = 0.0f;
+  uint32_t tot = 0;
+  for (int i = 0; i < n; i++) {
+    float4 a = reinterpret_cast<const float4*>(g + i)[0];
+    uint32_t m = g[i].mass;
+    xs += a.x * (float)m;
+    ys += a.y * (float)m;
+    tot += m;
+  }
+  float fm = (float)tot;
+  return make_float4(xs / fm, ys / fm, __uint_as_float(tot), __int_as_float(n));
+}
+
+// ------------------------------------------------------------------------------------------------
+// bots
+// ------------------------------------------------------------------------------------------------
+// Bot::nearest_pellet, Bot.hpp:92-129: first index attaining the minimum of sqrtf(d^2) among d > 0.01
+__device__ void nearest_pellet(Ctx& c, float lx, float ly, float& tx, float& ty) {
+  if (c.n_pellets == 0) {  // std::rand() % arena: not replayable (flagged), same stand-in as the oracle
+    c.flags |= AGARCL_FLAG_RAND_SITE;
+    tx = 0.0f; ty = 0.0f;
+    return;
+  }
+  float best = 3.402823466e+38f;
+  uint32_t best_i = 0xffffffffu;
+  for (int i = c.lane; i < c.n_pellets; i += 32) {
+    float2 p = reinterpret_cast<const float2*>(c.pel)[i];
+    float d = sqrtf(sqr_dist(lx, ly, p.x, p.y));  // (other - this).norm()
+    if (d < best && (double)d > 0.01) { best = d; best_i = (uint32_t)i; }
+  }
+  // global first-min: smallest distance, then smallest index
+  float gbest = best;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gbest = fminf(gbest, __shfl_xor_sync(AG_FULL, gbest, o));
+  uint32_t cand = (best == gbest && best_i != 0xffffffffu) ? best_i : 0xffffffffu;
+  cand = warp_min_u32(cand);
+  if (cand == 0xffffffffu) { tx = 0.0f; ty = 0.0f; return; }  // nothing qualified: Location() default
+  float2 p = reinterpret_cast<const float2*>(c.pel)[cand];
+  tx = p.x; ty = p.y;
+}
+
+// flee loop of HungryShyBot.hpp:26-40 / AggressiveShyBot.hpp:30-43.  `other.mass() > mass()` compares
+// against the TYPE agario::mass value-initialised to 0 (core/types.hpp:52), i.e. "other is alive".
+__device__ bool bot_flee(Ctx& c, int p, float lx, float ly, float& tx, float& ty) {
+  const int P = c.P.L.P;
+  for (int base = 0; base < P; base += 32) {
+    int k = base + c.lane;
+    bool cond = false;
+    float ox = 0.f, oy = 0.f;
+    if (k < P) {
+      int o = c.P.L.order[k];
+      float4 s = c.sm.psum[o];
+      ox = s.x; oy = s.y;
+      float d = sqrtf(sqr_dist(ox, oy, lx, ly));
+      cond = (o != p) && (d < 25.0f) && (__float_as_uint(s.z) > 0u);
+    }
+    unsigned m = __ballot_sync(AG_FULL, cond);
+    if (m) {
+      int src = __ffs(m) - 1;
+      ox = __shfl_sync(AG_FULL, ox, src);
+      oy = __shfl_sync(AG_FULL, oy, src);
+      tx = lx - (ox - lx);
+      ty = ly - (oy - ly);
+      return true;
+    }
+  }
+  return false;
+}
+
+// chase loop of AggressiveBot.hpp:33-49 / AggressiveShyBot.hpp:47-64 with Bot::edible_mass and
+// Bot::target_player (Bot.hpp:55-88)
+__device__ bool bot_chase(Ctx& c, int p, const Cell& me, int n, float lx, float ly, float& tx, float& ty) {
+  // Bot::largest_cell: first maximum
+  uint32_t mymass = c.lane < n ? me.mass : 0u;
+  uint32_t big = warp_max_u32(mymass);
+  const int P = c.P.L.P;
+  for (int base = 0; base < P; base += 32) {
+    int k = base + c.lane;
+    bool near = false;
+    if (k < P) {
+      int o = c.P.L.order[k];
+      float4 s = c.sm.psum[o];
+      float d = sqrtf(sqr_dist(s.x, s.y, lx, ly));
+      near = (o != p) && (d <= 20.0f);
+    }
+    unsigned m = __ballot_sync(AG_FULL, near);
+    while (m) {
+      int src = __ffs(m) - 1;
+      m &= m - 1;
+      int o = c.P.L.order[base + src];
+      int on = __float_as_int(c.sm.psum[o].w);
+      Cell oc;
+      oc.mass = 0; oc.x = 0.f; oc.y = 0.f;
+      if (c.lane < on) {
+        const agarcl_cell* g = c.pcells(o) + c.lane;
+        float4 a = reinterpret_cast<const float4*>(g)[0];
+        oc.x = a.x; oc.y = a.y; oc.mass = g->mass;
+      }
+      bool edible = c.lane < on && cell_can_eat_cell(big, oc.mass);
+      unsigned em = __ballot_sync(AG_FULL, edible);
+      if (em) {
+        float sx = 0.0f, sy = 0.0f;
+        uint32_t sm = 0;
+        for (int i = 0; i < on; i++) {
+          float x = __shfl_sync(AG_FULL, oc.x, i), y = __shfl_sync(AG_FULL, oc.y, i);
+          uint32_t mm = __shfl_sync(AG_FULL, oc.mass, i);
+          if (em & (1u << i)) { sx += x * (float)mm; sy += y * (float)mm; sm += mm; }
+        }
+        float dsx = sx / (float)sm - lx, dsy = sy / (float)sm - ly;
+        tx = lx + dsx * 3.0f;
+        ty = ly + dsy * 3.0f;
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-tick builds: pellet spatial hash (warp counting sort in shared memory) and virus cache
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int hash_coord(const Ctx& c, float v) {
+  int h = (int)(v * c.P.hash_scale);
+  return min(max(h, 0), c.P.HG - 1);
+}
+__device__ void build_pellet_hash(Ctx& c) {
+  const int HG = c.P.HG, nc = HG * HG;
+  for (int i = c.lane; i < nc; i += 32) c.sm.hcnt[i] = 0u;
+  __syncwarp();
+  for (int i = c.lane; i < c.n_pellets; i += 32) {
+    float2 p = reinterpret_cast<const float2*>(c.pel)[i];
+    atomicAdd(&c.sm.hcnt[hash_coord(c, p.y) * HG + hash_coord(c, p.x)], 1u);
+  }
+  __syncwarp();
+  // exclusive scan over nc counters, 32 at a time
+  uint32_t carry = 0;
+  for (int base = 0; base < nc; base += 32) {
+    int i = base + c.lane;
+    uint32_t v = i < nc ? c.sm.hcnt[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(AG_FULL, incl, o);
+      if (c.lane >= o) incl += t;
+    }
+    if (i < nc) c.sm.hcnt[i] = carry + incl - v;
+    carry += __shfl_sync(AG_FULL, incl, 31);
+  }
+  __syncwarp();
+  for (int i = c.lane; i < c.n_pellets; i += 32) {
+    float2 p = reinterpret_cast<const float2*>(c.pel)[i];
+    uint32_t pos = atomicAdd(&c.sm.hcnt[hash_coord(c, p.y) * HG + hash_coord(c, p.x)], 1u);
+    c.sm.hsorted[pos] = (uint16_t)i;
+  }
+  __syncwarp();
+  // now hcnt[k] = end of cell k; start of cell k = (k ? hcnt[k-1] : 0)
+}
+__device__ void build_virus_cache(Ctx& c) {
+  for (int v = c.lane; v < c.n_viruses; v += 32) {
+    const float4 a = reinterpret_cast<const float4*>(c.vir + v)[0];  // x, y, mass, hits
+    uint32_t vm = __float_as_uint(a.z);
+    c.sm.vcache[v] = make_float4(a.x, a.y, radius_of(c.P.T, vm), a.z);
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Engine::tick_player
+// ------------------------------------------------------------------------------------------------
+__device__ void tick_player(Ctx& c, int p) {
+  const Luts& T = c.P.T;
+  agarcl_player* pl = c.players + p;
+  int n = pl->n_cells;
+  if (n == 0) return;  // dead players are not ticked (Engine.hpp:216)
+  const int lane = c.lane;
+  float tx = pl->target_x, ty = pl->target_y;
+  int action = pl->action;
+  const int bot_type = pl->bot_type;
+  int elapsed = pl->elapsed_ticks + 1;
+
+  Cell me;
+  me.x = me.y = me.vx = me.vy = me.svx = me.svy = 0.0f;
+  me.mass = 0; me.id = 0; me.rec = 0;
+  if (lane < n) me = cell_load(c.pcells(p) + lane);
+
+  // ---- bots decide every 10th tick (Engine.hpp:498-499)
+  if (c.tick % 10u == 0u && bot_type >= 0) {
+    float4 s = c.sm.psum[p];
+    float lx = s.x, ly = s.y;
+    bool decided = false;
+    if (bot_type == 1 || bot_type == 3) {
+      if (bot_type == 1) action = 0;
+      decided = bot_flee(c, p, lx, ly, tx, ty);
+    }
+    if (!decided && (bot_type == 2 || bot_type == 3)) decided = bot_chase(c, p, me, n, lx, ly, tx, ty);
+    if (!decided) {
+      action = 0;
+      nearest_pellet(c, lx, ly, tx, ty);
+    }
+  }
+
+  // ---- Engine::move_player
+  uint32_t smallest = 0xffffffffu;
+  if (lane < n) {
+    me.vx = 3.0f * (tx - me.x);
+    me.vy = 3.0f * (ty - me.y);
+    smallest = me.mass;
+    float limit = max_speed_of(T, me.mass, c.flags);
+    if (vmag(me.vx, me.vy) > limit) {  // Velocity::clamp_speed + set_speed (quirk Q8)
+      me.vx *= limit / vmag(me.vx, me.vy);
+      me.vy *= limit / vmag(me.vx, me.vy);
+    }
+    cell_move(me, c.dt);
+    decelerate(me.svx, me.svy, 80.0f, c.dt);
+    bound_cell(c, me);
+  }
+  smallest = warp_min_u32(smallest);
+  c.flags = __reduce_or_sync(AG_FULL, c.flags);
+  if (n >= 2) self_collisions(c, me, n, tx, ty);
+
+  // ---- created cells accumulate in lanes [n, n+created) (they are inactive until add_cells)
+  int created = 0;
+  int create_limit = AGARCL_PLAYER_CELL_LIMIT - n;
+  const bool can_eat_virus = n >= AGARCL_PLAYER_CELL_LIMIT;
+  int viruses_eaten_inc = 0;
+  int vet_count = pl->vet_count;
+
+  // ---- optimized_check_virus_collisions: first hit in (cell, dx, dy, virus index) order
+  if (c.n_viruses > 0) {
+    for (int i = 0; i < n; i++) {
+      float cx = __shfl_sync(AG_FULL, me.x, i), cy = __shfl_sync(AG_FULL, me.y, i);
+      uint32_t cm = __shfl_sync(AG_FULL, me.mass, i);
+      float cr = radius_of(T, cm);
+      int gx = (int)cx / 25, gy = (int)cy / 25;
+      uint32_t bestkey = 0xffffffffu;
+      for (int base = 0; base < c.n_viruses; base += 32) {
+        int v = base + lane;
+        uint32_t key = 0xffffffffu;
+        if (v < c.n_viruses) {
+          float4 vc = c.sm.vcache[v];
+          int vgx = (int)vc.x / 25, vgy = (int)vc.y / 25;
+          int ddx = vgx - gx, ddy = vgy - gy;
+          uint32_t vm = __float_as_uint(vc.w);
+          bool ok = ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1 && vgx < c.P.gw_virus && vgy < c.P.gw_virus &&
+                    can_eat_mass(cm, vm) && collides(cx, cy, cr, vc.x, vc.y, vc.z);
+          if (ok) key = ((uint32_t)((ddx + 1) * 3 + (ddy + 1)) << 16) | (uint32_t)v;
+        }
+        bestkey = min(bestkey, warp_min_u32(key));
+      }
+      if (bestkey != 0xffffffffu) {
+        int v = (int)(bestkey & 0xffffu);
+        float4 vc = c.sm.vcache[v];
+        uint32_t vm = __float_as_uint(vc.w);
+        if (can_eat_virus) {
+          if (lane == i) me.mass = floor_mass(me.mass + vm);
+        } else {
+          // Engine::disrupt
+          Cell par = cell_bcast(me, i);
+          uint32_t total = par.mass;
+          uint32_t m2 = floor_mass((uint32_t)((float)par.mass / 2.0f));
+          m2 = floor_mass(m2 + (total - m2) % 25u);
+          uint32_t pop = total - m2;
+          int num = (int)((pop + 24u) / 25u);
+          if (create_limit < num) num = create_limit;
+          if (num < 0) num = 0;
+          if (n + num > 32) { num = 32 - n; c.flags |= AGARCL_FLAG_CELL_OVERFLOW; }
+          float theta = vel_direction(par.vx, par.vy);
+          float sp = max_speed_of(T, 25u, c.flags);
+          int ci = lane - n;
+          if (ci >= 0 && ci < num) {
+            float dvel = theta + (float)(2 * AG_PI * ci / num);
+            float ang = theta + dvel;
+            double sn, cs;
+            p_sincos((double)ang, &sn, &cs);
+            me.x = vc.x; me.y = vc.y;
+            me.vx = par.vx; me.vy = par.vy;
+            me.svx = sp * (float)cs; me.svy = sp * (float)sn;
+            me.mass = 25u;
+            me.id = c.next_id + (uint32_t)ci;
+            me.rec = c.tick + AGARCL_RECOMBINE_TICKS;
+          }
+          if (lane == i) { me.mass = m2; me.rec = c.tick + AGARCL_RECOMBINE_TICKS; }
+          created += num;
+          c.next_id += (uint32_t)num;
+        }
+        if (c.nvrem < kVremCap) { if (lane == 0) c.sm.vrem[c.nvrem] = (uint16_t)v; c.nvrem++; }
+        else c.flags |= AGARCL_FLAG_REMOVE_OVERFLOW;
+        if (vet_count < AGARCL_VET_CAP) { if (lane == 0) pl->vet_ticks[vet_count] = elapsed; vet_count++; }
+        else c.flags |= AGARCL_FLAG_VET_OVERFLOW;
+        viruses_eaten_inc = 1;
+        break;  // only collide once (Engine.hpp:1244)
+      }
+    }
+  }
+
+  // ---- get_pellets_to_remove_and_increment_cells
+  int pellets_eaten = 0;
+  if (c.n_pellets > 0) {
+    const int HG = c.P.HG;
+    const float rp = radius_of(T, 1u);
+    for (int i = 0; i < n; i++) {
+      float cx = __shfl_sync(AG_FULL, me.x, i), cy = __shfl_sync(AG_FULL, me.y, i);
+      uint32_t cm = __shfl_sync(AG_FULL, me.mass, i);
+      const int gx = (int)cx / 510, gy = (int)cy / 510;
+      float Rc = fmax_std(radius_of(T, cm + (uint32_t)kCandCap), rp);
+      float Rc2 = Rc * Rc;
+      int hx0 = hash_coord(c, cx - Rc), hx1 = hash_coord(c, cx + Rc);
+      int hy0 = hash_coord(c, cy - Rc), hy1 = hash_coord(c, cy + Rc);
+      int ncand = 0;
+      for (int hy = hy0; hy <= hy1; hy++) {
+        int k0 = hy * HG + hx0, k1 = hy * HG + hx1;
+        int s = k0 ? (int)c.sm.hcnt[k0 - 1] : 0, e = (int)c.sm.hcnt[k1];
+        for (int jb = s; jb < e; jb += 32) {
+          int j = jb + lane;
+          bool cand = false;
+          uint32_t key = 0;
+          float d2 = 0.f;
+          if (j < e) {
+            int idx = c.sm.hsorted[j];
+            float2 q = reinterpret_cast<const float2*>(c.pel)[idx];
+            d2 = sqr_dist(cx, cy, q.x, q.y);
+            int bx = (int)q.x / 510 - gx, by = (int)q.y / 510 - gy;
+            cand = d2 <= Rc2 && bx >= -1 && bx <= 1 && by >= -1 && by <= 1;
+            key = ((uint32_t)((bx + 1) * 3 + (by + 1)) << 16) | (uint32_t)idx;
+          }
+          unsigned m = __ballot_sync(AG_FULL, cand);
+          if (cand) {
+            int pos = ncand + __popc(m & lanemask_lt(lane));
+            if (pos < kCandCap) c.sm.cand[pos] = make_uint2(key, __float_as_uint(d2));
+          }
+          ncand += __popc(m);
+        }
+      }
+      if (ncand == 0) continue;
+      __syncwarp();
+      uint32_t newmass = cm;
+      if (ncand <= kCandCap) {
+        // replay the candidates in reference order with the growing mass
+        uint2 mine = lane < ncand ? c.sm.cand[lane] : make_uint2(0xffffffffu, 0u);
+        for (int it = 0; it < ncand; it++) {
+          uint32_t kmin = warp_min_u32(mine.x);
+          unsigned wm = __ballot_sync(AG_FULL, mine.x == kmin);
+          int w = __ffs(wm) - 1;
+          float d2 = __uint_as_float(__shfl_sync(AG_FULL, mine.y, w));
+          float r = fmax_std(radius_of(T, newmass), rp);
+          if (r * r >= d2) {  // Ball::collides_with; can_eat(pellet) always holds for mass >= 25
+            if (c.nprem < kPremCap) { if (lane == 0) c.sm.prem[c.nprem] = (uint16_t)(kmin & 0xffffu); c.nprem++; }
+            else c.flags |= AGARCL_FLAG_REMOVE_OVERFLOW;
+            newmass = floor_mass(newmass + 1u);
+            pellets_eaten++;
+          }
+          if (lane == w) mine.x = 0xffffffffu;
+        }
+      } else {
+        // dense case (giant cell): ordered scan of ALL pellets in the reference's own order
+        float Rf = fmax_std(radius_of(T, cm + (uint32_t)c.n_pellets), rp);
+        float Rf2 = Rf * Rf;
+        for (int dxb = -1; dxb <= 1; dxb++)
+          for (int dyb = -1; dyb <= 1; dyb++) {
+            int nx = gx + dxb, ny = gy + dyb;
+            if (!(nx >= 0 && nx < c.P.gw_pellet && ny >= 0 && ny < c.P.gw_pellet)) continue;
+            for (int base = 0; base < c.n_pellets; base += 32) {
+              int idx = base + lane;
+              bool cand = false;
+              float d2 = 0.f;
+              if (idx < c.n_pellets) {
+                float2 q = reinterpret_cast<const float2*>(c.pel)[idx];
+                d2 = sqr_dist(cx, cy, q.x, q.y);
+                cand = ((int)q.x / 510 == nx) && ((int)q.y / 510 == ny) && d2 <= Rf2;
+              }
+              unsigned m = __ballot_sync(AG_FULL, cand);
+              while (m) {
+                int w = __ffs(m) - 1;
+                m &= m - 1;
+                float dd = __shfl_sync(AG_FULL, d2, w);
+                float r = fmax_std(radius_of(T, newmass), rp);
+                if (r * r >= dd) {
+                  if (c.nprem < kPremCap) { if (lane == 0) c.sm.prem[c.nprem] = (uint16_t)(base + w); c.nprem++; }
+                  else c.flags |= AGARCL_FLAG_REMOVE_OVERFLOW;
+                  newmass = floor_mass(newmass + 1u);
+                  pellets_eaten++;
+                }
+              }
+            }
+          }
+      }
+      if (lane == i) me.mass = newmass;
+      __syncwarp();
+    }
+  }
+  int food_eaten = pl->food_eaten + pellets_eaten;
+  uint32_t total_mass = warp_sum_u32(lane < n ? me.mass : 0u);
+  uint32_t highest = max(pl->highest_mass, total_mass);
+
+  // ---- may_be_auto_split for every cell (children keep cell order), then eat_food cell by cell
+  {
+    bool big = lane < n && me.mass >= AGARCL_MAX_MASS_IN_THE_GAME;
+    unsigned bm = __ballot_sync(AG_FULL, big);
+    if (bm) {
+      if (n < AGARCL_PLAYER_CELL_LIMIT) {
+        // Engine::cell_split on the parent lanes
+        float chx = 0.f, chy = 0.f, chvx = 0.f, chvy = 0.f;
+        uint32_t chm = 0;
+        if (big) {
+          uint32_t split_mass = me.mass / 2u, remaining = me.mass - split_mass;
+          me.mass = floor_mass(remaining);
+          float ddx = tx - me.x, ddy = ty - me.y;
+          float norm = sqrtf(fabsf(ddx) * fabsf(ddx) + fabsf(ddy) * fabsf(ddy));
+          float dirx = ddx / norm, diry = ddy / norm;
+          float r = radius_of(T, me.mass);
+          chx = bound_axis(me.x + dirx * r, r, c.W);
+          chy = bound_axis(me.y + diry * r, r, c.W);
+          float sp = split_speed_of(T, split_mass, c.flags);
+          chvx = dirx * sp; chvy = diry * sp;
+          chm = split_mass;
+          me.rec = c.tick + AGARCL_RECOMBINE_TICKS;
+        }
+        int cnt = __popc(bm);
+        if (n + created + cnt > 32) c.flags |= AGARCL_FLAG_CELL_OVERFLOW;
+        int r = lane - (n + created);
+        int src = (r >= 0 && r < cnt) ? (int)__fns(bm, 0, r + 1) : lane;
+        float gx_ = __shfl_sync(AG_FULL, chx, src), gy_ = __shfl_sync(AG_FULL, chy, src);
+        float gvx = __shfl_sync(AG_FULL, chvx, src), gvy = __shfl_sync(AG_FULL, chvy, src);
+        uint32_t gm = __shfl_sync(AG_FULL, chm, src);
+        if (r >= 0 && r < cnt) {
+          me.x = gx_; me.y = gy_; me.vx = gvx; me.vy = gvy; me.svx = gvx; me.svy = gvy;
+          me.mass = floor_mass(gm);
+          me.id = c.next_id + (uint32_t)r;
+          me.rec = c.tick + AGARCL_RECOMBINE_TICKS;
+        }
+        created += cnt;
+        c.next_id += (uint32_t)cnt;
+      } else if (big) {
+        me.mass = AGARCL_NEW_MASS_IF_NO_SPLIT;
+      }
+    }
+  }
+  if (c.n_foods > 0) {
+    const float rf = radius_of(T, AGARCL_FOOD_MASS);
+    for (int i = 0; i < n; i++) {
+      float cx = __shfl_sync(AG_FULL, me.x, i), cy = __shfl_sync(AG_FULL, me.y, i);
+      uint32_t cm = __shfl_sync(AG_FULL, me.mass, i);
+      float cr = radius_of(T, cm);
+      bool eater = can_eat_mass(cm, AGARCL_FOOD_MASS);
+      int w = 0;
+      const int nf = c.n_foods;
+      for (int base = 0; base < nf; base += 32) {
+        int j = base + lane;
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool keep = false;
+        if (j < nf) {
+          f = reinterpret_cast<const float4*>(c.food)[j];
+          keep = !(eater && collides(cx, cy, cr, f.x, f.y, rf));
+        }
+        unsigned km = __ballot_sync(AG_FULL, keep);
+        int dst = w + __popc(km & lanemask_lt(lane));
+        if (keep && dst != j) reinterpret_cast<float4*>(c.food)[dst] = f;
+        w += __popc(km);
+        __syncwarp();
+      }
+      int num = nf - w;
+      if (num) {
+        c.n_foods = w;
+        if (lane == i) me.mass = floor_mass(me.mass + (uint32_t)num * AGARCL_FOOD_MASS);
+        food_eaten += num;
+      }
+    }
+  }
+  create_limit -= created;
+
+  // ---- maybe_emit_food / emit_foods
+  int feed_cd = pl->feed_cd, split_cd = pl->split_cd;
+  if (feed_cd > 0) feed_cd -= 1;
+  if (action == 1 && feed_cd == 0) {
+    bool emit = lane < n && me.mass >= AGARCL_CELL_MIN_SIZE + AGARCL_FOOD_MASS;
+    unsigned em = __ballot_sync(AG_FULL, emit);
+    if (emit) {
+      float ddx = tx - me.x, ddy = ty - me.y;
+      float norm = sqrtf(fabsf(ddx) * fabsf(ddx) + fabsf(ddy) * fabsf(ddy));
+      float dirx = ddx / norm, diry = ddy / norm;
+      float r = radius_of(T, me.mass);
+      int slot = c.n_foods + __popc(em & lanemask_lt(lane));
+      if (slot < c.P.L.cap_foods)
+        reinterpret_cast<float4*>(c.food)[slot] = make_float4(me.x + dirx * r, me.y + diry * r, dirx * 100.0f, diry * 100.0f);
+      me.mass = floor_mass(me.mass - AGARCL_FOOD_MASS);
+    }
+    int add = __popc(em);
+    if (c.n_foods + add > c.P.L.cap_foods) { c.flags |= AGARCL_FLAG_FOOD_OVERFLOW; add = c.P.L.cap_foods - c.n_foods; }
+    c.n_foods += add;
+    feed_cd = 10;
+    __syncwarp();
+  }
+
+  // ---- maybe_split / player_split
+  if (split_cd > 0) split_cd -= 1;
+  if (action == 2 && split_cd == 0) {
+    if (create_limit != 0) {
+      bool elig = lane < n && !(me.mass < AGARCL_CELL_SPLIT_MINIMUM || me.mass < 2u * AGARCL_CELL_MIN_SIZE);
+      unsigned eligm = __ballot_sync(AG_FULL, elig);
+      int rank = __popc(eligm & lanemask_lt(lane));
+      bool split = elig && (create_limit < 0 || rank < create_limit);
+      unsigned sm_ = __ballot_sync(AG_FULL, split);
+      float chx = 0.f, chy = 0.f, chvx = 0.f, chvy = 0.f;
+      uint32_t chm = 0;
+      if (split) {
+        uint32_t split_mass = me.mass / 2u, remaining = me.mass - split_mass;
+        me.mass = floor_mass(remaining);
+        float ddx = tx - me.x, ddy = ty - me.y;
+        float norm = sqrtf(fabsf(ddx) * fabsf(ddx) + fabsf(ddy) * fabsf(ddy));
+        float dirx = ddx / norm, diry = ddy / norm;  // NaN when the target is the cell itself (quirk Q19)
+        float r = radius_of(T, me.mass);
+        chx = bound_axis(me.x + dirx * r, r, c.W);
+        chy = bound_axis(me.y + diry * r, r, c.W);
+        float sp = split_speed_of(T, split_mass, c.flags);
+        chvx = dirx * sp; chvy = diry * sp;
+        chm = split_mass;
+        me.rec = c.tick + AGARCL_RECOMBINE_TICKS;
+      }
+      int cnt = __popc(sm_);
+      if (n + created + cnt > 32) c.flags |= AGARCL_FLAG_CELL_OVERFLOW;
+      int r = lane - (n + created);
+      int src = (r >= 0 && r < cnt) ? (int)__fns(sm_, 0, r + 1) : lane;
+      float gx_ = __shfl_sync(AG_FULL, chx, src), gy_ = __shfl_sync(AG_FULL, chy, src);
+      float gvx = __shfl_sync(AG_FULL, chvx, src), gvy = __shfl_sync(AG_FULL, chvy, src);
+      uint32_t gm = __shfl_sync(AG_FULL, chm, src);
+      if (r >= 0 && r < cnt) {
+        me.x = gx_; me.y = gy_; me.vx = gvx; me.vy = gvy; me.svx = gvx; me.svy = gvy;
+        me.mass = floor_mass(gm);
+        me.id = c.next_id + (uint32_t)r;
+        me.rec = c.tick + AGARCL_RECOMBINE_TICKS;
+      }
+      created += cnt;
+      c.next_id += (uint32_t)cnt;
+    }
+    split_cd = 30;
+  }
+  c.flags = __reduce_or_sync(AG_FULL, c.flags);
+
+  // ---- Player::add_cells
+  n = min(n + created, 32);
+
+  // ---- recombine_cells (swap-with-back semantics)
+  if (n >= 2) {
+    for (int a = 0; a < n; a++) {
+      uint32_t arec = __shfl_sync(AG_FULL, me.rec, a);
+      if (!(c.tick >= arec)) continue;
+      int b_cur = a + 1;
+      while (true) {
+        float ax = __shfl_sync(AG_FULL, me.x, a), ay = __shfl_sync(AG_FULL, me.y, a);
+        uint32_t am = __shfl_sync(AG_FULL, me.mass, a);
+        bool t = lane >= b_cur && lane < n && c.tick >= me.rec && touches(T, ax, ay, am, me.x, me.y, me.mass);
+        unsigned m = __ballot_sync(AG_FULL, t);
+        if (!m) break;
+        int b = __ffs(m) - 1;
+        uint32_t bmass = __shfl_sync(AG_FULL, me.mass, b);
+        Cell last = cell_bcast(me, n - 1);
+        if (lane == a) me.mass = floor_mass(me.mass + bmass);
+        if (lane == b) me = last;
+        n--;
+        b_cur = b;
+      }
+    }
+  }
+
+  // ---- once per 60 player-ticks: anti-team + decay
+  float atd = pl->anti_team_decay;
+  int last_decay = pl->last_decay_tick;
+  if (c.P.L.mass_decay && elapsed % 60 == 0) {
+    int fall_off = elapsed - 60 * 60;
+    __syncwarp();
+    int t = (lane < vet_count) ? pl->vet_ticks[lane] : 0;
+    __syncwarp();
+    bool keep = lane < vet_count && !(t < fall_off);
+    unsigned km = __ballot_sync(AG_FULL, keep);
+    if (keep) pl->vet_ticks[__popc(km & lanemask_lt(lane))] = t;
+    vet_count = __popc(km);
+    if (vet_count > 0) atd = T.anti_team[vet_count];
+    if (elapsed - last_decay >= 60) {
+      if (lane < n) {
+        uint32_t nm = (uint32_t)((double)me.mass * (1 - 0.002 * (double)atd));
+        me.mass = nm > AGARCL_CELL_MIN_SIZE ? nm : AGARCL_CELL_MIN_SIZE;
+      }
+      last_decay = elapsed;
+    }
+    __syncwarp();
+  }
+
+  // ---- publish: centroid for later readers this tick, cells and player record back to the blob
+  float4 s = centroid_of(me, n);
+  if (lane < n) cell_store(c.pcells(p) + lane, me);
+  if (lane == 0) {
+    c.sm.psum[p] = s;
+    pl->n_cells = n;
+    pl->target_x = tx; pl->target_y = ty;
+    pl->action = action;
+    pl->split_cd = split_cd; pl->feed_cd = feed_cd;
+    pl->anti_team_decay = atd;
+    pl->elapsed_ticks = elapsed; pl->last_decay_tick = last_decay;
+    pl->min_mass_cell = smallest;
+    pl->food_eaten = food_eaten;
+    pl->highest_mass = highest;
+    pl->viruses_eaten += viruses_eaten_inc;
+    pl->vet_count = vet_count;
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// after the player loop: removals, players_collision, foods, regen
+// ------------------------------------------------------------------------------------------------
+__device__ void apply_removals(Ctx& c) {  // Engine.hpp:1002-1009,1253-1260 incl. stale/duplicate indices (Q4/Q5)
+  if (c.lane == 0) {
+    for (int k = 0; k < c.nprem; k++) {
+      uint32_t idx = c.sm.prem[k], size = (uint32_t)c.n_pellets;
+      if (idx < size - 1u && size > 1u) reinterpret_cast<float2*>(c.pel)[idx] = reinterpret_cast<float2*>(c.pel)[size - 1u];
+      if (size >= 1u) c.n_pellets--;
+    }
+    for (int k = 0; k < c.nvrem; k++) {
+      uint32_t idx = c.sm.vrem[k], size = (uint32_t)c.n_viruses;
+      if (idx < size - 1u && size > 1u) {
+        reinterpret_cast<float4*>(c.vir + idx)[0] = reinterpret_cast<float4*>(c.vir + size - 1u)[0];
+        reinterpret_cast<float4*>(c.vir + idx)[1] = reinterpret_cast<float4*>(c.vir + size - 1u)[1];
+      }
+      if (size >= 1u) c.n_viruses--;
+    }
+  }
+  c.n_pellets = __shfl_sync(AG_FULL, c.n_pellets, 0);
+  c.n_viruses = __shfl_sync(AG_FULL, c.n_viruses, 0);
+  c.nprem = 0;
+  c.nvrem = 0;
+  __syncwarp();
+}
+
+// sort(player.cells) by id (Engine.hpp:157): every tick, for every player, even without collisions
+__device__ void sort_player_cells(Ctx& c, int p, int n) {
+  Cell me;
+  me.x = me.y = me.vx = me.vy = me.svx = me.svy = 0.f; me.mass = 0; me.id = 0xffffffffu; me.rec = 0;
+  if (c.lane < n) me = cell_load(c.pcells(p) + c.lane);
+  uint32_t prev = __shfl_up_sync(AG_FULL, me.id, 1);
+  bool bad = c.lane > 0 && c.lane < n && prev > me.id;
+  if (!__ballot_sync(AG_FULL, bad)) return;
+  int rank = 0;
+  for (int j = 0; j < n; j++) {
+    uint32_t oid = __shfl_sync(AG_FULL, me.id, j);
+    rank += (oid < me.id) ? 1 : 0;
+  }
+  if (c.lane < n) cell_store(c.pcells(p) + rank, me);
+  __syncwarp();
+  Cell s;
+  s.x = s.y = s.vx = s.vy = s.svx = s.svy = 0.f; s.mass = 0; s.id = 0; s.rec = 0;
+  if (c.lane < n) s = cell_load(c.pcells(p) + c.lane);
+  float4 sum = centroid_of(s, n);  // summation order changed
+  if (c.lane == 0) c.sm.psum[p] = sum;
+  __syncwarp();
+}
+
+__device__ __forceinline__ int get_row(float x, float W) { return (int)(x / W * 100.0f); }  // collision_detection.hpp:17-19
+
+// libstdc++ unordered_map<int,...> insertion-order model: place `key` in `list`
+__device__ void umap_place(uint16_t* list, int& n, int nb, int key) {
+  int b = key % nb, pos = -1;
+  for (int i = 0; i < n; i++)
+    if (list[i] % nb == b) { pos = i; break; }
+  if (pos < 0) pos = 0;
+  for (int i = n; i > pos; i--) list[i] = list[i - 1];
+  list[pos] = (uint16_t)key;
+  n++;
+}
+
+struct PairRec { uint16_t q, g; uint32_t eaten_mass, eater_id, eaten_id; };  // 16 B
+
+// exact PrecisionCollisionDetection::solve + application, run by ONE lane (rare path: only for the
+// query cells the all-pairs pre-test flagged; everything the strip sweep can return is in that set).
+__device__ void players_collision_exact(Ctx& c, int total, int nhit) {
+  const Luts& T = c.P.T;
+  const uint16_t* ref = c.sm.cellref;  // (player << 8 | cell) in snapshot order
+  int16_t* rows = c.sm.rows;           // strip id of every snapshot cell
+  uint16_t* strip = c.sm.strip;        // one strip, sorted by y (stable)
+  PairRec* pairs = reinterpret_cast<PairRec*>(c.sm.pairs);
+  uint16_t* rkeys = c.sm.reskeys;      // query ids with results, first-insert order
+  uint16_t* rorder = c.sm.resorder;    // iteration order of the results map
+  auto cellp = [&](int g) -> const agarcl_cell* { return c.pcells(ref[g] >> 8) + (ref[g] & 0xff); };
+  for (int g = 0; g < total; g++) rows[g] = (int16_t)get_row(cellp(g)->x, c.W);
+  int npairs = 0, nres = 0;
+  for (int hq = 0; hq < nhit; hq++) {
+    int q = c.sm.hitq[hq];
+    int qp = ref[q] >> 8;
+    const agarcl_cell* qc = cellp(q);
+    float qx = qc->x, qy = qc->y;
+    uint32_t qm = qc->mass;
+    float qr = radius_of(T, qm);
+    float left = qx - qr, right = qx + qr;
+    int top = get_row(left, c.W), bottom = get_row(right, c.W);
+    bool opened = false;
+    for (int row = top; row <= bottom; row++) {
+      int l = 0;
+      for (int g = 0; g < total; g++) {
+        if (rows[g] != row) continue;
+        float gy = cellp(g)->y;  // insertion sort by y == libstdc++ std::sort for <= 16 elements
+        int b = l - 1;
+        while (b >= 0 && gy < cellp(strip[b])->y) { strip[b + 1] = strip[b]; b--; }
+        strip[b + 1] = (uint16_t)g;
+        l++;
+      }
+      if (l == 0) continue;
+      if (l > 16)
+        for (int a = 1; a < l; a++)
+          if (cellp(strip[a])->y == cellp(strip[a - 1])->y) c.flags |= AGARCL_FLAG_PCD_TIE;
+      int start_pos = 0;
+      for (int j = 10; j >= 0; j--)
+        if (start_pos + (1 << j) < l && cellp(strip[start_pos + (1 << j)])->y < left) start_pos += (1 << j);
+      for (int j = start_pos; j < l; j++) {
+        int g = strip[j];
+        int gp = ref[g] >> 8;
+        if (gp == qp) break;  // quirk Q7: the scan stops at the first own cell
+        const agarcl_cell* gc = cellp(g);
+        uint32_t gm = gc->mass;
+        if (collides(qx, qy, qr, gc->x, gc->y, radius_of(T, gm)) && cell_can_eat_cell(qm, gm)) {
+          if (npairs < kPairCap) {
+            if (!opened) { rkeys[nres++] = (uint16_t)q; opened = true; }
+            pairs[npairs].q = (uint16_t)q; pairs[npairs].g = (uint16_t)g;
+            pairs[npairs].eaten_mass = gm; pairs[npairs].eater_id = qc->id; pairs[npairs].eaten_id = gc->id;
+            npairs++;
+          } else c.flags |= AGARCL_FLAG_EATER_OVERFLOW;
+        }
+      }
+    }
+  }
+  if (npairs == 0) return;
+  // iteration order of std::unordered_map<int, vector<...>> results (Engine.hpp:168)
+  int cnt = 0, nb = 1, next_resize = 0;
+  for (int k = 0; k < nres; k++) {
+    if (cnt + 1 > next_resize) {
+      int floor_min = (cnt + 1 > (next_resize ? 0 : 11)) ? cnt + 1 : (next_resize ? 0 : 11);
+      if (floor_min >= nb) {
+        int want = floor_min + 1;
+        if (nb * 2 > want) want = nb * 2;
+        int nnb = want <= 13 ? 13 : want <= 29 ? 29 : want <= 59 ? 59 : want <= 127 ? 127 : want <= 257 ? 257 : 541;
+        next_resize = nnb;
+        uint16_t* tmp = strip;  // strip scratch is free now
+        for (int i = 0; i < cnt; i++) tmp[i] = rorder[i];
+        int m = 0;
+        for (int i = 0; i < cnt; i++) umap_place(rorder, m, nnb, tmp[i]);
+        nb = nnb;
+      } else next_resize = nb;
+    }
+    umap_place(rorder, cnt, nb, rkeys[k]);
+  }
+  // apply (Engine.hpp:168-194): eater found by lower_bound on its CURRENT cell list, eaten erased
+  for (int oi = 0; oi < cnt; oi++) {
+    int q = rorder[oi];
+    for (int k = 0; k < npairs; k++) {
+      if (pairs[k].q != q) continue;
+      int g = pairs[k].g;
+      int pp = ref[q] >> 8, ep = ref[g] >> 8;
+      agarcl_player* ppl = c.players + pp;
+      agarcl_player* epl = c.players + ep;
+      agarcl_cell* pc = c.pcells(pp);
+      int pn = ppl->n_cells, it = 0;
+      while (it < pn && pc[it].id < pairs[k].eater_id) it++;
+      if (it != pn) {
+        pc[it].mass = floor_mass(pc[it].mass + pairs[k].eaten_mass);
+        ppl->cells_eaten++;
+      }
+      agarcl_cell* ec = c.pcells(ep);
+      int en = epl->n_cells, eit = 0;
+      while (eit < en && ec[eit].id < pairs[k].eaten_id) eit++;
+      if (eit != en) {
+        for (int m = eit; m + 1 < en; m++) {
+          reinterpret_cast<uint4*>(ec + m)[0] = reinterpret_cast<uint4*>(ec + m + 1)[0];
+          reinterpret_cast<uint4*>(ec + m)[1] = reinterpret_cast<uint4*>(ec + m + 1)[1];
+          reinterpret_cast<uint4*>(ec + m)[2] = reinterpret_cast<uint4*>(ec + m + 1)[2];
+        }
+        epl->n_cells = en - 1;
+      }
+    }
+  }
+}
+
+__device__ void players_collision(Ctx& c) {
+  const int P = c.P.L.P;
+  // 1. sort multi-cell players by id; snapshot enumeration (map order, then cell order)
+  int total = 0;
+  for (int k = 0; k < P; k++) {
+    int p = c.P.L.order[k];
+    int n = __float_as_int(c.sm.psum[p].w);
+    if (n >= 2) sort_player_cells(c, p, n);
+    for (int i = c.lane; i < n; i += 32)
+      if (total + i < kCellRefCap) c.sm.cellref[total + i] = (uint16_t)((p << 8) | i);
+    total += n;
+  }
+  if (total > kCellRefCap) { c.flags |= AGARCL_FLAG_EATER_OVERFLOW; total = kCellRefCap; }
+  __syncwarp();
+  // 2. all-pairs pre-test (superset of what the strip sweep can return); hit queries in ascending order
+  int nhit = 0;
+  for (int qb = 0; qb < total; qb += 32) {
+    int q = qb + c.lane;
+    float qx = 0.f, qy = 0.f, qr = 0.f;
+    uint32_t qm = 0;
+    int qp = -1;
+    if (q < total) {
+      int r = c.sm.cellref[q];
+      qp = r >> 8;
+      const agarcl_cell* g = c.pcells(qp) + (r & 0xff);
+      float4 a = reinterpret_cast<const float4*>(g)[0];
+      qx = a.x; qy = a.y; qm = g->mass;
+      qr = radius_of(c.P.T, qm);
+    }
+    bool hungry = qm > 25u;
+    if (!__ballot_sync(AG_FULL, hungry)) continue;
+    bool hit = false;
+    for (int g = 0; g < total; g++) {
+      int r = c.sm.cellref[g];
+      int gp = r >> 8;
+      const agarcl_cell* gc = c.pcells(gp) + (r & 0xff);
+      float4 a = reinterpret_cast<const float4*>(gc)[0];
+      uint32_t gm = gc->mass;
+      if (hungry && gp != qp && collides(qx, qy, qr, a.x, a.y, radius_of(c.P.T, gm)) && cell_can_eat_cell(qm, gm)) hit = true;
+    }
+    unsigned hm = __ballot_sync(AG_FULL, hit);
+    if (hit) {
+      int pos = nhit + __popc(hm & lanemask_lt(c.lane));
+      if (pos < kPairCap) c.sm.hitq[pos] = (uint16_t)q;
+    }
+    nhit += __popc(hm);
+  }
+  if (nhit == 0) return;
+  if (nhit > kPairCap) { c.flags |= AGARCL_FLAG_EATER_OVERFLOW; nhit = kPairCap; }
+  __syncwarp();
+  // 3. exact path
+  if (c.lane == 0) players_collision_exact(c, total, nhit);
+  __syncwarp();
+  c.flags = __shfl_sync(AG_FULL, c.flags, 0);
+  // 4. refresh summaries (masses / counts changed)
+  for (int base = 0; base < P; base += 32) {
+    int p = base + c.lane;
+    if (p < P) c.sm.psum[p] = centroid_from_global(c.pcells(p), c.players[p].n_cells);
+  }
+  __syncwarp();
+}
+
+// Engine::move_foods + maybe_hit_virus, literal and serial (one lane); used when a food may hit a virus
+__device__ void move_foods_serial(Ctx& c) {
+  const Luts& T = c.P.T;
+  const float rf = radius_of(T, AGARCL_FOOD_MASS);
+  const float dt = c.dt;
+  int nf = c.n_foods, nv = c.n_viruses;
+  for (int i = 0; i < nf;) {
+    agarcl_food f = c.food[i];
+    if (vmag(f.vx, f.vy) == 0.0f) { i++; continue; }
+    float fvx = f.vx, fvy = f.vy;
+    decelerate(f.vx, f.vy, 80.0f, dt);
+    f.x += f.vx * dt;
+    f.y += f.vy * dt;
+    f.x = bound_axis(f.x, rf, c.W);
+    f.y = bound_axis(f.y, rf, c.W);
+    c.food[i] = f;
+    bool hit = false;
+    for (int v = 0; v < nv; v++) {
+      agarcl_virus* vr = c.vir + v;
+      if (collides(f.x, f.y, rf, vr->x, vr->y, radius_of(T, vr->mass))) {
+        if (vr->hits >= 7) {
+          vr->hits = 0;
+          vr->mass = AGARCL_VIRUS_INITIAL_MASS;
+          float dt10 = (float)((1.0 / 30.0) * 10);
+          float rv = radius_of(T, AGARCL_VIRUS_INITIAL_MASS);
+          float nx = bound_axis(vr->x + fvx * dt10, rv, c.W);
+          float ny = bound_axis(vr->y + fvy * dt10, rv, c.W);
+          if (nv < c.P.L.cap_viruses) {
+            agarcl_virus* nw = c.vir + nv;
+            nw->x = nx; nw->y = ny; nw->mass = AGARCL_VIRUS_INITIAL_MASS; nw->hits = 0; nw->vx = fvx; nw->vy = fvy;
+            nw->pad[0] = 0; nw->pad[1] = 0;
+            nv++;
+          } else c.flags |= AGARCL_FLAG_VIRUS_OVERFLOW;
+        } else {
+          vr->hits += 1;
+          vr->mass += AGARCL_FOOD_MASS;
+        }
+        hit = true;
+        break;
+      }
+    }
+    if (hit) {
+      if (nf > 1) c.food[i] = c.food[nf - 1];
+      nf--;
+    } else i++;
+  }
+  c.n_foods = nf;
+  c.n_viruses = nv;
+}
+
+__device__ void move_foods(Ctx& c) {
+  if (c.n_foods == 0) return;
+  const Luts& T = c.P.T;
+  const float rf = radius_of(T, AGARCL_FOOD_MASS);
+  // pass 1 (pure): would any moving food end inside any virus, even one grown by 70 mass this tick?
+  bool danger = false;
+  for (int base = 0; base < c.n_foods; base += 32) {
+    int j = base + c.lane;
+    if (j < c.n_foods) {
+      float4 f = reinterpret_cast<const float4*>(c.food)[j];
+      if (vmag(f.z, f.w) != 0.0f) {
+        decelerate(f.z, f.w, 80.0f, c.dt);
+        f.x = bound_axis(f.x + f.z * c.dt, rf, c.W);
+        f.y = bound_axis(f.y + f.w * c.dt, rf, c.W);
+        for (int v = 0; v < c.n_viruses; v++) {
+          float r = fmax_std(radius_of(T, max(c.vir[v].mass, 180u) + 10u), rf);  // a fed virus never exceeds 100 + 7*10
+          if (r * r >= sqr_dist(f.x, f.y, c.vir[v].x, c.vir[v].y)) danger = true;
+        }
+      }
+    }
+  }
+  if (__ballot_sync(AG_FULL, danger)) {
+    if (c.lane == 0) move_foods_serial(c);
+    __syncwarp();
+    c.n_foods = __shfl_sync(AG_FULL, c.n_foods, 0);
+    c.n_viruses = __shfl_sync(AG_FULL, c.n_viruses, 0);
+    c.flags = __shfl_sync(AG_FULL, c.flags, 0);
+    return;
+  }
+  // pass 2: no virus can be hit -> foods move independently
+  for (int base = 0; base < c.n_foods; base += 32) {
+    int j = base + c.lane;
+    if (j < c.n_foods) {
+      float4 f = reinterpret_cast<const float4*>(c.food)[j];
+      if (vmag(f.z, f.w) != 0.0f) {
+        decelerate(f.z, f.w, 80.0f, c.dt);
+        f.x += f.z * c.dt;
+        f.y += f.w * c.dt;
+        f.x = bound_axis(f.x, rf, c.W);
+        f.y = bound_axis(f.y, rf, c.W);
+        reinterpret_cast<float4*>(c.food)[j] = f;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// add_pellets / add_viruses for the regen tick (Engine.hpp:230-237)
+__device__ void regen(Ctx& c) {
+  int dp = c.P.target_pellets - c.n_pellets;
+  if (dp > 0) {
+    float r = radius_of(c.P.T, AGARCL_PELLET_MASS);
+    for (int k = c.lane; k < dp; k += 32) {
+      float x, y;
+      random_location_at(c, c.cursor + 2u * (uint32_t)k, r, x, y);
+      if (c.n_pellets + k < c.P.L.cap_pellets) reinterpret_cast<float2*>(c.pel)[c.n_pellets + k] = make_float2(x, y);
+    }
+    c.cursor += 2u * (uint32_t)dp;
+    c.n_pellets = min(c.n_pellets + dp, c.P.L.cap_pellets);
+  }
+  int dv = c.P.target_viruses - c.n_viruses;
+  if (dv > 0) {
+    float r = radius_of(c.P.T, AGARCL_VIRUS_INITIAL_MASS);
+    int room = c.P.L.cap_viruses - c.n_viruses;
+    for (int k = c.lane; k < dv; k += 32) {
+      float x, y;
+      random_location_at(c, c.cursor + 2u * (uint32_t)k, r, x, y);
+      if (k < room) {
+        float4* v = reinterpret_cast<float4*>(c.vir + c.n_viruses + k);
+        v[0] = make_float4(x, y, __uint_as_float(AGARCL_VIRUS_INITIAL_MASS), __int_as_float(0));
+        v[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    c.cursor += 2u * (uint32_t)dv;
+    if (dv > room) { c.flags |= AGARCL_FLAG_VIRUS_OVERFLOW; dv = room; }
+    c.n_viruses += dv;
+  }
+  c.flags = __reduce_or_sync(AG_FULL, c.flags);
+  __syncwarp();
+}
+
+// Engine::tick
+__device__ void engine_tick(Ctx& c) {
+  build_pellet_hash(c);
+  build_virus_cache(c);
+  c.nprem = 0;
+  c.nvrem = 0;
+  const int P = c.P.L.P;
+  for (int k = 0; k < P; k++) tick_player(c, c.P.L.order[k]);
+  apply_removals(c);
+  players_collision(c);
+  move_foods(c);
+  if (c.P.L.regen && c.tick % 120u == 0u) regen(c);
+  c.tick++;
+}
+
+// Player::kill + Engine::respawn for a dead player, spawn point from draw pair `k` (Engine.hpp:119-137)
+__device__ void respawn_player(Ctx& c, int p, uint32_t k) {
+  agarcl_player* pl = c.players + p;
+  uint32_t mass = (uint32_t)(c.P.L.agent_mass > 25 ? c.P.L.agent_mass : 25);
+  float r25 = radius_of(c.P.T, AGARCL_CELL_MIN_SIZE);
+  float x, y;
+  if (c.n_pellets > 0 && c.P.L.squared_pellets) {
+    float2 p0 = reinterpret_cast<const float2*>(c.pel)[0];
+    x = fmin_std(p0.x + 2.0f * r25, c.W - r25);
+    y = fmin_std(p0.y + 2.0f * r25, c.W - r25);
+  } else {
+    random_location_at(c, k, r25, x, y);
+  }
+  Cell n;
+  n.x = x; n.y = y; n.vx = n.vy = n.svx = n.svy = 0.0f;
+  n.mass = floor_mass(mass);
+  n.id = 0;  // assigned by the caller (needs the ordered rank)
+  n.rec = c.tick;
+  cell_store(c.pcells(p), n);
+  pl->n_cells = 1;
+  pl->min_mass_cell = AGARCL_CELL_MIN_SIZE;
+  pl->split_cd = 0; pl->feed_cd = 0;
+  pl->anti_team_decay = 1.0f;
+  pl->elapsed_ticks = 0; pl->last_decay_tick = 0;
+  pl->vet_count = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel: BaseEnvironment::step for one instance per warp
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_step(const __grid_constant__ SimParams P) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int inst = blockIdx.x * kWarpsPerCta + warp;
+  if (inst >= P.N) return;
+  Ctx c(P);
+  c.lane = lane;
+  c.inst_local = inst;
+  c.inst_global = (uint32_t)(P.instance_base + inst);
+  c.blob = P.state + (size_t)inst * P.L.stride;
+  c.players = reinterpret_cast<agarcl_player*>(c.blob + P.L.off_players);
+  c.cells = reinterpret_cast<agarcl_cell*>(c.blob + P.L.off_cells);
+  c.vir = reinterpret_cast<agarcl_virus*>(c.blob + P.L.off_viruses);
+  c.food = reinterpret_cast<agarcl_food*>(c.blob + P.L.off_foods);
+  c.pel = reinterpret_cast<agarcl_pellet*>(c.blob + P.L.off_pellets);
+  c.sm = carve_warp_smem(smem_raw + (size_t)warp * P.smem_per_warp, P.L, P.HG);
+  agarcl_inst_hdr* hdr = reinterpret_cast<agarcl_inst_hdr*>(c.blob + P.L.off_hdr);
+  c.tick = hdr->tick; c.next_id = hdr->next_cell_id;
+  c.n_pellets = hdr->n_pellets; c.n_viruses = hdr->n_viruses; c.n_foods = hdr->n_foods;
+  c.cursor = hdr->rng_cursor; c.flags = hdr->flags;
+  c.seed_lo = hdr->seed_lo; c.seed_hi = hdr->seed_hi; c.done_sticky = hdr->done_sticky;
+  c.nprem = 0; c.nvrem = 0;
+  c.W = P.W;
+  c.dt = (float)(1.0 / 30.0);
+  const int Pn = P.L.P, A = P.L.A;
+
+  // player summaries (centroid, mass, count)
+  for (int base = 0; base < Pn; base += 32) {
+    int p = base + lane;
+    if (p < Pn) c.sm.psum[p] = centroid_from_global(c.pcells(p), c.players[p].n_cells);
+  }
+  __syncwarp();
+
+  if (P.do_begin) {
+    if (lane == 0) { hdr->respawned_lo = 0u; hdr->respawned_hi = 0u; }
+    // BaseEnvironment::take_actions + `before = masses<float>()`
+    for (int a = lane; a < A; a += 32) {
+      float4 s = c.sm.psum[a];
+      uint32_t m = __float_as_uint(s.z);
+      size_t gi = (size_t)inst * A + a;
+      P.before[gi] = (float)m;
+      if (__float_as_int(s.w) > 0) {
+        agarcl_player* pl = c.players + a;
+        pl->target_x = s.x + P.dxdy[2 * gi] * 10.0f;
+        pl->target_y = s.y + P.dxdy[2 * gi + 1] * 10.0f;
+        pl->action = P.act[gi];
+      }
+      if (P.mode == 3 && m >= 23000u) c.done_sticky = 1u;
+    }
+    c.done_sticky = __reduce_or_sync(AG_FULL, c.done_sticky);
+    __syncwarp();
+  }
+
+  for (int t = 0; t < P.n_ticks; t++) engine_tick(c);
+
+  if (P.do_end) {
+    if (P.mode == 0) {
+      // repsawn_all_players in map order: the r-th dead player takes draw pair r
+      uint32_t rank_base = 0;
+      uint32_t resp_lo = 0, resp_hi = 0;
+      for (int base = 0; base < Pn; base += 32) {
+        int k = base + lane;
+        int p = k < Pn ? P.L.order[k] : 0;
+        bool dead = k < Pn && __float_as_int(c.sm.psum[p].w) == 0;
+        unsigned dm = __ballot_sync(AG_FULL, dead);
+        if (dead) {
+          uint32_t r = rank_base + (uint32_t)__popc(dm & lanemask_lt(lane));
+          respawn_player(c, p, c.cursor + 2u * r);
+          c.pcells(p)->id = c.next_id + r;
+          c.sm.psum[p] = centroid_from_global(c.pcells(p), 1);
+        }
+        rank_base += (uint32_t)__popc(dm);
+        // dead players in map-order slots -> bit per PLAYER index
+        unsigned long long bit = dead ? (1ull << p) : 0ull;
+        resp_lo |= __reduce_or_sync(AG_FULL, (uint32_t)(bit & 0xffffffffull));
+        resp_hi |= __reduce_or_sync(AG_FULL, (uint32_t)(bit >> 32));
+      }
+      if (lane == 0) { hdr->respawned_lo = resp_lo; hdr->respawned_hi = resp_hi; }
+      c.next_id += rank_base;
+      if (!(P.L.squared_pellets && c.n_pellets > 0)) c.cursor += 2u * rank_base;
+      c.flags = __reduce_or_sync(AG_FULL, c.flags);
+      __syncwarp();
+    } else if (P.mode > 6) {
+      bool dead = false;
+      for (int p = lane; p < Pn; p += 32) dead |= __float_as_int(c.sm.psum[p].w) == 0;
+      c.done_sticky = __ballot_sync(AG_FULL, dead) ? 1u : 0u;  // dones_[0] rewritten every step (BaseEnvironment.hpp:103-114)
+    }
+    for (int a = lane; a < A; a += 32) {
+      uint32_t m = __float_as_uint(c.sm.psum[a].z);
+      if (P.mode == 3 && m >= 23000u) c.done_sticky = 1u;
+    }
+    c.done_sticky = __reduce_or_sync(AG_FULL, c.done_sticky);
+    for (int a = lane; a < A; a += 32) {
+      size_t gi = (size_t)inst * A + a;
+      uint32_t m = __float_as_uint(c.sm.psum[a].z);
+      double r = (double)m;
+      if (P.reward_type) r -= (double)(P.before[gi] - 0.0f);
+      P.rewards[gi] = r;
+      P.dones[gi] = (a == 0) ? (uint8_t)(c.done_sticky != 0u) : (uint8_t)0;
+    }
+  }
+
+  c.flags = __reduce_or_sync(AG_FULL, c.flags);
+  if (lane == 0) {
+    hdr->tick = c.tick; hdr->next_cell_id = c.next_id;
+    hdr->n_pellets = c.n_pellets; hdr->n_viruses = c.n_viruses; hdr->n_foods = c.n_foods;
+    hdr->rng_cursor = c.cursor; hdr->flags = c.flags; hdr->done_sticky = c.done_sticky;
+  }
+}
+
+cudaError_t launch_step(const SimParams& P, cudaStream_t stream) {
+  int ctas = (P.N + kWarpsPerCta - 1) / kWarpsPerCta;
+  size_t smem = (size_t)P.smem_per_warp * kWarpsPerCta;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  k_step<<<ctas, kWarpsPerCta * 32, smem, stream>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace ag

@@ -1,0 +1,64 @@
+// sim_shared.cuh — shared-memory carve-up of one warp (= one game instance) in k_step.
+#pragma once
+#include <cstdint>
+
+#include "../../include/agarcl_b200.h"
+#include "sim_params.h"
+
+namespace ag {
+
+struct WarpSmem {
+  // pellet spatial hash, rebuilt every tick (valid during the player loop)
+  uint32_t* hcnt;      // [HG*HG]   counts -> offsets -> cell ends
+  uint16_t* hsorted;   // [cap_pellets] pellet indices grouped by hash cell
+  // players_collision scratch (valid after the player loop) — aliases the hash region
+  uint16_t* cellref;   // [kCellRefCap]
+  int16_t* rows;       // [kCellRefCap]
+  uint16_t* strip;     // [kCellRefCap]
+  uint4* pairs;        // [kPairCap] PairRec
+  uint16_t* reskeys;   // [kPairCap]
+  uint16_t* resorder;  // [kPairCap]
+  uint16_t* hitq;      // [kPairCap]
+  // live for the whole launch
+  float4* vcache;      // [cap_viruses] x, y, radius, mass bits
+  float4* psum;        // [P] centroid x, y, mass bits, n_cells bits
+  uint2* cand;         // [kCandCap] (order key, d^2 bits)
+  uint16_t* prem;      // [kPremCap]
+  uint16_t* vrem;      // [kVremCap]
+};
+
+__host__ __device__ inline uint32_t ag_align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+__host__ __device__ inline uint32_t hash_region_bytes(const agarcl_layout& L, int HG) {
+  uint32_t a = ag_align16((uint32_t)(HG * HG) * 4u) + ag_align16((uint32_t)L.cap_pellets * 2u);
+  uint32_t b = ag_align16(kCellRefCap * 2u) * 3u + ag_align16(kPairCap * 16u) + ag_align16(kPairCap * 2u) * 3u;
+  return a > b ? a : b;
+}
+__host__ __device__ inline uint32_t warp_smem_bytes(const agarcl_layout& L, int HG) {
+  return hash_region_bytes(L, HG) + ag_align16((uint32_t)L.cap_viruses * 16u) + ag_align16((uint32_t)L.P * 16u) +
+         ag_align16(kCandCap * 8u) + ag_align16(kPremCap * 2u) + ag_align16(kVremCap * 2u);
+}
+
+__device__ inline WarpSmem carve_warp_smem(uint8_t* base, const agarcl_layout& L, int HG) {
+  WarpSmem s;
+  uint8_t* p = base;
+  s.hcnt = reinterpret_cast<uint32_t*>(p);
+  s.hsorted = reinterpret_cast<uint16_t*>(p + ag_align16((uint32_t)(HG * HG) * 4u));
+  uint8_t* q = base;
+  s.cellref = reinterpret_cast<uint16_t*>(q); q += ag_align16(kCellRefCap * 2u);
+  s.rows = reinterpret_cast<int16_t*>(q);     q += ag_align16(kCellRefCap * 2u);
+  s.strip = reinterpret_cast<uint16_t*>(q);   q += ag_align16(kCellRefCap * 2u);
+  s.pairs = reinterpret_cast<uint4*>(q);      q += ag_align16(kPairCap * 16u);
+  s.reskeys = reinterpret_cast<uint16_t*>(q); q += ag_align16(kPairCap * 2u);
+  s.resorder = reinterpret_cast<uint16_t*>(q); q += ag_align16(kPairCap * 2u);
+  s.hitq = reinterpret_cast<uint16_t*>(q);
+  p += hash_region_bytes(L, HG);
+  s.vcache = reinterpret_cast<float4*>(p); p += ag_align16((uint32_t)L.cap_viruses * 16u);
+  s.psum = reinterpret_cast<float4*>(p);   p += ag_align16((uint32_t)L.P * 16u);
+  s.cand = reinterpret_cast<uint2*>(p);    p += ag_align16(kCandCap * 8u);
+  s.prem = reinterpret_cast<uint16_t*>(p); p += ag_align16(kPremCap * 2u);
+  s.vrem = reinterpret_cast<uint16_t*>(p);
+  return s;
+}
+
+}  // namespace ag

@@ -137,7 +137,9 @@ typedef struct agarcl_inst_hdr { /* 64 B */
   uint32_t flags;          /* AGARCL_FLAG_* */
   uint32_t seed_lo, seed_hi;
   uint32_t done_sticky;    /* mode 3 sticky done (BaseEnvironment.hpp:132-135) */
-  uint32_t pad[6];
+  uint32_t respawned_lo, respawned_hi; /* players respawned at the end of the last step: the step's
+                             observation is taken BEFORE repsawn_all_players (BaseEnvironment.hpp:96-101) */
+  uint32_t pad[4];
 } agarcl_inst_hdr;
 
 /* Byte offsets of one instance's arrays inside its blob. */

@@ -1,0 +1,35 @@
+"""-m gpu: the CUDA path against the oracle port through the C ABI (bit-exact)."""
+import numpy as np
+import pytest
+
+from gpu_parity_lib import run_parity
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    # BASELINE.json configs[0]: single agent, default arena, no bots
+    "c1_single_agent": (dict(num_bots=0, num_viruses=0), dict(steps=150)),
+    # configs[1]: 1 agent + default bots (tests/__init__.py:6-19 of the reference)
+    "c2_default_bots": (dict(), dict(steps=200)),
+    # configs[3]: multi-agent, split/eject heavy, agents boosted to 1000 mass
+    "c4_multi_agent_split_eject": (dict(num_agents=4, num_bots=8, cap_foods=2048), dict(steps=250, p_feed=0.3, p_split=0.3, boost=1000)),
+    "dense_small_arena": (dict(num_agents=2, num_bots=25, arena_size=300, num_pellets=300, num_viruses=10, cap_foods=2048), dict(steps=250, boost=3000)),
+    "giant_autosplit": (dict(num_agents=2, num_bots=6, arena_size=400, num_pellets=400, num_viruses=6, cap_foods=2048), dict(steps=200, boost=22400, p_feed=0.05, p_split=0.1)),
+    "virus_heavy": (dict(num_agents=3, num_bots=10, arena_size=250, num_pellets=200, num_viruses=40, cap_foods=2048, cap_viruses=256), dict(steps=200, boost=400, p_feed=0.5, p_split=0.1)),
+    "mode1_squares": (dict(num_bots=0, num_viruses=0, arena_size=350, num_pellets=500, mode_number=1), dict(steps=100)),
+    "mode3_done": (dict(num_bots=0, num_viruses=0, arena_size=350, num_pellets=500, mode_number=3), dict(steps=60, boost=22990)),
+    "mode5_mass1000": (dict(num_bots=0, num_viruses=0, arena_size=350, num_pellets=500, mode_number=5), dict(steps=100)),
+    "mode8_one_bot_done": (dict(num_bots=1, num_viruses=0, arena_size=100, num_pellets=50, mode_number=8), dict(steps=150, boost=200)),
+    "mode10": (dict(num_bots=1, num_viruses=3, arena_size=100, num_pellets=50, mode_number=10), dict(steps=100)),
+    "tps1_grid64_absreward": (dict(num_bots=5, ticks_per_step=1, grid_size=64, arena_size=200, num_pellets=100, num_viruses=2, reward_type=0), dict(steps=150)),
+    "obs_flags_off": (dict(num_bots=3, observe_pellets=False, observe_others=False, arena_size=200, num_pellets=100, num_viruses=2), dict(steps=60)),
+    "players_30": (dict(num_agents=2, num_bots=30, arena_size=500, num_pellets=500, num_viruses=10, cap_foods=2048), dict(steps=150, boost=500)),
+    "frames2": (dict(num_bots=4, num_frames=2, arena_size=200, num_pellets=100, num_viruses=2), dict(steps=40)),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_cuda_matches_oracle(name):
+    cfg_kwargs, run_kwargs = CASES[name]
+    stats = run_parity(cfg_kwargs, seeds=[11, 12, 13], **run_kwargs)
+    print(name, stats)
