@@ -87,6 +87,15 @@ class Batch:
         f = lambda a: a.ctypes.data_as(_vp) if a is not None else None
         _lib.check(_lib.lib().agarcl_batch_step_host(self._h, f(dxdy), f(act), f(obs_out), f(rewards_out), f(dones_out)))
 
+    def set_timing(self, enable=True):
+        _lib.check(_lib.lib().agarcl_batch_set_timing(self._h, int(enable)))
+
+    def get_timing(self):
+        """(engine-tick kernel ms, observation kernel ms, steps) accumulated since the last call"""
+        a, o, n = C.c_double(), C.c_double(), C.c_int32()
+        _lib.check(_lib.lib().agarcl_batch_get_timing(self._h, C.byref(a), C.byref(o), C.byref(n)))
+        return a.value, o.value, n.value
+
     def launches_per_step(self):
         return _lib.lib().agarcl_batch_launches_per_step(self._h)
 

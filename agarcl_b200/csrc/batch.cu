@@ -47,7 +47,35 @@ struct agarcl_batch {
   uint32_t smem_per_warp;
   bool was_reset = false;
   int launches_last_step = 0;
+  // optional per-kernel timing: (start, after sim, after obs) event triples of steps not yet collected
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used = 0;
+  double acc_sim_ms = 0.0, acc_obs_ms = 0.0;
+  int acc_steps = 0;
 };
+
+static cudaEvent_t next_event(agarcl_batch* b) {
+  if (b->ev_used == b->ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    b->ev.push_back(e);
+  }
+  return b->ev[b->ev_used++];
+}
+static void collect_timing(agarcl_batch* b) {
+  if (!b->ev_used) return;
+  cudaEventSynchronize(b->ev[b->ev_used - 1]);
+  for (size_t i = 0; i + 2 < b->ev_used; i += 3) {
+    float a = 0.f, c = 0.f;
+    cudaEventElapsedTime(&a, b->ev[i], b->ev[i + 1]);
+    cudaEventElapsedTime(&c, b->ev[i + 1], b->ev[i + 2]);
+    b->acc_sim_ms += a;
+    b->acc_obs_ms += c;
+    b->acc_steps++;
+  }
+  b->ev_used = 0;
+}
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -105,6 +133,7 @@ extern "C" int agarcl_batch_destroy(agarcl_batch* b) {
   cudaFree(b->d_state); cudaFree(b->d_obs); cudaFree(b->d_rewards); cudaFree(b->d_dones); cudaFree(b->d_before);
   cudaFree(b->d_dxdy); cudaFree(b->d_act); cudaFree(b->d_replay); cudaFree(b->d_seeds); cudaFree(b->d_mask);
   cudaFree(b->d_lut_radius); cudaFree(b->d_lut_speed); cudaFree(b->d_lut_split);
+  for (cudaEvent_t e : b->ev) cudaEventDestroy(e);
   delete b;
   return AGARCL_OK;
 }
@@ -315,8 +344,11 @@ extern "C" int agarcl_batch_step(agarcl_batch* b, void* stream) {
     if (frame >= 0) { int rc = render_frame(b, frame, s, 1); if (rc) return rc; launches++; }
   } else if (b->frames == 1) {
     P.n_ticks = tps; P.do_begin = 1; P.do_end = 1;
+    if (b->timing) { if (b->ev_used >= 3 * 2048) collect_timing(b); CK(cudaEventRecord(next_event(b), s)); }
     CK(ag::launch_step(P, s)); launches++;
+    if (b->timing) CK(cudaEventRecord(next_event(b), s));
     int rc = render_frame(b, 0, s, 1); if (rc) return rc; launches++;
+    if (b->timing) CK(cudaEventRecord(next_event(b), s));
   } else {
     // the last num_frames ticks of the step each contribute one frame (the documented intent of
     // GridEnvironment::_partial_observation, GridEnvironment.hpp:413-433)
@@ -331,6 +363,25 @@ extern "C" int agarcl_batch_step(agarcl_batch* b, void* stream) {
     CK(ag::launch_step(P, s)); launches++;
   }
   b->launches_last_step = launches;
+  return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_set_timing(agarcl_batch* b, int enable) {
+  if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");
+  collect_timing(b);
+  b->timing = enable != 0;
+  b->acc_sim_ms = b->acc_obs_ms = 0.0;
+  b->acc_steps = 0;
+  return AGARCL_OK;
+}
+extern "C" int agarcl_batch_get_timing(agarcl_batch* b, double* sim_ms, double* obs_ms, int32_t* steps) {
+  if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");
+  collect_timing(b);
+  if (sim_ms) *sim_ms = b->acc_sim_ms;
+  if (obs_ms) *obs_ms = b->acc_obs_ms;
+  if (steps) *steps = b->acc_steps;
+  b->acc_sim_ms = b->acc_obs_ms = 0.0;
+  b->acc_steps = 0;
   return AGARCL_OK;
 }
 

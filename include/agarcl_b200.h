@@ -192,6 +192,12 @@ int agarcl_batch_upload_state(agarcl_batch* b, int32_t instance, const void* blo
 int agarcl_batch_set_replay(agarcl_batch* b, int32_t instance, const float* draws, int32_t n);
 /* Run only the observation kernel on the current state (tests; add_frame on a cleared buffer). */
 int agarcl_batch_render(agarcl_batch* b, void* stream);
+/* Per-kernel device timing (bench.py roofline): when enabled, every agarcl_batch_step brackets the
+ * engine-tick kernel and the observation kernel with CUDA events on the launching stream.
+ * agarcl_batch_get_timing synchronises, returns the accumulated milliseconds and step count since the
+ * last call, and resets the accumulators. */
+int agarcl_batch_set_timing(agarcl_batch* b, int enable);
+int agarcl_batch_get_timing(agarcl_batch* b, double* sim_ms, double* obs_ms, int32_t* steps);
 /* Number of kernel launches issued by the last agarcl_batch_step. */
 int agarcl_batch_launches_per_step(const agarcl_batch* b);
 /* Host helper: first n canonical floats of std::mt19937_64(seed) as uniform_real_distribution<float>

@@ -323,29 +323,45 @@ int ref_dump_state(void* h, const agarcl_layout* L, void* blob_) {
 }
 
 /* ------------------------------------------------------------------------------------------
- * CPU baseline: M independent GridEnvironment instances over a pool of worker threads, the
- * pattern of BotEvaluator::run (agario/bots/benchmark.cpp:146-168).  Each work item builds an
- * env, seeds it, and runs `steps` env-steps of (random actions, step(), forced add_frame).
- * Returns env-steps per second over the stepping loops only (construction excluded by a
- * barrier), `threads` workers.
+ * CPU baseline: M independent GridEnvironment instances over the reference's own ThreadPool
+ * (utils/thread-pool.h:21), the pattern of BotEvaluator::run (agario/bots/benchmark.cpp:146-168):
+ * one thunk per instance runs `steps` env-steps of (random actions, step(), forced add_frame).
+ * Environments are built once (ref_pool_create) so that only stepping is timed.
  * ------------------------------------------------------------------------------------------ */
-double ref_bench(const agarcl_cfg* c, int instances, int threads, int steps, int with_obs, unsigned base_seed) {
-  std::vector<std::unique_ptr<RefEnv>> envs((size_t)instances);
-  {
-    CoutSilencer quiet;
-    for (int i = 0; i < instances; i++) {
-      envs[i].reset(static_cast<RefEnv*>(ref_create(c)));
-      ref_seed(envs[i].get(), base_seed + (unsigned)i);
-      ref_reset(envs[i].get());
-    }
+struct RefPool {
+  agarcl_cfg cfg;
+  std::vector<RefEnv*> envs;
+  std::vector<std::mt19937> arng;
+};
+
+void* ref_pool_create(const agarcl_cfg* c, int instances, unsigned base_seed) {
+  auto* p = new RefPool();
+  p->cfg = *c;
+  for (int i = 0; i < instances; i++) {
+    RefEnv* r = static_cast<RefEnv*>(ref_create(c));
+    ref_seed(r, base_seed + (unsigned)i);
+    ref_reset(r);
+    p->envs.push_back(r);
+    p->arng.emplace_back(base_seed * 7919u + (unsigned)i);
   }
-  auto work = [&](int i) {
+  return p;
+}
+void ref_pool_destroy(void* h) {
+  auto* p = static_cast<RefPool*>(h);
+  for (auto* r : p->envs) ref_destroy(r);
+  delete p;
+}
+/* returns wall seconds for `steps` env-steps of every instance on `threads` pool workers */
+double ref_pool_run(void* h, int threads, int steps, int with_obs) {
+  auto* p = static_cast<RefPool*>(h);
+  const agarcl_cfg* c = &p->cfg;
+  auto work = [p, c, steps, with_obs](int i) {
     std::vector<float> dxdy((size_t)c->num_agents * 2);
     std::vector<int32_t> act((size_t)c->num_agents);
     std::vector<double> rew((size_t)c->num_agents);
-    RefEnv* r = envs[i].get();
+    RefEnv* r = p->envs[i];
     std::vector<int32_t> obs((size_t)r->forced->length());
-    std::mt19937 arng(base_seed * 7919u + (unsigned)i);
+    std::mt19937& arng = p->arng[i];
     std::uniform_real_distribution<float> u(-1.0f, 1.0f);
     for (int s = 0; s < steps; s++) {
       for (int a = 0; a < c->num_agents; a++) {
@@ -362,11 +378,17 @@ double ref_bench(const agarcl_cfg* c, int instances, int threads, int steps, int
   auto t0 = std::chrono::high_resolution_clock::now();
   {
     ThreadPool pool((size_t)threads);
-    for (int i = 0; i < instances; i++) pool.schedule([&work, i]() { work(i); });
+    for (int i = 0; i < (int)p->envs.size(); i++) pool.schedule([&work, i]() { work(i); });
     pool.wait();
   }
   auto t1 = std::chrono::high_resolution_clock::now();
-  double sec = std::chrono::duration<double>(t1 - t0).count();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+double ref_bench(const agarcl_cfg* c, int instances, int threads, int steps, int with_obs, unsigned base_seed) {
+  void* p = ref_pool_create(c, instances, base_seed);
+  double sec = ref_pool_run(p, threads, steps, with_obs);
+  ref_pool_destroy(p);
   return (double)instances * (double)steps / sec;
 }
 
