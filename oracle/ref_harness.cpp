@@ -322,6 +322,14 @@ int ref_dump_state(void* h, const agarcl_layout* L, void* blob_) {
   return miss;
 }
 
+/* iteration order of a real std::unordered_map<int, ...> after inserting keys in order (pins oracle_umap_order) */
+void ref_umap_order(const int* keys, int n, int* out) {
+  std::unordered_map<int, std::vector<int>> m;
+  for (int i = 0; i < n; i++) m[keys[i]].push_back(i);
+  int k = 0;
+  for (auto& kv : m) out[k++] = kv.first;
+}
+
 /* ------------------------------------------------------------------------------------------
  * CPU baseline: M independent GridEnvironment instances over the reference's own ThreadPool
  * (utils/thread-pool.h:21), the pattern of BotEvaluator::run (agario/bots/benchmark.cpp:146-168):

@@ -1,0 +1,145 @@
+"""-m gpu: the reference-shaped Python surface over the C ABI (GridEnvironment / BatchedGridEnvironment),
+size-independent properties at the full BASELINE size, the int16 observation dtype, and strict_reference."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_grid_environment_drop_in_against_oracle():
+    """agarcl.GridEnvironment semantics: seed -> reset -> take_actions -> step -> get_state/dones, with the
+    mt19937_64 spawn stream the reference would consume for the same seed."""
+    from _helpers import Oracle, oracle_lib
+    from agarcl_b200 import make_cfg, RNG_REPLAY
+    from agarcl_b200.env import GridEnvironment
+    oracle_lib().oracle_set_trig_mode(1)
+    env = GridEnvironment(2, 4, 500, True, 300, 5, 6, 1, 0, 0)
+    env.seed(77)
+    env.reset()
+    cfg = make_cfg(num_agents=2, ticks_per_step=4, arena_size=500, num_pellets=300, num_viruses=5, num_bots=6, rng_mode=RNG_REPLAY,
+                   cap_replay=16384)
+    ora = Oracle(cfg)
+    ora.seed_mt(77, 16384)
+    ora.reset()
+    L = ora.L
+    agents_in_map_order = [p for p in list(L.order)[:L.P] if p < L.A]
+    rng = np.random.default_rng(0)
+    for st in range(40):
+        acts = [(float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1)), int(rng.integers(0, 3))) for _ in range(2)]
+        env.take_actions(acts)
+        rew = env.step()
+        ora.set_actions(np.array([[a[0], a[1]] for a in acts], np.float32), np.array([a[2] for a in acts], np.int32))
+        orew, odone, oobs = ora.step(with_obs=True)
+        assert rew == [float(orew[p]) for p in agents_in_map_order]  # quirk Q15 ordering
+        assert env.dones() == [bool(x) for x in odone]
+        state = env.get_state()
+        assert len(state) == 2 and state[0].shape == (8, 128, 128) and state[0].dtype == np.int32
+        for a in range(2):
+            assert np.array_equal(state[a], oobs[a])
+    env.close()
+
+
+def test_full_size_batch_properties():
+    """BASELINE.json configs[1] at full size (4096 instances): conservation-style invariants that do not need
+    the oracle — counts within capacity, masses >= 25, cells inside the arena, observation consistent with the
+    state (channel sums), rewards == mass deltas, no overflow flags, determinism across two identical runs."""
+    import torch
+    from agarcl_b200.env import BatchedGridEnvironment
+    N = 4096
+    finals = []
+    for rep in range(2):
+        env = BatchedGridEnvironment(N)
+        env.seed(1000)
+        env.reset()
+        b = env.batch
+        g = torch.Generator(device="cuda")
+        g.manual_seed(5)
+        mass_before = None
+        for st in range(30):
+            dxdy = (torch.rand((N, 2), device="cuda", generator=g) * 2 - 1).float()
+            act = torch.randint(0, 3, (N,), device="cuda", generator=g, dtype=torch.int32)
+            obs, rew, done = env.step(dxdy, act)
+        torch.cuda.synchronize()
+        assert obs.shape == (N, 8, 128, 128) and obs.dtype == torch.int32
+        # observation structure: ch0 in {0,-1}; pellet presence <= count; own-mass channel sums to the agent mass when in view
+        assert set(torch.unique(obs[:, 0]).tolist()) <= {0, -1}
+        assert bool((obs[:, 1] <= obs[:, 2]).all()) and bool((obs[:, 1] >= 0).all())
+        assert bool((obs[:, 6] <= obs[:, 7]).all())
+        for i in (0, 1, N // 2, N - 1):
+            sv = b.download_state(i)
+            assert int(sv.hdr["flags"]) == 0, sv.flag_names()
+            assert 0 < int(sv.hdr["n_pellets"]) <= 1000 and int(sv.hdr["tick"]) == 120
+            for p in range(26):
+                n = int(sv.players["n_cells"][p])
+                assert 1 <= n <= 32  # mode 0 respawns every dead player at the end of the step
+                c = sv.cells[p][:n]
+                assert (c["mass"] >= 25).all()
+                assert (c["x"] >= 0).all() and (c["x"] <= 1000).all() and (c["y"] >= 0).all() and (c["y"] <= 1000).all()
+            own_mass = int(sv.cells[0][:int(sv.players["n_cells"][0])]["mass"].sum())
+            assert int(obs[i, 5].sum()) == own_mass  # every own cell is inside its own view
+        finals.append((obs.sum(dtype=torch.int64).item(), rew.sum().item(), b.download_state(N - 1).blob.copy()))
+        env.close()
+    assert finals[0][0] == finals[1][0] and finals[0][1] == finals[1][1]
+    assert np.array_equal(finals[0][2], finals[1][2]), "two identical runs diverged (non-determinism)"
+
+
+def test_results_independent_of_sharding():
+    """An instance keyed by its GLOBAL index evolves identically whether it is instance 5 of one batch or
+    instance 1 of a shard starting at 4 (what the N-GPU sharding relies on)."""
+    import torch
+    from agarcl_b200.env import BatchedGridEnvironment
+    a = BatchedGridEnvironment(8, num_bots=5, arena_size=300, num_pellets=200, num_viruses=3)
+    b = BatchedGridEnvironment(4, num_bots=5, arena_size=300, num_pellets=200, num_viruses=3, instance_base=4)
+    a.seed(50)
+    b.seed(np.arange(4, 8, dtype=np.uint64) + np.uint64(50))
+    a.reset()
+    b.reset()
+    rng = np.random.default_rng(1)
+    for st in range(25):
+        dxdy = rng.uniform(-1, 1, size=(8, 2)).astype(np.float32)
+        act = rng.integers(0, 3, size=8).astype(np.int32)
+        a.step(dxdy, act)
+        b.step(dxdy[4:], act[4:])
+    torch.cuda.synchronize()
+    sa, sb = a.batch.download_state(5), b.batch.download_state(1)
+    from agarcl_b200._abi import compare_states
+    assert not compare_states(sa, sb)
+    assert np.array_equal(a.batch.obs_tensor()[5].cpu().numpy(), b.batch.obs_tensor()[1].cpu().numpy())
+
+
+def test_int16_observation_matches_int32():
+    import torch
+    from agarcl_b200 import OBS_I16
+    from agarcl_b200.env import BatchedGridEnvironment
+    e32 = BatchedGridEnvironment(16, num_agents=2, num_bots=8, arena_size=300, num_pellets=300, num_viruses=5)
+    e16 = BatchedGridEnvironment(16, num_agents=2, num_bots=8, arena_size=300, num_pellets=300, num_viruses=5, obs_dtype=OBS_I16)
+    for e in (e32, e16):
+        e.seed(9)
+        e.reset()
+    rng = np.random.default_rng(2)
+    for st in range(30):
+        dxdy = rng.uniform(-1, 1, size=(32, 2)).astype(np.float32)
+        act = rng.integers(0, 3, size=32).astype(np.int32)
+        o32, _, _ = e32.step(dxdy, act)
+        o16, _, _ = e16.step(dxdy, act)
+    torch.cuda.synchronize()
+    assert o16.dtype == torch.int16
+    assert torch.equal(o32.clamp(-32768, 32767).to(torch.int16), o16)
+
+
+def test_strict_reference_frame_quirk_q11():
+    """With the shipped frame-index arithmetic (tps 4, num_frames 1) the reference's observation is all zeros."""
+    import torch
+    from agarcl_b200.env import BatchedGridEnvironment
+    e = BatchedGridEnvironment(4, num_bots=3, arena_size=200, num_pellets=100, num_viruses=2, strict_reference=True)
+    e.seed(1)
+    e.reset()
+    obs, _, _ = e.step(np.zeros((4, 2), np.float32), np.zeros(4, np.int32))
+    torch.cuda.synchronize()
+    assert int(obs.abs().sum()) == 0
+    e2 = BatchedGridEnvironment(4, num_bots=3, arena_size=200, num_pellets=100, num_viruses=2, ticks_per_step=1, strict_reference=True)
+    e2.seed(1)
+    e2.reset()
+    obs2, _, _ = e2.step(np.zeros((4, 2), np.float32), np.zeros(4, np.int32))
+    torch.cuda.synchronize()
+    assert int(obs2.abs().sum()) > 0  # tps == num_frames: frame 0 is filled

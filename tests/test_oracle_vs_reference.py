@@ -1,0 +1,126 @@
+"""CPU: pins oracle/oracle.c against the COMPILED REFERENCE (oracle/_ref) step by step — every discrete
+field and every fp32 field bit-exact, rewards, dones, forced add_frame observations.  Skipped only where the
+reference could not be built (no /root/reference and no prebuilt oracle/_ref)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from _helpers import Oracle, Reference, fptr, oracle_layout, oracle_lib, random_actions, ref_lib
+from agarcl_b200._abi import compare_states, make_cfg
+
+pytestmark = pytest.mark.skipif(ref_lib() is None, reason="compiled reference not available")
+
+
+def lockstep(cfg_kwargs, seed, steps, p_feed=1 / 3, p_split=1 / 3, boost=None, obs_every=10):
+    oracle_lib().oracle_set_trig_mode(0)  # libm trig == what the reference executes
+    cfg = make_cfg(**cfg_kwargs)
+    L = oracle_layout(cfg)
+    ref = Reference(cfg, L)
+    ref.seed(seed)
+    ora = Oracle(cfg, L)
+    ora.seed_mt(seed, 1 << 16)  # the oracle's own mt19937_64 restatement feeds the same stream
+    assert np.array_equal(ref.peek_draws(4096), ora.replay[:4096])
+    ref.reset()
+    ora.reset()
+    assert ref.order() == list(L.order)[:L.P]
+    if boost:
+        for a in range(L.A):
+            ref.set_cell_mass(a, 0, boost)
+            ora.state.cells[a][0]["mass"] = boost
+    rs, miss = ref.dump()
+    assert miss == 0 and not compare_states(rs, ora.state)
+    rng = np.random.default_rng(seed)
+    for st in range(steps):
+        dxdy, act = random_actions(rng, L.A, p_feed, p_split)
+        ref.set_actions(dxdy, act)
+        ora.set_actions(dxdy, act)
+        rr, rd = ref.step()
+        orr, od, _ = ora.step()
+        rs, miss = ref.dump()
+        assert miss == 0, f"reference exceeded a blob capacity at step {st}"
+        d = compare_states(rs, ora.state)
+        assert not d, f"step {st}: {d[:6]}"
+        assert np.array_equal(rr, orr) and np.array_equal(rd, od), (st, rr, orr, rd, od)
+        if st % obs_every == 0:
+            for a in range(L.A):
+                assert np.array_equal(ref.obs(a), ora.obs(a)), f"step {st} agent {a}: observation differs"
+    return ora.state
+
+
+CASES = {
+    "c1_single_agent": (dict(num_bots=0, num_viruses=0), dict(steps=150)),
+    "c2_default_bots": (dict(), dict(steps=120)),
+    "c4_multi_agent_split_eject": (dict(num_agents=4, num_bots=8, cap_foods=2048), dict(steps=200, p_feed=0.3, p_split=0.3, boost=1000)),
+    "dense_small_arena": (dict(num_agents=2, num_bots=25, arena_size=300, num_pellets=300, num_viruses=10, cap_foods=2048), dict(steps=200, boost=3000)),
+    "giant_autosplit": (dict(num_agents=2, num_bots=6, arena_size=400, num_pellets=400, num_viruses=6, cap_foods=2048), dict(steps=200, boost=22400, p_feed=0.05, p_split=0.1)),
+    "virus_heavy": (dict(num_agents=3, num_bots=10, arena_size=250, num_pellets=200, num_viruses=40, cap_foods=2048, cap_viruses=256), dict(steps=200, boost=400, p_feed=0.5, p_split=0.1)),
+    "players_30": (dict(num_agents=2, num_bots=30, arena_size=500, num_pellets=500, num_viruses=10, cap_foods=2048), dict(steps=100, boost=500)),
+    "tps1_grid64_absreward": (dict(num_bots=5, ticks_per_step=1, grid_size=64, arena_size=200, num_pellets=100, num_viruses=2, reward_type=0), dict(steps=150)),
+    "obs_flags_off": (dict(num_bots=3, observe_pellets=False, observe_others=False, arena_size=200, num_pellets=100, num_viruses=2), dict(steps=60)),
+}
+for m in range(1, 11):
+    bots = 1 if m > 6 else 0
+    CASES[f"mode{m}"] = (dict(num_bots=bots, num_viruses=3 if m in (4, 6, 10) else 0, arena_size=350 if m < 8 else 100,
+                              num_pellets=500 if m < 8 else 50, mode_number=m), dict(steps=100, boost=22000 if m == 3 else None))
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_matches_reference(name):
+    ck, rk = CASES[name]
+    lockstep(ck, seed=31 + len(name), **rk)
+
+
+def test_recombine_after_300_ticks():
+    # a split cell pair merges once the (sim-time) recombine timer expires: 10 s = 300 ticks (Entities.hpp:183-193)
+    s = lockstep(dict(num_agents=1, num_bots=0, num_viruses=0, arena_size=200, num_pellets=50), seed=5, steps=120,
+                 p_feed=0.0, p_split=0.05, boost=400)
+    assert int(s.hdr["tick"]) == 480
+
+
+def test_virus_feeding_and_shooting():
+    # an agent parked next to a virus ejects food into it: 7 hits grow it, the 8th shoots a new virus (Engine.hpp:661-687)
+    oracle_lib().oracle_set_trig_mode(0)
+    cfg = make_cfg(num_agents=1, num_bots=0, num_viruses=1, arena_size=300, num_pellets=0, cap_foods=512)
+    L = oracle_layout(cfg)
+    ref = Reference(cfg, L)
+    ref.seed(3)
+    ora = Oracle(cfg, L)
+    ora.seed_mt(3, 1 << 14)
+    ref.reset()
+    ora.reset()
+    for obj in (ref,):
+        obj.set_cell_mass(0, 0, 400)  # 30 units away: never touches the virus, enough mass for 30+ ejections
+        obj.set_cell_pos(0, 0, 100.0, 150.0)
+        obj.set_virus(0, 130.0, 150.0)
+    ora.state.cells[0][0]["mass"] = 400
+    ora.state.cells[0][0]["x"], ora.state.cells[0][0]["y"] = 100.0, 150.0
+    ora.state.viruses[0]["x"], ora.state.viruses[0]["y"] = 130.0, 150.0
+    max_vir = 0
+    for st in range(140):
+        dxdy = np.array([[0.02, 0.0]], np.float32)   # keep aiming at the virus, barely moving
+        act = np.array([1], np.int32)                 # feed
+        ref.set_actions(dxdy, act)
+        ora.set_actions(dxdy, act)
+        rr, rd = ref.step()
+        orr, od, _ = ora.step()
+        rs, miss = ref.dump()
+        d = compare_states(rs, ora.state)
+        assert not d and miss == 0, f"step {st}: {d[:4]}"
+        max_vir = max(max_vir, int(ora.state.hdr["n_viruses"]))
+    assert max_vir >= 2, "the fed virus never shot a new one"
+
+
+def test_umap_iteration_order_emulation():
+    # the oracle's libstdc++ unordered_map model vs the real container (ref_umap_order), random key sets
+    rng = np.random.default_rng(0)
+    lib, ref = oracle_lib(), ref_lib()
+    for n in list(range(1, 40)) + [60, 61, 130, 300]:
+        for rep in range(4):
+            keys = np.sort(rng.choice(600, size=n, replace=False)).astype(np.int32) if rep % 2 == 0 else \
+                rng.choice(600, size=n, replace=False).astype(np.int32)
+            a = np.zeros(n, np.int32)
+            b = np.zeros(n, np.int32)
+            lib.oracle_umap_order(fptr(keys), n, fptr(a))
+            ref.ref_umap_order(fptr(keys), n, fptr(b))
+            assert np.array_equal(a, b), (n, keys.tolist())
