@@ -23,6 +23,8 @@ CASES = {
     "c4_multi_agent": (dict(num_agents=4, num_bots=8, cap_foods=1024), dict(seed=103, steps=160, p_feed=0.3, p_split=0.3, boost=1000)),
     "dense_small_arena": (dict(num_agents=2, num_bots=25, arena_size=300, num_pellets=300, num_viruses=10, cap_foods=1024),
                           dict(seed=104, steps=160, boost=3000)),
+    "dense_no_virus": (dict(num_agents=2, num_bots=20, arena_size=250, num_pellets=250, num_viruses=0, cap_foods=1024),
+                       dict(seed=107, steps=160, boost=2000)),
     "mode2_squares_decay": (dict(num_bots=0, num_viruses=0, arena_size=350, num_pellets=500, mode_number=2), dict(seed=105, steps=100)),
     "mode9_one_bot": (dict(num_bots=1, num_viruses=0, arena_size=100, num_pellets=50, mode_number=9), dict(seed=106, steps=120, boost=150)),
 }
@@ -47,10 +49,12 @@ def make(name, cfg_kwargs, seed, steps, p_feed=1 / 3, p_split=1 / 3, boost=None,
     rew = np.zeros((steps, A), np.float64)
     done = np.zeros((steps, A), np.uint8)
     blobs, blob_steps, obs, obs_steps = [], [], [], []
+    virus_hits = np.zeros(steps, np.int32)  # cumulative virus contacts (pop or eat) after each step
     for st in range(steps):
         dxdy[st], act[st] = random_actions(rng, A, p_feed, p_split)
         ref.set_actions(dxdy[st], act[st])
         rew[st], done[st] = ref.step()
+        virus_hits[st] = int(ref.dump()[0].players["viruses_eaten"].sum())
         if (st + 1) % every == 0 or st == steps - 1:
             s, miss = ref.dump()
             assert miss == 0, (name, st, miss)
@@ -62,7 +66,7 @@ def make(name, cfg_kwargs, seed, steps, p_feed=1 / 3, p_split=1 / 3, boost=None,
     np.savez_compressed(os.path.join(HERE, name + ".npz"), cfg=np.frombuffer(bytes(cfg), dtype=np.int32), seed=seed,
                         boost=boost or 0, draws=draws, dxdy=dxdy, act=act, rew=rew, done=done, blob0=s0.blob,
                         blobs=np.stack(blobs), blob_steps=np.array(blob_steps), obs=np.stack(obs).astype(np.int16),
-                        obs_steps=np.array(obs_steps), order=np.array(ref.order()))
+                        obs_steps=np.array(obs_steps), order=np.array(ref.order()), virus_hits=virus_hits)
     print(name, "ok", os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024, "KiB")
 
 
