@@ -83,6 +83,7 @@ __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
   return v;
 }
 __device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
+constexpr int kHashDead = 0xffff;  // hash entry of a pellet removed since the hash was built
 
 // ------------------------------------------------------------------------------------------------
 // per-warp context: uniform registers + pointers
@@ -101,6 +102,9 @@ struct Ctx {
   uint32_t tick, next_id, cursor, flags, seed_lo, seed_hi, done_sticky;
   int n_pellets, n_viruses, n_foods;
   int nprem, nvrem;
+  int emitted;          // foods appended by the last tick_player (Engine::emit_foods)
+  bool hash_valid;      // the pellet hash in shared memory matches the pellet array
+  uint32_t min_vmass;   // smallest virus mass this tick (0xffffffff without viruses)
   uint32_t inst_global;
   int inst_local;
   float W, dt;
@@ -451,11 +455,14 @@ __device__ void build_pellet_hash(Ctx& c) {
   // now hcnt[k] = end of cell k; start of cell k = (k ? hcnt[k-1] : 0)
 }
 __device__ void build_virus_cache(Ctx& c) {
+  uint32_t mn = 0xffffffffu;
   for (int v = c.lane; v < c.n_viruses; v += 32) {
     const float4 a = reinterpret_cast<const float4*>(c.vir + v)[0];  // x, y, mass, hits
     uint32_t vm = __float_as_uint(a.z);
+    mn = min(mn, vm);
     c.sm.vcache[v] = make_float4(a.x, a.y, radius_of(c.P.T, vm), a.z);
   }
+  c.min_vmass = warp_min_u32(mn);
   __syncwarp();
 }
 
@@ -466,6 +473,7 @@ __device__ void tick_player(Ctx& c, int p) {
   const Luts& T = c.P.T;
   agarcl_player* pl = c.players + p;
   int n = pl->n_cells;
+  c.emitted = 0;
   if (n == 0) return;  // dead players are not ticked (Engine.hpp:216)
   const int lane = c.lane;
   float tx = pl->target_x, ty = pl->target_y;
@@ -612,11 +620,13 @@ __device__ void tick_player(Ctx& c, int p) {
           float d2 = 0.f;
           if (j < e) {
             int idx = c.sm.hsorted[j];
-            float2 q = reinterpret_cast<const float2*>(c.pel)[idx];
-            d2 = sqr_dist(cx, cy, q.x, q.y);
-            int bx = (int)q.x / 510 - gx, by = (int)q.y / 510 - gy;
-            cand = d2 <= Rc2 && bx >= -1 && bx <= 1 && by >= -1 && by <= 1;
-            key = ((uint32_t)((bx + 1) * 3 + (by + 1)) << 16) | (uint32_t)idx;
+            if (idx != kHashDead) {
+              float2 q = reinterpret_cast<const float2*>(c.pel)[idx];
+              d2 = sqr_dist(cx, cy, q.x, q.y);
+              int bx = (int)q.x / 510 - gx, by = (int)q.y / 510 - gy;
+              cand = d2 <= Rc2 && bx >= -1 && bx <= 1 && by >= -1 && by <= 1;
+              key = ((uint32_t)((bx + 1) * 3 + (by + 1)) << 16) | (uint32_t)idx;
+            }
           }
           unsigned m = __ballot_sync(AG_FULL, cand);
           if (cand) {
@@ -782,6 +792,7 @@ __device__ void tick_player(Ctx& c, int p) {
     int add = __popc(em);
     if (c.n_foods + add > c.P.L.cap_foods) { c.flags |= AGARCL_FLAG_FOOD_OVERFLOW; add = c.P.L.cap_foods - c.n_foods; }
     c.n_foods += add;
+    c.emitted = add;
     feed_cd = 10;
     __syncwarp();
   }
@@ -901,14 +912,314 @@ __device__ void tick_player(Ctx& c, int p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// lane-per-player phase.  Inside Engine::tick's player loop (Engine.hpp:214-218) two players only
+// interact through (a) the foods list (eat_food / emit_foods) and (b) bots that read the other
+// players when they decide (HungryShy / Aggressive / AggressiveShy, every 10th tick); pellets and
+// viruses are not removed until the loop is over (:221-222).  A single-cell player that does
+// nothing structural this tick (no virus contact, no split / eject, no food in reach, <= kLaneCand
+// pellet candidates) is therefore ticked by ONE LANE, up to 32 players at a time, speculatively in
+// registers; results are then committed in the reference's player order, and every player that
+// does not qualify is ticked by the whole warp (tick_player) at its place in that order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void hash_range(const Ctx& c, int k0, int k1, int& s, int& e) {
+  s = k0 ? (int)c.sm.hcnt[k0 - 1] : 0;
+  e = (int)c.sm.hcnt[k1];
+}
+
+// Bot::nearest_pellet (Bot.hpp:92-129) by one lane: rings of hash cells around the bot until no
+// pellet outside the searched block can be nearer; first index among equal sqrtf(d^2).
+__device__ void lane_nearest_pellet(const Ctx& c, float lx, float ly, float& tx, float& ty) {
+  const int HG = c.P.HG;
+  const float cw = c.W / (float)HG;
+  const float2* pel = reinterpret_cast<const float2*>(c.pel);
+  const int hx = hash_coord(c, lx), hy = hash_coord(c, ly);
+  float best = 3.402823466e+38f;
+  uint32_t best_i = 0xffffffffu;
+  for (int r = 0; r < HG; r++) {
+    const int x0 = hx - r, x1 = hx + r, y0 = hy - r, y1 = hy + r;
+    const int cx0 = max(x0, 0), cx1 = min(x1, HG - 1);
+    for (int yy = max(y0, 0); yy <= min(y1, HG - 1); yy++) {
+      const bool edge = (yy == y0) || (yy == y1);
+      for (int side = 0; side < 2; side++) {
+        int a, b;
+        if (edge) { if (side) break; a = cx0; b = cx1; }
+        else if (side == 0) { if (x0 < 0) continue; a = b = x0; }
+        else { if (x1 >= HG) continue; a = b = x1; }
+        int s, e;
+        hash_range(c, yy * HG + a, yy * HG + b, s, e);
+        for (int j = s; j < e; j++) {
+          uint32_t idx = c.sm.hsorted[j];
+          if (idx == (uint32_t)kHashDead) continue;
+          float2 q = pel[idx];
+          float d = sqrtf(sqr_dist(lx, ly, q.x, q.y));
+          if ((d < best || (d == best && idx < best_i)) && (double)d > 0.01) { best = d; best_i = idx; }
+        }
+      }
+    }
+    // every pellet outside the block lies beyond one of its sides (0.01 covers all fp32 rounding)
+    float bound = 3.402823466e+38f;
+    if (x0 > 0) bound = fminf(bound, lx - (float)x0 * cw);
+    if (x1 < HG - 1) bound = fminf(bound, (float)(x1 + 1) * cw - lx);
+    if (y0 > 0) bound = fminf(bound, ly - (float)y0 * cw);
+    if (y1 < HG - 1) bound = fminf(bound, (float)(y1 + 1) * cw - ly);
+    if (bound == 3.402823466e+38f) break;  // the block covers the arena
+    if (best < bound - 0.01f) break;
+  }
+  if (best_i == 0xffffffffu) { tx = 0.0f; ty = 0.0f; return; }  // nothing qualified: Location() default
+  float2 q = pel[best_i];
+  tx = q.x; ty = q.y;
+}
+
+// get_pellets_to_remove_and_increment_cells (Engine.hpp:976-1000) for one cell by one lane: the
+// candidates (same superset as the warp-wide path) are taken in the reference's order by repeated
+// selection of the next key.  false: too many candidates for a lane.
+__device__ bool lane_eat_pellets(const Ctx& c, float cx, float cy, uint32_t& mass, int& ne, uint16_t* out) {
+  const Luts& T = c.P.T;
+  const int HG = c.P.HG;
+  const float2* pel = reinterpret_cast<const float2*>(c.pel);
+  const float rp = radius_of(T, 1u);
+  const int gx = (int)cx / 510, gy = (int)cy / 510;
+  const float Rc = fmax_std(radius_of(T, mass + (uint32_t)kCandCap), rp);
+  const float Rc2 = Rc * Rc;
+  const int hx0 = hash_coord(c, cx - Rc), hx1 = hash_coord(c, cx + Rc);
+  const int hy0 = hash_coord(c, cy - Rc), hy1 = hash_coord(c, cy + Rc);
+  uint32_t prev = 0u, newmass = mass;  // keys are kept +1 so that 0 means "none yet"
+  int remaining = -1;
+  ne = 0;
+  while (true) {
+    uint32_t best = 0xffffffffu;
+    float bestd2 = 0.0f;
+    int cnt = 0;
+    for (int hy = hy0; hy <= hy1; hy++) {
+      int s, e;
+      hash_range(c, hy * HG + hx0, hy * HG + hx1, s, e);
+      for (int j = s; j < e; j++) {
+        uint32_t idx = c.sm.hsorted[j];
+        if (idx == (uint32_t)kHashDead) continue;
+        float2 q = pel[idx];
+        float d2 = sqr_dist(cx, cy, q.x, q.y);
+        int bx = (int)q.x / 510 - gx, by = (int)q.y / 510 - gy;
+        if (d2 <= Rc2 && bx >= -1 && bx <= 1 && by >= -1 && by <= 1) {
+          cnt++;
+          uint32_t key = (((uint32_t)((bx + 1) * 3 + (by + 1)) << 16) | idx) + 1u;
+          if (key > prev && key < best) { best = key; bestd2 = d2; }
+        }
+      }
+    }
+    if (remaining < 0) {
+      if (cnt > kLaneCand) return false;
+      remaining = cnt;
+    }
+    if (best == 0xffffffffu) break;
+    float r = fmax_std(radius_of(T, newmass), rp);
+    if (r * r >= bestd2) {  // Ball::collides_with; can_eat(pellet) always holds for mass >= 25
+      out[ne++] = (uint16_t)((best - 1u) & 0xffffu);
+      newmass = floor_mass(newmass + 1u);
+    }
+    prev = best;
+    if (--remaining <= 0) break;
+  }
+  mass = newmass;
+  return true;
+}
+
+__device__ void tick_players_block(Ctx& c, int base) {
+  const Luts& T = c.P.T;
+  const int lane = c.lane;
+  const int k = base + lane;
+  const bool valid = k < c.P.L.P;
+  const int p = valid ? c.P.L.order[k] : 0;
+  agarcl_player* pl = c.players + p;
+  const int n = valid ? pl->n_cells : 0;
+  bool serial = n >= 2;
+  bool ok = n == 1;  // dead players are not ticked (Engine.hpp:216)
+  Cell me;
+  me.x = me.y = me.vx = me.vy = me.svx = me.svy = 0.0f;
+  me.mass = 0; me.id = 0; me.rec = 0;
+  int4 w0 = make_int4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;  // first 64 B of the player record
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t food_mass = 0;  // mass at the time of eat_food (after pellets, before decay)
+  int ne = 0;
+  uint16_t* myeat = c.sm.lprem + lane * kLaneCand;
+
+  if (ok) do {
+    const int4* rec = reinterpret_cast<const int4*>(pl);
+    w0 = rec[0]; w1 = rec[1]; w2 = rec[2]; w3 = rec[3];
+    float tx = __int_as_float(w0.y), ty = __int_as_float(w0.z);
+    int action = w0.w;
+    int split_cd = w1.x, feed_cd = w1.y;
+    const float atd = __int_as_float(w1.z);
+    const int elapsed = w1.w + 1;
+    int last_decay = w2.x;
+    const int bot_type = w2.y;
+    const int vet_count = w3.w;
+    me = cell_load(c.pcells(p));
+
+    // ---- bots decide every 10th tick (Engine.hpp:498-499); the ones that look at other players go serial
+    if (c.tick % 10u == 0u && bot_type >= 0) {
+      if (bot_type != 0 || c.n_pellets == 0) { ok = false; serial = true; break; }
+      float4 s = c.sm.psum[p];
+      action = 0;
+      lane_nearest_pellet(c, s.x, s.y, tx, ty);
+    }
+
+    // ---- Engine::move_player (no self-collisions with one cell)
+    const uint32_t smallest = me.mass;
+    me.vx = 3.0f * (tx - me.x);
+    me.vy = 3.0f * (ty - me.y);
+    {
+      float limit = max_speed_of(T, me.mass, c.flags);
+      if (vmag(me.vx, me.vy) > limit) {  // Velocity::clamp_speed + set_speed (quirk Q8)
+        me.vx *= limit / vmag(me.vx, me.vy);
+        me.vy *= limit / vmag(me.vx, me.vy);
+      }
+    }
+    cell_move(me, c.dt);
+    decelerate(me.svx, me.svy, 80.0f, c.dt);
+    bound_cell(c, me);
+
+    // ---- optimized_check_virus_collisions: any contact (eat or disrupt) is structural -> serial
+    if (c.n_viruses > 0 && can_eat_mass(me.mass, c.min_vmass)) {
+      const float cr = radius_of(T, me.mass);
+      const int gx = (int)me.x / 25, gy = (int)me.y / 25;
+      bool hit = false;
+      for (int v = 0; v < c.n_viruses; v++) {
+        float4 vc = c.sm.vcache[v];
+        if (collides(me.x, me.y, cr, vc.x, vc.y, vc.z)) {
+          int vgx = (int)vc.x / 25, vgy = (int)vc.y / 25;
+          int ddx = vgx - gx, ddy = vgy - gy;
+          if (ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1 && vgx < c.P.gw_virus && vgy < c.P.gw_virus &&
+              can_eat_mass(me.mass, __float_as_uint(vc.w)))
+            hit = true;
+        }
+      }
+      if (hit) { ok = false; serial = true; break; }
+    }
+
+    // ---- pellets
+    if (c.n_pellets > 0 && !lane_eat_pellets(c, me.x, me.y, me.mass, ne, myeat)) { ok = false; serial = true; break; }
+    const int food_eaten = w2.w + ne;
+    const uint32_t highest = max((uint32_t)w3.x, me.mass);
+
+    // ---- may_be_auto_split / eat_food / emit / split: anything that happens goes serial
+    if (me.mass >= AGARCL_MAX_MASS_IN_THE_GAME) { ok = false; serial = true; break; }
+    food_mass = me.mass;
+    if (c.n_foods > 0 && can_eat_mass(me.mass, AGARCL_FOOD_MASS)) {
+      const float cr = radius_of(T, me.mass), rf = radius_of(T, AGARCL_FOOD_MASS);
+      bool hit = false;
+      for (int j = 0; j < c.n_foods; j++) {
+        float4 f = reinterpret_cast<const float4*>(c.food)[j];
+        if (collides(me.x, me.y, cr, f.x, f.y, rf)) hit = true;
+      }
+      if (hit) { ok = false; serial = true; break; }
+    }
+    if (feed_cd > 0) feed_cd -= 1;
+    if (action == 1 && feed_cd == 0) {
+      if (me.mass >= AGARCL_CELL_MIN_SIZE + AGARCL_FOOD_MASS) { ok = false; serial = true; break; }
+      feed_cd = 10;
+    }
+    if (split_cd > 0) split_cd -= 1;
+    if (action == 2 && split_cd == 0) {
+      if (!(me.mass < AGARCL_CELL_SPLIT_MINIMUM || me.mass < 2u * AGARCL_CELL_MIN_SIZE)) { ok = false; serial = true; break; }
+      split_cd = 30;
+    }
+
+    // ---- once per 60 player-ticks: anti-team (only with remembered virus hits -> serial) + decay
+    if (c.P.L.mass_decay && elapsed % 60 == 0) {
+      if (vet_count > 0) { ok = false; serial = true; break; }
+      if (elapsed - last_decay >= 60) {
+        uint32_t nm = (uint32_t)((double)me.mass * (1 - 0.002 * (double)atd));
+        me.mass = nm > AGARCL_CELL_MIN_SIZE ? nm : AGARCL_CELL_MIN_SIZE;
+        last_decay = elapsed;
+      }
+    }
+
+    // ---- results (Player::x / y / mass with one cell: same fp32 expression as centroid_of)
+    float fm = (float)me.mass;
+    sum = make_float4((0.0f + me.x * fm) / fm, (0.0f + me.y * fm) / fm, __uint_as_float(me.mass), __int_as_float(1));
+    w0.y = __float_as_int(tx); w0.z = __float_as_int(ty); w0.w = action;
+    w1.x = split_cd; w1.y = feed_cd; w1.w = elapsed;
+    w2.x = last_decay; w2.z = (int)smallest; w2.w = food_eaten;
+    w3.x = (int)highest;
+  } while (0);
+
+  // ---- ordered commit: runs of lane-ticked players, whole-warp tick_player in between
+  unsigned serm = __ballot_sync(AG_FULL, serial);
+  int pos = 0;
+  while (true) {
+    unsigned rest = serm & ~lanemask_lt(pos);
+    const int nxt = rest ? __ffs(rest) - 1 : 32;
+    const bool mine = ok && lane >= pos && lane < nxt;
+    if (__ballot_sync(AG_FULL, mine && ne > 0)) {
+      // pellets_to_remove keeps the player order (Engine.hpp:212,221)
+      int v = mine ? ne : 0, incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(AG_FULL, incl, o);
+        if (lane >= o) incl += t;
+      }
+      int off = c.nprem + incl - v;
+      for (int e = 0; e < v; e++) {
+        if (off + e < kPremCap) c.sm.prem[off + e] = myeat[e];
+        else c.flags |= AGARCL_FLAG_REMOVE_OVERFLOW;
+      }
+      c.nprem = min(c.nprem + __shfl_sync(AG_FULL, incl, 31), kPremCap);
+    }
+    if (mine) {
+      cell_store(c.pcells(p), me);
+      int4* rec = reinterpret_cast<int4*>(pl);
+      rec[0] = w0; rec[1] = w1; rec[2] = w2; rec[3] = w3;
+      c.sm.psum[p] = sum;
+    }
+    __syncwarp();
+    if (nxt >= 32) break;
+    tick_player(c, c.P.L.order[base + nxt]);
+    if (c.emitted > 0) {
+      // foods emitted by this player can be eaten by later players in the same tick (Engine.hpp:1011-1025)
+      bool hit = false;
+      if (ok && lane > nxt && can_eat_mass(food_mass, AGARCL_FOOD_MASS)) {
+        const float cr = radius_of(T, food_mass), rf = radius_of(T, AGARCL_FOOD_MASS);
+        for (int j = c.n_foods - c.emitted; j < c.n_foods; j++) {
+          float4 f = reinterpret_cast<const float4*>(c.food)[j];
+          if (collides(me.x, me.y, cr, f.x, f.y, rf)) hit = true;
+        }
+      }
+      if (hit) { ok = false; serial = true; }
+      serm = __ballot_sync(AG_FULL, serial);
+    }
+    pos = nxt + 1;
+    if (pos >= 32) break;
+  }
+  c.flags = __reduce_or_sync(AG_FULL, c.flags);
+}
+
+// ------------------------------------------------------------------------------------------------
 // after the player loop: removals, players_collision, foods, regen
 // ------------------------------------------------------------------------------------------------
+// the pellet hash is kept across ticks: rename entry `from` of the hash cell containing `pos`
+__device__ __forceinline__ void hash_patch(Ctx& c, uint32_t from, uint32_t to, float2 pos) {
+  int k = hash_coord(c, pos.y) * c.P.HG + hash_coord(c, pos.x);
+  int s = k ? (int)c.sm.hcnt[k - 1] : 0, e = (int)c.sm.hcnt[k];
+  for (int j = s; j < e; j++)
+    if (c.sm.hsorted[j] == from) { c.sm.hsorted[j] = (uint16_t)to; break; }
+}
+
 __device__ void apply_removals(Ctx& c) {  // Engine.hpp:1002-1009,1253-1260 incl. stale/duplicate indices (Q4/Q5)
+  if (c.nprem == 0 && c.nvrem == 0) return;
   if (c.lane == 0) {
+    float2* pel = reinterpret_cast<float2*>(c.pel);
     for (int k = 0; k < c.nprem; k++) {
       uint32_t idx = c.sm.prem[k], size = (uint32_t)c.n_pellets;
-      if (idx < size - 1u && size > 1u) reinterpret_cast<float2*>(c.pel)[idx] = reinterpret_cast<float2*>(c.pel)[size - 1u];
-      if (size >= 1u) c.n_pellets--;
+      if (size == 0u) continue;
+      uint32_t last = size - 1u;
+      if (idx < last) {  // swap-with-back: the pellet at `idx` disappears, the last one takes its index
+        float2 pi = pel[idx], pl_ = pel[last];
+        if (c.hash_valid) { hash_patch(c, idx, kHashDead, pi); hash_patch(c, last, idx, pl_); }
+        pel[idx] = pl_;
+      } else if (c.hash_valid) {  // idx == last, or a stale index (Q4): the last pellet is popped
+        hash_patch(c, last, kHashDead, pel[last]);
+      }
+      c.n_pellets--;
     }
     for (int k = 0; k < c.nvrem; k++) {
       uint32_t idx = c.sm.vrem[k], size = (uint32_t)c.n_viruses;
@@ -1074,23 +1385,48 @@ __device__ void players_collision_exact(Ctx& c, int total, int nhit) {
 
 __device__ void players_collision(Ctx& c) {
   const int P = c.P.L.P;
+  const int lane = c.lane;
   // 1. sort multi-cell players by id; snapshot enumeration (map order, then cell order)
   int total = 0;
-  for (int k = 0; k < P; k++) {
-    int p = c.P.L.order[k];
-    int n = __float_as_int(c.sm.psum[p].w);
-    if (n >= 2) sort_player_cells(c, p, n);
-    for (int i = c.lane; i < n; i += 32)
-      if (total + i < kCellRefCap) c.sm.cellref[total + i] = (uint16_t)((p << 8) | i);
-    total += n;
+  for (int base = 0; base < P; base += 32) {
+    const int k = base + lane;
+    const int p = k < P ? c.P.L.order[k] : 0;
+    const int n = k < P ? __float_as_int(c.sm.psum[p].w) : 0;
+    unsigned multi = __ballot_sync(AG_FULL, n >= 2);
+    while (multi) {
+      int src = __ffs(multi) - 1;
+      multi &= multi - 1;
+      sort_player_cells(c, __shfl_sync(AG_FULL, p, src), __shfl_sync(AG_FULL, n, src));
+    }
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(AG_FULL, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int off = total + incl - n;
+    for (int i = 0; i < n; i++)
+      if (off + i < kCellRefCap) c.sm.cellref[off + i] = (uint16_t)((p << 8) | i);
+    total += __shfl_sync(AG_FULL, incl, 31);
   }
   if (total > kCellRefCap) { c.flags |= AGARCL_FLAG_EATER_OVERFLOW; total = kCellRefCap; }
   __syncwarp();
-  // 2. all-pairs pre-test (superset of what the strip sweep can return); hit queries in ascending order
+  // 2. all-pairs pre-test (superset of what the strip sweep can return); hit queries in ascending order.
+  //    q can only eat g if mass_q > mass_g, so max(r_q, r_g) = r_q in Ball::collides_with.
+  const bool staged = total <= kSnapCap;
+  if (staged) {
+    for (int g = lane; g < total; g += 32) {
+      int r = c.sm.cellref[g];
+      const agarcl_cell* gc = c.pcells(r >> 8) + (r & 0xff);
+      float4 a = reinterpret_cast<const float4*>(gc)[0];
+      c.sm.snap[g] = make_float4(a.x, a.y, __uint_as_float(gc->mass), __int_as_float(r >> 8));
+    }
+    __syncwarp();
+  }
   int nhit = 0;
   for (int qb = 0; qb < total; qb += 32) {
-    int q = qb + c.lane;
-    float qx = 0.f, qy = 0.f, qr = 0.f;
+    int q = qb + lane;
+    float qx = 0.f, qy = 0.f, qr2 = 0.f;
     uint32_t qm = 0;
     int qp = -1;
     if (q < total) {
@@ -1099,22 +1435,32 @@ __device__ void players_collision(Ctx& c) {
       const agarcl_cell* g = c.pcells(qp) + (r & 0xff);
       float4 a = reinterpret_cast<const float4*>(g)[0];
       qx = a.x; qy = a.y; qm = g->mass;
-      qr = radius_of(c.P.T, qm);
+      float qr = radius_of(c.P.T, qm);
+      qr2 = qr * qr;
     }
     bool hungry = qm > 25u;
     if (!__ballot_sync(AG_FULL, hungry)) continue;
     bool hit = false;
-    for (int g = 0; g < total; g++) {
-      int r = c.sm.cellref[g];
-      int gp = r >> 8;
-      const agarcl_cell* gc = c.pcells(gp) + (r & 0xff);
-      float4 a = reinterpret_cast<const float4*>(gc)[0];
-      uint32_t gm = gc->mass;
-      if (hungry && gp != qp && collides(qx, qy, qr, a.x, a.y, radius_of(c.P.T, gm)) && cell_can_eat_cell(qm, gm)) hit = true;
+    if (staged) {
+      for (int g = 0; g < total; g++) {
+        float4 sg = c.sm.snap[g];
+        if (qr2 >= sqr_dist(qx, qy, sg.x, sg.y) && hungry && __float_as_int(sg.w) != qp &&
+            can_eat_mass(qm, __float_as_uint(sg.z)))
+          hit = true;
+      }
+    } else {
+      for (int g = 0; g < total; g++) {
+        int r = c.sm.cellref[g];
+        int gp = r >> 8;
+        const agarcl_cell* gc = c.pcells(gp) + (r & 0xff);
+        float4 a = reinterpret_cast<const float4*>(gc)[0];
+        uint32_t gm = gc->mass;
+        if (hungry && gp != qp && qr2 >= sqr_dist(qx, qy, a.x, a.y) && can_eat_mass(qm, gm)) hit = true;
+      }
     }
     unsigned hm = __ballot_sync(AG_FULL, hit);
     if (hit) {
-      int pos = nhit + __popc(hm & lanemask_lt(c.lane));
+      int pos = nhit + __popc(hm & lanemask_lt(lane));
       if (pos < kPairCap) c.sm.hitq[pos] = (uint16_t)q;
     }
     nhit += __popc(hm);
@@ -1123,12 +1469,12 @@ __device__ void players_collision(Ctx& c) {
   if (nhit > kPairCap) { c.flags |= AGARCL_FLAG_EATER_OVERFLOW; nhit = kPairCap; }
   __syncwarp();
   // 3. exact path
-  if (c.lane == 0) players_collision_exact(c, total, nhit);
+  if (lane == 0) players_collision_exact(c, total, nhit);
   __syncwarp();
   c.flags = __shfl_sync(AG_FULL, c.flags, 0);
   // 4. refresh summaries (masses / counts changed)
   for (int base = 0; base < P; base += 32) {
-    int p = base + c.lane;
+    int p = base + lane;
     if (p < P) c.sm.psum[p] = centroid_from_global(c.pcells(p), c.players[p].n_cells);
   }
   __syncwarp();
@@ -1243,6 +1589,7 @@ __device__ void regen(Ctx& c) {
     }
     c.cursor += 2u * (uint32_t)dp;
     c.n_pellets = min(c.n_pellets + dp, c.P.L.cap_pellets);
+    c.hash_valid = false;
   }
   int dv = c.P.target_viruses - c.n_viruses;
   if (dv > 0) {
@@ -1267,12 +1614,12 @@ __device__ void regen(Ctx& c) {
 
 // Engine::tick
 __device__ void engine_tick(Ctx& c) {
-  build_pellet_hash(c);
+  if (!c.hash_valid) { build_pellet_hash(c); c.hash_valid = true; }
   build_virus_cache(c);
   c.nprem = 0;
   c.nvrem = 0;
   const int P = c.P.L.P;
-  for (int k = 0; k < P; k++) tick_player(c, c.P.L.order[k]);
+  for (int base = 0; base < P; base += 32) tick_players_block(c, base);
   apply_removals(c);
   players_collision(c);
   move_foods(c);
@@ -1332,6 +1679,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_step(const __grid_cons
   c.cursor = hdr->rng_cursor; c.flags = hdr->flags;
   c.seed_lo = hdr->seed_lo; c.seed_hi = hdr->seed_hi; c.done_sticky = hdr->done_sticky;
   c.nprem = 0; c.nvrem = 0;
+  c.emitted = 0; c.hash_valid = false; c.min_vmass = 0xffffffffu;
   c.W = P.W;
   c.dt = (float)(1.0 / 30.0);
   const int Pn = P.L.P, A = P.L.A;

@@ -11,6 +11,8 @@ constexpr int kWarpsPerCta = 4;       // one warp owns one game instance; a CTA 
 constexpr int kPremCap = 192;         // pellets_to_remove entries per tick (Engine.hpp:212)
 constexpr int kVremCap = 32;          // viruses_to_remove entries per tick (Engine.hpp:213)
 constexpr int kCandCap = 32;          // pellet candidates resolved in registers per cell
+constexpr int kLaneCand = 8;          // pellet candidates a single lane resolves in the lane-per-player phase
+constexpr int kSnapCap = 128;         // cells staged in shared memory by the players_collision pre-test
 constexpr int kPairCap = 48;          // (eater, eaten) pairs per tick in players_collision
 constexpr int kCellRefCap = 512;      // total live cells per instance handled by players_collision
 

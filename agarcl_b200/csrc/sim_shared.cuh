@@ -11,7 +11,8 @@ struct WarpSmem {
   // pellet spatial hash, rebuilt every tick (valid during the player loop)
   uint32_t* hcnt;      // [HG*HG]   counts -> offsets -> cell ends
   uint16_t* hsorted;   // [cap_pellets] pellet indices grouped by hash cell
-  // players_collision scratch (valid after the player loop) — aliases the hash region
+  // (the hash persists across the ticks of a launch and is patched on removals, so nothing aliases it)
+  // players_collision scratch
   uint16_t* cellref;   // [kCellRefCap]
   int16_t* rows;       // [kCellRefCap]
   uint16_t* strip;     // [kCellRefCap]
@@ -25,18 +26,22 @@ struct WarpSmem {
   uint2* cand;         // [kCandCap] (order key, d^2 bits)
   uint16_t* prem;      // [kPremCap]
   uint16_t* vrem;      // [kVremCap]
+  uint16_t* lprem;     // [32][kLaneCand] pellets eaten by each lane's player in the lane-per-player phase
+  float4* snap;        // [kSnapCap] players_collision snapshot: x, y, mass bits, player
 };
 
 __host__ __device__ inline uint32_t ag_align16(uint32_t x) { return (x + 15u) & ~15u; }
 
 __host__ __device__ inline uint32_t hash_region_bytes(const agarcl_layout& L, int HG) {
-  uint32_t a = ag_align16((uint32_t)(HG * HG) * 4u) + ag_align16((uint32_t)L.cap_pellets * 2u);
-  uint32_t b = ag_align16(kCellRefCap * 2u) * 3u + ag_align16(kPairCap * 16u) + ag_align16(kPairCap * 2u) * 3u;
-  return a > b ? a : b;
+  return ag_align16((uint32_t)(HG * HG) * 4u) + ag_align16((uint32_t)L.cap_pellets * 2u);
+}
+__host__ __device__ inline uint32_t coll_region_bytes() {
+  return ag_align16(kCellRefCap * 2u) * 3u + ag_align16(kPairCap * 16u) + ag_align16(kPairCap * 2u) * 3u;
 }
 __host__ __device__ inline uint32_t warp_smem_bytes(const agarcl_layout& L, int HG) {
-  return hash_region_bytes(L, HG) + ag_align16((uint32_t)L.cap_viruses * 16u) + ag_align16((uint32_t)L.P * 16u) +
-         ag_align16(kCandCap * 8u) + ag_align16(kPremCap * 2u) + ag_align16(kVremCap * 2u);
+  return hash_region_bytes(L, HG) + coll_region_bytes() + ag_align16((uint32_t)L.cap_viruses * 16u) +
+         ag_align16((uint32_t)L.P * 16u) + ag_align16(kCandCap * 8u) + ag_align16(kPremCap * 2u) + ag_align16(kVremCap * 2u) +
+         ag_align16(32u * kLaneCand * 2u) + ag_align16(kSnapCap * 16u);
 }
 
 __device__ inline WarpSmem carve_warp_smem(uint8_t* base, const agarcl_layout& L, int HG) {
@@ -44,7 +49,7 @@ __device__ inline WarpSmem carve_warp_smem(uint8_t* base, const agarcl_layout& L
   uint8_t* p = base;
   s.hcnt = reinterpret_cast<uint32_t*>(p);
   s.hsorted = reinterpret_cast<uint16_t*>(p + ag_align16((uint32_t)(HG * HG) * 4u));
-  uint8_t* q = base;
+  uint8_t* q = base + hash_region_bytes(L, HG);
   s.cellref = reinterpret_cast<uint16_t*>(q); q += ag_align16(kCellRefCap * 2u);
   s.rows = reinterpret_cast<int16_t*>(q);     q += ag_align16(kCellRefCap * 2u);
   s.strip = reinterpret_cast<uint16_t*>(q);   q += ag_align16(kCellRefCap * 2u);
@@ -52,12 +57,14 @@ __device__ inline WarpSmem carve_warp_smem(uint8_t* base, const agarcl_layout& L
   s.reskeys = reinterpret_cast<uint16_t*>(q); q += ag_align16(kPairCap * 2u);
   s.resorder = reinterpret_cast<uint16_t*>(q); q += ag_align16(kPairCap * 2u);
   s.hitq = reinterpret_cast<uint16_t*>(q);
-  p += hash_region_bytes(L, HG);
+  p += hash_region_bytes(L, HG) + coll_region_bytes();
   s.vcache = reinterpret_cast<float4*>(p); p += ag_align16((uint32_t)L.cap_viruses * 16u);
   s.psum = reinterpret_cast<float4*>(p);   p += ag_align16((uint32_t)L.P * 16u);
   s.cand = reinterpret_cast<uint2*>(p);    p += ag_align16(kCandCap * 8u);
   s.prem = reinterpret_cast<uint16_t*>(p); p += ag_align16(kPremCap * 2u);
-  s.vrem = reinterpret_cast<uint16_t*>(p);
+  s.vrem = reinterpret_cast<uint16_t*>(p);  p += ag_align16(kVremCap * 2u);
+  s.lprem = reinterpret_cast<uint16_t*>(p); p += ag_align16(32u * kLaneCand * 2u);
+  s.snap = reinterpret_cast<float4*>(p);
   return s;
 }
 
