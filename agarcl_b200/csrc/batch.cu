@@ -46,6 +46,7 @@ struct agarcl_batch {
   int HG;
   uint32_t smem_per_warp;
   bool was_reset = false;
+  int fuse_clear = 1;  // engine-tick kernel clears observation channels 1..C-1 (AGARCL_FUSE_CLEAR=0 disables, for A/B timing)
   int launches_last_step = 0;
   // optional per-kernel timing: (start, after sim, after obs) event triples of steps not yet collected
   bool timing = false;
@@ -108,10 +109,26 @@ static void fill_sim_params(const agarcl_batch* b, ag::SimParams& P) {
   P.gw_pellet = (int)(((float)b->cfg.arena_size + 510.0f - 1.0f) / 510.0f);
   P.gw_virus = (int)(((float)b->cfg.arena_size + 25.0f - 1.0f) / 25.0f);
   P.smem_per_warp = b->smem_per_warp;
+  P.obs = nullptr;
+  P.zero_vec_per_agent = 0; P.zero_skip_vec = 0; P.agent_stride_vec = 0;
 }
 
-static void fill_obs_params(const agarcl_batch* b, ag::ObsParams& P, int frame, int pre_respawn) {
+// Lets the engine-tick kernel clear channels 1..C-1 of frame slot `frame` (see SimParams); false when
+// the planes are not 16-byte multiples.
+static bool fuse_obs_clear(const agarcl_batch* b, ag::SimParams& P, int frame) {
+  const size_t esz = b->cfg.obs_dtype == AGARCL_OBS_I16 ? 2 : 4;
+  const size_t plane = (size_t)b->G * b->G * esz;
+  if (plane % 16 != 0 || b->C < 2 || b->fuse_clear == 0) return false;
+  P.obs = (uint8_t*)b->d_obs + (size_t)frame * b->C * plane;
+  P.zero_skip_vec = (uint32_t)(plane / 16);
+  P.zero_vec_per_agent = (uint32_t)((size_t)(b->C - 1) * plane / 16);
+  P.agent_stride_vec = (uint32_t)((size_t)b->frames * b->C * plane / 16);
+  return true;
+}
+
+static void fill_obs_params(const agarcl_batch* b, ag::ObsParams& P, int frame, int pre_respawn, int skip_zero = 0) {
   P.pre_respawn = pre_respawn;
+  P.skip_zero = skip_zero;
   P.L = b->L;
   P.state = b->d_state;
   P.obs = b->d_obs;
@@ -160,13 +177,14 @@ extern "C" int agarcl_batch_create(const agarcl_cfg* cfg, agarcl_batch** out) {
   b->G = cfg->grid_size;
   b->C = L.obs_channels;
   b->frames = cfg->num_frames;
+  if (const char* e = std::getenv("AGARCL_FUSE_CLEAR")) b->fuse_clear = std::atoi(e);
   b->obs_elems = (size_t)b->N * b->A * b->frames * b->C * b->G * b->G;
   b->obs_bytes = b->obs_elems * (cfg->obs_dtype == AGARCL_OBS_I16 ? 2 : 4);
   // spatial hash resolution: about 3 pellets per hash cell, 4..64 cells per side
   int hg = (int)std::floor(std::sqrt((double)L.cap_pellets / 3.0));
   b->HG = hg < 4 ? 4 : (hg > 64 ? 64 : hg);
   b->smem_per_warp = ag::warp_smem_bytes(L, b->HG);
-  if ((size_t)b->smem_per_warp * ag::kWarpsPerCta > 200 * 1024) {
+  if ((size_t)b->smem_per_warp * ag::kWarpsPerCta + ag::kZeroTileBytes > 200 * 1024) {
     delete b;
     return agarcl_set_error(AGARCL_ERR_INVALID, "configuration needs %u B of shared memory per instance (too many pellets/viruses)", b->smem_per_warp);
   }
@@ -261,9 +279,9 @@ extern "C" int agarcl_batch_set_replay(agarcl_batch* b, int32_t instance, const 
   return AGARCL_OK;
 }
 
-static int render_frame(agarcl_batch* b, int frame, cudaStream_t s, int pre_respawn) {
+static int render_frame(agarcl_batch* b, int frame, cudaStream_t s, int pre_respawn, int skip_zero = 0) {
   ag::ObsParams P;
-  fill_obs_params(b, P, frame, pre_respawn);
+  fill_obs_params(b, P, frame, pre_respawn, skip_zero);
   CK(ag::launch_obs(P, s));
   return AGARCL_OK;
 }
@@ -344,10 +362,11 @@ extern "C" int agarcl_batch_step(agarcl_batch* b, void* stream) {
     if (frame >= 0) { int rc = render_frame(b, frame, s, 1); if (rc) return rc; launches++; }
   } else if (b->frames == 1) {
     P.n_ticks = tps; P.do_begin = 1; P.do_end = 1;
+    const int fused = fuse_obs_clear(b, P, 0) ? 1 : 0;
     if (b->timing) { if (b->ev_used >= 3 * 2048) collect_timing(b); CK(cudaEventRecord(next_event(b), s)); }
     CK(ag::launch_step(P, s)); launches++;
     if (b->timing) CK(cudaEventRecord(next_event(b), s));
-    int rc = render_frame(b, 0, s, 1); if (rc) return rc; launches++;
+    int rc = render_frame(b, 0, s, 1, fused); if (rc) return rc; launches++;
     if (b->timing) CK(cudaEventRecord(next_event(b), s));
   } else {
     // the last num_frames ticks of the step each contribute one frame (the documented intent of

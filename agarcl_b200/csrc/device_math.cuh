@@ -29,7 +29,15 @@ __device__ __forceinline__ float clamp_std(float x, float lo, float hi) { return
 // Engine::check_boundary_collisions on one axis, Engine.hpp:695-698 (NaN -> 0, quirk Q19)
 __device__ __forceinline__ float bound_axis(float x, float r, float W) { return fmax_std(0.0f, clamp_std(x, r, W - r)); }
 
-__device__ __forceinline__ float radius_exact(uint32_t m) { return (float)sqrt((double)m / 1.0 / AG_PI); }
+// the beyond-the-table paths are cold: kept out of line so that they do not dilute the hot code in the I-cache
+static __device__ __noinline__ float radius_exact(uint32_t m) { return (float)sqrt((double)m / 1.0 / AG_PI); }
+static __device__ __noinline__ float max_speed_exact(uint32_t m) { return (float)(300.0 / pow((double)m, 0.439)); }
+static __device__ __noinline__ float split_speed_exact(uint32_t m) {
+  double v = 3.0 * pow((double)(float)(300.0 / pow((double)m, 0.439)), 1.2);
+  v = (130.0 < v) ? 130.0 : v;
+  v = (v < 20.0) ? 20.0 : v;
+  return (float)v;
+}
 __device__ __forceinline__ float radius_of(const Luts& T, uint32_t m) {
   return m < AGARCL_LUT_SIZE ? T.radius[m] : radius_exact(m);
 }
@@ -37,15 +45,12 @@ __device__ __forceinline__ float radius_of(const Luts& T, uint32_t m) {
 __device__ __forceinline__ float max_speed_of(const Luts& T, uint32_t m, uint32_t& flags) {
   if (m < AGARCL_LUT_SIZE) return T.max_speed[m];
   flags |= AGARCL_FLAG_MASS_LUT;
-  return (float)(300.0 / pow((double)m, 0.439));
+  return max_speed_exact(m);
 }
 __device__ __forceinline__ float split_speed_of(const Luts& T, uint32_t m, uint32_t& flags) {
   if (m < AGARCL_LUT_SIZE) return T.split_speed[m];
   flags |= AGARCL_FLAG_MASS_LUT;
-  double v = 3.0 * pow((double)(float)(300.0 / pow((double)m, 0.439)), 1.2);
-  v = (130.0 < v) ? 130.0 : v;
-  v = (v < 20.0) ? 20.0 : v;
-  return (float)v;
+  return split_speed_exact(m);
 }
 
 // Coordinate::norm_sqr of a difference, core/types.hpp:83-87

@@ -115,9 +115,11 @@ __global__ void __launch_bounds__(kObsThreads) k_obs(const __grid_constant__ Obs
       int xm = (s_xmask[i] != 0) ? -1 : 0;
       __stcs(out4 + v, make_int4(ym.x | xm, ym.y | xm, ym.z | xm, ym.w | xm));
     }
-    const int4 zero = make_int4(0, 0, 0, 0);
+    if (!P.skip_zero) {
+      const int4 zero = make_int4(0, 0, 0, 0);
 #pragma unroll 8
-    for (int v = nvec0 + tid; v < nvec; v += kObsThreads) __stcs(out4 + v, zero);
+      for (int v = nvec0 + tid; v < nvec; v += kObsThreads) __stcs(out4 + v, zero);
+    }
   } else {
     const size_t nel = (size_t)C * plane;
     for (size_t e = tid; e < nel; e += kObsThreads) {

@@ -105,6 +105,10 @@ struct Ctx {
   int emitted;          // foods appended by the last tick_player (Engine::emit_foods)
   bool hash_valid;      // the pellet hash in shared memory matches the pellet array
   uint32_t min_vmass;   // smallest virus mass this tick (0xffffffff without viruses)
+  uint32_t zagent, zoff, zchunk;  // fused observation clear: cursor (agent, vector) and vectors per chunk
+  uint32_t zero_tile;   // shared-memory address of the CTA's all-zero tile (source of the bulk stores)
+  uint64_t zpolicy;     // L2 evict-first policy for the observation stream
+  bool vc_valid;        // the virus cache in shared memory matches the virus array
   uint32_t inst_global;
   int inst_local;
   float W, dt;
@@ -1030,21 +1034,24 @@ __device__ void tick_players_block(Ctx& c, int base) {
   const bool valid = k < c.P.L.P;
   const int p = valid ? c.P.L.order[k] : 0;
   agarcl_player* pl = c.players + p;
-  const int n = valid ? pl->n_cells : 0;
-  bool serial = n >= 2;
-  bool ok = n == 1;  // dead players are not ticked (Engine.hpp:216)
   Cell me;
   me.x = me.y = me.vx = me.vy = me.svx = me.svy = 0.0f;
   me.mass = 0; me.id = 0; me.rec = 0;
   int4 w0 = make_int4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;  // first 64 B of the player record
+  if (valid) {  // record and first cell in ONE round trip (the cell slot exists even for a dead player)
+    const int4* rec = reinterpret_cast<const int4*>(pl);
+    w0 = rec[0]; w1 = rec[1]; w2 = rec[2]; w3 = rec[3];
+    me = cell_load(c.pcells(p));
+  }
+  const int n = w0.x;
+  bool serial = n >= 2;
+  bool ok = n == 1;  // dead players are not ticked (Engine.hpp:216)
   float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t food_mass = 0;  // mass at the time of eat_food (after pellets, before decay)
   int ne = 0;
   uint16_t* myeat = c.sm.lprem + lane * kLaneCand;
 
   if (ok) do {
-    const int4* rec = reinterpret_cast<const int4*>(pl);
-    w0 = rec[0]; w1 = rec[1]; w2 = rec[2]; w3 = rec[3];
     float tx = __int_as_float(w0.y), ty = __int_as_float(w0.z);
     int action = w0.w;
     int split_cd = w1.x, feed_cd = w1.y;
@@ -1053,7 +1060,6 @@ __device__ void tick_players_block(Ctx& c, int base) {
     int last_decay = w2.x;
     const int bot_type = w2.y;
     const int vet_count = w3.w;
-    me = cell_load(c.pcells(p));
 
     // ---- bots decide every 10th tick (Engine.hpp:498-499); the ones that look at other players go serial
     if (c.tick % 10u == 0u && bot_type >= 0) {
@@ -1232,6 +1238,7 @@ __device__ void apply_removals(Ctx& c) {  // Engine.hpp:1002-1009,1253-1260 incl
   }
   c.n_pellets = __shfl_sync(AG_FULL, c.n_pellets, 0);
   c.n_viruses = __shfl_sync(AG_FULL, c.n_viruses, 0);
+  if (c.nvrem > 0) c.vc_valid = false;
   c.nprem = 0;
   c.nvrem = 0;
   __syncwarp();
@@ -1277,23 +1284,26 @@ struct PairRec { uint16_t q, g; uint32_t eaten_mass, eater_id, eaten_id; };  // 
 
 // exact PrecisionCollisionDetection::solve + application, run by ONE lane (rare path: only for the
 // query cells the all-pairs pre-test flagged; everything the strip sweep can return is in that set).
-__device__ void players_collision_exact(Ctx& c, int total, int nhit) {
+__device__ void players_collision_exact(Ctx& c, int total, int nhit, bool staged) {
   const Luts& T = c.P.T;
   const uint16_t* ref = c.sm.cellref;  // (player << 8 | cell) in snapshot order
-  int16_t* rows = c.sm.rows;           // strip id of every snapshot cell
+  const int16_t* rows = c.sm.rows;     // strip id of every snapshot cell (filled by the caller)
   uint16_t* strip = c.sm.strip;        // one strip, sorted by y (stable)
   PairRec* pairs = reinterpret_cast<PairRec*>(c.sm.pairs);
   uint16_t* rkeys = c.sm.reskeys;      // query ids with results, first-insert order
   uint16_t* rorder = c.sm.resorder;    // iteration order of the results map
   auto cellp = [&](int g) -> const agarcl_cell* { return c.pcells(ref[g] >> 8) + (ref[g] & 0xff); };
-  for (int g = 0; g < total; g++) rows[g] = (int16_t)get_row(cellp(g)->x, c.W);
+  // the sweep reads the pre-application snapshot (Engine.hpp:153-166): shared-memory copy when staged
+  auto gy_of = [&](int g) -> float { return staged ? c.sm.snap[g].y : cellp(g)->y; };
+  auto gx_of = [&](int g) -> float { return staged ? c.sm.snap[g].x : cellp(g)->x; };
+  auto gm_of = [&](int g) -> uint32_t { return staged ? __float_as_uint(c.sm.snap[g].z) : cellp(g)->mass; };
   int npairs = 0, nres = 0;
   for (int hq = 0; hq < nhit; hq++) {
     int q = c.sm.hitq[hq];
     int qp = ref[q] >> 8;
     const agarcl_cell* qc = cellp(q);
-    float qx = qc->x, qy = qc->y;
-    uint32_t qm = qc->mass;
+    float qx = gx_of(q), qy = gy_of(q);
+    uint32_t qm = gm_of(q);
     float qr = radius_of(T, qm);
     float left = qx - qr, right = qx + qr;
     int top = get_row(left, c.W), bottom = get_row(right, c.W);
@@ -1302,26 +1312,26 @@ __device__ void players_collision_exact(Ctx& c, int total, int nhit) {
       int l = 0;
       for (int g = 0; g < total; g++) {
         if (rows[g] != row) continue;
-        float gy = cellp(g)->y;  // insertion sort by y == libstdc++ std::sort for <= 16 elements
+        float gy = gy_of(g);  // insertion sort by y == libstdc++ std::sort for <= 16 elements
         int b = l - 1;
-        while (b >= 0 && gy < cellp(strip[b])->y) { strip[b + 1] = strip[b]; b--; }
+        while (b >= 0 && gy < gy_of(strip[b])) { strip[b + 1] = strip[b]; b--; }
         strip[b + 1] = (uint16_t)g;
         l++;
       }
       if (l == 0) continue;
       if (l > 16)
         for (int a = 1; a < l; a++)
-          if (cellp(strip[a])->y == cellp(strip[a - 1])->y) c.flags |= AGARCL_FLAG_PCD_TIE;
+          if (gy_of(strip[a]) == gy_of(strip[a - 1])) c.flags |= AGARCL_FLAG_PCD_TIE;
       int start_pos = 0;
       for (int j = 10; j >= 0; j--)
-        if (start_pos + (1 << j) < l && cellp(strip[start_pos + (1 << j)])->y < left) start_pos += (1 << j);
+        if (start_pos + (1 << j) < l && gy_of(strip[start_pos + (1 << j)]) < left) start_pos += (1 << j);
       for (int j = start_pos; j < l; j++) {
         int g = strip[j];
         int gp = ref[g] >> 8;
         if (gp == qp) break;  // quirk Q7: the scan stops at the first own cell
-        const agarcl_cell* gc = cellp(g);
-        uint32_t gm = gc->mass;
-        if (collides(qx, qy, qr, gc->x, gc->y, radius_of(T, gm)) && cell_can_eat_cell(qm, gm)) {
+        uint32_t gm = gm_of(g);
+        if (collides(qx, qy, qr, gx_of(g), gy_of(g), radius_of(T, gm)) && cell_can_eat_cell(qm, gm)) {
+          const agarcl_cell* gc = cellp(g);
           if (npairs < kPairCap) {
             if (!opened) { rkeys[nres++] = (uint16_t)q; opened = true; }
             pairs[npairs].q = (uint16_t)q; pairs[npairs].g = (uint16_t)g;
@@ -1430,11 +1440,16 @@ __device__ void players_collision(Ctx& c) {
     uint32_t qm = 0;
     int qp = -1;
     if (q < total) {
-      int r = c.sm.cellref[q];
-      qp = r >> 8;
-      const agarcl_cell* g = c.pcells(qp) + (r & 0xff);
-      float4 a = reinterpret_cast<const float4*>(g)[0];
-      qx = a.x; qy = a.y; qm = g->mass;
+      if (staged) {
+        float4 sg = c.sm.snap[q];
+        qx = sg.x; qy = sg.y; qm = __float_as_uint(sg.z); qp = __float_as_int(sg.w);
+      } else {
+        int r = c.sm.cellref[q];
+        qp = r >> 8;
+        const agarcl_cell* g = c.pcells(qp) + (r & 0xff);
+        float4 a = reinterpret_cast<const float4*>(g)[0];
+        qx = a.x; qy = a.y; qm = g->mass;
+      }
       float qr = radius_of(c.P.T, qm);
       qr2 = qr * qr;
     }
@@ -1468,8 +1483,15 @@ __device__ void players_collision(Ctx& c) {
   if (nhit == 0) return;
   if (nhit > kPairCap) { c.flags |= AGARCL_FLAG_EATER_OVERFLOW; nhit = kPairCap; }
   __syncwarp();
-  // 3. exact path
-  if (lane == 0) players_collision_exact(c, total, nhit);
+  // 3. exact path: strip ids of the snapshot cells by all lanes, then the serial sweep by one
+  for (int g = lane; g < total; g += 32) {
+    float x;
+    if (staged) x = c.sm.snap[g].x;
+    else { int r = c.sm.cellref[g]; x = (c.pcells(r >> 8) + (r & 0xff))->x; }
+    c.sm.rows[g] = (int16_t)get_row(x, c.W);
+  }
+  __syncwarp();
+  if (lane == 0) players_collision_exact(c, total, nhit, staged);
   __syncwarp();
   c.flags = __shfl_sync(AG_FULL, c.flags, 0);
   // 4. refresh summaries (masses / counts changed)
@@ -1552,6 +1574,7 @@ __device__ void move_foods(Ctx& c) {
     }
   }
   if (__ballot_sync(AG_FULL, danger)) {
+    c.vc_valid = false;  // a virus may be fed / reset / shot
     if (c.lane == 0) move_foods_serial(c);
     __syncwarp();
     c.n_foods = __shfl_sync(AG_FULL, c.n_foods, 0);
@@ -1607,19 +1630,51 @@ __device__ void regen(Ctx& c) {
     c.cursor += 2u * (uint32_t)dv;
     if (dv > room) { c.flags |= AGARCL_FLAG_VIRUS_OVERFLOW; dv = room; }
     c.n_viruses += dv;
+    c.vc_valid = false;
   }
   c.flags = __reduce_or_sync(AG_FULL, c.flags);
   __syncwarp();
 }
 
+// Fused observation clear: queue the next `nvec` zero vectors of this instance's agent frames as TMA
+// bulk stores (cp.async.bulk shared -> global) from the CTA's all-zero tile.  One lane issues one
+// instruction per kZeroTileBytes; the copy engine streams them to HBM while the warp goes on ticking,
+// so the 7/8 of the observation bytes that do not depend on the state cost no issue slots and never
+// stall the tick (the warp only waits for the tile READS to finish before it exits).
+__device__ __forceinline__ void zero_chunk(Ctx& c, uint32_t nvec) {
+  const uint32_t per = c.P.zero_vec_per_agent;
+  if (per == 0u) return;
+  while (nvec > 0u && c.zagent < (uint32_t)c.P.L.A) {
+    const uint32_t n = min(nvec, per - c.zoff);
+    if (c.lane == 0) {
+      uint8_t* dst = reinterpret_cast<uint8_t*>(c.P.obs) +
+                     16ull * (((size_t)c.inst_local * c.P.L.A + c.zagent) * c.P.agent_stride_vec + c.P.zero_skip_vec + c.zoff);
+      uint32_t bytes = n * 16u;
+      while (bytes > 0u) {
+        const uint32_t b = min(bytes, (uint32_t)kZeroTileBytes);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                     :: "l"(dst), "r"(c.zero_tile), "r"(b), "l"(c.zpolicy) : "memory");
+        dst += b;
+        bytes -= b;
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    nvec -= n;
+    c.zoff += n;
+    if (c.zoff == per) { c.zoff = 0u; c.zagent++; }
+  }
+}
+
 // Engine::tick
 __device__ void engine_tick(Ctx& c) {
+  zero_chunk(c, c.zchunk);
   if (!c.hash_valid) { build_pellet_hash(c); c.hash_valid = true; }
-  build_virus_cache(c);
+  if (!c.vc_valid) { build_virus_cache(c); c.vc_valid = true; }
   c.nprem = 0;
   c.nvrem = 0;
   const int P = c.P.L.P;
   for (int base = 0; base < P; base += 32) tick_players_block(c, base);
+  zero_chunk(c, c.zchunk);
   apply_removals(c);
   players_collision(c);
   move_foods(c);
@@ -1658,9 +1713,14 @@ __device__ void respawn_player(Ctx& c, int p, uint32_t k) {
 // kernel: BaseEnvironment::step for one instance per warp
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_step(const __grid_constant__ SimParams P) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int inst = blockIdx.x * kWarpsPerCta + warp;
+  // the CTA's all-zero tile (first kZeroTileBytes of shared memory), made visible to the async proxy
+  for (int i = threadIdx.x; i < kZeroTileBytes / 16; i += kWarpsPerCta * 32)
+    reinterpret_cast<int4*>(smem_raw)[i] = make_int4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
   if (inst >= P.N) return;
   Ctx c(P);
   c.lane = lane;
@@ -1672,14 +1732,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_step(const __grid_cons
   c.vir = reinterpret_cast<agarcl_virus*>(c.blob + P.L.off_viruses);
   c.food = reinterpret_cast<agarcl_food*>(c.blob + P.L.off_foods);
   c.pel = reinterpret_cast<agarcl_pellet*>(c.blob + P.L.off_pellets);
-  c.sm = carve_warp_smem(smem_raw + (size_t)warp * P.smem_per_warp, P.L, P.HG);
+  c.sm = carve_warp_smem(smem_raw + kZeroTileBytes + (size_t)warp * P.smem_per_warp, P.L, P.HG);
+  c.zero_tile = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(c.zpolicy));
   agarcl_inst_hdr* hdr = reinterpret_cast<agarcl_inst_hdr*>(c.blob + P.L.off_hdr);
   c.tick = hdr->tick; c.next_id = hdr->next_cell_id;
   c.n_pellets = hdr->n_pellets; c.n_viruses = hdr->n_viruses; c.n_foods = hdr->n_foods;
   c.cursor = hdr->rng_cursor; c.flags = hdr->flags;
   c.seed_lo = hdr->seed_lo; c.seed_hi = hdr->seed_hi; c.done_sticky = hdr->done_sticky;
   c.nprem = 0; c.nvrem = 0;
-  c.emitted = 0; c.hash_valid = false; c.min_vmass = 0xffffffffu;
+  c.emitted = 0; c.hash_valid = false; c.vc_valid = false; c.min_vmass = 0xffffffffu;
   c.W = P.W;
   c.dt = (float)(1.0 / 30.0);
   const int Pn = P.L.P, A = P.L.A;
@@ -1711,7 +1773,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_step(const __grid_cons
     __syncwarp();
   }
 
+  c.zagent = 0u; c.zoff = 0u;
+  {
+    const uint32_t total = P.zero_vec_per_agent * (uint32_t)A;
+    const uint32_t chunks = (uint32_t)(2 * (P.n_ticks > 0 ? P.n_ticks : 1));
+    c.zchunk = (total + chunks - 1u) / chunks;
+  }
   for (int t = 0; t < P.n_ticks; t++) engine_tick(c);
+  zero_chunk(c, 0xffffffffu);  // whatever is left (n_ticks == 0, rounding)
 
   if (P.do_end) {
     if (P.mode == 0) {
@@ -1761,6 +1830,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_step(const __grid_cons
   }
 
   c.flags = __reduce_or_sync(AG_FULL, c.flags);
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the zero tile outlives its readers
   if (lane == 0) {
     hdr->tick = c.tick; hdr->next_cell_id = c.next_id;
     hdr->n_pellets = c.n_pellets; hdr->n_viruses = c.n_viruses; hdr->n_foods = c.n_foods;
@@ -1770,7 +1840,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_step(const __grid_cons
 
 cudaError_t launch_step(const SimParams& P, cudaStream_t stream) {
   int ctas = (P.N + kWarpsPerCta - 1) / kWarpsPerCta;
-  size_t smem = (size_t)P.smem_per_warp * kWarpsPerCta;
+  size_t smem = (size_t)kZeroTileBytes + (size_t)P.smem_per_warp * kWarpsPerCta;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -12,6 +12,7 @@ constexpr int kPremCap = 192;         // pellets_to_remove entries per tick (Eng
 constexpr int kVremCap = 32;          // viruses_to_remove entries per tick (Engine.hpp:213)
 constexpr int kCandCap = 32;          // pellet candidates resolved in registers per cell
 constexpr int kLaneCand = 8;          // pellet candidates a single lane resolves in the lane-per-player phase
+constexpr int kZeroTileBytes = 4096;  // CTA-shared all-zero tile, source of the TMA bulk stores that clear the observation
 constexpr int kSnapCap = 128;         // cells staged in shared memory by the players_collision pre-test
 constexpr int kPairCap = 48;          // (eater, eaten) pairs per tick in players_collision
 constexpr int kCellRefCap = 512;      // total live cells per instance handled by players_collision
@@ -39,6 +40,13 @@ struct SimParams {
   int32_t gw_pellet;       // reference pellet bucket grid width (bucket 510, Engine.hpp:962-965)
   int32_t gw_virus;        // reference virus bucket grid width (bucket 25, Engine.hpp:1207-1211)
   uint32_t smem_per_warp;  // bytes
+  // fused observation clear: the engine-tick kernel streams the zeros of channels 1..C-1 of every
+  // agent frame (state independent, 7/8 of all bytes of the step) while it computes; k_obs then only
+  // writes channel 0 and scatters the entities.  zero_vec_per_agent == 0 disables it.
+  void* obs;                    // frame slot of agent 0 of instance 0
+  uint32_t zero_vec_per_agent;  // 16-byte vectors to clear per agent frame
+  uint32_t zero_skip_vec;       // vectors of channel 0 in front of them
+  uint32_t agent_stride_vec;    // vectors between consecutive agents' frame slots
 };
 
 struct ResetParams {
@@ -61,6 +69,7 @@ struct ObsParams {
   int32_t observe_cells, observe_others, observe_viruses, observe_pellets;
   int32_t obs_dtype;
   int32_t pre_respawn;     // 1: show players respawned at the end of the step as still dead
+  int32_t skip_zero;       // 1: channels 1..C-1 were already cleared by the engine-tick kernel
   float W;
 };
 
