@@ -109,6 +109,7 @@ struct Ctx {
   uint32_t zero_tile;   // shared-memory address of the CTA's all-zero tile (source of the bulk stores)
   uint64_t zpolicy;     // L2 evict-first policy for the observation stream
   bool vc_valid;        // the virus cache in shared memory matches the virus array
+  bool lanes_dirty;     // players_collision changed players: lanes must reload their registers
   uint32_t inst_global;
   int inst_local;
   float W, dt;
@@ -426,6 +427,16 @@ __device__ __forceinline__ int hash_coord(const Ctx& c, float v) {
   int h = (int)(v * c.P.hash_scale);
   return min(max(h, 0), c.P.HG - 1);
 }
+// Quantised copy of a pellet position (2 x 16 bits) kept next to its hash entry: the lane-per-player
+// scans filter on it from shared memory and touch the exact fp32 position in HBM/L2 only for the
+// few entries that can matter.  |x - dequant| < q_inv per axis, so sqrt(2) * q_inv bounds the distance error.
+__device__ __forceinline__ uint32_t quantize_xy(const Ctx& c, float x, float y) {
+  int qx = min(max((int)(x * c.P.q_scale), 0), 65535), qy = min(max((int)(y * c.P.q_scale), 0), 65535);
+  return (uint32_t)qx | ((uint32_t)qy << 16);
+}
+__device__ __forceinline__ float2 dequantize_xy(const Ctx& c, uint32_t q) {
+  return make_float2(((float)(q & 0xffffu) + 0.5f) * c.P.q_inv, ((float)(q >> 16) + 0.5f) * c.P.q_inv);
+}
 __device__ void build_pellet_hash(Ctx& c) {
   const int HG = c.P.HG, nc = HG * HG;
   for (int i = c.lane; i < nc; i += 32) c.sm.hcnt[i] = 0u;
@@ -454,6 +465,7 @@ __device__ void build_pellet_hash(Ctx& c) {
     float2 p = reinterpret_cast<const float2*>(c.pel)[i];
     uint32_t pos = atomicAdd(&c.sm.hcnt[hash_coord(c, p.y) * HG + hash_coord(c, p.x)], 1u);
     c.sm.hsorted[pos] = (uint16_t)i;
+    c.sm.hq[pos] = quantize_xy(c, p.x, p.y);
   }
   __syncwarp();
   // now hcnt[k] = end of cell k; start of cell k = (k ? hcnt[k-1] : 0)
@@ -900,6 +912,7 @@ __device__ void tick_player(Ctx& c, int p) {
   if (lane < n) cell_store(c.pcells(p) + lane, me);
   if (lane == 0) {
     c.sm.psum[p] = s;
+    c.sm.pcell[p].w = -1.0f;  // not lane-ticked: the collision snapshot reads this player from memory
     pl->n_cells = n;
     pl->target_x = tx; pl->target_y = ty;
     pl->action = action;
@@ -930,44 +943,74 @@ __device__ __forceinline__ void hash_range(const Ctx& c, int k0, int k1, int& s,
   e = (int)c.sm.hcnt[k1];
 }
 
-// Bot::nearest_pellet (Bot.hpp:92-129) by one lane: rings of hash cells around the bot until no
-// pellet outside the searched block can be nearer; first index among equal sqrtf(d^2).
+// Visits the hash entries of ring `r` (Chebyshev distance r in hash cells) around cell (hx, hy).
+template <typename F>
+__device__ __forceinline__ void ring_visit(const Ctx& c, int hx, int hy, int r, F&& f) {
+  const int HG = c.P.HG;
+  const int x0 = hx - r, x1 = hx + r, y0 = hy - r, y1 = hy + r;
+  const int cx0 = max(x0, 0), cx1 = min(x1, HG - 1);
+#pragma unroll 1
+  for (int yy = max(y0, 0); yy <= min(y1, HG - 1); yy++) {
+    const bool edge = (yy == y0) || (yy == y1);
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+      int a, b;
+      if (edge) { if (side) break; a = cx0; b = cx1; }
+      else if (side == 0) { if (x0 < 0) continue; a = b = x0; }
+      else { if (x1 >= HG) continue; a = b = x1; }
+      int s, e;
+      hash_range(c, yy * HG + a, yy * HG + b, s, e);
+#pragma unroll 1
+      for (int j = s; j < e; j++) f(j);
+    }
+  }
+}
+
+// Bot::nearest_pellet (Bot.hpp:92-129) by one lane.  Phase 1 walks rings of hash cells on the
+// QUANTISED positions (shared memory only) until no pellet outside the searched block can be nearer,
+// and yields an upper bound U of the true minimum; phase 2 evaluates exactly (fp32 position from
+// global memory, the reference's own comparison) the few entries whose quantised distance is within
+// the quantisation margin of U.  First index among equal sqrtf(d^2); d <= 0.01 is skipped as in the reference.
 __device__ void lane_nearest_pellet(const Ctx& c, float lx, float ly, float& tx, float& ty) {
   const int HG = c.P.HG;
   const float cw = c.W / (float)HG;
+  const float M = 1.5f * c.P.q_inv;  // > sqrt(2) * q_inv
   const float2* pel = reinterpret_cast<const float2*>(c.pel);
   const int hx = hash_coord(c, lx), hy = hash_coord(c, ly);
-  float best = 3.402823466e+38f;
-  uint32_t best_i = 0xffffffffu;
+  const float INF = 3.402823466e+38f;
+  float U = INF;
+  int rstop = HG - 1;
+#pragma unroll 1
   for (int r = 0; r < HG; r++) {
-    const int x0 = hx - r, x1 = hx + r, y0 = hy - r, y1 = hy + r;
-    const int cx0 = max(x0, 0), cx1 = min(x1, HG - 1);
-    for (int yy = max(y0, 0); yy <= min(y1, HG - 1); yy++) {
-      const bool edge = (yy == y0) || (yy == y1);
-      for (int side = 0; side < 2; side++) {
-        int a, b;
-        if (edge) { if (side) break; a = cx0; b = cx1; }
-        else if (side == 0) { if (x0 < 0) continue; a = b = x0; }
-        else { if (x1 >= HG) continue; a = b = x1; }
-        int s, e;
-        hash_range(c, yy * HG + a, yy * HG + b, s, e);
-        for (int j = s; j < e; j++) {
-          uint32_t idx = c.sm.hsorted[j];
-          if (idx == (uint32_t)kHashDead) continue;
-          float2 q = pel[idx];
-          float d = sqrtf(sqr_dist(lx, ly, q.x, q.y));
-          if ((d < best || (d == best && idx < best_i)) && (double)d > 0.01) { best = d; best_i = idx; }
-        }
-      }
-    }
+    ring_visit(c, hx, hy, r, [&](int j) {
+      if (c.sm.hsorted[j] == (uint16_t)kHashDead) return;
+      float2 q = dequantize_xy(c, c.sm.hq[j]);
+      float dq = sqrtf(sqr_dist(lx, ly, q.x, q.y));
+      if (dq > 0.01f + M) U = fminf(U, dq + M);  // certainly farther than 0.01: a true qualifier
+    });
     // every pellet outside the block lies beyond one of its sides (0.01 covers all fp32 rounding)
-    float bound = 3.402823466e+38f;
+    const int x0 = hx - r, x1 = hx + r, y0 = hy - r, y1 = hy + r;
+    float bound = INF;
     if (x0 > 0) bound = fminf(bound, lx - (float)x0 * cw);
     if (x1 < HG - 1) bound = fminf(bound, (float)(x1 + 1) * cw - lx);
     if (y0 > 0) bound = fminf(bound, ly - (float)y0 * cw);
     if (y1 < HG - 1) bound = fminf(bound, (float)(y1 + 1) * cw - ly);
-    if (bound == 3.402823466e+38f) break;  // the block covers the arena
-    if (best < bound - 0.01f) break;
+    if (bound == INF || U < bound - 0.01f) { rstop = r; break; }
+  }
+  float best = INF;
+  uint32_t best_i = 0xffffffffu;
+  const float lim = U + M;  // INF stays INF: then everything is evaluated exactly
+#pragma unroll 1
+  for (int r = 0; r <= rstop; r++) {
+    ring_visit(c, hx, hy, r, [&](int j) {
+      uint32_t idx = c.sm.hsorted[j];
+      if (idx == (uint32_t)kHashDead) return;
+      float2 qq = dequantize_xy(c, c.sm.hq[j]);
+      if (!(sqrtf(sqr_dist(lx, ly, qq.x, qq.y)) <= lim)) return;
+      float2 q = pel[idx];
+      float d = sqrtf(sqr_dist(lx, ly, q.x, q.y));  // (other - this).norm()
+      if ((d < best || (d == best && idx < best_i)) && (double)d > 0.01) { best = d; best_i = idx; }
+    });
   }
   if (best_i == 0xffffffffu) { tx = 0.0f; ty = 0.0f; return; }  // nothing qualified: Location() default
   float2 q = pel[best_i];
@@ -976,7 +1019,8 @@ __device__ void lane_nearest_pellet(const Ctx& c, float lx, float ly, float& tx,
 
 // get_pellets_to_remove_and_increment_cells (Engine.hpp:976-1000) for one cell by one lane: the
 // candidates (same superset as the warp-wide path) are taken in the reference's order by repeated
-// selection of the next key.  false: too many candidates for a lane.
+// selection of the next key.  Entries are pre-filtered on their quantised position in shared memory;
+// only possible candidates are read exactly.  false: too many candidates for a lane.
 __device__ bool lane_eat_pellets(const Ctx& c, float cx, float cy, uint32_t& mass, int& ne, uint16_t* out) {
   const Luts& T = c.P.T;
   const int HG = c.P.HG;
@@ -985,6 +1029,7 @@ __device__ bool lane_eat_pellets(const Ctx& c, float cx, float cy, uint32_t& mas
   const int gx = (int)cx / 510, gy = (int)cy / 510;
   const float Rc = fmax_std(radius_of(T, mass + (uint32_t)kCandCap), rp);
   const float Rc2 = Rc * Rc;
+  const float Rq = Rc + 1.5f * c.P.q_inv, Rq2 = Rq * Rq;
   const int hx0 = hash_coord(c, cx - Rc), hx1 = hash_coord(c, cx + Rc);
   const int hy0 = hash_coord(c, cy - Rc), hy1 = hash_coord(c, cy + Rc);
   uint32_t prev = 0u, newmass = mass;  // keys are kept +1 so that 0 means "none yet"
@@ -994,10 +1039,14 @@ __device__ bool lane_eat_pellets(const Ctx& c, float cx, float cy, uint32_t& mas
     uint32_t best = 0xffffffffu;
     float bestd2 = 0.0f;
     int cnt = 0;
+#pragma unroll 1
     for (int hy = hy0; hy <= hy1; hy++) {
       int s, e;
       hash_range(c, hy * HG + hx0, hy * HG + hx1, s, e);
+#pragma unroll 1
       for (int j = s; j < e; j++) {
+        float2 qq = dequantize_xy(c, c.sm.hq[j]);
+        if (!(sqr_dist(cx, cy, qq.x, qq.y) <= Rq2)) continue;
         uint32_t idx = c.sm.hsorted[j];
         if (idx == (uint32_t)kHashDead) continue;
         float2 q = pel[idx];
@@ -1027,23 +1076,29 @@ __device__ bool lane_eat_pellets(const Ctx& c, float cx, float cy, uint32_t& mas
   return true;
 }
 
-__device__ void tick_players_block(Ctx& c, int base) {
+// What a lane keeps in registers about its player between the ticks of a launch.
+struct LaneState {
+  Cell me;
+  int4 w0, w1, w2, w3;  // first 64 B of the player record
+  bool fresh;           // registers == global memory (the lane committed this player itself)
+};
+
+__device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
   const Luts& T = c.P.T;
   const int lane = c.lane;
   const int k = base + lane;
   const bool valid = k < c.P.L.P;
   const int p = valid ? c.P.L.order[k] : 0;
   agarcl_player* pl = c.players + p;
-  Cell me;
-  me.x = me.y = me.vx = me.vy = me.svx = me.svy = 0.0f;
-  me.mass = 0; me.id = 0; me.rec = 0;
-  int4 w0 = make_int4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;  // first 64 B of the player record
-  if (valid) {  // record and first cell in ONE round trip (the cell slot exists even for a dead player)
+  Cell& me = ls.me;
+  int4 &w0 = ls.w0, &w1 = ls.w1, &w2 = ls.w2, &w3 = ls.w3;
+  if (valid && !ls.fresh) {  // record and first cell in ONE round trip (the cell slot exists even for a dead player)
     const int4* rec = reinterpret_cast<const int4*>(pl);
     w0 = rec[0]; w1 = rec[1]; w2 = rec[2]; w3 = rec[3];
     me = cell_load(c.pcells(p));
+    ls.fresh = true;
   }
-  const int n = w0.x;
+  const int n = valid ? w0.x : 0;
   bool serial = n >= 2;
   bool ok = n == 1;  // dead players are not ticked (Engine.hpp:216)
   float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1149,6 +1204,7 @@ __device__ void tick_players_block(Ctx& c, int base) {
     w3.x = (int)highest;
   } while (0);
 
+  if (serial) ls.fresh = false;  // ticked by the whole warp below: registers are stale afterwards
   // ---- ordered commit: runs of lane-ticked players, whole-warp tick_player in between
   unsigned serm = __ballot_sync(AG_FULL, serial);
   int pos = 0;
@@ -1176,6 +1232,7 @@ __device__ void tick_players_block(Ctx& c, int base) {
       int4* rec = reinterpret_cast<int4*>(pl);
       rec[0] = w0; rec[1] = w1; rec[2] = w2; rec[3] = w3;
       c.sm.psum[p] = sum;
+      c.sm.pcell[p] = make_float4(me.x, me.y, __uint_as_float(me.mass), 1.0f);
     }
     __syncwarp();
     if (nxt >= 32) break;
@@ -1190,7 +1247,7 @@ __device__ void tick_players_block(Ctx& c, int base) {
           if (collides(me.x, me.y, cr, f.x, f.y, rf)) hit = true;
         }
       }
-      if (hit) { ok = false; serial = true; }
+      if (hit) { ok = false; serial = true; ls.fresh = false; }
       serm = __ballot_sync(AG_FULL, serial);
     }
     pos = nxt + 1;
@@ -1427,9 +1484,14 @@ __device__ void players_collision(Ctx& c) {
   if (staged) {
     for (int g = lane; g < total; g += 32) {
       int r = c.sm.cellref[g];
-      const agarcl_cell* gc = c.pcells(r >> 8) + (r & 0xff);
-      float4 a = reinterpret_cast<const float4*>(gc)[0];
-      c.sm.snap[g] = make_float4(a.x, a.y, __uint_as_float(gc->mass), __int_as_float(r >> 8));
+      float4 pc = c.sm.pcell[r >> 8];
+      if (pc.w >= 0.0f) {  // lane-ticked single-cell player: its cell is already in shared memory
+        c.sm.snap[g] = make_float4(pc.x, pc.y, pc.z, __int_as_float(r >> 8));
+      } else {
+        const agarcl_cell* gc = c.pcells(r >> 8) + (r & 0xff);
+        float4 a = reinterpret_cast<const float4*>(gc)[0];
+        c.sm.snap[g] = make_float4(a.x, a.y, __uint_as_float(gc->mass), __int_as_float(r >> 8));
+      }
     }
     __syncwarp();
   }
@@ -1494,10 +1556,14 @@ __device__ void players_collision(Ctx& c) {
   if (lane == 0) players_collision_exact(c, total, nhit, staged);
   __syncwarp();
   c.flags = __shfl_sync(AG_FULL, c.flags, 0);
+  c.lanes_dirty = true;  // masses / cell lists changed under the lanes' registers
   // 4. refresh summaries (masses / counts changed)
   for (int base = 0; base < P; base += 32) {
     int p = base + lane;
-    if (p < P) c.sm.psum[p] = centroid_from_global(c.pcells(p), c.players[p].n_cells);
+    if (p < P) {
+      c.sm.psum[p] = centroid_from_global(c.pcells(p), c.players[p].n_cells);
+      c.sm.pcell[p].w = -1.0f;
+    }
   }
   __syncwarp();
 }
@@ -1666,14 +1732,23 @@ __device__ __forceinline__ void zero_chunk(Ctx& c, uint32_t nvec) {
 }
 
 // Engine::tick
-__device__ void engine_tick(Ctx& c) {
+__device__ void engine_tick(Ctx& c, LaneState& ls) {
   zero_chunk(c, c.zchunk);
   if (!c.hash_valid) { build_pellet_hash(c); c.hash_valid = true; }
   if (!c.vc_valid) { build_virus_cache(c); c.vc_valid = true; }
   c.nprem = 0;
   c.nvrem = 0;
   const int P = c.P.L.P;
-  for (int base = 0; base < P; base += 32) tick_players_block(c, base);
+  if (c.lanes_dirty) { ls.fresh = false; c.lanes_dirty = false; }
+  tick_players_block(c, 0, ls);
+  for (int base = 32; base < P; base += 32) {  // more than 32 players: the further blocks reload every tick
+    LaneState tmp;
+    tmp.fresh = false;
+    tmp.w0 = tmp.w1 = tmp.w2 = tmp.w3 = make_int4(0, 0, 0, 0);
+    tmp.me.x = tmp.me.y = tmp.me.vx = tmp.me.vy = tmp.me.svx = tmp.me.svy = 0.0f;
+    tmp.me.mass = 0; tmp.me.id = 0; tmp.me.rec = 0;
+    tick_players_block(c, base, tmp);
+  }
   zero_chunk(c, c.zchunk);
   apply_removals(c);
   players_collision(c);
@@ -1712,7 +1787,7 @@ __device__ void respawn_player(Ctx& c, int p, uint32_t k) {
 // ------------------------------------------------------------------------------------------------
 // kernel: BaseEnvironment::step for one instance per warp
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_step(const __grid_constant__ SimParams P) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3) k_step(const __grid_constant__ SimParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int inst = blockIdx.x * kWarpsPerCta + warp;
@@ -1741,7 +1816,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_step(const __grid_cons
   c.cursor = hdr->rng_cursor; c.flags = hdr->flags;
   c.seed_lo = hdr->seed_lo; c.seed_hi = hdr->seed_hi; c.done_sticky = hdr->done_sticky;
   c.nprem = 0; c.nvrem = 0;
-  c.emitted = 0; c.hash_valid = false; c.vc_valid = false; c.min_vmass = 0xffffffffu;
+  c.emitted = 0; c.hash_valid = false; c.vc_valid = false; c.lanes_dirty = false; c.min_vmass = 0xffffffffu;
   c.W = P.W;
   c.dt = (float)(1.0 / 30.0);
   const int Pn = P.L.P, A = P.L.A;
@@ -1749,7 +1824,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_step(const __grid_cons
   // player summaries (centroid, mass, count)
   for (int base = 0; base < Pn; base += 32) {
     int p = base + lane;
-    if (p < Pn) c.sm.psum[p] = centroid_from_global(c.pcells(p), c.players[p].n_cells);
+    if (p < Pn) {
+      c.sm.psum[p] = centroid_from_global(c.pcells(p), c.players[p].n_cells);
+      c.sm.pcell[p] = make_float4(0.f, 0.f, 0.f, -1.0f);
+    }
   }
   __syncwarp();
 
@@ -1779,7 +1857,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_step(const __grid_cons
     const uint32_t chunks = (uint32_t)(2 * (P.n_ticks > 0 ? P.n_ticks : 1));
     c.zchunk = (total + chunks - 1u) / chunks;
   }
-  for (int t = 0; t < P.n_ticks; t++) engine_tick(c);
+  LaneState ls;
+  ls.fresh = false;
+  ls.w0 = ls.w1 = ls.w2 = ls.w3 = make_int4(0, 0, 0, 0);
+  ls.me.x = ls.me.y = ls.me.vx = ls.me.vy = ls.me.svx = ls.me.svy = 0.0f;
+  ls.me.mass = 0; ls.me.id = 0; ls.me.rec = 0;
+  for (int t = 0; t < P.n_ticks; t++) engine_tick(c, ls);
   zero_chunk(c, 0xffffffffu);  // whatever is left (n_ticks == 0, rounding)
 
   if (P.do_end) {

@@ -7,15 +7,15 @@
 
 namespace ag {
 
-constexpr int kWarpsPerCta = 4;       // one warp owns one game instance; a CTA is 4 independent warps
+constexpr int kWarpsPerCta = 5;       // one warp owns one game instance; a CTA is 5 independent warps (3 CTAs / SM)
 constexpr int kPremCap = 192;         // pellets_to_remove entries per tick (Engine.hpp:212)
 constexpr int kVremCap = 32;          // viruses_to_remove entries per tick (Engine.hpp:213)
 constexpr int kCandCap = 32;          // pellet candidates resolved in registers per cell
 constexpr int kLaneCand = 8;          // pellet candidates a single lane resolves in the lane-per-player phase
 constexpr int kZeroTileBytes = 4096;  // CTA-shared all-zero tile, source of the TMA bulk stores that clear the observation
-constexpr int kSnapCap = 128;         // cells staged in shared memory by the players_collision pre-test
+constexpr int kSnapCap = 64;          // cells staged in shared memory by the players_collision pre-test
 constexpr int kPairCap = 48;          // (eater, eaten) pairs per tick in players_collision
-constexpr int kCellRefCap = 512;      // total live cells per instance handled by players_collision
+constexpr int kCellRefCap = 256;      // total live cells per instance handled by players_collision
 
 struct SimParams {
   agarcl_layout L;
@@ -37,6 +37,7 @@ struct SimParams {
   int32_t HG;              // spatial hash is HG x HG over the arena
   float W;                 // arena width == height
   float hash_scale;        // HG / W
+  float q_scale, q_inv;    // pellet quantisation: q = int(x * q_scale), x ~ (q + 0.5) * q_inv, |error| < q_inv per axis
   int32_t gw_pellet;       // reference pellet bucket grid width (bucket 510, Engine.hpp:962-965)
   int32_t gw_virus;        // reference virus bucket grid width (bucket 25, Engine.hpp:1207-1211)
   uint32_t smem_per_warp;  // bytes
