@@ -45,6 +45,7 @@ struct agarcl_batch {
   ag::Luts T;
   int HG;
   uint32_t smem_per_warp;
+  ag::SmemOff so;
   bool was_reset = false;
   int fuse_clear = 1;  // engine-tick kernel clears observation channels 1..C-1 (AGARCL_FUSE_CLEAR=0 disables, for A/B timing)
   int launches_last_step = 0;
@@ -111,6 +112,7 @@ static void fill_sim_params(const agarcl_batch* b, ag::SimParams& P) {
   P.gw_pellet = (int)(((float)b->cfg.arena_size + 510.0f - 1.0f) / 510.0f);
   P.gw_virus = (int)(((float)b->cfg.arena_size + 25.0f - 1.0f) / 25.0f);
   P.smem_per_warp = b->smem_per_warp;
+  P.so = b->so;
   P.obs = nullptr;
   P.zero_vec_per_agent = 0; P.zero_skip_vec = 0; P.agent_stride_vec = 0;
 }
@@ -185,7 +187,7 @@ extern "C" int agarcl_batch_create(const agarcl_cfg* cfg, agarcl_batch** out) {
   // spatial hash resolution: about 3 pellets per hash cell, 4..64 cells per side
   int hg = (int)std::floor(std::sqrt((double)L.cap_pellets / 3.0));
   b->HG = hg < 4 ? 4 : (hg > 64 ? 64 : hg);
-  b->smem_per_warp = ag::warp_smem_bytes(L, b->HG);
+  b->smem_per_warp = ag::make_smem_offsets(L, b->HG, b->so);
   if ((size_t)b->smem_per_warp * ag::kWarpsPerCta + ag::kZeroTileBytes > 200 * 1024) {
     delete b;
     return agarcl_set_error(AGARCL_ERR_INVALID, "configuration needs %u B of shared memory per instance (too many pellets/viruses)", b->smem_per_warp);

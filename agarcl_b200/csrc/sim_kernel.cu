@@ -91,35 +91,36 @@ constexpr int kHashDead = 0xffff;  // hash entry of a pellet removed since the h
 struct Ctx {
   const SimParams& P;
   int lane;
-  uint8_t* blob;
-  agarcl_player* players;
-  agarcl_cell* cells;
-  agarcl_virus* vir;
-  agarcl_food* food;
-  agarcl_pellet* pel;
+  uint8_t* blob;  // this instance's state; the arrays are blob + constant-bank offsets, formed where used
   WarpSmem sm;
+  __device__ __forceinline__ agarcl_player* players_() const { return reinterpret_cast<agarcl_player*>(blob + P.L.off_players); }
+  __device__ __forceinline__ agarcl_cell* cells_() const { return reinterpret_cast<agarcl_cell*>(blob + P.L.off_cells); }
+  __device__ __forceinline__ agarcl_virus* vir_() const { return reinterpret_cast<agarcl_virus*>(blob + P.L.off_viruses); }
+  __device__ __forceinline__ agarcl_food* food_() const { return reinterpret_cast<agarcl_food*>(blob + P.L.off_foods); }
+  __device__ __forceinline__ agarcl_pellet* pel_() const { return reinterpret_cast<agarcl_pellet*>(blob + P.L.off_pellets); }
   // header, kept in registers for the whole launch
-  uint32_t tick, next_id, cursor, flags, seed_lo, seed_hi, done_sticky;
+  uint32_t tick, next_id, cursor, flags, done_sticky;
   int n_pellets, n_viruses, n_foods;
   int nprem, nvrem;
   int emitted;          // foods appended by the last tick_player (Engine::emit_foods)
   bool hash_valid;      // the pellet hash in shared memory matches the pellet array
   uint32_t min_vmass;   // smallest virus mass this tick (0xffffffff without viruses)
   uint32_t zagent, zoff, zchunk;  // fused observation clear: cursor (agent, vector) and vectors per chunk
-  uint32_t zero_tile;   // shared-memory address of the CTA's all-zero tile (source of the bulk stores)
-  uint64_t zpolicy;     // L2 evict-first policy for the observation stream
   bool vc_valid;        // the virus cache in shared memory matches the virus array
   bool lanes_dirty;     // players_collision changed players: lanes must reload their registers
-  uint32_t inst_global;
   int inst_local;
-  float W, dt;
+  float W;
+  static constexpr float dt = (float)(1.0 / 30.0);
   __device__ Ctx(const SimParams& p) : P(p) {}
-  __device__ __forceinline__ agarcl_cell* pcells(int p) const { return cells + (size_t)p * AGARCL_MAX_CELLS; }
+  __device__ __forceinline__ agarcl_cell* pcells(int p) const { return cells_() + (size_t)p * AGARCL_MAX_CELLS; }
 };
 
 // one uniform draw in [0,1): k-th draw of this instance (Engine::random<T>, Engine.hpp:1304-1311)
 __device__ __forceinline__ float draw_at(Ctx& c, uint32_t k) {
-  if (c.P.rng_mode == AGARCL_RNG_PHILOX) return philox_uniform(c.seed_lo, c.seed_hi, c.inst_global, k);
+  if (c.P.rng_mode == AGARCL_RNG_PHILOX) {  // seed lives in the header: draws are rare (regen, respawn)
+    const agarcl_inst_hdr* hdr = reinterpret_cast<const agarcl_inst_hdr*>(c.blob + c.P.L.off_hdr);
+    return philox_uniform(hdr->seed_lo, hdr->seed_hi, (uint32_t)(c.P.instance_base + c.inst_local), k);
+  }
   if ((int)k < c.P.L.cap_replay && c.P.replay) return c.P.replay[(size_t)c.inst_local * c.P.L.cap_replay + k];
   c.flags |= AGARCL_FLAG_REPLAY_EXHAUSTED;
   return 0.5f;
@@ -328,7 +329,7 @@ __device__ void nearest_pellet(Ctx& c, float lx, float ly, float& tx, float& ty)
   float best = 3.402823466e+38f;
   uint32_t best_i = 0xffffffffu;
   for (int i = c.lane; i < c.n_pellets; i += 32) {
-    float2 p = reinterpret_cast<const float2*>(c.pel)[i];
+    float2 p = reinterpret_cast<const float2*>(c.pel_())[i];
     float d = sqrtf(sqr_dist(lx, ly, p.x, p.y));  // (other - this).norm()
     if (d < best && (double)d > 0.01) { best = d; best_i = (uint32_t)i; }
   }
@@ -339,7 +340,7 @@ __device__ void nearest_pellet(Ctx& c, float lx, float ly, float& tx, float& ty)
   uint32_t cand = (best == gbest && best_i != 0xffffffffu) ? best_i : 0xffffffffu;
   cand = warp_min_u32(cand);
   if (cand == 0xffffffffu) { tx = 0.0f; ty = 0.0f; return; }  // nothing qualified: Location() default
-  float2 p = reinterpret_cast<const float2*>(c.pel)[cand];
+  float2 p = reinterpret_cast<const float2*>(c.pel_())[cand];
   tx = p.x; ty = p.y;
 }
 
@@ -353,7 +354,7 @@ __device__ bool bot_flee(Ctx& c, int p, float lx, float ly, float& tx, float& ty
     float ox = 0.f, oy = 0.f;
     if (k < P) {
       int o = c.P.L.order[k];
-      float4 s = c.sm.psum[o];
+      float4 s = c.sm.psum()[o];
       ox = s.x; oy = s.y;
       float d = sqrtf(sqr_dist(ox, oy, lx, ly));
       cond = (o != p) && (d < 25.0f) && (__float_as_uint(s.z) > 0u);
@@ -383,7 +384,7 @@ __device__ bool bot_chase(Ctx& c, int p, const Cell& me, int n, float lx, float 
     bool near = false;
     if (k < P) {
       int o = c.P.L.order[k];
-      float4 s = c.sm.psum[o];
+      float4 s = c.sm.psum()[o];
       float d = sqrtf(sqr_dist(s.x, s.y, lx, ly));
       near = (o != p) && (d <= 20.0f);
     }
@@ -392,7 +393,7 @@ __device__ bool bot_chase(Ctx& c, int p, const Cell& me, int n, float lx, float 
       int src = __ffs(m) - 1;
       m &= m - 1;
       int o = c.P.L.order[base + src];
-      int on = __float_as_int(c.sm.psum[o].w);
+      int on = __float_as_int(c.sm.psum()[o].w);
       Cell oc;
       oc.mass = 0; oc.x = 0.f; oc.y = 0.f;
       if (c.lane < on) {
@@ -439,33 +440,47 @@ __device__ __forceinline__ float2 dequantize_xy(const Ctx& c, uint32_t q) {
 }
 __device__ void build_pellet_hash(Ctx& c) {
   const int HG = c.P.HG, nc = HG * HG;
-  for (int i = c.lane; i < nc; i += 32) c.sm.hcnt[i] = 0u;
+  for (int i = c.lane; i < nc; i += 32) c.sm.hcnt()[i] = 0u;
   __syncwarp();
-  for (int i = c.lane; i < c.n_pellets; i += 32) {
-    float2 p = reinterpret_cast<const float2*>(c.pel)[i];
-    atomicAdd(&c.sm.hcnt[hash_coord(c, p.y) * HG + hash_coord(c, p.x)], 1u);
+  // 8 independent loads in flight per lane: the two passes over the pellet array are latency, not bandwidth
+  const float2* pel = reinterpret_cast<const float2*>(c.pel_());
+  for (int base = 0; base < c.n_pellets; base += 256) {
+    float2 p[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) { int i = base + u * 32 + c.lane; p[u] = i < c.n_pellets ? pel[i] : make_float2(0.f, 0.f); }
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (base + u * 32 + c.lane < c.n_pellets) atomicAdd(&c.sm.hcnt()[hash_coord(c, p[u].y) * HG + hash_coord(c, p[u].x)], 1u);
   }
   __syncwarp();
   // exclusive scan over nc counters, 32 at a time
   uint32_t carry = 0;
   for (int base = 0; base < nc; base += 32) {
     int i = base + c.lane;
-    uint32_t v = i < nc ? c.sm.hcnt[i] : 0u;
+    uint32_t v = i < nc ? c.sm.hcnt()[i] : 0u;
     uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       uint32_t t = __shfl_up_sync(AG_FULL, incl, o);
       if (c.lane >= o) incl += t;
     }
-    if (i < nc) c.sm.hcnt[i] = carry + incl - v;
+    if (i < nc) c.sm.hcnt()[i] = carry + incl - v;
     carry += __shfl_sync(AG_FULL, incl, 31);
   }
   __syncwarp();
-  for (int i = c.lane; i < c.n_pellets; i += 32) {
-    float2 p = reinterpret_cast<const float2*>(c.pel)[i];
-    uint32_t pos = atomicAdd(&c.sm.hcnt[hash_coord(c, p.y) * HG + hash_coord(c, p.x)], 1u);
-    c.sm.hsorted[pos] = (uint16_t)i;
-    c.sm.hq[pos] = quantize_xy(c, p.x, p.y);
+  for (int base = 0; base < c.n_pellets; base += 256) {
+    float2 p[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) { int i = base + u * 32 + c.lane; p[u] = i < c.n_pellets ? pel[i] : make_float2(0.f, 0.f); }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      int i = base + u * 32 + c.lane;
+      if (i < c.n_pellets) {
+        uint32_t pos = atomicAdd(&c.sm.hcnt()[hash_coord(c, p[u].y) * HG + hash_coord(c, p[u].x)], 1u);
+        c.sm.hsorted()[pos] = (uint16_t)i;
+        c.sm.hq()[pos] = quantize_xy(c, p[u].x, p[u].y);
+      }
+    }
   }
   __syncwarp();
   // now hcnt[k] = end of cell k; start of cell k = (k ? hcnt[k-1] : 0)
@@ -473,10 +488,10 @@ __device__ void build_pellet_hash(Ctx& c) {
 __device__ void build_virus_cache(Ctx& c) {
   uint32_t mn = 0xffffffffu;
   for (int v = c.lane; v < c.n_viruses; v += 32) {
-    const float4 a = reinterpret_cast<const float4*>(c.vir + v)[0];  // x, y, mass, hits
+    const float4 a = reinterpret_cast<const float4*>(c.vir_() + v)[0];  // x, y, mass, hits
     uint32_t vm = __float_as_uint(a.z);
     mn = min(mn, vm);
-    c.sm.vcache[v] = make_float4(a.x, a.y, radius_of(c.P.T, vm), a.z);
+    c.sm.vcache()[v] = make_float4(a.x, a.y, radius_of(c.P.T, vm), a.z);
   }
   c.min_vmass = warp_min_u32(mn);
   __syncwarp();
@@ -487,7 +502,7 @@ __device__ void build_virus_cache(Ctx& c) {
 // ------------------------------------------------------------------------------------------------
 __device__ void tick_player(Ctx& c, int p) {
   const Luts& T = c.P.T;
-  agarcl_player* pl = c.players + p;
+  agarcl_player* pl = c.players_() + p;
   int n = pl->n_cells;
   c.emitted = 0;
   if (n == 0) return;  // dead players are not ticked (Engine.hpp:216)
@@ -504,7 +519,7 @@ __device__ void tick_player(Ctx& c, int p) {
 
   // ---- bots decide every 10th tick (Engine.hpp:498-499)
   if (c.tick % 10u == 0u && bot_type >= 0) {
-    float4 s = c.sm.psum[p];
+    float4 s = c.sm.psum()[p];
     float lx = s.x, ly = s.y;
     bool decided = false;
     if (bot_type == 1 || bot_type == 3) {
@@ -556,7 +571,7 @@ __device__ void tick_player(Ctx& c, int p) {
         int v = base + lane;
         uint32_t key = 0xffffffffu;
         if (v < c.n_viruses) {
-          float4 vc = c.sm.vcache[v];
+          float4 vc = c.sm.vcache()[v];
           int vgx = (int)vc.x / 25, vgy = (int)vc.y / 25;
           int ddx = vgx - gx, ddy = vgy - gy;
           uint32_t vm = __float_as_uint(vc.w);
@@ -568,7 +583,7 @@ __device__ void tick_player(Ctx& c, int p) {
       }
       if (bestkey != 0xffffffffu) {
         int v = (int)(bestkey & 0xffffu);
-        float4 vc = c.sm.vcache[v];
+        float4 vc = c.sm.vcache()[v];
         uint32_t vm = __float_as_uint(vc.w);
         if (can_eat_virus) {
           if (lane == i) me.mass = floor_mass(me.mass + vm);
@@ -602,7 +617,7 @@ __device__ void tick_player(Ctx& c, int p) {
           created += num;
           c.next_id += (uint32_t)num;
         }
-        if (c.nvrem < kVremCap) { if (lane == 0) c.sm.vrem[c.nvrem] = (uint16_t)v; c.nvrem++; }
+        if (c.nvrem < kVremCap) { if (lane == 0) c.sm.vrem()[c.nvrem] = (uint16_t)v; c.nvrem++; }
         else c.flags |= AGARCL_FLAG_REMOVE_OVERFLOW;
         if (vet_count < AGARCL_VET_CAP) { if (lane == 0) pl->vet_ticks[vet_count] = elapsed; vet_count++; }
         else c.flags |= AGARCL_FLAG_VET_OVERFLOW;
@@ -628,16 +643,16 @@ __device__ void tick_player(Ctx& c, int p) {
       int ncand = 0;
       for (int hy = hy0; hy <= hy1; hy++) {
         int k0 = hy * HG + hx0, k1 = hy * HG + hx1;
-        int s = k0 ? (int)c.sm.hcnt[k0 - 1] : 0, e = (int)c.sm.hcnt[k1];
+        int s = k0 ? (int)c.sm.hcnt()[k0 - 1] : 0, e = (int)c.sm.hcnt()[k1];
         for (int jb = s; jb < e; jb += 32) {
           int j = jb + lane;
           bool cand = false;
           uint32_t key = 0;
           float d2 = 0.f;
           if (j < e) {
-            int idx = c.sm.hsorted[j];
+            int idx = c.sm.hsorted()[j];
             if (idx != kHashDead) {
-              float2 q = reinterpret_cast<const float2*>(c.pel)[idx];
+              float2 q = reinterpret_cast<const float2*>(c.pel_())[idx];
               d2 = sqr_dist(cx, cy, q.x, q.y);
               int bx = (int)q.x / 510 - gx, by = (int)q.y / 510 - gy;
               cand = d2 <= Rc2 && bx >= -1 && bx <= 1 && by >= -1 && by <= 1;
@@ -647,7 +662,7 @@ __device__ void tick_player(Ctx& c, int p) {
           unsigned m = __ballot_sync(AG_FULL, cand);
           if (cand) {
             int pos = ncand + __popc(m & lanemask_lt(lane));
-            if (pos < kCandCap) c.sm.cand[pos] = make_uint2(key, __float_as_uint(d2));
+            if (pos < kCandCap) c.sm.cand()[pos] = make_uint2(key, __float_as_uint(d2));
           }
           ncand += __popc(m);
         }
@@ -657,7 +672,7 @@ __device__ void tick_player(Ctx& c, int p) {
       uint32_t newmass = cm;
       if (ncand <= kCandCap) {
         // replay the candidates in reference order with the growing mass
-        uint2 mine = lane < ncand ? c.sm.cand[lane] : make_uint2(0xffffffffu, 0u);
+        uint2 mine = lane < ncand ? c.sm.cand()[lane] : make_uint2(0xffffffffu, 0u);
         for (int it = 0; it < ncand; it++) {
           uint32_t kmin = warp_min_u32(mine.x);
           unsigned wm = __ballot_sync(AG_FULL, mine.x == kmin);
@@ -665,7 +680,7 @@ __device__ void tick_player(Ctx& c, int p) {
           float d2 = __uint_as_float(__shfl_sync(AG_FULL, mine.y, w));
           float r = fmax_std(radius_of(T, newmass), rp);
           if (r * r >= d2) {  // Ball::collides_with; can_eat(pellet) always holds for mass >= 25
-            if (c.nprem < kPremCap) { if (lane == 0) c.sm.prem[c.nprem] = (uint16_t)(kmin & 0xffffu); c.nprem++; }
+            if (c.nprem < kPremCap) { if (lane == 0) c.sm.prem()[c.nprem] = (uint16_t)(kmin & 0xffffu); c.nprem++; }
             else c.flags |= AGARCL_FLAG_REMOVE_OVERFLOW;
             newmass = floor_mass(newmass + 1u);
             pellets_eaten++;
@@ -685,7 +700,7 @@ __device__ void tick_player(Ctx& c, int p) {
               bool cand = false;
               float d2 = 0.f;
               if (idx < c.n_pellets) {
-                float2 q = reinterpret_cast<const float2*>(c.pel)[idx];
+                float2 q = reinterpret_cast<const float2*>(c.pel_())[idx];
                 d2 = sqr_dist(cx, cy, q.x, q.y);
                 cand = ((int)q.x / 510 == nx) && ((int)q.y / 510 == ny) && d2 <= Rf2;
               }
@@ -696,7 +711,7 @@ __device__ void tick_player(Ctx& c, int p) {
                 float dd = __shfl_sync(AG_FULL, d2, w);
                 float r = fmax_std(radius_of(T, newmass), rp);
                 if (r * r >= dd) {
-                  if (c.nprem < kPremCap) { if (lane == 0) c.sm.prem[c.nprem] = (uint16_t)(base + w); c.nprem++; }
+                  if (c.nprem < kPremCap) { if (lane == 0) c.sm.prem()[c.nprem] = (uint16_t)(base + w); c.nprem++; }
                   else c.flags |= AGARCL_FLAG_REMOVE_OVERFLOW;
                   newmass = floor_mass(newmass + 1u);
                   pellets_eaten++;
@@ -770,12 +785,12 @@ __device__ void tick_player(Ctx& c, int p) {
         float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
         bool keep = false;
         if (j < nf) {
-          f = reinterpret_cast<const float4*>(c.food)[j];
+          f = reinterpret_cast<const float4*>(c.food_())[j];
           keep = !(eater && collides(cx, cy, cr, f.x, f.y, rf));
         }
         unsigned km = __ballot_sync(AG_FULL, keep);
         int dst = w + __popc(km & lanemask_lt(lane));
-        if (keep && dst != j) reinterpret_cast<float4*>(c.food)[dst] = f;
+        if (keep && dst != j) reinterpret_cast<float4*>(c.food_())[dst] = f;
         w += __popc(km);
         __syncwarp();
       }
@@ -802,7 +817,7 @@ __device__ void tick_player(Ctx& c, int p) {
       float r = radius_of(T, me.mass);
       int slot = c.n_foods + __popc(em & lanemask_lt(lane));
       if (slot < c.P.L.cap_foods)
-        reinterpret_cast<float4*>(c.food)[slot] = make_float4(me.x + dirx * r, me.y + diry * r, dirx * 100.0f, diry * 100.0f);
+        reinterpret_cast<float4*>(c.food_())[slot] = make_float4(me.x + dirx * r, me.y + diry * r, dirx * 100.0f, diry * 100.0f);
       me.mass = floor_mass(me.mass - AGARCL_FOOD_MASS);
     }
     int add = __popc(em);
@@ -911,8 +926,8 @@ __device__ void tick_player(Ctx& c, int p) {
   float4 s = centroid_of(me, n);
   if (lane < n) cell_store(c.pcells(p) + lane, me);
   if (lane == 0) {
-    c.sm.psum[p] = s;
-    c.sm.pcell[p].w = -1.0f;  // not lane-ticked: the collision snapshot reads this player from memory
+    c.sm.psum()[p] = s;
+    c.sm.pcell()[p].w = -1.0f;  // not lane-ticked: the collision snapshot reads this player from memory
     pl->n_cells = n;
     pl->target_x = tx; pl->target_y = ty;
     pl->action = action;
@@ -939,8 +954,8 @@ __device__ void tick_player(Ctx& c, int p) {
 // does not qualify is ticked by the whole warp (tick_player) at its place in that order.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void hash_range(const Ctx& c, int k0, int k1, int& s, int& e) {
-  s = k0 ? (int)c.sm.hcnt[k0 - 1] : 0;
-  e = (int)c.sm.hcnt[k1];
+  s = k0 ? (int)c.sm.hcnt()[k0 - 1] : 0;
+  e = (int)c.sm.hcnt()[k1];
 }
 
 // Visits the hash entries of ring `r` (Chebyshev distance r in hash cells) around cell (hx, hy).
@@ -975,7 +990,7 @@ __device__ void lane_nearest_pellet(const Ctx& c, float lx, float ly, float& tx,
   const int HG = c.P.HG;
   const float cw = c.W / (float)HG;
   const float M = 1.5f * c.P.q_inv;  // > sqrt(2) * q_inv
-  const float2* pel = reinterpret_cast<const float2*>(c.pel);
+  const float2* pel = reinterpret_cast<const float2*>(c.pel_());
   const int hx = hash_coord(c, lx), hy = hash_coord(c, ly);
   const float INF = 3.402823466e+38f;
   float U = INF;
@@ -983,8 +998,8 @@ __device__ void lane_nearest_pellet(const Ctx& c, float lx, float ly, float& tx,
 #pragma unroll 1
   for (int r = 0; r < HG; r++) {
     ring_visit(c, hx, hy, r, [&](int j) {
-      if (c.sm.hsorted[j] == (uint16_t)kHashDead) return;
-      float2 q = dequantize_xy(c, c.sm.hq[j]);
+      if (c.sm.hsorted()[j] == (uint16_t)kHashDead) return;
+      float2 q = dequantize_xy(c, c.sm.hq()[j]);
       float dq = sqrtf(sqr_dist(lx, ly, q.x, q.y));
       if (dq > 0.01f + M) U = fminf(U, dq + M);  // certainly farther than 0.01: a true qualifier
     });
@@ -1003,9 +1018,9 @@ __device__ void lane_nearest_pellet(const Ctx& c, float lx, float ly, float& tx,
 #pragma unroll 1
   for (int r = 0; r <= rstop; r++) {
     ring_visit(c, hx, hy, r, [&](int j) {
-      uint32_t idx = c.sm.hsorted[j];
+      uint32_t idx = c.sm.hsorted()[j];
       if (idx == (uint32_t)kHashDead) return;
-      float2 qq = dequantize_xy(c, c.sm.hq[j]);
+      float2 qq = dequantize_xy(c, c.sm.hq()[j]);
       if (!(sqrtf(sqr_dist(lx, ly, qq.x, qq.y)) <= lim)) return;
       float2 q = pel[idx];
       float d = sqrtf(sqr_dist(lx, ly, q.x, q.y));  // (other - this).norm()
@@ -1024,7 +1039,7 @@ __device__ void lane_nearest_pellet(const Ctx& c, float lx, float ly, float& tx,
 __device__ bool lane_eat_pellets(const Ctx& c, float cx, float cy, uint32_t& mass, int& ne, uint16_t* out) {
   const Luts& T = c.P.T;
   const int HG = c.P.HG;
-  const float2* pel = reinterpret_cast<const float2*>(c.pel);
+  const float2* pel = reinterpret_cast<const float2*>(c.pel_());
   const float rp = radius_of(T, 1u);
   const int gx = (int)cx / 510, gy = (int)cy / 510;
   const float Rc = fmax_std(radius_of(T, mass + (uint32_t)kCandCap), rp);
@@ -1045,9 +1060,9 @@ __device__ bool lane_eat_pellets(const Ctx& c, float cx, float cy, uint32_t& mas
       hash_range(c, hy * HG + hx0, hy * HG + hx1, s, e);
 #pragma unroll 1
       for (int j = s; j < e; j++) {
-        float2 qq = dequantize_xy(c, c.sm.hq[j]);
+        float2 qq = dequantize_xy(c, c.sm.hq()[j]);
         if (!(sqr_dist(cx, cy, qq.x, qq.y) <= Rq2)) continue;
-        uint32_t idx = c.sm.hsorted[j];
+        uint32_t idx = c.sm.hsorted()[j];
         if (idx == (uint32_t)kHashDead) continue;
         float2 q = pel[idx];
         float d2 = sqr_dist(cx, cy, q.x, q.y);
@@ -1089,7 +1104,7 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
   const int k = base + lane;
   const bool valid = k < c.P.L.P;
   const int p = valid ? c.P.L.order[k] : 0;
-  agarcl_player* pl = c.players + p;
+  agarcl_player* pl = c.players_() + p;
   Cell& me = ls.me;
   int4 &w0 = ls.w0, &w1 = ls.w1, &w2 = ls.w2, &w3 = ls.w3;
   if (valid && !ls.fresh) {  // record and first cell in ONE round trip (the cell slot exists even for a dead player)
@@ -1104,7 +1119,7 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
   float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t food_mass = 0;  // mass at the time of eat_food (after pellets, before decay)
   int ne = 0;
-  uint16_t* myeat = c.sm.lprem + lane * kLaneCand;
+  uint16_t* myeat = c.sm.lprem() + lane * kLaneCand;
 
   if (ok) do {
     float tx = __int_as_float(w0.y), ty = __int_as_float(w0.z);
@@ -1119,7 +1134,7 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
     // ---- bots decide every 10th tick (Engine.hpp:498-499); the ones that look at other players go serial
     if (c.tick % 10u == 0u && bot_type >= 0) {
       if (bot_type != 0 || c.n_pellets == 0) { ok = false; serial = true; break; }
-      float4 s = c.sm.psum[p];
+      float4 s = c.sm.psum()[p];
       action = 0;
       lane_nearest_pellet(c, s.x, s.y, tx, ty);
     }
@@ -1145,7 +1160,7 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
       const int gx = (int)me.x / 25, gy = (int)me.y / 25;
       bool hit = false;
       for (int v = 0; v < c.n_viruses; v++) {
-        float4 vc = c.sm.vcache[v];
+        float4 vc = c.sm.vcache()[v];
         if (collides(me.x, me.y, cr, vc.x, vc.y, vc.z)) {
           int vgx = (int)vc.x / 25, vgy = (int)vc.y / 25;
           int ddx = vgx - gx, ddy = vgy - gy;
@@ -1169,7 +1184,7 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
       const float cr = radius_of(T, me.mass), rf = radius_of(T, AGARCL_FOOD_MASS);
       bool hit = false;
       for (int j = 0; j < c.n_foods; j++) {
-        float4 f = reinterpret_cast<const float4*>(c.food)[j];
+        float4 f = reinterpret_cast<const float4*>(c.food_())[j];
         if (collides(me.x, me.y, cr, f.x, f.y, rf)) hit = true;
       }
       if (hit) { ok = false; serial = true; break; }
@@ -1222,7 +1237,7 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
       }
       int off = c.nprem + incl - v;
       for (int e = 0; e < v; e++) {
-        if (off + e < kPremCap) c.sm.prem[off + e] = myeat[e];
+        if (off + e < kPremCap) c.sm.prem()[off + e] = myeat[e];
         else c.flags |= AGARCL_FLAG_REMOVE_OVERFLOW;
       }
       c.nprem = min(c.nprem + __shfl_sync(AG_FULL, incl, 31), kPremCap);
@@ -1231,8 +1246,8 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
       cell_store(c.pcells(p), me);
       int4* rec = reinterpret_cast<int4*>(pl);
       rec[0] = w0; rec[1] = w1; rec[2] = w2; rec[3] = w3;
-      c.sm.psum[p] = sum;
-      c.sm.pcell[p] = make_float4(me.x, me.y, __uint_as_float(me.mass), 1.0f);
+      c.sm.psum()[p] = sum;
+      c.sm.pcell()[p] = make_float4(me.x, me.y, __uint_as_float(me.mass), 1.0f);
     }
     __syncwarp();
     if (nxt >= 32) break;
@@ -1243,7 +1258,7 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
       if (ok && lane > nxt && can_eat_mass(food_mass, AGARCL_FOOD_MASS)) {
         const float cr = radius_of(T, food_mass), rf = radius_of(T, AGARCL_FOOD_MASS);
         for (int j = c.n_foods - c.emitted; j < c.n_foods; j++) {
-          float4 f = reinterpret_cast<const float4*>(c.food)[j];
+          float4 f = reinterpret_cast<const float4*>(c.food_())[j];
           if (collides(me.x, me.y, cr, f.x, f.y, rf)) hit = true;
         }
       }
@@ -1262,17 +1277,17 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
 // the pellet hash is kept across ticks: rename entry `from` of the hash cell containing `pos`
 __device__ __forceinline__ void hash_patch(Ctx& c, uint32_t from, uint32_t to, float2 pos) {
   int k = hash_coord(c, pos.y) * c.P.HG + hash_coord(c, pos.x);
-  int s = k ? (int)c.sm.hcnt[k - 1] : 0, e = (int)c.sm.hcnt[k];
+  int s = k ? (int)c.sm.hcnt()[k - 1] : 0, e = (int)c.sm.hcnt()[k];
   for (int j = s; j < e; j++)
-    if (c.sm.hsorted[j] == from) { c.sm.hsorted[j] = (uint16_t)to; break; }
+    if (c.sm.hsorted()[j] == from) { c.sm.hsorted()[j] = (uint16_t)to; break; }
 }
 
 __device__ void apply_removals(Ctx& c) {  // Engine.hpp:1002-1009,1253-1260 incl. stale/duplicate indices (Q4/Q5)
   if (c.nprem == 0 && c.nvrem == 0) return;
   if (c.lane == 0) {
-    float2* pel = reinterpret_cast<float2*>(c.pel);
+    float2* pel = reinterpret_cast<float2*>(c.pel_());
     for (int k = 0; k < c.nprem; k++) {
-      uint32_t idx = c.sm.prem[k], size = (uint32_t)c.n_pellets;
+      uint32_t idx = c.sm.prem()[k], size = (uint32_t)c.n_pellets;
       if (size == 0u) continue;
       uint32_t last = size - 1u;
       if (idx < last) {  // swap-with-back: the pellet at `idx` disappears, the last one takes its index
@@ -1285,10 +1300,10 @@ __device__ void apply_removals(Ctx& c) {  // Engine.hpp:1002-1009,1253-1260 incl
       c.n_pellets--;
     }
     for (int k = 0; k < c.nvrem; k++) {
-      uint32_t idx = c.sm.vrem[k], size = (uint32_t)c.n_viruses;
+      uint32_t idx = c.sm.vrem()[k], size = (uint32_t)c.n_viruses;
       if (idx < size - 1u && size > 1u) {
-        reinterpret_cast<float4*>(c.vir + idx)[0] = reinterpret_cast<float4*>(c.vir + size - 1u)[0];
-        reinterpret_cast<float4*>(c.vir + idx)[1] = reinterpret_cast<float4*>(c.vir + size - 1u)[1];
+        reinterpret_cast<float4*>(c.vir_() + idx)[0] = reinterpret_cast<float4*>(c.vir_() + size - 1u)[0];
+        reinterpret_cast<float4*>(c.vir_() + idx)[1] = reinterpret_cast<float4*>(c.vir_() + size - 1u)[1];
       }
       if (size >= 1u) c.n_viruses--;
     }
@@ -1320,7 +1335,7 @@ __device__ void sort_player_cells(Ctx& c, int p, int n) {
   s.x = s.y = s.vx = s.vy = s.svx = s.svy = 0.f; s.mass = 0; s.id = 0; s.rec = 0;
   if (c.lane < n) s = cell_load(c.pcells(p) + c.lane);
   float4 sum = centroid_of(s, n);  // summation order changed
-  if (c.lane == 0) c.sm.psum[p] = sum;
+  if (c.lane == 0) c.sm.psum()[p] = sum;
   __syncwarp();
 }
 
@@ -1343,20 +1358,20 @@ struct PairRec { uint16_t q, g; uint32_t eaten_mass, eater_id, eaten_id; };  // 
 // query cells the all-pairs pre-test flagged; everything the strip sweep can return is in that set).
 __device__ void players_collision_exact(Ctx& c, int total, int nhit, bool staged) {
   const Luts& T = c.P.T;
-  const uint16_t* ref = c.sm.cellref;  // (player << 8 | cell) in snapshot order
-  const int16_t* rows = c.sm.rows;     // strip id of every snapshot cell (filled by the caller)
-  uint16_t* strip = c.sm.strip;        // one strip, sorted by y (stable)
-  PairRec* pairs = reinterpret_cast<PairRec*>(c.sm.pairs);
-  uint16_t* rkeys = c.sm.reskeys;      // query ids with results, first-insert order
-  uint16_t* rorder = c.sm.resorder;    // iteration order of the results map
+  const uint16_t* ref = c.sm.cellref();  // (player << 8 | cell) in snapshot order
+  const int16_t* rows = c.sm.rows();     // strip id of every snapshot cell (filled by the caller)
+  uint16_t* strip = c.sm.strip();        // one strip, sorted by y (stable)
+  PairRec* pairs = reinterpret_cast<PairRec*>(c.sm.pairs());
+  uint16_t* rkeys = c.sm.reskeys();      // query ids with results, first-insert order
+  uint16_t* rorder = c.sm.resorder();    // iteration order of the results map
   auto cellp = [&](int g) -> const agarcl_cell* { return c.pcells(ref[g] >> 8) + (ref[g] & 0xff); };
   // the sweep reads the pre-application snapshot (Engine.hpp:153-166): shared-memory copy when staged
-  auto gy_of = [&](int g) -> float { return staged ? c.sm.snap[g].y : cellp(g)->y; };
-  auto gx_of = [&](int g) -> float { return staged ? c.sm.snap[g].x : cellp(g)->x; };
-  auto gm_of = [&](int g) -> uint32_t { return staged ? __float_as_uint(c.sm.snap[g].z) : cellp(g)->mass; };
+  auto gy_of = [&](int g) -> float { return staged ? c.sm.snap()[g].y : cellp(g)->y; };
+  auto gx_of = [&](int g) -> float { return staged ? c.sm.snap()[g].x : cellp(g)->x; };
+  auto gm_of = [&](int g) -> uint32_t { return staged ? __float_as_uint(c.sm.snap()[g].z) : cellp(g)->mass; };
   int npairs = 0, nres = 0;
   for (int hq = 0; hq < nhit; hq++) {
-    int q = c.sm.hitq[hq];
+    int q = c.sm.hitq()[hq];
     int qp = ref[q] >> 8;
     const agarcl_cell* qc = cellp(q);
     float qx = gx_of(q), qy = gy_of(q);
@@ -1426,8 +1441,8 @@ __device__ void players_collision_exact(Ctx& c, int total, int nhit, bool staged
       if (pairs[k].q != q) continue;
       int g = pairs[k].g;
       int pp = ref[q] >> 8, ep = ref[g] >> 8;
-      agarcl_player* ppl = c.players + pp;
-      agarcl_player* epl = c.players + ep;
+      agarcl_player* ppl = c.players_() + pp;
+      agarcl_player* epl = c.players_() + ep;
       agarcl_cell* pc = c.pcells(pp);
       int pn = ppl->n_cells, it = 0;
       while (it < pn && pc[it].id < pairs[k].eater_id) it++;
@@ -1458,7 +1473,7 @@ __device__ void players_collision(Ctx& c) {
   for (int base = 0; base < P; base += 32) {
     const int k = base + lane;
     const int p = k < P ? c.P.L.order[k] : 0;
-    const int n = k < P ? __float_as_int(c.sm.psum[p].w) : 0;
+    const int n = k < P ? __float_as_int(c.sm.psum()[p].w) : 0;
     unsigned multi = __ballot_sync(AG_FULL, n >= 2);
     while (multi) {
       int src = __ffs(multi) - 1;
@@ -1473,7 +1488,7 @@ __device__ void players_collision(Ctx& c) {
     }
     const int off = total + incl - n;
     for (int i = 0; i < n; i++)
-      if (off + i < kCellRefCap) c.sm.cellref[off + i] = (uint16_t)((p << 8) | i);
+      if (off + i < kCellRefCap) c.sm.cellref()[off + i] = (uint16_t)((p << 8) | i);
     total += __shfl_sync(AG_FULL, incl, 31);
   }
   if (total > kCellRefCap) { c.flags |= AGARCL_FLAG_EATER_OVERFLOW; total = kCellRefCap; }
@@ -1483,14 +1498,14 @@ __device__ void players_collision(Ctx& c) {
   const bool staged = total <= kSnapCap;
   if (staged) {
     for (int g = lane; g < total; g += 32) {
-      int r = c.sm.cellref[g];
-      float4 pc = c.sm.pcell[r >> 8];
+      int r = c.sm.cellref()[g];
+      float4 pc = c.sm.pcell()[r >> 8];
       if (pc.w >= 0.0f) {  // lane-ticked single-cell player: its cell is already in shared memory
-        c.sm.snap[g] = make_float4(pc.x, pc.y, pc.z, __int_as_float(r >> 8));
+        c.sm.snap()[g] = make_float4(pc.x, pc.y, pc.z, __int_as_float(r >> 8));
       } else {
         const agarcl_cell* gc = c.pcells(r >> 8) + (r & 0xff);
         float4 a = reinterpret_cast<const float4*>(gc)[0];
-        c.sm.snap[g] = make_float4(a.x, a.y, __uint_as_float(gc->mass), __int_as_float(r >> 8));
+        c.sm.snap()[g] = make_float4(a.x, a.y, __uint_as_float(gc->mass), __int_as_float(r >> 8));
       }
     }
     __syncwarp();
@@ -1503,10 +1518,10 @@ __device__ void players_collision(Ctx& c) {
     int qp = -1;
     if (q < total) {
       if (staged) {
-        float4 sg = c.sm.snap[q];
+        float4 sg = c.sm.snap()[q];
         qx = sg.x; qy = sg.y; qm = __float_as_uint(sg.z); qp = __float_as_int(sg.w);
       } else {
-        int r = c.sm.cellref[q];
+        int r = c.sm.cellref()[q];
         qp = r >> 8;
         const agarcl_cell* g = c.pcells(qp) + (r & 0xff);
         float4 a = reinterpret_cast<const float4*>(g)[0];
@@ -1520,14 +1535,14 @@ __device__ void players_collision(Ctx& c) {
     bool hit = false;
     if (staged) {
       for (int g = 0; g < total; g++) {
-        float4 sg = c.sm.snap[g];
+        float4 sg = c.sm.snap()[g];
         if (qr2 >= sqr_dist(qx, qy, sg.x, sg.y) && hungry && __float_as_int(sg.w) != qp &&
             can_eat_mass(qm, __float_as_uint(sg.z)))
           hit = true;
       }
     } else {
       for (int g = 0; g < total; g++) {
-        int r = c.sm.cellref[g];
+        int r = c.sm.cellref()[g];
         int gp = r >> 8;
         const agarcl_cell* gc = c.pcells(gp) + (r & 0xff);
         float4 a = reinterpret_cast<const float4*>(gc)[0];
@@ -1538,7 +1553,7 @@ __device__ void players_collision(Ctx& c) {
     unsigned hm = __ballot_sync(AG_FULL, hit);
     if (hit) {
       int pos = nhit + __popc(hm & lanemask_lt(lane));
-      if (pos < kPairCap) c.sm.hitq[pos] = (uint16_t)q;
+      if (pos < kPairCap) c.sm.hitq()[pos] = (uint16_t)q;
     }
     nhit += __popc(hm);
   }
@@ -1548,9 +1563,9 @@ __device__ void players_collision(Ctx& c) {
   // 3. exact path: strip ids of the snapshot cells by all lanes, then the serial sweep by one
   for (int g = lane; g < total; g += 32) {
     float x;
-    if (staged) x = c.sm.snap[g].x;
-    else { int r = c.sm.cellref[g]; x = (c.pcells(r >> 8) + (r & 0xff))->x; }
-    c.sm.rows[g] = (int16_t)get_row(x, c.W);
+    if (staged) x = c.sm.snap()[g].x;
+    else { int r = c.sm.cellref()[g]; x = (c.pcells(r >> 8) + (r & 0xff))->x; }
+    c.sm.rows()[g] = (int16_t)get_row(x, c.W);
   }
   __syncwarp();
   if (lane == 0) players_collision_exact(c, total, nhit, staged);
@@ -1561,8 +1576,8 @@ __device__ void players_collision(Ctx& c) {
   for (int base = 0; base < P; base += 32) {
     int p = base + lane;
     if (p < P) {
-      c.sm.psum[p] = centroid_from_global(c.pcells(p), c.players[p].n_cells);
-      c.sm.pcell[p].w = -1.0f;
+      c.sm.psum()[p] = centroid_from_global(c.pcells(p), c.players_()[p].n_cells);
+      c.sm.pcell()[p].w = -1.0f;
     }
   }
   __syncwarp();
@@ -1575,7 +1590,7 @@ __device__ void move_foods_serial(Ctx& c) {
   const float dt = c.dt;
   int nf = c.n_foods, nv = c.n_viruses;
   for (int i = 0; i < nf;) {
-    agarcl_food f = c.food[i];
+    agarcl_food f = c.food_()[i];
     if (vmag(f.vx, f.vy) == 0.0f) { i++; continue; }
     float fvx = f.vx, fvy = f.vy;
     decelerate(f.vx, f.vy, 80.0f, dt);
@@ -1583,10 +1598,10 @@ __device__ void move_foods_serial(Ctx& c) {
     f.y += f.vy * dt;
     f.x = bound_axis(f.x, rf, c.W);
     f.y = bound_axis(f.y, rf, c.W);
-    c.food[i] = f;
+    c.food_()[i] = f;
     bool hit = false;
     for (int v = 0; v < nv; v++) {
-      agarcl_virus* vr = c.vir + v;
+      agarcl_virus* vr = c.vir_() + v;
       if (collides(f.x, f.y, rf, vr->x, vr->y, radius_of(T, vr->mass))) {
         if (vr->hits >= 7) {
           vr->hits = 0;
@@ -1596,7 +1611,7 @@ __device__ void move_foods_serial(Ctx& c) {
           float nx = bound_axis(vr->x + fvx * dt10, rv, c.W);
           float ny = bound_axis(vr->y + fvy * dt10, rv, c.W);
           if (nv < c.P.L.cap_viruses) {
-            agarcl_virus* nw = c.vir + nv;
+            agarcl_virus* nw = c.vir_() + nv;
             nw->x = nx; nw->y = ny; nw->mass = AGARCL_VIRUS_INITIAL_MASS; nw->hits = 0; nw->vx = fvx; nw->vy = fvy;
             nw->pad[0] = 0; nw->pad[1] = 0;
             nv++;
@@ -1610,7 +1625,7 @@ __device__ void move_foods_serial(Ctx& c) {
       }
     }
     if (hit) {
-      if (nf > 1) c.food[i] = c.food[nf - 1];
+      if (nf > 1) c.food_()[i] = c.food_()[nf - 1];
       nf--;
     } else i++;
   }
@@ -1627,14 +1642,14 @@ __device__ void move_foods(Ctx& c) {
   for (int base = 0; base < c.n_foods; base += 32) {
     int j = base + c.lane;
     if (j < c.n_foods) {
-      float4 f = reinterpret_cast<const float4*>(c.food)[j];
+      float4 f = reinterpret_cast<const float4*>(c.food_())[j];
       if (vmag(f.z, f.w) != 0.0f) {
         decelerate(f.z, f.w, 80.0f, c.dt);
         f.x = bound_axis(f.x + f.z * c.dt, rf, c.W);
         f.y = bound_axis(f.y + f.w * c.dt, rf, c.W);
         for (int v = 0; v < c.n_viruses; v++) {
-          float r = fmax_std(radius_of(T, max(c.vir[v].mass, 180u) + 10u), rf);  // a fed virus never exceeds 100 + 7*10
-          if (r * r >= sqr_dist(f.x, f.y, c.vir[v].x, c.vir[v].y)) danger = true;
+          float r = fmax_std(radius_of(T, max(c.vir_()[v].mass, 180u) + 10u), rf);  // a fed virus never exceeds 100 + 7*10
+          if (r * r >= sqr_dist(f.x, f.y, c.vir_()[v].x, c.vir_()[v].y)) danger = true;
         }
       }
     }
@@ -1652,14 +1667,14 @@ __device__ void move_foods(Ctx& c) {
   for (int base = 0; base < c.n_foods; base += 32) {
     int j = base + c.lane;
     if (j < c.n_foods) {
-      float4 f = reinterpret_cast<const float4*>(c.food)[j];
+      float4 f = reinterpret_cast<const float4*>(c.food_())[j];
       if (vmag(f.z, f.w) != 0.0f) {
         decelerate(f.z, f.w, 80.0f, c.dt);
         f.x += f.z * c.dt;
         f.y += f.w * c.dt;
         f.x = bound_axis(f.x, rf, c.W);
         f.y = bound_axis(f.y, rf, c.W);
-        reinterpret_cast<float4*>(c.food)[j] = f;
+        reinterpret_cast<float4*>(c.food_())[j] = f;
       }
     }
   }
@@ -1674,7 +1689,7 @@ __device__ void regen(Ctx& c) {
     for (int k = c.lane; k < dp; k += 32) {
       float x, y;
       random_location_at(c, c.cursor + 2u * (uint32_t)k, r, x, y);
-      if (c.n_pellets + k < c.P.L.cap_pellets) reinterpret_cast<float2*>(c.pel)[c.n_pellets + k] = make_float2(x, y);
+      if (c.n_pellets + k < c.P.L.cap_pellets) reinterpret_cast<float2*>(c.pel_())[c.n_pellets + k] = make_float2(x, y);
     }
     c.cursor += 2u * (uint32_t)dp;
     c.n_pellets = min(c.n_pellets + dp, c.P.L.cap_pellets);
@@ -1688,7 +1703,7 @@ __device__ void regen(Ctx& c) {
       float x, y;
       random_location_at(c, c.cursor + 2u * (uint32_t)k, r, x, y);
       if (k < room) {
-        float4* v = reinterpret_cast<float4*>(c.vir + c.n_viruses + k);
+        float4* v = reinterpret_cast<float4*>(c.vir_() + c.n_viruses + k);
         v[0] = make_float4(x, y, __uint_as_float(AGARCL_VIRUS_INITIAL_MASS), __int_as_float(0));
         v[1] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -1713,13 +1728,17 @@ __device__ __forceinline__ void zero_chunk(Ctx& c, uint32_t nvec) {
   while (nvec > 0u && c.zagent < (uint32_t)c.P.L.A) {
     const uint32_t n = min(nvec, per - c.zoff);
     if (c.lane == 0) {
+      extern __shared__ __align__(128) uint8_t smem_raw[];
+      const uint32_t zero_tile = (uint32_t)__cvta_generic_to_shared(smem_raw);
+      uint64_t zpolicy;  // L2 evict-first: the observation stream must not push the game state out of L2
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(zpolicy));
       uint8_t* dst = reinterpret_cast<uint8_t*>(c.P.obs) +
                      16ull * (((size_t)c.inst_local * c.P.L.A + c.zagent) * c.P.agent_stride_vec + c.P.zero_skip_vec + c.zoff);
       uint32_t bytes = n * 16u;
       while (bytes > 0u) {
         const uint32_t b = min(bytes, (uint32_t)kZeroTileBytes);
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                     :: "l"(dst), "r"(c.zero_tile), "r"(b), "l"(c.zpolicy) : "memory");
+                     :: "l"(dst), "r"(zero_tile), "r"(b), "l"(zpolicy) : "memory");
         dst += b;
         bytes -= b;
       }
@@ -1733,9 +1752,9 @@ __device__ __forceinline__ void zero_chunk(Ctx& c, uint32_t nvec) {
 
 // Engine::tick
 __device__ void engine_tick(Ctx& c, LaneState& ls) {
-  zero_chunk(c, c.zchunk);
   if (!c.hash_valid) { build_pellet_hash(c); c.hash_valid = true; }
   if (!c.vc_valid) { build_virus_cache(c); c.vc_valid = true; }
+  zero_chunk(c, c.zchunk);
   c.nprem = 0;
   c.nvrem = 0;
   const int P = c.P.L.P;
@@ -1751,7 +1770,9 @@ __device__ void engine_tick(Ctx& c, LaneState& ls) {
   }
   zero_chunk(c, c.zchunk);
   apply_removals(c);
+  zero_chunk(c, c.zchunk);
   players_collision(c);
+  zero_chunk(c, c.zchunk);
   move_foods(c);
   if (c.P.L.regen && c.tick % 120u == 0u) regen(c);
   c.tick++;
@@ -1759,12 +1780,12 @@ __device__ void engine_tick(Ctx& c, LaneState& ls) {
 
 // Player::kill + Engine::respawn for a dead player, spawn point from draw pair `k` (Engine.hpp:119-137)
 __device__ void respawn_player(Ctx& c, int p, uint32_t k) {
-  agarcl_player* pl = c.players + p;
+  agarcl_player* pl = c.players_() + p;
   uint32_t mass = (uint32_t)(c.P.L.agent_mass > 25 ? c.P.L.agent_mass : 25);
   float r25 = radius_of(c.P.T, AGARCL_CELL_MIN_SIZE);
   float x, y;
   if (c.n_pellets > 0 && c.P.L.squared_pellets) {
-    float2 p0 = reinterpret_cast<const float2*>(c.pel)[0];
+    float2 p0 = reinterpret_cast<const float2*>(c.pel_())[0];
     x = fmin_std(p0.x + 2.0f * r25, c.W - r25);
     y = fmin_std(p0.y + 2.0f * r25, c.W - r25);
   } else {
@@ -1787,7 +1808,7 @@ __device__ void respawn_player(Ctx& c, int p, uint32_t k) {
 // ------------------------------------------------------------------------------------------------
 // kernel: BaseEnvironment::step for one instance per warp
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 3) k_step(const __grid_constant__ SimParams P) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_step(const __grid_constant__ SimParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int inst = blockIdx.x * kWarpsPerCta + warp;
@@ -1800,33 +1821,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) k_step(const __grid_cons
   Ctx c(P);
   c.lane = lane;
   c.inst_local = inst;
-  c.inst_global = (uint32_t)(P.instance_base + inst);
   c.blob = P.state + (size_t)inst * P.L.stride;
-  c.players = reinterpret_cast<agarcl_player*>(c.blob + P.L.off_players);
-  c.cells = reinterpret_cast<agarcl_cell*>(c.blob + P.L.off_cells);
-  c.vir = reinterpret_cast<agarcl_virus*>(c.blob + P.L.off_viruses);
-  c.food = reinterpret_cast<agarcl_food*>(c.blob + P.L.off_foods);
-  c.pel = reinterpret_cast<agarcl_pellet*>(c.blob + P.L.off_pellets);
-  c.sm = carve_warp_smem(smem_raw + kZeroTileBytes + (size_t)warp * P.smem_per_warp, P.L, P.HG);
-  c.zero_tile = (uint32_t)__cvta_generic_to_shared(smem_raw);
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(c.zpolicy));
+  c.sm.base = smem_raw + kZeroTileBytes + (size_t)warp * P.smem_per_warp;
+  c.sm.o = &P.so;
   agarcl_inst_hdr* hdr = reinterpret_cast<agarcl_inst_hdr*>(c.blob + P.L.off_hdr);
   c.tick = hdr->tick; c.next_id = hdr->next_cell_id;
   c.n_pellets = hdr->n_pellets; c.n_viruses = hdr->n_viruses; c.n_foods = hdr->n_foods;
   c.cursor = hdr->rng_cursor; c.flags = hdr->flags;
-  c.seed_lo = hdr->seed_lo; c.seed_hi = hdr->seed_hi; c.done_sticky = hdr->done_sticky;
+  c.done_sticky = hdr->done_sticky;
   c.nprem = 0; c.nvrem = 0;
   c.emitted = 0; c.hash_valid = false; c.vc_valid = false; c.lanes_dirty = false; c.min_vmass = 0xffffffffu;
   c.W = P.W;
-  c.dt = (float)(1.0 / 30.0);
   const int Pn = P.L.P, A = P.L.A;
 
   // player summaries (centroid, mass, count)
   for (int base = 0; base < Pn; base += 32) {
     int p = base + lane;
     if (p < Pn) {
-      c.sm.psum[p] = centroid_from_global(c.pcells(p), c.players[p].n_cells);
-      c.sm.pcell[p] = make_float4(0.f, 0.f, 0.f, -1.0f);
+      c.sm.psum()[p] = centroid_from_global(c.pcells(p), c.players_()[p].n_cells);
+      c.sm.pcell()[p] = make_float4(0.f, 0.f, 0.f, -1.0f);
     }
   }
   __syncwarp();
@@ -1835,12 +1848,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) k_step(const __grid_cons
     if (lane == 0) { hdr->respawned_lo = 0u; hdr->respawned_hi = 0u; }
     // BaseEnvironment::take_actions + `before = masses<float>()`
     for (int a = lane; a < A; a += 32) {
-      float4 s = c.sm.psum[a];
+      float4 s = c.sm.psum()[a];
       uint32_t m = __float_as_uint(s.z);
       size_t gi = (size_t)inst * A + a;
       P.before[gi] = (float)m;
       if (__float_as_int(s.w) > 0) {
-        agarcl_player* pl = c.players + a;
+        agarcl_player* pl = c.players_() + a;
         pl->target_x = s.x + P.dxdy[2 * gi] * 10.0f;
         pl->target_y = s.y + P.dxdy[2 * gi + 1] * 10.0f;
         pl->action = P.act[gi];
@@ -1854,7 +1867,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) k_step(const __grid_cons
   c.zagent = 0u; c.zoff = 0u;
   {
     const uint32_t total = P.zero_vec_per_agent * (uint32_t)A;
-    const uint32_t chunks = (uint32_t)(2 * (P.n_ticks > 0 ? P.n_ticks : 1));
+    const uint32_t chunks = (uint32_t)(4 * (P.n_ticks > 0 ? P.n_ticks : 1));
     c.zchunk = (total + chunks - 1u) / chunks;
   }
   LaneState ls;
@@ -1873,13 +1886,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) k_step(const __grid_cons
       for (int base = 0; base < Pn; base += 32) {
         int k = base + lane;
         int p = k < Pn ? P.L.order[k] : 0;
-        bool dead = k < Pn && __float_as_int(c.sm.psum[p].w) == 0;
+        bool dead = k < Pn && __float_as_int(c.sm.psum()[p].w) == 0;
         unsigned dm = __ballot_sync(AG_FULL, dead);
         if (dead) {
           uint32_t r = rank_base + (uint32_t)__popc(dm & lanemask_lt(lane));
           respawn_player(c, p, c.cursor + 2u * r);
           c.pcells(p)->id = c.next_id + r;
-          c.sm.psum[p] = centroid_from_global(c.pcells(p), 1);
+          c.sm.psum()[p] = centroid_from_global(c.pcells(p), 1);
         }
         rank_base += (uint32_t)__popc(dm);
         // dead players in map-order slots -> bit per PLAYER index
@@ -1894,17 +1907,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) k_step(const __grid_cons
       __syncwarp();
     } else if (P.mode > 6) {
       bool dead = false;
-      for (int p = lane; p < Pn; p += 32) dead |= __float_as_int(c.sm.psum[p].w) == 0;
+      for (int p = lane; p < Pn; p += 32) dead |= __float_as_int(c.sm.psum()[p].w) == 0;
       c.done_sticky = __ballot_sync(AG_FULL, dead) ? 1u : 0u;  // dones_[0] rewritten every step (BaseEnvironment.hpp:103-114)
     }
     for (int a = lane; a < A; a += 32) {
-      uint32_t m = __float_as_uint(c.sm.psum[a].z);
+      uint32_t m = __float_as_uint(c.sm.psum()[a].z);
       if (P.mode == 3 && m >= 23000u) c.done_sticky = 1u;
     }
     c.done_sticky = __reduce_or_sync(AG_FULL, c.done_sticky);
     for (int a = lane; a < A; a += 32) {
       size_t gi = (size_t)inst * A + a;
-      uint32_t m = __float_as_uint(c.sm.psum[a].z);
+      uint32_t m = __float_as_uint(c.sm.psum()[a].z);
       double r = (double)m;
       if (P.reward_type) r -= (double)(P.before[gi] - 0.0f);
       P.rewards[gi] = r;

@@ -7,7 +7,7 @@
 
 namespace ag {
 
-constexpr int kWarpsPerCta = 5;       // one warp owns one game instance; a CTA is 5 independent warps (3 CTAs / SM)
+constexpr int kWarpsPerCta = 7;       // one warp owns one game instance; a CTA is 7 independent warps, 2 CTAs / SM (14 warps, 144 registers)
 constexpr int kPremCap = 192;         // pellets_to_remove entries per tick (Engine.hpp:212)
 constexpr int kVremCap = 32;          // viruses_to_remove entries per tick (Engine.hpp:213)
 constexpr int kCandCap = 32;          // pellet candidates resolved in registers per cell
@@ -16,6 +16,11 @@ constexpr int kZeroTileBytes = 4096;  // CTA-shared all-zero tile, source of the
 constexpr int kSnapCap = 64;          // cells staged in shared memory by the players_collision pre-test
 constexpr int kPairCap = 48;          // (eater, eaten) pairs per tick in players_collision
 constexpr int kCellRefCap = 256;      // total live cells per instance handled by players_collision
+
+// byte offsets of one warp's shared-memory arrays (sim_shared.cuh)
+struct SmemOff {
+  uint32_t hcnt, hsorted, hq, cellref, rows, strip, hitq, snap, vcache, psum, pcell, pairs, reskeys, resorder, cand, prem, vrem, lprem;
+};
 
 struct SimParams {
   agarcl_layout L;
@@ -41,6 +46,7 @@ struct SimParams {
   int32_t gw_pellet;       // reference pellet bucket grid width (bucket 510, Engine.hpp:962-965)
   int32_t gw_virus;        // reference virus bucket grid width (bucket 25, Engine.hpp:1207-1211)
   uint32_t smem_per_warp;  // bytes
+  SmemOff so;
   // fused observation clear: the engine-tick kernel streams the zeros of channels 1..C-1 of every
   // agent frame (state independent, 7/8 of all bytes of the step) while it computes; k_obs then only
   // writes channel 0 and scatters the entities.  zero_vec_per_agent == 0 disables it.
