@@ -47,7 +47,8 @@ struct agarcl_batch {
   uint32_t smem_per_warp;
   ag::SmemOff so;
   bool was_reset = false;
-  int fuse_clear = 1;  // engine-tick kernel clears observation channels 1..C-1 (AGARCL_FUSE_CLEAR=0 disables, for A/B timing)
+  int fuse_clear = 2;  // 0: k_obs writes everything; 1: the engine-tick kernel clears channels 1..C-1 while ticking;
+                       // 2: it also writes channel 0 and scatters the entities (one kernel per step).  AGARCL_FUSE_CLEAR overrides (A/B timing)
   int launches_last_step = 0;
   // optional per-kernel timing: (start, after sim, after obs) event triples of steps not yet collected
   bool timing = false;
@@ -115,6 +116,9 @@ static void fill_sim_params(const agarcl_batch* b, ag::SimParams& P) {
   P.so = b->so;
   P.obs = nullptr;
   P.zero_vec_per_agent = 0; P.zero_skip_vec = 0; P.agent_stride_vec = 0;
+  P.obs_finish = 0; P.obs_G = b->G; P.obs_C = b->C;
+  P.observe_cells = b->cfg.observe_cells; P.observe_others = b->cfg.observe_others;
+  P.observe_viruses = b->cfg.observe_viruses; P.observe_pellets = b->cfg.observe_pellets;
 }
 
 // Lets the engine-tick kernel clear channels 1..C-1 of frame slot `frame` (see SimParams); false when
@@ -127,6 +131,9 @@ static bool fuse_obs_clear(const agarcl_batch* b, ag::SimParams& P, int frame) {
   P.zero_skip_vec = (uint32_t)(plane / 16);
   P.zero_vec_per_agent = (uint32_t)((size_t)(b->C - 1) * plane / 16);
   P.agent_stride_vec = (uint32_t)((size_t)b->frames * b->C * plane / 16);
+  // the whole observation in the engine-tick kernel: int32, rows of whole 16-byte vectors, masks fit the scratch
+  P.obs_finish = (b->fuse_clear >= 2 && b->cfg.obs_dtype == AGARCL_OBS_I32 && b->G % 4 == 0 &&
+                  (size_t)2 * b->G * 4 <= (size_t)(b->so.vcache - b->so.cellref)) ? 1 : 0;
   return true;
 }
 
@@ -370,7 +377,7 @@ extern "C" int agarcl_batch_step(agarcl_batch* b, void* stream) {
     if (b->timing) { if (b->ev_used >= 3 * 2048) collect_timing(b); CK(cudaEventRecord(next_event(b), s)); }
     CK(ag::launch_step(P, s)); launches++;
     if (b->timing) CK(cudaEventRecord(next_event(b), s));
-    int rc = render_frame(b, 0, s, 1, fused); if (rc) return rc; launches++;
+    if (!P.obs_finish) { int rc = render_frame(b, 0, s, 1, fused); if (rc) return rc; launches++; }
     if (b->timing) CK(cudaEventRecord(next_event(b), s));
   } else {
     // the last num_frames ticks of the step each contribute one frame (the documented intent of

@@ -53,6 +53,12 @@ __device__ __forceinline__ float split_speed_of(const Luts& T, uint32_t m, uint3
   return split_speed_exact(m);
 }
 
+// static_cast<int>(float) as x86-64 cvttss2si does it: NaN / out of range -> INT_MIN (quirk Q20)
+__device__ __forceinline__ int to_int_x86(float v) {
+  if (!(v > -2147483904.0f && v < 2147483648.0f)) return (int)0x80000000;
+  return (int)v;
+}
+
 // Coordinate::norm_sqr of a difference, core/types.hpp:83-87
 __device__ __forceinline__ float sqr_dist(float ax, float ay, float bx, float by) {
   float dx = fabsf(ax - bx), dy = fabsf(ay - by);

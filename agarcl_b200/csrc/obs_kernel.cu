@@ -19,11 +19,6 @@ namespace ag {
 
 constexpr int kObsThreads = 256;
 
-// static_cast<int>(float) as x86-64 cvttss2si does it: NaN / out of range -> INT_MIN (quirk Q20)
-__device__ __forceinline__ int to_int_x86(float v) {
-  if (!(v > -2147483904.0f && v < 2147483648.0f)) return (int)0x80000000;
-  return (int)v;
-}
 
 template <typename T> struct ObsOps;
 template <> struct ObsOps<int32_t> {

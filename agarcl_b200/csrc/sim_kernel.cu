@@ -1750,6 +1750,154 @@ __device__ __forceinline__ void zero_chunk(Ctx& c, uint32_t nvec) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// GridObservation::add_frame by the warp that owns the instance (environment/envs/GridEnvironment.hpp:
+// add_frame 91-123, _store_entities 212-232, _mark_out_of_bounds 235-248, _view_size 251-254,
+// _world_to_grid 257-267, _grid_to_world 270-279).  Channels 1..C-1 were cleared by this warp's own
+// TMA bulk stores during the ticks; here channel 0 (separable out-of-bounds mask) is streamed and
+// the in-view entities are scattered with L2 atomics.  Runs BEFORE repsawn_all_players, like the
+// reference (BaseEnvironment.hpp:96-101).  Same arithmetic as k_obs (obs_kernel.cu), int32 only.
+// ------------------------------------------------------------------------------------------------
+__device__ void obs_finish_warp(Ctx& c) {
+  const SimParams& P = c.P;
+  const int G = P.obs_G, lane = c.lane, A = P.L.A, Pn = P.L.P;
+  const size_t plane = (size_t)G * G;
+  int32_t* xmask = reinterpret_cast<int32_t*>(c.sm.cellref());  // [G] then [G]: the collision scratch is free now
+  int32_t* ymask = xmask + G;
+  // the zero vectors of this instance must have landed before anything is scattered onto them
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __syncwarp();
+  __threadfence();
+  const float W = c.W;
+  const float centering = (float)(G / 2.0);
+  const float2* pel = reinterpret_cast<const float2*>(c.pel_());
+  const agarcl_virus* vir = c.vir_();
+  for (int a = 0; a < A; a++) {
+    int32_t* out = reinterpret_cast<int32_t*>(P.obs) + ((size_t)c.inst_local * A + a) * ((size_t)P.agent_stride_vec * 4u);
+    const float4 s = c.sm.psum()[a];
+    const float px = s.x, py = s.y;  // Player::x / y: NaN for a dead agent (quirk Q20)
+    const uint32_t tot = __float_as_uint(s.z);
+    const int n = __float_as_int(s.w);
+    const float view = clamp_std((float)(2u * tot), 100.0f, 300.0f);
+    for (int i = lane; i < G; i += 32) {  // _grid_to_world + _in_bounds, separable in i (x) and j (y)
+      float d = (float)i - centering;
+      float wx = px + d * view / (float)G, wy = py + d * view / (float)G;
+      xmask[i] = (0 <= wx && wx < W) ? 0 : -1;
+      ymask[i] = (0 <= wy && wy < W) ? 0 : -1;
+    }
+    __syncwarp();
+    {
+      const int vec_per_row = G / 4, nvec0 = (int)(plane / 4);
+      int4* out4 = reinterpret_cast<int4*>(out);
+#pragma unroll 4
+      for (int v = lane; v < nvec0; v += 32) {
+        int i = v / vec_per_row, jv = v - i * vec_per_row;
+        int4 ym = reinterpret_cast<const int4*>(ymask)[jv];
+        int xm = xmask[i];
+        __stcs(out4 + v, make_int4(ym.x | xm, ym.y | xm, ym.z | xm, ym.w | xm));
+      }
+    }
+    __syncwarp();  // the masks are rewritten for the next agent
+    if (n == 0) continue;  // dead agent: nothing lands inside the grid
+    auto grid_of = [&](float x, float y, int& gx, int& gy) -> bool {
+      gx = to_int_x86((float)G * (x - px) / view + centering);
+      gy = to_int_x86((float)G * (y - py) / view + centering);
+      return 0 <= gx && gx < G && 0 <= gy && gy < G;
+    };
+    int channel = 0;
+    if (P.observe_pellets) {
+      int32_t* ch1 = out + (size_t)(channel + 1) * plane;
+      int32_t* ch2 = out + (size_t)(channel + 2) * plane;
+      auto put_pellet = [&](float2 q) {
+        int gx, gy;
+        if (grid_of(q.x, q.y, gx, gy)) {
+          ch1[(size_t)gx * G + gy] = 1;             // at_least_: data = mass (1)
+          atomicAdd(ch2 + (size_t)gx * G + gy, 1);  // total_mass_
+        }
+      };
+      if (c.hash_valid) {
+        // only the hash cells under the view: grid_of truncates towards zero, so column 0 reaches one grid
+        // cell beyond -view/2; one more world unit of slack on top (grid_of itself is the exact test)
+        const int HG = P.HG;
+        const float h = 0.5f * view + view / (float)G + 1.0f;
+        const int hx0 = hash_coord(c, px - h), hx1 = hash_coord(c, px + h);
+        const int hy0 = hash_coord(c, py - h), hy1 = hash_coord(c, py + h);
+        for (int hy = hy0; hy <= hy1; hy++) {
+          int s0, e0;
+          hash_range(c, hy * HG + hx0, hy * HG + hx1, s0, e0);
+#pragma unroll 2
+          for (int j = s0 + lane; j < e0; j += 32) {
+            uint32_t idx = c.sm.hsorted()[j];
+            if (idx != (uint32_t)kHashDead) put_pellet(pel[idx]);
+          }
+        }
+      } else {
+#pragma unroll 4
+        for (int k = lane; k < c.n_pellets; k += 32) put_pellet(pel[k]);
+      }
+      channel += 2;
+    }
+    if (P.observe_viruses) {
+      int32_t* ch3 = out + (size_t)(channel + 1) * plane;
+      int32_t* ch4 = out + (size_t)(channel + 2) * plane;
+      const int nv = c.n_viruses;
+      for (int k = lane; k < nv; k += 32) {
+        int gx, gy;
+        if (grid_of(vir[k].x, vir[k].y, gx, gy)) {
+          atomicAdd(ch4 + (size_t)gx * G + gy, (int)vir[k].mass);
+          // at_least_ keeps the LAST writer in index order: write only if no later virus shares the cell
+          bool last = true;
+          for (int k2 = k + 1; k2 < nv; k2++) {
+            int hx, hy;
+            if (grid_of(vir[k2].x, vir[k2].y, hx, hy) && hx == gx && hy == gy) { last = false; break; }
+          }
+          if (last) ch3[(size_t)gx * G + gy] = (int)vir[k].mass;
+        }
+      }
+      channel += 2;
+    }
+    if (P.observe_cells) {
+      int32_t* ch5 = out + (size_t)(channel + 1) * plane;
+      const agarcl_cell* pc = c.pcells(a);
+      for (int k = lane; k < n; k += 32) {
+        int gx, gy;
+        if (grid_of(pc[k].x, pc[k].y, gx, gy)) atomicAdd(ch5 + (size_t)gx * G + gy, (int)pc[k].mass);
+      }
+      channel += 1;
+    }
+    if (P.observe_others) {
+      int32_t* ch6 = out + (size_t)(channel + 1) * plane;  // min over non-empty
+      int32_t* ch7 = out + (size_t)(channel + 2) * plane;  // max
+      auto put = [&](float x, float y, uint32_t m) {
+        int gx, gy;
+        if (grid_of(x, y, gx, gy)) {
+          int32_t* p6 = ch6 + (size_t)gx * G + gy;
+          int old = atomicCAS(p6, 0, (int)m);  // empty cell: take the mass; otherwise minimum (masses are > 0)
+          if (old != 0) atomicMin(p6, (int)m);
+          atomicMax(ch7 + (size_t)gx * G + gy, (int)m);
+        }
+      };
+      for (int base = 0; base < Pn; base += 32) {
+        const int p = base + lane;
+        const int np = p < Pn ? __float_as_int(c.sm.psum()[p].w) : 0;
+        if (p != a && np >= 1) {  // first cells: one player per lane
+          float4 pcv = c.sm.pcell()[p];
+          if (pcv.w >= 0.0f) put(pcv.x, pcv.y, __float_as_uint(pcv.z));
+          else { const agarcl_cell* oc = c.pcells(p); put(oc->x, oc->y, oc->mass); }
+        }
+        unsigned multi = __ballot_sync(AG_FULL, p != a && np >= 2);
+        while (multi) {  // further cells of split players: one cell per lane
+          const int src = __ffs(multi) - 1;
+          multi &= multi - 1;
+          const int mp = base + src, mn = __shfl_sync(AG_FULL, np, src);
+          const agarcl_cell* oc = c.pcells(mp);
+          if (lane + 1 < mn) put(oc[lane + 1].x, oc[lane + 1].y, oc[lane + 1].mass);
+        }
+      }
+    }
+  }
+}
+
 // Engine::tick
 __device__ void engine_tick(Ctx& c, LaneState& ls) {
   if (!c.hash_valid) { build_pellet_hash(c); c.hash_valid = true; }
@@ -1867,7 +2015,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_step(const __grid_cons
   c.zagent = 0u; c.zoff = 0u;
   {
     const uint32_t total = P.zero_vec_per_agent * (uint32_t)A;
-    const uint32_t chunks = (uint32_t)(4 * (P.n_ticks > 0 ? P.n_ticks : 1));
+    // with the finish fused, the clear is done one tick early so that it has drained before the scatter
+    const int zt = P.n_ticks - (P.obs_finish && P.n_ticks > 1 ? 1 : 0);
+    const uint32_t chunks = (uint32_t)(4 * (zt > 0 ? zt : 1));
     c.zchunk = (total + chunks - 1u) / chunks;
   }
   LaneState ls;
@@ -1879,6 +2029,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_step(const __grid_cons
   zero_chunk(c, 0xffffffffu);  // whatever is left (n_ticks == 0, rounding)
 
   if (P.do_end) {
+    if (P.obs_finish) obs_finish_warp(c);
     if (P.mode == 0) {
       // repsawn_all_players in map order: the r-th dead player takes draw pair r
       uint32_t rank_base = 0;

@@ -54,6 +54,10 @@ struct SimParams {
   uint32_t zero_vec_per_agent;  // 16-byte vectors to clear per agent frame
   uint32_t zero_skip_vec;       // vectors of channel 0 in front of them
   uint32_t agent_stride_vec;    // vectors between consecutive agents' frame slots
+  // fused observation finish (int32, one frame): after the last tick each warp also writes channel 0
+  // and scatters the entities of its instance, so the step is ONE kernel.  obs_finish == 0: k_obs does it.
+  int32_t obs_finish, obs_G, obs_C;
+  int32_t observe_cells, observe_others, observe_viruses, observe_pellets;
 };
 
 struct ResetParams {
