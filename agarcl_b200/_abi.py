@@ -19,6 +19,13 @@ FLAG_NAMES = {
 }
 
 RNG_PHILOX, RNG_REPLAY, RNG_MT19937 = 0, 1, 2
+# structured ("ram") observation record, include/agarcl_b200.h
+RAM_HDR, RAM_KP, RAM_KV, RAM_KS, RAM_KC = 8, 192, 16, 32, 32
+RAM_OFF_FOOD = RAM_HDR
+RAM_OFF_VIRUS = RAM_OFF_FOOD + 4 * RAM_KP
+RAM_OFF_SPORE = RAM_OFF_VIRUS + 4 * RAM_KV
+RAM_OFF_CLONE = RAM_OFF_SPORE + 4 * RAM_KS
+RAM_RECORD = RAM_OFF_CLONE + 8 * RAM_KC
 OBS_I32, OBS_I16 = 0, 1
 
 
@@ -30,7 +37,7 @@ class Cfg(C.Structure):
         "reward_type", "c_death", "mode_number",
         "num_frames", "grid_size", "observe_cells", "observe_others", "observe_viruses", "observe_pellets",
         "obs_dtype", "strict_reference", "rng_mode",
-        "cap_viruses", "cap_foods", "cap_replay", "device", "instance_base")] + [("reserved", C.c_int32 * 3)]
+        "cap_viruses", "cap_foods", "cap_replay", "device", "instance_base", "ram_obs")] + [("reserved", C.c_int32 * 2)]
 
 
 class Layout(C.Structure):
@@ -66,7 +73,7 @@ def make_cfg(n_instances=1, num_agents=1, ticks_per_step=4, arena_size=1000, pel
              num_pellets=1000, num_viruses=25, num_bots=25, reward_type=1, c_death=0, mode_number=0,
              num_frames=1, grid_size=128, observe_cells=True, observe_others=True, observe_viruses=True,
              observe_pellets=True, obs_dtype=OBS_I32, strict_reference=False, rng_mode=RNG_PHILOX,
-             cap_viruses=0, cap_foods=0, cap_replay=0, device=0, instance_base=0):
+             cap_viruses=0, cap_foods=0, cap_replay=0, device=0, instance_base=0, ram_obs=False):
     c = Cfg()
     for k, v in list(locals().items()):
         if k in ("c",):

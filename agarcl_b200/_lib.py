@@ -16,7 +16,7 @@ SYMBOLS = [
     "agarcl_batch_seed", "agarcl_batch_reset", "agarcl_batch_set_actions", "agarcl_batch_step",
     "agarcl_batch_obs", "agarcl_batch_rewards", "agarcl_batch_dones", "agarcl_batch_step_host",
     "agarcl_batch_download_state", "agarcl_batch_upload_state", "agarcl_batch_set_replay",
-    "agarcl_batch_render", "agarcl_batch_launches_per_step", "agarcl_batch_set_timing", "agarcl_batch_get_timing", "agarcl_mt19937_draws",
+    "agarcl_batch_render", "agarcl_batch_ram", "agarcl_batch_render_ram", "agarcl_batch_launches_per_step", "agarcl_batch_set_timing", "agarcl_batch_get_timing", "agarcl_mt19937_draws",
     "agarcl_last_error", "agarcl_version",
 ]
 
@@ -50,6 +50,8 @@ def lib():
         L.agarcl_batch_upload_state.argtypes = [_vp, C.c_int32, _vp]
         L.agarcl_batch_set_replay.argtypes = [_vp, C.c_int32, _vp, C.c_int32]
         L.agarcl_batch_render.argtypes = [_vp, _vp]
+        L.agarcl_batch_ram.argtypes = [_vp, C.POINTER(_vp), C.POINTER(C.c_int64 * 3)]
+        L.agarcl_batch_render_ram.argtypes = [_vp, _vp]
         L.agarcl_batch_launches_per_step.argtypes = [_vp]
         L.agarcl_batch_set_timing.argtypes = [_vp, C.c_int]
         L.agarcl_batch_get_timing.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]

@@ -83,6 +83,16 @@ class Batch:
     def render(self, stream=0):
         _lib.check(_lib.lib().agarcl_batch_render(self._h, _vp(stream)))
 
+    def render_ram(self, stream=0):
+        _lib.check(_lib.lib().agarcl_batch_render_ram(self._h, _vp(stream)))
+
+    def ram_tensor(self):
+        """structured observation records [N, P, RAM_RECORD] float32 on the device (cfg.ram_obs)"""
+        import torch
+        p, shape = _vp(), (C.c_int64 * 3)()
+        _lib.check(_lib.lib().agarcl_batch_ram(self._h, C.byref(p), C.byref(shape)))
+        return torch.as_tensor(_CudaView(p.value, tuple(shape), "<f4", self), device=f"cuda:{self.cfg.device}")
+
     def step_host(self, dxdy, act, obs_out=None, rewards_out=None, dones_out=None):
         f = lambda a: a.ctypes.data_as(_vp) if a is not None else None
         _lib.check(_lib.lib().agarcl_batch_step_host(self._h, f(dxdy), f(act), f(obs_out), f(rewards_out), f(dones_out)))

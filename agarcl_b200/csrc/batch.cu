@@ -21,6 +21,7 @@ namespace ag {
 cudaError_t launch_step(const SimParams& P, cudaStream_t stream);
 cudaError_t launch_obs(const ObsParams& P, cudaStream_t stream);
 cudaError_t launch_reset(const ResetParams& P, cudaStream_t stream);
+cudaError_t launch_ram(const RamParams& P, cudaStream_t stream);
 }  // namespace ag
 
 struct agarcl_batch {
@@ -30,6 +31,7 @@ struct agarcl_batch {
   size_t obs_elems, obs_bytes;
   uint8_t* d_state = nullptr;
   void* d_obs = nullptr;
+  float* d_ram = nullptr;  // structured observation records [N][P][AGARCL_RAM_RECORD], only with cfg.ram_obs
   double* d_rewards = nullptr;
   uint8_t* d_dones = nullptr;
   float* d_before = nullptr;
@@ -158,6 +160,7 @@ static void fill_obs_params(const agarcl_batch* b, ag::ObsParams& P, int frame, 
 
 extern "C" int agarcl_batch_destroy(agarcl_batch* b) {
   if (!b) return AGARCL_OK;
+  cudaFree(b->d_ram);
   cudaFree(b->d_state); cudaFree(b->d_obs); cudaFree(b->d_rewards); cudaFree(b->d_dones); cudaFree(b->d_before);
   cudaFree(b->d_dxdy); cudaFree(b->d_act); cudaFree(b->d_replay); cudaFree(b->d_seeds); cudaFree(b->d_mask);
   cudaFree(b->d_lut_radius); cudaFree(b->d_lut_speed); cudaFree(b->d_lut_split);
@@ -218,6 +221,10 @@ extern "C" int agarcl_batch_create(const agarcl_cfg* cfg, agarcl_batch** out) {
   ALLOC(b->d_seeds, (size_t)b->N * sizeof(uint64_t));
   ALLOC(b->d_mask, (size_t)b->N);
   if (L.cap_replay > 0) ALLOC(b->d_replay, (size_t)b->N * L.cap_replay * sizeof(float));
+  if (cfg->ram_obs) {
+    ALLOC(b->d_ram, (size_t)b->N * L.P * AGARCL_RAM_RECORD * sizeof(float));
+    cudaMemset(b->d_ram, 0, (size_t)b->N * L.P * AGARCL_RAM_RECORD * sizeof(float));
+  }
   ALLOC(b->d_lut_radius, AGARCL_LUT_SIZE * sizeof(float));
   ALLOC(b->d_lut_speed, AGARCL_LUT_SIZE * sizeof(float));
   ALLOC(b->d_lut_split, AGARCL_LUT_SIZE * sizeof(float));
@@ -297,6 +304,34 @@ static int render_frame(agarcl_batch* b, int frame, cudaStream_t s, int pre_resp
   return AGARCL_OK;
 }
 
+static int render_ram(agarcl_batch* b, cudaStream_t s, int pre_respawn) {
+  ag::RamParams P;
+  P.L = b->L;
+  P.T = b->T;
+  P.state = b->d_state;
+  P.ram = b->d_ram;
+  P.N = b->N;
+  P.G = b->G;
+  P.pre_respawn = pre_respawn;
+  CK(ag::launch_ram(P, s));
+  return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_ram(agarcl_batch* b, float** dev_ptr, int64_t shape[3]) {
+  if (!b || !dev_ptr) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  if (!b->d_ram) return agarcl_set_error(AGARCL_ERR_STATE, "batch was created without cfg.ram_obs");
+  *dev_ptr = b->d_ram;
+  if (shape) { shape[0] = b->N; shape[1] = b->L.P; shape[2] = AGARCL_RAM_RECORD; }
+  return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_render_ram(agarcl_batch* b, void* stream) {
+  if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");
+  if (!b->d_ram) return agarcl_set_error(AGARCL_ERR_STATE, "batch was created without cfg.ram_obs");
+  CK(cudaSetDevice(b->cfg.device));
+  return render_ram(b, (cudaStream_t)stream, 0);
+}
+
 extern "C" int agarcl_batch_render(agarcl_batch* b, void* stream) {
   if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");
   CK(cudaSetDevice(b->cfg.device));
@@ -327,6 +362,13 @@ extern "C" int agarcl_batch_reset(agarcl_batch* b, const uint8_t* mask, void* st
   P.W = (float)b->cfg.arena_size;
   CK(ag::launch_reset(P, s));
   b->was_reset = true;
+  if (b->d_ram) {  // GoBiggerEnvironment::reset ends with observation.clear() (GoBiggerEnvironment.hpp:698-702)
+    const size_t per = (size_t)b->L.P * AGARCL_RAM_RECORD * sizeof(float);
+    if (!mask) CK(cudaMemsetAsync(b->d_ram, 0, per * b->N, s));
+    else
+      for (int i = 0; i < b->N; i++)
+        if (mask[i]) CK(cudaMemsetAsync((uint8_t*)b->d_ram + per * i, 0, per, s));
+  }
   // the reference ends reset() with _partial_observation (BaseEnvironment.hpp:202-203)
   if (b->cfg.strict_reference) {
     CK(cudaMemsetAsync(b->d_obs, 0, b->obs_bytes, s));
@@ -392,6 +434,7 @@ extern "C" int agarcl_batch_step(agarcl_batch* b, void* stream) {
     P.n_ticks = 0; P.do_begin = 0; P.do_end = 1;
     CK(ag::launch_step(P, s)); launches++;
   }
+  if (b->d_ram) { int rc = render_ram(b, s, 1); if (rc) return rc; launches++; }
   b->launches_last_step = launches;
   return AGARCL_OK;
 }

@@ -84,4 +84,13 @@ struct ObsParams {
   float W;
 };
 
+struct RamParams {
+  agarcl_layout L;
+  Luts T;
+  const uint8_t* state;
+  float* ram;              // [N][P][AGARCL_RAM_RECORD]
+  int32_t N, G;
+  int32_t pre_respawn;     // 1: players respawned at the end of the step are still dead (BaseEnvironment.hpp:96-101)
+};
+
 }  // namespace ag

@@ -48,12 +48,77 @@ def algorithmic_bytes(n_pel=1000, n_vir=25, n_food=0, n_cell=40, P=26, A=1, C_=8
     return dict(obs_kernel=obs + s_state, sim_kernel=2 * s_state + A * 21, step=obs + 2 * s_state + A * 21, s_state=s_state)
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this same command (profiles/traffic.json); None when there is none."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if kernel is None or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f).get(kernel)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class NvmlSampler:
+    """SM clock / power / throttle reasons polled through NVML every few ms DURING the timed region (the
+    region lasts tens of ms, too short for `nvidia-smi -lms`); same quantities as the B200_PROFILING.md recipe."""
+
+    def __init__(self, index, period_s=0.003):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        self.period = period_s
+        self.samples = []
+        self._stop = threading.Event()
+        self.thread = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, rs))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        nv = self.nv
+        self._stop.set()
+        self.thread.join(timeout=1)
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted({k for _, rs in self.samples for k, bit in names.items() if rs & bit})
+        sm = [x for x, _ in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm), "source": "nvml"}
+
+
+def make_sampler(index):
+    try:
+        return NvmlSampler(index)
+    except Exception:
+        return ClockSampler(index)
 
 
 class ClockSampler:
@@ -221,7 +286,7 @@ def run_ours(args):
     for i in range(W_):
         one_step(i)
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = make_sampler(local_rank)
     if rank == 0:
         sampler.start()
     b.set_timing(True)
@@ -280,13 +345,23 @@ def run_ours(args):
         ab = algorithmic_bytes(n_pel=int(sv.hdr["n_pellets"]), n_vir=int(sv.hdr["n_viruses"]), n_food=int(sv.hdr["n_foods"]),
                                n_cell=n_cell)
         sim_avg, obs_avg = sim_ms / max(tsteps, 1), obs_ms / max(tsteps, 1)
-        kern = {"k_step": (sim_avg, ab["sim_kernel"] * N), "k_obs": (obs_avg, ab["obs_kernel"] * N)}
+        fuse = int(os.environ.get("AGARCL_FUSE_CLEAR", "2"))
+        obs_b = A * 8 * 128 * 128 * 4
+        if launches == K:      # one kernel per step: ticks + the whole observation
+            kern = {"k_step": (sim_avg, ab["step"] * N)}
+        elif fuse == 1:        # k_step also streams channels 1..7, k_obs writes channel 0 + scatter
+            kern = {"k_step": (sim_avg, (ab["sim_kernel"] + obs_b * 7 // 8) * N),
+                    "k_obs": (obs_avg, (obs_b // 8 + ab["s_state"]) * N)}
+        else:
+            kern = {"k_step": (sim_avg, ab["sim_kernel"] * N), "k_obs": (obs_avg, ab["obs_kernel"] * N)}
         dom = max(kern, key=lambda k: kern[k][0])
+        traffic = measured_traffic(dom if launches == K else None)
         def rf(k):
             t_ms, byt = kern[k]
             ach = byt / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
             return {"kernel": k, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "avg_launch_ms": t_ms, "algorithmic_bytes_per_launch": byt, "traffic": None, "peak_source": peak_src}
+                    "avg_launch_ms": t_ms, "algorithmic_bytes_per_launch": byt, "traffic": traffic if k == dom else None,
+                    "peak_source": peak_src}
         value = world * N * K / (ms * 1e-3)
         whole = ab["step"] * value / 1e9 / world
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,

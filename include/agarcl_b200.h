@@ -89,7 +89,8 @@ typedef struct agarcl_cfg {
   int32_t cap_viruses, cap_foods, cap_replay; /* 0 = defaults */
   int32_t device;           /* CUDA device ordinal */
   int32_t instance_base;    /* global index of local instance 0 (multi-GPU sharding; keys the RNG) */
-  int32_t reserved[3];
+  int32_t ram_obs;          /* 1: every step also produces the structured observation (agarcl_batch_ram) */
+  int32_t reserved[2];
 } agarcl_cfg;
 
 /* ------------------------------------------------------------- state records */
@@ -184,6 +185,35 @@ int agarcl_batch_dones(agarcl_batch* b, uint8_t** dev_ptr);  /* dones(), u8[N*A]
  * out (any of the out pointers may be NULL) and synchronises.  This is what `e2e` in bench.py times. */
 int agarcl_batch_step_host(agarcl_batch* b, const float* dxdy, const int32_t* act,
                            void* obs_out, double* rewards_out, uint8_t* dones_out);
+
+/* ---------------------------------------------------- structured ("ram") observation
+ * GoBiggerObservation::add_frame (environment/envs/GoBiggerEnvironment.hpp:515-548, _store_entities
+ * 446-513): for EVERY player of the instance, the in-view viruses, pellets ("food"), ejected foods
+ * ("spores") and the player's own cells ("clones"), player-relative, in entity index order — what
+ * agarcl.GoBiggerEnvironment.get_state() (environment/bindings.cpp:28-47,323-374) hands out as
+ * PlayerState objects.  Here one player is one fixed-size float32 record, zero padded:
+ *   hdr   [8]      n_food, n_virus, n_spore, n_clone (true in-view counts), score (= player mass),
+ *                  player x, player y, overflow mask (bit0 food, bit1 virus, bit2 spore, bit3 clone)
+ *   food  [KP][4]  dx, dy, radius, score            (FoodInfo)
+ *   virus [KV][4]  dx, dy, radius, score            (VirusInfo; its velocity is the constant (0,0))
+ *   spore [KS][4]  dx, dy, radius, score            (SporeInfo; velocity (0,0), owner = this player)
+ *   clone [KC][8]  dx, dy, radius, score, vx, vy, direction, owner   (CloneInfo; teamId is always 0)
+ * A player with nothing in view (a dead one) keeps its previous record, like the reference, whose
+ * PlayerState is only committed when an entity lands inside the grid (:495-509).  reset() clears.   */
+#define AGARCL_RAM_HDR 8
+#define AGARCL_RAM_KP 192
+#define AGARCL_RAM_KV 16
+#define AGARCL_RAM_KS 32
+#define AGARCL_RAM_KC 32
+#define AGARCL_RAM_OFF_FOOD AGARCL_RAM_HDR
+#define AGARCL_RAM_OFF_VIRUS (AGARCL_RAM_OFF_FOOD + 4 * AGARCL_RAM_KP)
+#define AGARCL_RAM_OFF_SPORE (AGARCL_RAM_OFF_VIRUS + 4 * AGARCL_RAM_KV)
+#define AGARCL_RAM_OFF_CLONE (AGARCL_RAM_OFF_SPORE + 4 * AGARCL_RAM_KS)
+#define AGARCL_RAM_RECORD (AGARCL_RAM_OFF_CLONE + 8 * AGARCL_RAM_KC) /* 1224 floats per player */
+/* Device pointer to the records [N, P, AGARCL_RAM_RECORD] float32 (cfg.ram_obs must be 1). */
+int agarcl_batch_ram(agarcl_batch* b, float** dev_ptr, int64_t shape[3]);
+/* Run only the structured-observation kernel on the current state (tests). */
+int agarcl_batch_render_ram(agarcl_batch* b, void* stream);
 
 /* Parity / snapshot transport: one instance's blob (layout.stride bytes) to / from host memory. */
 int agarcl_batch_download_state(agarcl_batch* b, int32_t instance, void* blob);

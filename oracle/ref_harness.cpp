@@ -96,17 +96,25 @@ class FBOException : public std::runtime_error { using runtime_error::runtime_er
 #define private public
 #define protected public
 #include <environment/envs/GridEnvironment.hpp> /* scratch copy in oracle/_ref/gen shadows line 374 */
+/* GoBiggerObservation only: the scratch copy in oracle/_ref/gen stops before the GoBiggerEnvironment class
+ * (it needs the OpenGL frame buffer); the header's `#define f first` / `#define s second` are undone. */
+#include <environment/envs/GoBiggerEnvironment.hpp>
+#undef f
+#undef s
 #undef private
 #undef protected
 #undef steady_clock
 
 using RefEnvT = agario::env::GridEnvironment<int, false>;
 using RefObsT = agario::env::GridObservation<int, false>;
+using RefRamT = agario::env::GoBiggerObservation<false>;
 using SimClock = std::chrono::agarcl_sim_clock;
 
 struct RefEnv {
   std::unique_ptr<RefEnvT> env;
   std::unique_ptr<RefObsT> forced; /* add_frame(...,0) target, see Q11 */
+  std::unique_ptr<RefRamT> ram;    /* GoBiggerObservation fed with this engine's state */
+  int arena;
   int num_agents, grid, channels;
   void bind_clock() { SimClock::tick_ptr = &env->engine_.state.ticks; }
 };
@@ -142,6 +150,7 @@ void* ref_create(const agarcl_cfg* c) {
   r->forced.reset(new RefObsT(1, c->grid_size, c->observe_cells != 0, c->observe_others != 0,
                               c->observe_viruses != 0, c->observe_pellets != 0));
   r->num_agents = c->num_agents;
+  r->arena = c->arena_size;
   r->grid = c->grid_size;
   r->channels = std::get<0>(r->forced->shape());
   return r;
@@ -191,6 +200,60 @@ void ref_obs(void* h, int agent, int32_t* out) {
   r->forced->clear_data();
   r->forced->add_frame(player, r->env->engine_.game_state(), 0);
   std::memcpy(out, r->forced->data(), sizeof(int32_t) * (size_t)r->forced->length());
+}
+
+/* GoBiggerObservation::add_frame(player 0, state, 0) (GoBiggerEnvironment.hpp:515-548), flattened into the
+ * agarcl ram records [P][AGARCL_RAM_RECORD].  The observation object persists between calls, so players
+ * with nothing in view keep their previous PlayerState exactly as in the reference; ref_ram_clear is
+ * GoBiggerEnvironment::reset's observation.clear(). */
+void ref_ram_clear(void* h) {
+  auto* r = static_cast<RefEnv*>(h);
+  if (r->ram) r->ram->clear();
+}
+void ref_ram_obs(void* h, int P, float* out) {
+  auto* r = static_cast<RefEnv*>(h);
+  r->bind_clock();
+  CoutSilencer quiet;
+  std::streambuf* olderr = std::cerr.rdbuf(quiet.sink.rdbuf());
+  if (!r->ram) {
+    r->ram.reset(new RefRamT(r->arena, r->arena, 0, 0, r->num_agents));
+    r->ram->configure(1, r->grid, true, true, true, true);
+  }
+  auto& player = r->env->engine_.player(r->env->pids_[0]);
+  r->ram->add_frame(player, r->env->engine_.game_state(), 0);
+  std::cerr.rdbuf(olderr);
+  for (auto& kv : r->ram->get_player_states().get_all_player_states()) {
+    int pid = kv.first;
+    if (pid < 0 || pid >= P) continue;
+    const auto& ps = kv.second;
+    float* rec = out + (size_t)pid * AGARCL_RAM_RECORD;
+    std::memset(rec, 0, sizeof(float) * AGARCL_RAM_RECORD);
+    const auto& fo = ps.get_food_infos();
+    const auto& vi = ps.get_virus_infos();
+    const auto& sp = ps.get_spore_infos();
+    const auto& cl = ps.get_clone_infos();
+    for (size_t i = 0; i < fo.size() && i < AGARCL_RAM_KP; i++) {
+      float* e = rec + AGARCL_RAM_OFF_FOOD + 4 * i;
+      e[0] = fo[i].position.x; e[1] = fo[i].position.y; e[2] = (float)fo[i].radius; e[3] = (float)fo[i].score;
+    }
+    for (size_t i = 0; i < vi.size() && i < AGARCL_RAM_KV; i++) {
+      float* e = rec + AGARCL_RAM_OFF_VIRUS + 4 * i;
+      e[0] = vi[i].position.x; e[1] = vi[i].position.y; e[2] = (float)vi[i].radius; e[3] = (float)vi[i].score;
+    }
+    for (size_t i = 0; i < sp.size() && i < AGARCL_RAM_KS; i++) {
+      float* e = rec + AGARCL_RAM_OFF_SPORE + 4 * i;
+      e[0] = sp[i].position.x; e[1] = sp[i].position.y; e[2] = (float)sp[i].radius; e[3] = (float)sp[i].score;
+    }
+    for (size_t i = 0; i < cl.size() && i < AGARCL_RAM_KC; i++) {
+      float* e = rec + AGARCL_RAM_OFF_CLONE + 8 * i;
+      e[0] = cl[i].position.x; e[1] = cl[i].position.y; e[2] = (float)cl[i].radius; e[3] = (float)cl[i].score;
+      e[4] = (float)cl[i].velocity.first; e[5] = (float)cl[i].velocity.second; e[6] = cl[i].direction; e[7] = (float)cl[i].owner;
+    }
+    rec[0] = (float)fo.size(); rec[1] = (float)vi.size(); rec[2] = (float)sp.size(); rec[3] = (float)cl.size();
+    rec[4] = (float)ps.get_score();
+    rec[7] = (float)((fo.size() > AGARCL_RAM_KP ? 1 : 0) | (vi.size() > AGARCL_RAM_KV ? 2 : 0) | (sp.size() > AGARCL_RAM_KS ? 4 : 0) |
+                     (cl.size() > AGARCL_RAM_KC ? 8 : 0));
+  }
 }
 
 /* what the reference's own step()/get_state() left in its buffer (quirk Q11) */

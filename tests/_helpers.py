@@ -6,7 +6,7 @@ import subprocess
 
 import numpy as np
 
-from agarcl_b200._abi import (Cfg, Layout, StateView, compare_states, make_cfg)
+from agarcl_b200._abi import (Cfg, Layout, RAM_RECORD, StateView, compare_states, make_cfg)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
@@ -102,6 +102,27 @@ class Oracle:
         self.lib.oracle_obs(C.byref(self.cfg), C.byref(self.L), self.state.ptr, agent, 0, fptr(out))
         return out
 
+    # ---- structured ("ram") observation: records persist between calls (players with nothing in view keep theirs)
+    def ram_clear(self):
+        self.ram = np.zeros((self.L.P, RAM_RECORD), np.float32)
+
+    def ram_obs(self):
+        """oracle_ram_obs on the CURRENT state"""
+        if not hasattr(self, "ram"):
+            self.ram_clear()
+        self.lib.oracle_ram_obs(C.byref(self.cfg), C.byref(self.L), self.state.ptr, fptr(self.ram))
+        return self.ram
+
+    def step_with_ram(self):
+        """oracle_step with the records taken where the reference takes them (after the ticks, before respawn)"""
+        if not hasattr(self, "ram"):
+            self.ram_clear()
+        self.lib.oracle_set_ram_out(fptr(self.ram))
+        try:
+            return self.step()
+        finally:
+            self.lib.oracle_set_ram_out(None)
+
 
 class Reference:
     """One instance of the compiled reference GridEnvironment<int,false>."""
@@ -161,6 +182,17 @@ class Reference:
         out = np.zeros((self.L.obs_channels, self.cfg.grid_size, self.cfg.grid_size), np.int32)
         self.lib.ref_obs(self.h, agent, fptr(out))
         return out
+
+    def ram_clear(self):
+        self.ram = np.zeros((self.L.P, RAM_RECORD), np.float32)
+        self.lib.ref_ram_clear(self.h)
+
+    def ram_obs(self):
+        """GoBiggerObservation::add_frame on the current reference state, flattened into agarcl records"""
+        if not hasattr(self, "ram"):
+            self.ram_clear()
+        self.lib.ref_ram_obs(self.h, self.L.P, fptr(self.ram))
+        return self.ram
 
     def set_cell_mass(self, pid, cell, mass):
         self.lib.ref_set_cell_mass(self.h, pid, cell, C.c_uint(mass))

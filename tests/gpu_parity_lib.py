@@ -31,11 +31,11 @@ def philox_uniform_np(seed, instance, k):
 
 
 def run_parity(cfg_kwargs, seeds, steps, p_feed=1 / 3, p_split=1 / 3, boost=None, obs_every=5, replay_len=1 << 16,
-               with_obs_in_step=True):
+               with_obs_in_step=True, ram=False):
     """Runs len(seeds) instances on the GPU in one batch and each one through the oracle."""
     oracle_lib().oracle_set_trig_mode(1)
     n = len(seeds)
-    cfg = make_cfg(n_instances=n, rng_mode=RNG_REPLAY, cap_replay=replay_len, **cfg_kwargs)
+    cfg = make_cfg(n_instances=n, rng_mode=RNG_REPLAY, cap_replay=replay_len, ram_obs=ram, **cfg_kwargs)
     b = Batch(cfg)
     L = b.layout
     Lo = oracle_layout(cfg)
@@ -65,6 +65,10 @@ def run_parity(cfg_kwargs, seeds, steps, p_feed=1 / 3, p_split=1 / 3, boost=None
     obs_t = b.obs_tensor()
     rew_t = b.rewards_tensor()
     done_t = b.dones_tensor()
+    ram_t = b.ram_tensor() if ram else None
+    if ram:
+        for o in oras:
+            o.ram_clear()
     rngs = [np.random.default_rng(s) for s in seeds]
     A = L.A
     for st in range(steps):
@@ -79,9 +83,10 @@ def run_parity(cfg_kwargs, seeds, steps, p_feed=1 / 3, p_split=1 / 3, boost=None
         g_done = done_t.cpu().numpy().reshape(n, A)
         want_obs = (st % obs_every == 0)
         g_obs = obs_t.cpu().numpy().reshape(n, A, *b.obs_shape[1:]) if want_obs else None
+        g_ram = ram_t.cpu().numpy() if ram else None
         for i, o in enumerate(oras):
             o.set_actions(dxdy[i], act[i])
-            o_rew, o_done, o_obs = o.step(with_obs=want_obs and with_obs_in_step)
+            o_rew, o_done, o_obs = o.step_with_ram() if ram else o.step(with_obs=want_obs and with_obs_in_step)
             gs = b.download_state(i)
             d = compare_states(o.state, gs)
             assert not d, f"step {st} inst {i} (seed {seeds[i]}): {d[:6]} flags gpu={gs.flag_names()} oracle={o.state.flag_names()}"
@@ -89,6 +94,12 @@ def run_parity(cfg_kwargs, seeds, steps, p_feed=1 / 3, p_split=1 / 3, boost=None
             assert int(gs.hdr["rng_cursor"]) == int(o.state.hdr["rng_cursor"]), (st, i)
             assert np.array_equal(g_rew[i], o_rew), f"step {st} inst {i}: rewards {g_rew[i]} vs {o_rew}"
             assert np.array_equal(g_done[i], o_done), f"step {st} inst {i}: dones {g_done[i]} vs {o_done}"
+            if ram:
+                same = (g_ram[i].view(np.uint32) == o.ram.view(np.uint32)) | (np.isnan(g_ram[i]) & np.isnan(o.ram))
+                if not same.all():
+                    bad = np.argwhere(~same)[:8].tolist()
+                    raise AssertionError(f"step {st} inst {i}: ram records differ at (player, slot) {bad}: "
+                                         f"{[(float(g_ram[i][p, k]), float(o.ram[p, k])) for p, k in bad]}")
             if want_obs:
                 if o_obs is None:
                     o_obs = np.stack([o.obs(a) for a in range(A)])

@@ -28,6 +28,26 @@ CASES = {
 }
 
 
+RAM_CASES = {
+    # BASELINE.json configs[2]: the structured ("ram") observation, continuous random actions
+    "c3_ram_default": (dict(num_bots=8, num_viruses=10), dict(steps=120, p_feed=0.0, p_split=0.0)),
+    "ram_split_eject": (dict(num_agents=3, num_bots=6, arena_size=400, num_pellets=400, num_viruses=8, cap_foods=2048),
+                        dict(steps=150, p_feed=0.4, p_split=0.3, boost=600)),
+    "ram_no_respawn_mode4": (dict(num_agents=2, num_bots=0, arena_size=150, num_pellets=100, num_viruses=3, mode_number=4, cap_foods=1024),
+                             dict(steps=150, p_feed=0.2, p_split=0.2, boost=300)),
+    "ram_dense_overflow": (dict(num_agents=1, num_bots=2, arena_size=200, num_pellets=1500, num_viruses=30, cap_viruses=128),
+                           dict(steps=30, boost=160)),
+}
+
+
+@pytest.mark.parametrize("name", list(RAM_CASES))
+def test_cuda_ram_observation_matches_oracle(name):
+    """k_ram (GoBiggerObservation::add_frame) inside agarcl_batch_step vs the oracle, every record bit-exact"""
+    cfg_kwargs, run_kwargs = RAM_CASES[name]
+    stats = run_parity(cfg_kwargs, seeds=[21, 22, 23], ram=True, **run_kwargs)
+    print(name, stats)
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_cuda_matches_oracle(name):
     cfg_kwargs, run_kwargs = CASES[name]
