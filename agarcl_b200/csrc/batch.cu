@@ -142,6 +142,7 @@ static bool fuse_obs_clear(const agarcl_batch* b, ag::SimParams& P, int frame) {
 static void fill_obs_params(const agarcl_batch* b, ag::ObsParams& P, int frame, int pre_respawn, int skip_zero = 0) {
   P.pre_respawn = pre_respawn;
   P.skip_zero = skip_zero;
+  P.mask = nullptr;
   P.L = b->L;
   P.state = b->d_state;
   P.obs = b->d_obs;
@@ -297,9 +298,11 @@ extern "C" int agarcl_batch_set_replay(agarcl_batch* b, int32_t instance, const 
   return AGARCL_OK;
 }
 
-static int render_frame(agarcl_batch* b, int frame, cudaStream_t s, int pre_respawn, int skip_zero = 0) {
+static int render_frame(agarcl_batch* b, int frame, cudaStream_t s, int pre_respawn, int skip_zero = 0,
+                        const uint8_t* d_mask = nullptr) {
   ag::ObsParams P;
   fill_obs_params(b, P, frame, pre_respawn, skip_zero);
+  P.mask = d_mask;
   CK(ag::launch_obs(P, s));
   return AGARCL_OK;
 }
@@ -370,14 +373,26 @@ extern "C" int agarcl_batch_reset(agarcl_batch* b, const uint8_t* mask, void* st
         if (mask[i]) CK(cudaMemsetAsync((uint8_t*)b->d_ram + per * i, 0, per, s));
   }
   // the reference ends reset() with _partial_observation (BaseEnvironment.hpp:202-203)
+  // (a masked reset touches only the observations of the instances it resets)
+  const uint8_t* dm = mask ? b->d_mask : nullptr;
+  auto clear_obs = [&]() -> cudaError_t {
+    if (!mask) return cudaMemsetAsync(b->d_obs, 0, b->obs_bytes, s);
+    const size_t per = b->obs_bytes / (size_t)b->N;
+    for (int i = 0; i < b->N; i++)
+      if (mask[i]) {
+        cudaError_t e = cudaMemsetAsync((uint8_t*)b->d_obs + per * i, 0, per, s);
+        if (e != cudaSuccess) return e;
+      }
+    return cudaSuccess;
+  };
   if (b->cfg.strict_reference) {
-    CK(cudaMemsetAsync(b->d_obs, 0, b->obs_bytes, s));
+    CK(clear_obs());
     int frame = 0 - (b->cfg.ticks_per_step - b->frames);
-    if (frame >= 0) return render_frame(b, frame, s, 0);
+    if (frame >= 0) return render_frame(b, frame, s, 0, 0, dm);
     return AGARCL_OK;
   }
-  if (b->frames > 1) CK(cudaMemsetAsync(b->d_obs, 0, b->obs_bytes, s));
-  return render_frame(b, b->frames - 1, s, 0);
+  if (b->frames > 1) CK(clear_obs());
+  return render_frame(b, b->frames - 1, s, 0, 0, dm);
 }
 
 extern "C" int agarcl_batch_set_actions(agarcl_batch* b, const float* dxdy, const int32_t* act, int on_device, void* stream) {

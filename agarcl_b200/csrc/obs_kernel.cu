@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(kObsThreads) k_obs(const __grid_constant__ Obs
   __shared__ T s_xmask[1024];                // 0 / -1 per gx
   const int A = P.L.A, G = P.G, C = P.C;
   const int inst = blockIdx.x / A, agent = blockIdx.x % A;
+  if (P.mask && !P.mask[inst]) return;
   const uint8_t* blob = P.state + (size_t)inst * P.L.stride;
   const agarcl_inst_hdr* hdr = reinterpret_cast<const agarcl_inst_hdr*>(blob + P.L.off_hdr);
   const agarcl_player* players = reinterpret_cast<const agarcl_player*>(blob + P.L.off_players);

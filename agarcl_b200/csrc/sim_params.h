@@ -81,6 +81,7 @@ struct ObsParams {
   int32_t obs_dtype;
   int32_t pre_respawn;     // 1: show players respawned at the end of the step as still dead
   int32_t skip_zero;       // 1: channels 1..C-1 were already cleared by the engine-tick kernel
+  const uint8_t* mask;     // [N] or nullptr: render only the instances with mask != 0 (masked reset)
   float W;
 };
 

@@ -143,3 +143,90 @@ def test_strict_reference_frame_quirk_q11():
     obs2, _, _ = e2.step(np.zeros((4, 2), np.float32), np.zeros(4, np.int32))
     torch.cuda.synchronize()
     assert int(obs2.abs().sum()) > 0  # tps == num_frames: frame 0 is filled
+
+
+def test_gym_wrapper_mirrors_reference_interface():
+    """gym_agario.AgarioEnv surface: ids, action format, 5-tuple step, HWC observation, episodic truncation."""
+    from agarcl_b200.gym_env import make
+    env = make("agario-grid-v0", num_bots=3, arena_size=200, num_pellets=100, num_viruses=2, number_steps=5)
+    env.seed(3)
+    obs, info = env.reset()
+    assert obs.shape == (128, 128, 8) and obs.dtype == np.int32 and info == {}
+    assert env.observation_space.shape == (128, 128, 8)
+    done = False
+    for t in range(6):
+        obs, rew, done, trunc, info = env.step((np.array([0.5, -0.5], np.float32), 0))
+        assert obs.shape == (128, 128, 8) and isinstance(rew, float) and trunc is False and info["steps"] == t + 1
+    assert done is True  # number_steps reached (AgarioEnv.py:111-112)
+    with pytest.raises(ValueError):
+        env.step((np.array([2.0, 0.0], np.float32), 0))  # outside the action space
+    with pytest.raises(ValueError):
+        env.step([(np.zeros(2, np.float32), 0), (np.zeros(2, np.float32), 0)])  # wrong number of actions
+    env.close()
+    multi = make("agario-grid-v0", num_agents=2, num_bots=0, arena_size=100, num_pellets=50)
+    obs, _ = multi.reset()
+    assert isinstance(obs, list) and len(obs) == 2
+    obs, rew, done, trunc, _ = multi.step([(np.zeros(2, np.float32), 0), (np.zeros(2, np.float32), 1)])
+    assert len(rew) == 2 and len(done) == 2
+    multi.close()
+
+
+def test_gobigger_environment_get_state_against_oracle():
+    """agarcl.GoBiggerEnvironment.get_state(): PlayerState objects rebuilt from the device records == oracle records."""
+    from _helpers import Oracle, oracle_lib
+    from agarcl_b200 import make_cfg, RNG_REPLAY
+    from agarcl_b200.env import GoBiggerEnvironment
+    oracle_lib().oracle_set_trig_mode(1)
+    env = GoBiggerEnvironment(512, 512, 1000, 1, 4, 300, True, 200, 4, 5, 1)
+    env.seed(5)
+    env.reset()
+    cfg = make_cfg(num_agents=1, arena_size=300, num_pellets=200, num_viruses=4, num_bots=5, rng_mode=RNG_REPLAY, cap_replay=16384)
+    ora = Oracle(cfg)
+    ora.seed_mt(5, 16384)
+    ora.reset()
+    ora.ram_clear()
+    rng = np.random.default_rng(4)
+    for st in range(25):
+        a = (float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1)), int(rng.integers(0, 3)))
+        env.take_actions([a])
+        env.step()
+        ora.set_actions(np.array([[a[0], a[1]]], np.float32), np.array([a[2]], np.int32))
+        ora.step_with_ram()
+    st = env.get_state()
+    assert len(st) == 1 and set(st[0]) == {"global_state", "player_states"}
+    assert st[0]["global_state"].get_map_width() == 512 and st[0]["global_state"].get_team_num() == 1
+    ps = st[0]["player_states"].get_all_player_states()
+    assert set(ps) == {p for p in range(6) if ora.ram[p, :4].sum() > 0}
+    for p, s in ps.items():
+        rec = ora.ram[p]
+        assert [len(s.get_food_infos()), len(s.get_virus_infos()), len(s.get_spore_infos()), len(s.get_clone_infos())] == \
+            [int(min(rec[0], 192)), int(min(rec[1], 16)), int(min(rec[2], 32)), int(min(rec[3], 32))]
+        assert s.get_score() == float(rec[4])
+        c0 = s.get_clone_infos()[0]
+        assert np.float32(c0.position.x) == rec[968] and np.float32(c0.radius) == rec[970] and c0.owner == p
+    assert env.observation_shape() == (25, 512, 512)
+    env.close()
+
+
+def test_batched_vector_env_auto_reset():
+    import torch
+    from agarcl_b200.gym_env import BatchedAgarioEnv
+    env = BatchedAgarioEnv(64, obs_type="grid", num_bots=2, arena_size=150, num_pellets=80, num_viruses=2, number_steps=7)
+    env.seed(11)
+    obs, _ = env.reset()
+    assert obs.shape == (64, 8, 128, 128) and obs.is_cuda
+    n_done = 0
+    for t in range(20):
+        dxdy = torch.rand((64, 2), device="cuda") * 2 - 1
+        act = torch.zeros(64, dtype=torch.int32, device="cuda")
+        obs, rew, done, trunc, info = env.step(dxdy, act)
+        n_done += int(done.sum())
+        assert rew.dtype == torch.float32 and done.dtype == torch.bool
+        assert int(info["steps"].max()) <= 8
+    assert n_done == 64 * 2  # every instance hit number_steps twice in 20 steps (steps 8 and 16)
+    ram = BatchedAgarioEnv(8, obs_type="ram", num_bots=3, arena_size=150, num_pellets=80, num_viruses=2)
+    o, _ = ram.reset()
+    o, *_ = ram.step(torch.zeros((8, 2), device="cuda"), torch.zeros(8, dtype=torch.int32, device="cuda"))
+    assert o.shape == (8, 1, 1224) and float(o[:, 0, 3].min()) >= 1.0  # every agent sees its own cell
+    env.close()
+    ram.close()
