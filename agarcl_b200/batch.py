@@ -118,6 +118,12 @@ class Batch:
     def upload_state(self, i, sv):
         _lib.check(_lib.lib().agarcl_batch_upload_state(self._h, i, sv.ptr))
 
+    def save_env_state(self, i, path):
+        _lib.check(_lib.lib().agarcl_batch_save_env_state(self._h, i, str(path).encode()))
+
+    def load_env_state(self, i, path, lossless=False):
+        _lib.check(_lib.lib().agarcl_batch_load_env_state(self._h, i, str(path).encode(), int(lossless)))
+
     def set_replay(self, i, draws):
         d = np.ascontiguousarray(draws, dtype=np.float32)
         _lib.check(_lib.lib().agarcl_batch_set_replay(self._h, i, d.ctypes.data_as(_vp), d.size))

@@ -508,6 +508,38 @@ extern "C" int agarcl_batch_step_host(agarcl_batch* b, const float* dxdy, const 
   return AGARCL_OK;
 }
 
+extern "C" int agarcl_batch_save_env_state(agarcl_batch* b, int32_t instance, const char* path) {
+  if (!b || !path) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  if (instance < 0 || instance >= b->N) return agarcl_set_error(AGARCL_ERR_INVALID, "instance out of range");
+  CK(cudaSetDevice(b->cfg.device));
+  CK(cudaDeviceSynchronize());
+  std::vector<uint8_t> blob(b->L.stride);
+  CK(cudaMemcpy(blob.data(), b->d_state + (size_t)instance * b->L.stride, b->L.stride, cudaMemcpyDeviceToHost));
+  return agarcl_snapshot_write(&b->cfg, &b->L, blob.data(), path);
+}
+
+extern "C" int agarcl_batch_load_env_state(agarcl_batch* b, int32_t instance, const char* path, int lossless) {
+  if (!b || !path) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  if (instance < 0 || instance >= b->N) return agarcl_set_error(AGARCL_ERR_INVALID, "instance out of range");
+  if (!b->was_reset) return agarcl_set_error(AGARCL_ERR_STATE, "load_env_state() before reset()");
+  CK(cudaSetDevice(b->cfg.device));
+  CK(cudaDeviceSynchronize());
+  std::vector<uint8_t> blob(b->L.stride);
+  CK(cudaMemcpy(blob.data(), b->d_state + (size_t)instance * b->L.stride, b->L.stride, cudaMemcpyDeviceToHost));
+  int rc = agarcl_snapshot_read(&b->cfg, &b->L, blob.data(), path, lossless);
+  if (rc) return rc;
+  const agarcl_inst_hdr* hdr = reinterpret_cast<const agarcl_inst_hdr*>(blob.data() + b->L.off_hdr);
+  b->seeds[instance] = hdr->seed_lo;
+  CK(cudaMemcpy(b->d_seeds + instance, &b->seeds[instance], sizeof(uint64_t), cudaMemcpyHostToDevice));
+  if (b->cfg.rng_mode == AGARCL_RNG_MT19937) {  // Engine::seed(agarcl_data["seed"]): the mt19937_64 stream restarts
+    std::vector<float> draws(b->L.cap_replay);
+    agarcl_mt19937_draws(hdr->seed_lo, draws.data(), b->L.cap_replay);
+    CK(cudaMemcpy(b->d_replay + (size_t)instance * b->L.cap_replay, draws.data(), draws.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  CK(cudaMemcpy(b->d_state + (size_t)instance * b->L.stride, blob.data(), b->L.stride, cudaMemcpyHostToDevice));
+  return AGARCL_OK;
+}
+
 extern "C" int agarcl_batch_download_state(agarcl_batch* b, int32_t instance, void* blob) {
   if (!b || !blob) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
   if (instance < 0 || instance >= b->N) return agarcl_set_error(AGARCL_ERR_INVALID, "instance out of range");

@@ -115,7 +115,12 @@ class GridEnvironment(_Base):
         return [obs[a].copy() for a in range(self.num_agents)]
 
     def save_env_state(self, path):
-        raise RuntimeError("JSON snapshots are a later row of the scope table (SURVEY.md 8f rank 2)")
+        """BaseEnvironment::save_env_state (BaseEnvironment.hpp:213-318; bound at bindings.cpp:135)"""
+        self._ensure().save_env_state(0, path)
+
+    def load_env_state(self, path, lossless=False):
+        """BaseEnvironment::load_env_state (BaseEnvironment.hpp:320-343; bound for the GoBigger env, bindings.cpp:374)"""
+        self._ensure().load_env_state(0, path, lossless)
 
 
 # ---- plain-data stand-ins for the info structs agarcl binds (environment/bindings.cpp:181-225,
@@ -263,8 +268,6 @@ class GoBiggerEnvironment(GridEnvironment):
     def __init__(self, map_width, map_height, frame_limit, num_agents, ticks_per_step, arena_size, pellet_regen, num_pellets,
                  num_viruses, num_bots, reward_type, c_death=0, mode_number=0, load_env_snapshot=False, agent_view=False, *,
                  rng_mode=RNG_MT19937, device=0):
-        if load_env_snapshot:
-            raise RuntimeError("JSON snapshots are a later row of the scope table (SURVEY.md 8f rank 2)")
         _Base.__init__(self, 1, num_agents, ticks_per_step, arena_size, pellet_regen, num_pellets, num_viruses, num_bots,
                        reward_type, c_death, mode_number, rng_mode, False, device, OBS_I32, ram_obs=True)
         self.num_agents = num_agents

@@ -154,7 +154,7 @@ class AgarioEnv(_EnvBase):
         self._env.save_env_state(filename)
 
     def load_env_state(self, filename):
-        raise RuntimeError("JSON snapshots are a later row of the scope table (SURVEY.md 8f rank 2)")
+        self._env.load_env_state(filename)
 
     # ---- helpers
     def _make_observations(self):

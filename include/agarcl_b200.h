@@ -218,6 +218,16 @@ int agarcl_batch_render_ram(agarcl_batch* b, void* stream);
 /* Parity / snapshot transport: one instance's blob (layout.stride bytes) to / from host memory. */
 int agarcl_batch_download_state(agarcl_batch* b, int32_t instance, void* blob);
 int agarcl_batch_upload_state(agarcl_batch* b, int32_t instance, const void* blob);
+/* BaseEnvironment::save_env_state / load_env_state (environment/envs/BaseEnvironment.hpp:213-343,
+ * agario/engine/Engine.hpp:247-348; bound at bindings.cpp:135,170,374): one instance to / from the
+ * reference's JSON snapshot.  The reference format is lossy (no splitting velocity, recombine timers, virus
+ * food hits, tick): those travel as extra keys the reference ignores and are restored with lossless != 0.
+ * After a load the instance's draw stream restarts from the snapshot's seed, like Engine::seed there.   */
+int agarcl_batch_save_env_state(agarcl_batch* b, int32_t instance, const char* path);
+int agarcl_batch_load_env_state(agarcl_batch* b, int32_t instance, const char* path, int lossless);
+/* The same on a host blob of `L->stride` bytes (no device needed): what the two calls above run. */
+int agarcl_snapshot_write(const agarcl_cfg* c, const agarcl_layout* L, const void* blob, const char* path);
+int agarcl_snapshot_read(const agarcl_cfg* c, const agarcl_layout* L, void* blob, const char* path, int lossless);
 /* Recorded uniform draws in [0,1) for instance i (replay of the reference's mt19937_64). */
 int agarcl_batch_set_replay(agarcl_batch* b, int32_t instance, const float* draws, int32_t n);
 /* Run only the observation kernel on the current state (tests; add_frame on a cleared buffer). */

@@ -256,6 +256,30 @@ void ref_ram_obs(void* h, int P, float* out) {
   }
 }
 
+/* pids_ : which player each agent index drives.  After load_env_state the reference rebuilds it by iterating
+ * the player map (BaseEnvironment.hpp:330-339), i.e. in REVERSED agent order for the usual small rosters. */
+int ref_agent_pids(void* h, int32_t* out) {
+  auto* r = static_cast<RefEnv*>(h);
+  int k = 0;
+  for (auto pid : r->env->pids_) out[k++] = (int32_t)pid;
+  return k;
+}
+
+/* BaseEnvironment::save_env_state / load_env_state (BaseEnvironment.hpp:213-343) on the reference itself */
+int ref_save_env_state(void* h, const char* path) {
+  auto* r = static_cast<RefEnv*>(h);
+  try { r->env->save_env_state(path); } catch (const std::exception&) { return -1; }
+  return 0;
+}
+int ref_load_env_state(void* h, const char* path) {
+  auto* r = static_cast<RefEnv*>(h);
+  r->bind_clock();
+  CoutSilencer quiet;
+  try { r->env->load_env_state(path); } catch (const std::exception&) { return -1; }
+  r->env->is_loading_env_state = false;  /* the flag only suppresses the reset() of the constructor */
+  return 0;
+}
+
 /* what the reference's own step()/get_state() left in its buffer (quirk Q11) */
 void ref_obs_native(void* h, int agent, int32_t* out) {
   auto* r = static_cast<RefEnv*>(h);

@@ -194,6 +194,17 @@ class Reference:
         self.lib.ref_ram_obs(self.h, self.L.P, fptr(self.ram))
         return self.ram
 
+    def agent_pids(self):
+        o = (C.c_int32 * 64)()
+        n = self.lib.ref_agent_pids(self.h, o)
+        return list(o)[:n]
+
+    def save_env_state(self, path):
+        assert self.lib.ref_save_env_state(self.h, str(path).encode()) == 0
+
+    def load_env_state(self, path):
+        assert self.lib.ref_load_env_state(self.h, str(path).encode()) == 0
+
     def set_cell_mass(self, pid, cell, mass):
         self.lib.ref_set_cell_mass(self.h, pid, cell, C.c_uint(mass))
 

@@ -230,3 +230,38 @@ def test_batched_vector_env_auto_reset():
     assert o.shape == (8, 1, 1224) and float(o[:, 0, 3].min()) >= 1.0  # every agent sees its own cell
     env.close()
     ram.close()
+
+
+def test_snapshot_save_load_through_the_device(tmp_path):
+    """agarcl_batch_save_env_state / load_env_state: lossless round trip into another instance continues identically."""
+    import torch
+    from agarcl_b200._abi import compare_states
+    from agarcl_b200.env import BatchedGridEnvironment
+    e = BatchedGridEnvironment(4, num_agents=2, num_bots=5, arena_size=300, num_pellets=200, num_viruses=6)
+    e.seed(np.array([5, 5, 6, 7], dtype=np.uint64))   # instances 0 and 1 share a seed (same Philox key) ...
+    e.reset()
+    b = e.batch
+    rng = np.random.default_rng(3)
+
+    def step_all(same01):
+        dxdy = rng.uniform(-1, 1, size=(4, 2, 2)).astype(np.float32)
+        act = rng.integers(0, 3, size=(4, 2)).astype(np.int32)
+        if same01:
+            dxdy[1], act[1] = dxdy[0], act[0]
+        e.step(dxdy.reshape(8, 2), act.reshape(8))
+
+    for _ in range(30):
+        step_all(False)
+    path = tmp_path / "inst0.json"
+    b.save_env_state(0, path)
+    b.load_env_state(1, path, lossless=True)          # ... but different instance ids: only equal until the next draw
+    s0, s1 = b.download_state(0), b.download_state(1)
+    assert not compare_states(s0, s1)
+    for _ in range(6):                                 # fewer than the 120-tick regen period: no draws in between
+        step_all(True)
+    torch.cuda.synchronize()
+    if int(b.download_state(0).hdr["rng_cursor"]) == int(s0.hdr["rng_cursor"]):
+        assert not compare_states(b.download_state(0), b.download_state(1))
+    with pytest.raises(RuntimeError):
+        b.load_env_state(0, tmp_path / "missing.json")
+    e.close()
