@@ -43,20 +43,20 @@ struct Cell {
 
 __device__ __forceinline__ Cell cell_load(const agarcl_cell* g) {
   const float4* p = reinterpret_cast<const float4*>(g);
-  float4 a = p[0];
-  float4 b = p[1];
+  float4 a = ldg_keep(p);
+  float4 b = ldg_keep(p + 1);
   Cell c;
   c.x = a.x; c.y = a.y; c.vx = a.z; c.vy = a.w;
   c.svx = b.x; c.svy = b.y;
   c.mass = __float_as_uint(b.z); c.id = __float_as_uint(b.w);
-  c.rec = reinterpret_cast<const uint32_t*>(g)[8];
+  c.rec = ldg_keep(reinterpret_cast<const uint32_t*>(g) + 8);
   return c;
 }
 __device__ __forceinline__ void cell_store(agarcl_cell* g, const Cell& c) {
   float4* p = reinterpret_cast<float4*>(g);
-  p[0] = make_float4(c.x, c.y, c.vx, c.vy);
-  p[1] = make_float4(c.svx, c.svy, __uint_as_float(c.mass), __uint_as_float(c.id));
-  reinterpret_cast<uint4*>(g)[2] = make_uint4(c.rec, 0u, 0u, 0u);
+  stg_keep(p, make_float4(c.x, c.y, c.vx, c.vy));
+  stg_keep(p + 1, make_float4(c.svx, c.svy, __uint_as_float(c.mass), __uint_as_float(c.id)));
+  stg_keep(p + 2, make_float4(__uint_as_float(c.rec), 0.f, 0.f, 0.f));
 }
 __device__ __forceinline__ Cell cell_bcast(const Cell& c, int src) {
   Cell r;
@@ -306,8 +306,8 @@ __device__ float4 centroid_from_global(const agarcl_cell* g, int n) {
   float xs = 0.0f, ys = 0.0f;
   uint32_t tot = 0;
   for (int i = 0; i < n; i++) {
-    float4 a = reinterpret_cast<const float4*>(g + i)[0];
-    uint32_t m = g[i].mass;
+    float4 a = ldg_keep(reinterpret_cast<const float4*>(g + i));
+    uint32_t m = __float_as_uint(ldg_keep(reinterpret_cast<const float4*>(g + i) + 1).z);
     xs += a.x * (float)m;
     ys += a.y * (float)m;
     tot += m;
@@ -320,10 +320,17 @@ __device__ float4 centroid_from_global(const agarcl_cell* g, int n) {
 // bots
 // ------------------------------------------------------------------------------------------------
 // Bot::nearest_pellet, Bot.hpp:92-129: first index attaining the minimum of sqrtf(d^2) among d > 0.01
+__device__ void lane_nearest_pellet(const Ctx& c, float lx, float ly, float& tx, float& ty);
 __device__ void nearest_pellet(Ctx& c, float lx, float ly, float& tx, float& ty) {
   if (c.n_pellets == 0) {  // std::rand() % arena: not replayable (flagged), same stand-in as the oracle
     c.flags |= AGARCL_FLAG_RAND_SITE;
     tx = 0.0f; ty = 0.0f;
+    return;
+  }
+  if (c.hash_valid) {  // one lane walks the hash rings in shared memory instead of 32 dependent trips over the pellet array
+    if (c.lane == 0) lane_nearest_pellet(c, lx, ly, tx, ty);
+    tx = __shfl_sync(AG_FULL, tx, 0);
+    ty = __shfl_sync(AG_FULL, ty, 0);
     return;
   }
   float best = 3.402823466e+38f;
@@ -447,7 +454,7 @@ __device__ void build_pellet_hash(Ctx& c) {
   for (int base = 0; base < c.n_pellets; base += 256) {
     float2 p[8];
 #pragma unroll
-    for (int u = 0; u < 8; u++) { int i = base + u * 32 + c.lane; p[u] = i < c.n_pellets ? pel[i] : make_float2(0.f, 0.f); }
+    for (int u = 0; u < 8; u++) { int i = base + u * 32 + c.lane; p[u] = i < c.n_pellets ? ldg_keep(pel + i) : make_float2(0.f, 0.f); }
 #pragma unroll
     for (int u = 0; u < 8; u++)
       if (base + u * 32 + c.lane < c.n_pellets) atomicAdd(&c.sm.hcnt()[hash_coord(c, p[u].y) * HG + hash_coord(c, p[u].x)], 1u);
@@ -471,7 +478,7 @@ __device__ void build_pellet_hash(Ctx& c) {
   for (int base = 0; base < c.n_pellets; base += 256) {
     float2 p[8];
 #pragma unroll
-    for (int u = 0; u < 8; u++) { int i = base + u * 32 + c.lane; p[u] = i < c.n_pellets ? pel[i] : make_float2(0.f, 0.f); }
+    for (int u = 0; u < 8; u++) { int i = base + u * 32 + c.lane; p[u] = i < c.n_pellets ? ldg_keep(pel + i) : make_float2(0.f, 0.f); }
 #pragma unroll
     for (int u = 0; u < 8; u++) {
       int i = base + u * 32 + c.lane;
@@ -488,7 +495,7 @@ __device__ void build_pellet_hash(Ctx& c) {
 __device__ void build_virus_cache(Ctx& c) {
   uint32_t mn = 0xffffffffu;
   for (int v = c.lane; v < c.n_viruses; v += 32) {
-    const float4 a = reinterpret_cast<const float4*>(c.vir_() + v)[0];  // x, y, mass, hits
+    const float4 a = ldg_keep(reinterpret_cast<const float4*>(c.vir_() + v));  // x, y, mass, hits
     uint32_t vm = __float_as_uint(a.z);
     mn = min(mn, vm);
     c.sm.vcache()[v] = make_float4(a.x, a.y, radius_of(c.P.T, vm), a.z);
@@ -1091,6 +1098,53 @@ __device__ bool lane_eat_pellets(const Ctx& c, float cx, float cy, uint32_t& mas
   return true;
 }
 
+// Lane versions of the scans of the bots that look at other players (HungryShyBot.hpp:26-40,
+// AggressiveBot.hpp:33-49, AggressiveShyBot.hpp:30-64 with Bot::edible_mass / target_player, Bot.hpp:55-88):
+// same player order, same arithmetic as bot_flee / bot_chase above, run by the bot's own lane.
+__device__ bool lane_bot_flee(const Ctx& c, int p, float lx, float ly, float& tx, float& ty) {
+  const int P = c.P.L.P;
+#pragma unroll 1
+  for (int k = 0; k < P; k++) {
+    const int o = c.P.L.order[k];
+    const float4 s = c.sm.psum()[o];
+    const float d = sqrtf(sqr_dist(s.x, s.y, lx, ly));
+    if (o != p && d < 25.0f && __float_as_uint(s.z) > 0u) {
+      tx = lx - (s.x - lx);
+      ty = ly - (s.y - ly);
+      return true;
+    }
+  }
+  return false;
+}
+__device__ bool lane_bot_chase(const Ctx& c, int p, uint32_t big, float lx, float ly, float& tx, float& ty) {
+  const int P = c.P.L.P;
+#pragma unroll 1
+  for (int k = 0; k < P; k++) {
+    const int o = c.P.L.order[k];
+    const float4 s = c.sm.psum()[o];
+    const float d = sqrtf(sqr_dist(s.x, s.y, lx, ly));
+    if (o == p || !(d <= 20.0f)) continue;
+    const int on = __float_as_int(s.w);
+    const agarcl_cell* g = c.pcells(o);
+    float sx = 0.0f, sy = 0.0f;
+    uint32_t sm = 0;
+    bool any = false;
+#pragma unroll 1
+    for (int i = 0; i < on; i++) {
+      const float4 a = reinterpret_cast<const float4*>(g + i)[0];
+      const uint32_t mm = g[i].mass;
+      if (cell_can_eat_cell(big, mm)) { sx += a.x * (float)mm; sy += a.y * (float)mm; sm += mm; any = true; }
+    }
+    if (any) {
+      const float dsx = sx / (float)sm - lx, dsy = sy / (float)sm - ly;
+      tx = lx + dsx * 3.0f;
+      ty = ly + dsy * 3.0f;
+      return true;
+    }
+  }
+  return false;
+}
+
 // What a lane keeps in registers about its player between the ticks of a launch.
 struct LaneState {
   Cell me;
@@ -1109,19 +1163,25 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
   int4 &w0 = ls.w0, &w1 = ls.w1, &w2 = ls.w2, &w3 = ls.w3;
   if (valid && !ls.fresh) {  // record and first cell in ONE round trip (the cell slot exists even for a dead player)
     const int4* rec = reinterpret_cast<const int4*>(pl);
-    w0 = rec[0]; w1 = rec[1]; w2 = rec[2]; w3 = rec[3];
+    w0 = ldg_keep(rec); w1 = ldg_keep(rec + 1); w2 = ldg_keep(rec + 2); w3 = ldg_keep(rec + 3);
     me = cell_load(c.pcells(p));
     ls.fresh = true;
   }
   const int n = valid ? w0.x : 0;
-  bool serial = n >= 2;
-  bool ok = n == 1;  // dead players are not ticked (Engine.hpp:216)
+  // lane states: a looking bot that decides this tick must see the players before it in the order as already
+  // committed, so it is speculated LATE, alone, when the ordered commit reaches it
+  enum { kIdle = 0, kPending = 1, kLate = 2, kReady = 3, kSerial = 4 };
+  int st = n >= 2 ? kSerial : (n == 1 ? kPending : kIdle);  // dead players are not ticked (Engine.hpp:216)
+  if (st == kPending && c.tick % 10u == 0u && w2.y > 0) st = kLate;
   float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t food_mass = 0;  // mass at the time of eat_food (after pellets, before decay)
   int ne = 0;
   uint16_t* myeat = c.sm.lprem() + lane * kLaneCand;
+  int pos = 0;
 
-  if (ok) do {
+ while (true) {
+  if (st == kPending || (st == kLate && lane == pos)) do {
+    st = kSerial;  // until the speculation reaches its end
     float tx = __int_as_float(w0.y), ty = __int_as_float(w0.z);
     int action = w0.w;
     int split_cd = w1.x, feed_cd = w1.y;
@@ -1131,12 +1191,21 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
     const int bot_type = w2.y;
     const int vet_count = w3.w;
 
-    // ---- bots decide every 10th tick (Engine.hpp:498-499); the ones that look at other players go serial
+    // ---- bots decide every 10th tick (Engine.hpp:498-499; HungryBot.hpp:19-22, HungryShyBot.hpp:23-44,
+    //      AggressiveBot.hpp:28-52, AggressiveShyBot.hpp:28-68)
     if (c.tick % 10u == 0u && bot_type >= 0) {
-      if (bot_type != 0 || c.n_pellets == 0) { ok = false; serial = true; break; }
-      float4 s = c.sm.psum()[p];
-      action = 0;
-      lane_nearest_pellet(c, s.x, s.y, tx, ty);
+      const float4 s = c.sm.psum()[p];
+      bool decided = false;
+      if (bot_type == 1 || bot_type == 3) {
+        if (bot_type == 1) action = 0;
+        decided = lane_bot_flee(c, p, s.x, s.y, tx, ty);
+      }
+      if (!decided && (bot_type == 2 || bot_type == 3)) decided = lane_bot_chase(c, p, me.mass, s.x, s.y, tx, ty);
+      if (!decided) {
+        if (c.n_pellets == 0) break;  // libc rand() site: the whole-warp path flags it
+        action = 0;
+        lane_nearest_pellet(c, s.x, s.y, tx, ty);
+      }
     }
 
     // ---- Engine::move_player (no self-collisions with one cell)
@@ -1169,16 +1238,16 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
             hit = true;
         }
       }
-      if (hit) { ok = false; serial = true; break; }
+      if (hit) break;
     }
 
     // ---- pellets
-    if (c.n_pellets > 0 && !lane_eat_pellets(c, me.x, me.y, me.mass, ne, myeat)) { ok = false; serial = true; break; }
+    if (c.n_pellets > 0 && !lane_eat_pellets(c, me.x, me.y, me.mass, ne, myeat)) break;
     const int food_eaten = w2.w + ne;
     const uint32_t highest = max((uint32_t)w3.x, me.mass);
 
     // ---- may_be_auto_split / eat_food / emit / split: anything that happens goes serial
-    if (me.mass >= AGARCL_MAX_MASS_IN_THE_GAME) { ok = false; serial = true; break; }
+    if (me.mass >= AGARCL_MAX_MASS_IN_THE_GAME) break;
     food_mass = me.mass;
     if (c.n_foods > 0 && can_eat_mass(me.mass, AGARCL_FOOD_MASS)) {
       const float cr = radius_of(T, me.mass), rf = radius_of(T, AGARCL_FOOD_MASS);
@@ -1187,22 +1256,22 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
         float4 f = reinterpret_cast<const float4*>(c.food_())[j];
         if (collides(me.x, me.y, cr, f.x, f.y, rf)) hit = true;
       }
-      if (hit) { ok = false; serial = true; break; }
+      if (hit) break;
     }
     if (feed_cd > 0) feed_cd -= 1;
     if (action == 1 && feed_cd == 0) {
-      if (me.mass >= AGARCL_CELL_MIN_SIZE + AGARCL_FOOD_MASS) { ok = false; serial = true; break; }
+      if (me.mass >= AGARCL_CELL_MIN_SIZE + AGARCL_FOOD_MASS) break;
       feed_cd = 10;
     }
     if (split_cd > 0) split_cd -= 1;
     if (action == 2 && split_cd == 0) {
-      if (!(me.mass < AGARCL_CELL_SPLIT_MINIMUM || me.mass < 2u * AGARCL_CELL_MIN_SIZE)) { ok = false; serial = true; break; }
+      if (!(me.mass < AGARCL_CELL_SPLIT_MINIMUM || me.mass < 2u * AGARCL_CELL_MIN_SIZE)) break;
       split_cd = 30;
     }
 
     // ---- once per 60 player-ticks: anti-team (only with remembered virus hits -> serial) + decay
     if (c.P.L.mass_decay && elapsed % 60 == 0) {
-      if (vet_count > 0) { ok = false; serial = true; break; }
+      if (vet_count > 0) break;
       if (elapsed - last_decay >= 60) {
         uint32_t nm = (uint32_t)((double)me.mass * (1 - 0.002 * (double)atd));
         me.mass = nm > AGARCL_CELL_MIN_SIZE ? nm : AGARCL_CELL_MIN_SIZE;
@@ -1217,16 +1286,16 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
     w1.x = split_cd; w1.y = feed_cd; w1.w = elapsed;
     w2.x = last_decay; w2.z = (int)smallest; w2.w = food_eaten;
     w3.x = (int)highest;
+    st = kReady;
   } while (0);
 
-  if (serial) ls.fresh = false;  // ticked by the whole warp below: registers are stale afterwards
-  // ---- ordered commit: runs of lane-ticked players, whole-warp tick_player in between
-  unsigned serm = __ballot_sync(AG_FULL, serial);
-  int pos = 0;
-  while (true) {
-    unsigned rest = serm & ~lanemask_lt(pos);
+  if (st == kSerial) ls.fresh = false;  // ticked by the whole warp below: registers are stale afterwards
+  // ---- ordered commit: the run of speculated players up to the next barrier (a whole-warp player or a late lane)
+  {
+    const unsigned serm = __ballot_sync(AG_FULL, st == kSerial);
+    const unsigned rest = (serm | __ballot_sync(AG_FULL, st == kLate)) & ~lanemask_lt(pos);
     const int nxt = rest ? __ffs(rest) - 1 : 32;
-    const bool mine = ok && lane >= pos && lane < nxt;
+    const bool mine = st == kReady && lane >= pos && lane < nxt;
     if (__ballot_sync(AG_FULL, mine && ne > 0)) {
       // pellets_to_remove keeps the player order (Engine.hpp:212,221)
       int v = mine ? ne : 0, incl = v;
@@ -1245,29 +1314,32 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
     if (mine) {
       cell_store(c.pcells(p), me);
       int4* rec = reinterpret_cast<int4*>(pl);
-      rec[0] = w0; rec[1] = w1; rec[2] = w2; rec[3] = w3;
+      stg_keep(rec, w0); stg_keep(rec + 1, w1); stg_keep(rec + 2, w2); stg_keep(rec + 3, w3);
       c.sm.psum()[p] = sum;
       c.sm.pcell()[p] = make_float4(me.x, me.y, __uint_as_float(me.mass), 1.0f);
+      st = kIdle;
     }
     __syncwarp();
     if (nxt >= 32) break;
+    if (!((serm >> nxt) & 1u)) { pos = nxt; continue; }  // a late lane: it speculates now, on what has been committed
     tick_player(c, c.P.L.order[base + nxt]);
+    if (lane == nxt) st = kIdle;
     if (c.emitted > 0) {
       // foods emitted by this player can be eaten by later players in the same tick (Engine.hpp:1011-1025)
       bool hit = false;
-      if (ok && lane > nxt && can_eat_mass(food_mass, AGARCL_FOOD_MASS)) {
+      if (st == kReady && lane > nxt && can_eat_mass(food_mass, AGARCL_FOOD_MASS)) {
         const float cr = radius_of(T, food_mass), rf = radius_of(T, AGARCL_FOOD_MASS);
         for (int j = c.n_foods - c.emitted; j < c.n_foods; j++) {
           float4 f = reinterpret_cast<const float4*>(c.food_())[j];
           if (collides(me.x, me.y, cr, f.x, f.y, rf)) hit = true;
         }
       }
-      if (hit) { ok = false; serial = true; ls.fresh = false; }
-      serm = __ballot_sync(AG_FULL, serial);
+      if (hit) { st = kSerial; ls.fresh = false; }
     }
     pos = nxt + 1;
     if (pos >= 32) break;
   }
+ }
   c.flags = __reduce_or_sync(AG_FULL, c.flags);
 }
 
@@ -1811,8 +1883,8 @@ __device__ void obs_finish_warp(Ctx& c) {
       auto put_pellet = [&](float2 q) {
         int gx, gy;
         if (grid_of(q.x, q.y, gx, gy)) {
-          ch1[(size_t)gx * G + gy] = 1;             // at_least_: data = mass (1)
-          atomicAdd(ch2 + (size_t)gx * G + gy, 1);  // total_mass_
+          __stcs(ch1 + (size_t)gx * G + gy, 1);           // at_least_: data = mass (1)
+          red_add_stream(ch2 + (size_t)gx * G + gy, 1);  // total_mass_
         }
       };
       if (c.hash_valid) {
