@@ -42,6 +42,7 @@ struct agarcl_batch {
   float* d_replay = nullptr;
   uint64_t* d_seeds = nullptr;
   uint8_t* d_mask = nullptr;
+  uint32_t* d_tickets = nullptr;  // k_step's ticket counter pair (self-rewinding)
   float *d_lut_radius = nullptr, *d_lut_speed = nullptr, *d_lut_split = nullptr;
   std::vector<uint64_t> seeds;
   ag::Luts T;
@@ -99,6 +100,7 @@ static void fill_sim_params(const agarcl_batch* b, ag::SimParams& P) {
   P.dones = b->d_dones;
   P.before = b->d_before;
   P.replay = b->d_replay;
+  P.tickets = b->d_tickets;
   P.N = b->N;
   P.instance_base = b->cfg.instance_base;
   P.mode = b->cfg.mode_number;
@@ -119,6 +121,8 @@ static void fill_sim_params(const agarcl_batch* b, ag::SimParams& P) {
   P.obs = nullptr;
   P.zero_vec_per_agent = 0; P.zero_skip_vec = 0; P.agent_stride_vec = 0;
   P.obs_finish = 0; P.obs_G = b->G; P.obs_C = b->C;
+  P.zero_chunks = 0;
+  if (const char* e = std::getenv("AGARCL_ZERO_CHUNKS")) P.zero_chunks = std::atoi(e);
   P.observe_cells = b->cfg.observe_cells; P.observe_others = b->cfg.observe_others;
   P.observe_viruses = b->cfg.observe_viruses; P.observe_pellets = b->cfg.observe_pellets;
 }
@@ -135,7 +139,8 @@ static bool fuse_obs_clear(const agarcl_batch* b, ag::SimParams& P, int frame) {
   P.agent_stride_vec = (uint32_t)((size_t)b->frames * b->C * plane / 16);
   // the whole observation in the engine-tick kernel: int32, rows of whole 16-byte vectors, masks fit the scratch
   P.obs_finish = (b->fuse_clear >= 2 && b->cfg.obs_dtype == AGARCL_OBS_I32 && b->G % 4 == 0 &&
-                  (size_t)2 * b->G * 4 <= (size_t)(b->so.vcache - b->so.cellref)) ? 1 : 0;
+                  (size_t)b->G * 4 <= (size_t)ag::kZeroTileBytes &&  // one row of channel 0 = one bulk store from the ones tile
+                  (size_t)b->G * 4 <= (size_t)(b->so.vcache - b->so.cellref)) ? 1 : 0;
   return true;
 }
 
@@ -163,7 +168,7 @@ extern "C" int agarcl_batch_destroy(agarcl_batch* b) {
   if (!b) return AGARCL_OK;
   cudaFree(b->d_ram);
   cudaFree(b->d_state); cudaFree(b->d_obs); cudaFree(b->d_rewards); cudaFree(b->d_dones); cudaFree(b->d_before);
-  cudaFree(b->d_dxdy); cudaFree(b->d_act); cudaFree(b->d_replay); cudaFree(b->d_seeds); cudaFree(b->d_mask);
+  cudaFree(b->d_dxdy); cudaFree(b->d_act); cudaFree(b->d_replay); cudaFree(b->d_seeds); cudaFree(b->d_mask); cudaFree(b->d_tickets);
   cudaFree(b->d_lut_radius); cudaFree(b->d_lut_speed); cudaFree(b->d_lut_split);
   for (cudaEvent_t e : b->ev) cudaEventDestroy(e);
   delete b;
@@ -199,7 +204,7 @@ extern "C" int agarcl_batch_create(const agarcl_cfg* cfg, agarcl_batch** out) {
   int hg = (int)std::floor(std::sqrt((double)L.cap_pellets / 3.0));
   b->HG = hg < 4 ? 4 : (hg > 64 ? 64 : hg);
   b->smem_per_warp = ag::make_smem_offsets(L, b->HG, b->so);
-  if ((size_t)b->smem_per_warp * ag::kWarpsPerCta + ag::kZeroTileBytes > 200 * 1024) {
+  if ((size_t)b->smem_per_warp * ag::kWarpsPerCta + 2 * ag::kZeroTileBytes > 200 * 1024) {
     delete b;
     return agarcl_set_error(AGARCL_ERR_INVALID, "configuration needs %u B of shared memory per instance (too many pellets/viruses)", b->smem_per_warp);
   }
@@ -221,6 +226,8 @@ extern "C" int agarcl_batch_create(const agarcl_cfg* cfg, agarcl_batch** out) {
   ALLOC(b->d_act, NA * sizeof(int32_t));
   ALLOC(b->d_seeds, (size_t)b->N * sizeof(uint64_t));
   ALLOC(b->d_mask, (size_t)b->N);
+  ALLOC(b->d_tickets, 2 * sizeof(uint32_t));
+  cudaMemset(b->d_tickets, 0, 2 * sizeof(uint32_t));
   if (L.cap_replay > 0) ALLOC(b->d_replay, (size_t)b->N * L.cap_replay * sizeof(float));
   if (cfg->ram_obs) {
     ALLOC(b->d_ram, (size_t)b->N * L.P * AGARCL_RAM_RECORD * sizeof(float));

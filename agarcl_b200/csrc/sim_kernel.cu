@@ -1834,8 +1834,7 @@ __device__ void obs_finish_warp(Ctx& c) {
   const SimParams& P = c.P;
   const int G = P.obs_G, lane = c.lane, A = P.L.A, Pn = P.L.P;
   const size_t plane = (size_t)G * G;
-  int32_t* xmask = reinterpret_cast<int32_t*>(c.sm.cellref());  // [G] then [G]: the collision scratch is free now
-  int32_t* ymask = xmask + G;
+  int32_t* yrow = reinterpret_cast<int32_t*>(c.sm.cellref());  // [G]: the collision scratch is free now
   // the zero vectors of this instance must have landed before anything is scattered onto them
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   __syncwarp();
@@ -1844,6 +1843,9 @@ __device__ void obs_finish_warp(Ctx& c) {
   const float centering = (float)(G / 2.0);
   const float2* pel = reinterpret_cast<const float2*>(c.pel_());
   const agarcl_virus* vir = c.vir_();
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const uint32_t ones_tile = (uint32_t)__cvta_generic_to_shared(smem_raw + kZeroTileBytes);
+  const uint32_t yrow_s = (uint32_t)__cvta_generic_to_shared(yrow);
   for (int a = 0; a < A; a++) {
     int32_t* out = reinterpret_cast<int32_t*>(P.obs) + ((size_t)c.inst_local * A + a) * ((size_t)P.agent_stride_vec * 4u);
     const float4 s = c.sm.psum()[a];
@@ -1851,25 +1853,31 @@ __device__ void obs_finish_warp(Ctx& c) {
     const uint32_t tot = __float_as_uint(s.z);
     const int n = __float_as_int(s.w);
     const float view = clamp_std((float)(2u * tot), 100.0f, 300.0f);
-    for (int i = lane; i < G; i += 32) {  // _grid_to_world + _in_bounds, separable in i (x) and j (y)
-      float d = (float)i - centering;
-      float wx = px + d * view / (float)G, wy = py + d * view / (float)G;
-      xmask[i] = (0 <= wx && wx < W) ? 0 : -1;
-      ymask[i] = (0 <= wy && wy < W) ? 0 : -1;
+    // Channel 0 (_mark_out_of_bounds) is separable: cell (i, j) = xmask[i] | ymask[j] (_grid_to_world + _in_bounds).
+    // Row i is therefore either all -1 (x out of bounds) or THE row of y masks: the row lives in shared
+    // memory and every lane queues its rows as TMA bulk stores, from it or from the CTA's all-ones tile.
+    if (a > 0) {  // the previous agent's stores may still be reading the row
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
     }
+    for (int j = lane; j < G; j += 32) {
+      float wy = py + ((float)j - centering) * view / (float)G;
+      yrow[j] = (0 <= wy && wy < W) ? 0 : -1;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     {
-      const int vec_per_row = G / 4, nvec0 = (int)(plane / 4);
-      int4* out4 = reinterpret_cast<int4*>(out);
-#pragma unroll 4
-      for (int v = lane; v < nvec0; v += 32) {
-        int i = v / vec_per_row, jv = v - i * vec_per_row;
-        int4 ym = reinterpret_cast<const int4*>(ymask)[jv];
-        int xm = xmask[i];
-        __stcs(out4 + v, make_int4(ym.x | xm, ym.y | xm, ym.z | xm, ym.w | xm));
+      uint64_t zpolicy;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(zpolicy));
+      const uint32_t row_bytes = (uint32_t)G * 4u;
+      for (int i = lane; i < G; i += 32) {
+        float wx = px + ((float)i - centering) * view / (float)G;
+        const uint32_t src = (0 <= wx && wx < W) ? yrow_s : ones_tile;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                     :: "l"(out + (size_t)i * G), "r"(src), "r"(row_bytes), "l"(zpolicy) : "memory");
       }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    __syncwarp();  // the masks are rewritten for the next agent
     if (n == 0) continue;  // dead agent: nothing lands inside the grid
     auto grid_of = [&](float x, float y, int& gx, int& gy) -> bool {
       gx = to_int_x86((float)G * (x - px) / view + centering);
@@ -2028,21 +2036,12 @@ __device__ void respawn_player(Ctx& c, int p, uint32_t k) {
 // ------------------------------------------------------------------------------------------------
 // kernel: BaseEnvironment::step for one instance per warp
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_step(const __grid_constant__ SimParams P) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int inst = blockIdx.x * kWarpsPerCta + warp;
-  // the CTA's all-zero tile (first kZeroTileBytes of shared memory), made visible to the async proxy
-  for (int i = threadIdx.x; i < kZeroTileBytes / 16; i += kWarpsPerCta * 32)
-    reinterpret_cast<int4*>(smem_raw)[i] = make_int4(0, 0, 0, 0);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
-  if (inst >= P.N) return;
+__device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_raw, const int inst, const int warp, const int lane) {
   Ctx c(P);
   c.lane = lane;
   c.inst_local = inst;
   c.blob = P.state + (size_t)inst * P.L.stride;
-  c.sm.base = smem_raw + kZeroTileBytes + (size_t)warp * P.smem_per_warp;
+  c.sm.base = smem_raw + 2 * kZeroTileBytes + (size_t)warp * P.smem_per_warp;
   c.sm.o = &P.so;
   agarcl_inst_hdr* hdr = reinterpret_cast<agarcl_inst_hdr*>(c.blob + P.L.off_hdr);
   c.tick = hdr->tick; c.next_id = hdr->next_cell_id;
@@ -2087,9 +2086,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_step(const __grid_cons
   c.zagent = 0u; c.zoff = 0u;
   {
     const uint32_t total = P.zero_vec_per_agent * (uint32_t)A;
-    // with the finish fused, the clear is done one tick early so that it has drained before the scatter
-    const int zt = P.n_ticks - (P.obs_finish && P.n_ticks > 1 ? 1 : 0);
-    const uint32_t chunks = (uint32_t)(4 * (zt > 0 ? zt : 1));
+    // spread evenly over all ticks: bursts of stores slow the ticks' own loads down more than the
+    // last pieces cost the finish in waiting (measured, tools/exp_chunks.sh)
+    const uint32_t chunks = P.zero_chunks > 0 ? (uint32_t)P.zero_chunks : (uint32_t)(4 * (P.n_ticks > 0 ? P.n_ticks : 1));
     c.zchunk = (total + chunks - 1u) / chunks;
   }
   LaneState ls;
@@ -2149,23 +2148,61 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_step(const __grid_cons
   }
 
   c.flags = __reduce_or_sync(AG_FULL, c.flags);
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the zero tile outlives its readers
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the source tiles / rows outlive their readers
   if (lane == 0) {
     hdr->tick = c.tick; hdr->next_cell_id = c.next_id;
     hdr->n_pellets = c.n_pellets; hdr->n_viruses = c.n_viruses; hdr->n_foods = c.n_foods;
     hdr->rng_cursor = c.cursor; hdr->flags = c.flags; hdr->done_sticky = c.done_sticky;
   }
+  __syncwarp();
+}
+
+// PERSISTENT grid: as many CTAs as fit on the GPU at once (launch_step), every warp draws the next
+// instance from a global ticket counter until the batch is exhausted.  Instances differ a lot in cost
+// (bot-decision ticks, split players, eat events); with a ticket a warp that finishes early just takes
+// another instance instead of idling until the slowest warp of its CTA is done, and there is no tail wave.
+// tickets[0] = next instance, tickets[1] = warps that have left; the last warp to leave rewinds both,
+// so the next launch on the stream (stream order) starts from zero again without a memset.
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_step(const __grid_constant__ SimParams P) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the CTA's all-zero tile (first kZeroTileBytes of shared memory), made visible to the async proxy
+  // ... and its all-ones (-1) tile right behind it, source of the out-of-bounds rows of channel 0
+  for (int i = threadIdx.x; i < kZeroTileBytes / 16; i += kWarpsPerCta * 32) {
+    reinterpret_cast<int4*>(smem_raw)[i] = make_int4(0, 0, 0, 0);
+    reinterpret_cast<int4*>(smem_raw + kZeroTileBytes)[i] = make_int4(-1, -1, -1, -1);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  while (true) {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(P.tickets, 1u);
+    t = __shfl_sync(AG_FULL, t, 0);
+    if (t >= (uint32_t)P.N) break;
+    step_instance(P, smem_raw, (int)t, warp, lane);
+  }
+  if (lane == 0) {
+    const uint32_t left = atomicAdd(P.tickets + 1, 1u);
+    if (left == gridDim.x * (uint32_t)kWarpsPerCta - 1u) { P.tickets[0] = 0u; P.tickets[1] = 0u; }
+  }
 }
 
 cudaError_t launch_step(const SimParams& P, cudaStream_t stream) {
-  int ctas = (P.N + kWarpsPerCta - 1) / kWarpsPerCta;
-  size_t smem = (size_t)kZeroTileBytes + (size_t)P.smem_per_warp * kWarpsPerCta;
+  size_t smem = (size_t)2 * kZeroTileBytes + (size_t)P.smem_per_warp * kWarpsPerCta;
   static size_t configured = 0;
-  if (smem > configured) {
+  static int resident = 0;  // CTAs the device holds at once (SMs x CTAs per SM) for `configured` bytes of shared memory
+  if (smem > configured || resident == 0) {
     cudaError_t e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
+    int dev = 0, sms = 0, per_sm = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step, kWarpsPerCta * 32, smem)) != cudaSuccess) return e;
+    resident = sms * (per_sm > 0 ? per_sm : 1);
   }
+  int ctas = (P.N + kWarpsPerCta - 1) / kWarpsPerCta;
+  if (ctas > resident) ctas = resident;
   k_step<<<ctas, kWarpsPerCta * 32, smem, stream>>>(P);
   return cudaGetLastError();
 }

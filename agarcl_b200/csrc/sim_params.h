@@ -32,6 +32,7 @@ struct SimParams {
   uint8_t* dones;          // [N*A]
   float* before;           // [N*A] masses<float>() at step begin (BaseEnvironment.hpp:92)
   const float* replay;     // [N*cap_replay] or nullptr
+  uint32_t* tickets;       // [2] persistent-grid work counter: next instance, warps that have left (k_step)
   int32_t N;
   int32_t instance_base;
   int32_t n_ticks;         // ticks to run in this launch
@@ -57,6 +58,7 @@ struct SimParams {
   // fused observation finish (int32, one frame): after the last tick each warp also writes channel 0
   // and scatters the entities of its instance, so the step is ONE kernel.  obs_finish == 0: k_obs does it.
   int32_t obs_finish, obs_G, obs_C;
+  int32_t zero_chunks;          // > 0: the clear is queued in this many pieces (4 per tick); 0: spread over the ticks
   int32_t observe_cells, observe_others, observe_viruses, observe_pellets;
 };
 

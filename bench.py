@@ -401,9 +401,12 @@ def main():
     ap.add_argument("--settle", type=int, default=100, help="untimed steps before warm-up so games are mid-play")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tps", type=int, default=None, help="diagnostic only: ticks per env-step (the workload's is 4)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.tps is not None:
+        WORKLOAD["ticks_per_step"] = args.tps
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)
