@@ -111,8 +111,6 @@ static void fill_sim_params(const agarcl_batch* b, ag::SimParams& P) {
   P.HG = b->HG;
   P.W = (float)b->cfg.arena_size;
   P.hash_scale = (float)b->HG / (float)b->cfg.arena_size;
-  P.q_scale = 65535.0f / (float)b->cfg.arena_size;
-  P.q_inv = (float)b->cfg.arena_size / 65535.0f;
   // initialize_pellet_grid / initialize_virus_grid: int((W + size - 1) / size) in fp32 (Engine.hpp:962-965,1207-1211)
   P.gw_pellet = (int)(((float)b->cfg.arena_size + 510.0f - 1.0f) / 510.0f);
   P.gw_virus = (int)(((float)b->cfg.arena_size + 25.0f - 1.0f) / 25.0f);
@@ -204,7 +202,7 @@ extern "C" int agarcl_batch_create(const agarcl_cfg* cfg, agarcl_batch** out) {
   int hg = (int)std::floor(std::sqrt((double)L.cap_pellets / 3.0));
   b->HG = hg < 4 ? 4 : (hg > 64 ? 64 : hg);
   b->smem_per_warp = ag::make_smem_offsets(L, b->HG, b->so);
-  if ((size_t)b->smem_per_warp * ag::kWarpsPerCta + 2 * ag::kZeroTileBytes > 200 * 1024) {
+  if ((size_t)b->smem_per_warp + 2 * ag::kZeroTileBytes > 227 * 1024) {
     delete b;
     return agarcl_set_error(AGARCL_ERR_INVALID, "configuration needs %u B of shared memory per instance (too many pellets/viruses)", b->smem_per_warp);
   }

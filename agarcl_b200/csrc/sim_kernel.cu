@@ -1,7 +1,7 @@
 // sim_kernel.cu — the engine tick for N lockstep instances, hand-written for sm_100a.
 //
 // Mapping: ONE WARP OWNS ONE GAME INSTANCE for a whole env-step (ticks_per_step ticks); a CTA is
-// kWarpsPerCta independent warps (no block barriers at all — only __syncwarp / shuffles / ballots).
+// up to kMaxWarpsPerCta independent warps (no block barriers — only __syncwarp / shuffles / ballots).
 //   * a player's cells live in REGISTERS, one cell per lane (<= 32 cells), for the whole of its
 //     Engine::tick_player; order-dependent reference semantics (Gauss-Seidel self-collision,
 //     swap-pop recombine, eat order) are replayed with ballots + shuffles instead of loops over memory;
@@ -104,6 +104,7 @@ struct Ctx {
   int nprem, nvrem;
   int emitted;          // foods appended by the last tick_player (Engine::emit_foods)
   bool hash_valid;      // the pellet hash in shared memory matches the pellet array
+  bool pel_dirty;       // the pellet array in shared memory differs from the blob's (written back when the warp leaves the instance)
   uint32_t min_vmass;   // smallest virus mass this tick (0xffffffff without viruses)
   uint32_t zagent, zoff, zchunk;  // fused observation clear: cursor (agent, vector) and vectors per chunk
   bool vc_valid;        // the virus cache in shared memory matches the virus array
@@ -336,7 +337,7 @@ __device__ void nearest_pellet(Ctx& c, float lx, float ly, float& tx, float& ty)
   float best = 3.402823466e+38f;
   uint32_t best_i = 0xffffffffu;
   for (int i = c.lane; i < c.n_pellets; i += 32) {
-    float2 p = reinterpret_cast<const float2*>(c.pel_())[i];
+    float2 p = c.sm.spel()[i];
     float d = sqrtf(sqr_dist(lx, ly, p.x, p.y));  // (other - this).norm()
     if (d < best && (double)d > 0.01) { best = d; best_i = (uint32_t)i; }
   }
@@ -347,7 +348,7 @@ __device__ void nearest_pellet(Ctx& c, float lx, float ly, float& tx, float& ty)
   uint32_t cand = (best == gbest && best_i != 0xffffffffu) ? best_i : 0xffffffffu;
   cand = warp_min_u32(cand);
   if (cand == 0xffffffffu) { tx = 0.0f; ty = 0.0f; return; }  // nothing qualified: Location() default
-  float2 p = reinterpret_cast<const float2*>(c.pel_())[cand];
+  float2 p = c.sm.spel()[cand];
   tx = p.x; ty = p.y;
 }
 
@@ -435,29 +436,14 @@ __device__ __forceinline__ int hash_coord(const Ctx& c, float v) {
   int h = (int)(v * c.P.hash_scale);
   return min(max(h, 0), c.P.HG - 1);
 }
-// Quantised copy of a pellet position (2 x 16 bits) kept next to its hash entry: the lane-per-player
-// scans filter on it from shared memory and touch the exact fp32 position in HBM/L2 only for the
-// few entries that can matter.  |x - dequant| < q_inv per axis, so sqrt(2) * q_inv bounds the distance error.
-__device__ __forceinline__ uint32_t quantize_xy(const Ctx& c, float x, float y) {
-  int qx = min(max((int)(x * c.P.q_scale), 0), 65535), qy = min(max((int)(y * c.P.q_scale), 0), 65535);
-  return (uint32_t)qx | ((uint32_t)qy << 16);
-}
-__device__ __forceinline__ float2 dequantize_xy(const Ctx& c, uint32_t q) {
-  return make_float2(((float)(q & 0xffffu) + 0.5f) * c.P.q_inv, ((float)(q >> 16) + 0.5f) * c.P.q_inv);
-}
 __device__ void build_pellet_hash(Ctx& c) {
   const int HG = c.P.HG, nc = HG * HG;
   for (int i = c.lane; i < nc; i += 32) c.sm.hcnt()[i] = 0u;
   __syncwarp();
-  // 8 independent loads in flight per lane: the two passes over the pellet array are latency, not bandwidth
-  const float2* pel = reinterpret_cast<const float2*>(c.pel_());
-  for (int base = 0; base < c.n_pellets; base += 256) {
-    float2 p[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) { int i = base + u * 32 + c.lane; p[u] = i < c.n_pellets ? ldg_keep(pel + i) : make_float2(0.f, 0.f); }
-#pragma unroll
-    for (int u = 0; u < 8; u++)
-      if (base + u * 32 + c.lane < c.n_pellets) atomicAdd(&c.sm.hcnt()[hash_coord(c, p[u].y) * HG + hash_coord(c, p[u].x)], 1u);
+  const float2* pel = c.sm.spel();
+  for (int i = c.lane; i < c.n_pellets; i += 32) {
+    float2 p = pel[i];
+    atomicAdd(&c.sm.hcnt()[hash_coord(c, p.y) * HG + hash_coord(c, p.x)], 1u);
   }
   __syncwarp();
   // exclusive scan over nc counters, 32 at a time
@@ -475,19 +461,10 @@ __device__ void build_pellet_hash(Ctx& c) {
     carry += __shfl_sync(AG_FULL, incl, 31);
   }
   __syncwarp();
-  for (int base = 0; base < c.n_pellets; base += 256) {
-    float2 p[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) { int i = base + u * 32 + c.lane; p[u] = i < c.n_pellets ? ldg_keep(pel + i) : make_float2(0.f, 0.f); }
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      int i = base + u * 32 + c.lane;
-      if (i < c.n_pellets) {
-        uint32_t pos = atomicAdd(&c.sm.hcnt()[hash_coord(c, p[u].y) * HG + hash_coord(c, p[u].x)], 1u);
-        c.sm.hsorted()[pos] = (uint16_t)i;
-        c.sm.hq()[pos] = quantize_xy(c, p[u].x, p[u].y);
-      }
-    }
+  for (int i = c.lane; i < c.n_pellets; i += 32) {
+    float2 p = pel[i];
+    uint32_t pos = atomicAdd(&c.sm.hcnt()[hash_coord(c, p.y) * HG + hash_coord(c, p.x)], 1u);
+    c.sm.hsorted()[pos] = (uint16_t)i;
   }
   __syncwarp();
   // now hcnt[k] = end of cell k; start of cell k = (k ? hcnt[k-1] : 0)
@@ -659,7 +636,7 @@ __device__ void tick_player(Ctx& c, int p) {
           if (j < e) {
             int idx = c.sm.hsorted()[j];
             if (idx != kHashDead) {
-              float2 q = reinterpret_cast<const float2*>(c.pel_())[idx];
+              float2 q = c.sm.spel()[idx];
               d2 = sqr_dist(cx, cy, q.x, q.y);
               int bx = (int)q.x / 510 - gx, by = (int)q.y / 510 - gy;
               cand = d2 <= Rc2 && bx >= -1 && bx <= 1 && by >= -1 && by <= 1;
@@ -707,7 +684,7 @@ __device__ void tick_player(Ctx& c, int p) {
               bool cand = false;
               float d2 = 0.f;
               if (idx < c.n_pellets) {
-                float2 q = reinterpret_cast<const float2*>(c.pel_())[idx];
+                float2 q = c.sm.spel()[idx];
                 d2 = sqr_dist(cx, cy, q.x, q.y);
                 cand = ((int)q.x / 510 == nx) && ((int)q.y / 510 == ny) && d2 <= Rf2;
               }
@@ -988,27 +965,26 @@ __device__ __forceinline__ void ring_visit(const Ctx& c, int hx, int hy, int r, 
   }
 }
 
-// Bot::nearest_pellet (Bot.hpp:92-129) by one lane.  Phase 1 walks rings of hash cells on the
-// QUANTISED positions (shared memory only) until no pellet outside the searched block can be nearer,
-// and yields an upper bound U of the true minimum; phase 2 evaluates exactly (fp32 position from
-// global memory, the reference's own comparison) the few entries whose quantised distance is within
-// the quantisation margin of U.  First index among equal sqrtf(d^2); d <= 0.01 is skipped as in the reference.
+// Bot::nearest_pellet (Bot.hpp:92-129) by one lane: walks rings of hash cells around the bot until no
+// pellet outside the searched block can be nearer than the best one found, evaluating every entry with
+// the reference's own comparison on the exact fp32 position (shared memory).  First index among equal
+// sqrtf(d^2); d <= 0.01 is skipped as in the reference.
 __device__ void lane_nearest_pellet(const Ctx& c, float lx, float ly, float& tx, float& ty) {
   const int HG = c.P.HG;
   const float cw = c.W / (float)HG;
-  const float M = 1.5f * c.P.q_inv;  // > sqrt(2) * q_inv
-  const float2* pel = reinterpret_cast<const float2*>(c.pel_());
+  const float2* pel = c.sm.spel();
   const int hx = hash_coord(c, lx), hy = hash_coord(c, ly);
   const float INF = 3.402823466e+38f;
-  float U = INF;
-  int rstop = HG - 1;
+  float best = INF;
+  uint32_t best_i = 0xffffffffu;
 #pragma unroll 1
   for (int r = 0; r < HG; r++) {
     ring_visit(c, hx, hy, r, [&](int j) {
-      if (c.sm.hsorted()[j] == (uint16_t)kHashDead) return;
-      float2 q = dequantize_xy(c, c.sm.hq()[j]);
-      float dq = sqrtf(sqr_dist(lx, ly, q.x, q.y));
-      if (dq > 0.01f + M) U = fminf(U, dq + M);  // certainly farther than 0.01: a true qualifier
+      uint32_t idx = c.sm.hsorted()[j];
+      if (idx == (uint32_t)kHashDead) return;
+      float2 q = pel[idx];
+      float d = sqrtf(sqr_dist(lx, ly, q.x, q.y));  // (other - this).norm()
+      if ((d < best || (d == best && idx < best_i)) && (double)d > 0.01) { best = d; best_i = idx; }
     });
     // every pellet outside the block lies beyond one of its sides (0.01 covers all fp32 rounding)
     const int x0 = hx - r, x1 = hx + r, y0 = hy - r, y1 = hy + r;
@@ -1017,22 +993,7 @@ __device__ void lane_nearest_pellet(const Ctx& c, float lx, float ly, float& tx,
     if (x1 < HG - 1) bound = fminf(bound, (float)(x1 + 1) * cw - lx);
     if (y0 > 0) bound = fminf(bound, ly - (float)y0 * cw);
     if (y1 < HG - 1) bound = fminf(bound, (float)(y1 + 1) * cw - ly);
-    if (bound == INF || U < bound - 0.01f) { rstop = r; break; }
-  }
-  float best = INF;
-  uint32_t best_i = 0xffffffffu;
-  const float lim = U + M;  // INF stays INF: then everything is evaluated exactly
-#pragma unroll 1
-  for (int r = 0; r <= rstop; r++) {
-    ring_visit(c, hx, hy, r, [&](int j) {
-      uint32_t idx = c.sm.hsorted()[j];
-      if (idx == (uint32_t)kHashDead) return;
-      float2 qq = dequantize_xy(c, c.sm.hq()[j]);
-      if (!(sqrtf(sqr_dist(lx, ly, qq.x, qq.y)) <= lim)) return;
-      float2 q = pel[idx];
-      float d = sqrtf(sqr_dist(lx, ly, q.x, q.y));  // (other - this).norm()
-      if ((d < best || (d == best && idx < best_i)) && (double)d > 0.01) { best = d; best_i = idx; }
-    });
+    if (bound == INF || best < bound - 0.01f) break;
   }
   if (best_i == 0xffffffffu) { tx = 0.0f; ty = 0.0f; return; }  // nothing qualified: Location() default
   float2 q = pel[best_i];
@@ -1041,17 +1002,15 @@ __device__ void lane_nearest_pellet(const Ctx& c, float lx, float ly, float& tx,
 
 // get_pellets_to_remove_and_increment_cells (Engine.hpp:976-1000) for one cell by one lane: the
 // candidates (same superset as the warp-wide path) are taken in the reference's order by repeated
-// selection of the next key.  Entries are pre-filtered on their quantised position in shared memory;
-// only possible candidates are read exactly.  false: too many candidates for a lane.
+// selection of the next key.  false: too many candidates for a lane.
 __device__ bool lane_eat_pellets(const Ctx& c, float cx, float cy, uint32_t& mass, int& ne, uint16_t* out) {
   const Luts& T = c.P.T;
   const int HG = c.P.HG;
-  const float2* pel = reinterpret_cast<const float2*>(c.pel_());
+  const float2* pel = c.sm.spel();
   const float rp = radius_of(T, 1u);
   const int gx = (int)cx / 510, gy = (int)cy / 510;
   const float Rc = fmax_std(radius_of(T, mass + (uint32_t)kCandCap), rp);
   const float Rc2 = Rc * Rc;
-  const float Rq = Rc + 1.5f * c.P.q_inv, Rq2 = Rq * Rq;
   const int hx0 = hash_coord(c, cx - Rc), hx1 = hash_coord(c, cx + Rc);
   const int hy0 = hash_coord(c, cy - Rc), hy1 = hash_coord(c, cy + Rc);
   uint32_t prev = 0u, newmass = mass;  // keys are kept +1 so that 0 means "none yet"
@@ -1067,14 +1026,13 @@ __device__ bool lane_eat_pellets(const Ctx& c, float cx, float cy, uint32_t& mas
       hash_range(c, hy * HG + hx0, hy * HG + hx1, s, e);
 #pragma unroll 1
       for (int j = s; j < e; j++) {
-        float2 qq = dequantize_xy(c, c.sm.hq()[j]);
-        if (!(sqr_dist(cx, cy, qq.x, qq.y) <= Rq2)) continue;
         uint32_t idx = c.sm.hsorted()[j];
         if (idx == (uint32_t)kHashDead) continue;
         float2 q = pel[idx];
         float d2 = sqr_dist(cx, cy, q.x, q.y);
+        if (!(d2 <= Rc2)) continue;
         int bx = (int)q.x / 510 - gx, by = (int)q.y / 510 - gy;
-        if (d2 <= Rc2 && bx >= -1 && bx <= 1 && by >= -1 && by <= 1) {
+        if (bx >= -1 && bx <= 1 && by >= -1 && by <= 1) {
           cnt++;
           uint32_t key = (((uint32_t)((bx + 1) * 3 + (by + 1)) << 16) | idx) + 1u;
           if (key > prev && key < best) { best = key; bestd2 = d2; }
@@ -1357,7 +1315,7 @@ __device__ __forceinline__ void hash_patch(Ctx& c, uint32_t from, uint32_t to, f
 __device__ void apply_removals(Ctx& c) {  // Engine.hpp:1002-1009,1253-1260 incl. stale/duplicate indices (Q4/Q5)
   if (c.nprem == 0 && c.nvrem == 0) return;
   if (c.lane == 0) {
-    float2* pel = reinterpret_cast<float2*>(c.pel_());
+    float2* pel = c.sm.spel();
     for (int k = 0; k < c.nprem; k++) {
       uint32_t idx = c.sm.prem()[k], size = (uint32_t)c.n_pellets;
       if (size == 0u) continue;
@@ -1383,6 +1341,7 @@ __device__ void apply_removals(Ctx& c) {  // Engine.hpp:1002-1009,1253-1260 incl
   c.n_pellets = __shfl_sync(AG_FULL, c.n_pellets, 0);
   c.n_viruses = __shfl_sync(AG_FULL, c.n_viruses, 0);
   if (c.nvrem > 0) c.vc_valid = false;
+  if (c.nprem > 0) c.pel_dirty = true;
   c.nprem = 0;
   c.nvrem = 0;
   __syncwarp();
@@ -1761,11 +1720,12 @@ __device__ void regen(Ctx& c) {
     for (int k = c.lane; k < dp; k += 32) {
       float x, y;
       random_location_at(c, c.cursor + 2u * (uint32_t)k, r, x, y);
-      if (c.n_pellets + k < c.P.L.cap_pellets) reinterpret_cast<float2*>(c.pel_())[c.n_pellets + k] = make_float2(x, y);
+      if (c.n_pellets + k < c.P.L.cap_pellets) c.sm.spel()[c.n_pellets + k] = make_float2(x, y);
     }
     c.cursor += 2u * (uint32_t)dp;
     c.n_pellets = min(c.n_pellets + dp, c.P.L.cap_pellets);
     c.hash_valid = false;
+    c.pel_dirty = true;
   }
   int dv = c.P.target_viruses - c.n_viruses;
   if (dv > 0) {
@@ -1841,7 +1801,7 @@ __device__ void obs_finish_warp(Ctx& c) {
   __threadfence();
   const float W = c.W;
   const float centering = (float)(G / 2.0);
-  const float2* pel = reinterpret_cast<const float2*>(c.pel_());
+  const float2* pel = c.sm.spel();
   const agarcl_virus* vir = c.vir_();
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t ones_tile = (uint32_t)__cvta_generic_to_shared(smem_raw + kZeroTileBytes);
@@ -2013,7 +1973,7 @@ __device__ void respawn_player(Ctx& c, int p, uint32_t k) {
   float r25 = radius_of(c.P.T, AGARCL_CELL_MIN_SIZE);
   float x, y;
   if (c.n_pellets > 0 && c.P.L.squared_pellets) {
-    float2 p0 = reinterpret_cast<const float2*>(c.pel_())[0];
+    float2 p0 = c.sm.spel()[0];
     x = fmin_std(p0.x + 2.0f * r25, c.W - r25);
     y = fmin_std(p0.y + 2.0f * r25, c.W - r25);
   } else {
@@ -2036,13 +1996,24 @@ __device__ void respawn_player(Ctx& c, int p, uint32_t k) {
 // ------------------------------------------------------------------------------------------------
 // kernel: BaseEnvironment::step for one instance per warp
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_raw, const int inst, const int warp, const int lane) {
+__device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_raw, const int inst, const int warp, const int lane,
+                                              uint32_t& mbar_phase) {
   Ctx c(P);
   c.lane = lane;
   c.inst_local = inst;
   c.blob = P.state + (size_t)inst * P.L.stride;
   c.sm.base = smem_raw + 2 * kZeroTileBytes + (size_t)warp * P.smem_per_warp;
   c.sm.o = &P.so;
+  // the pellet array comes in by one TMA bulk load (whole capacity: the count is not known yet); everything
+  // below that does not touch pellets overlaps with it, build_pellet_hash is its first consumer
+  const uint32_t pel_bytes = ((uint32_t)P.L.cap_pellets * 8u + 15u) & ~15u;  // pellets are the blob's last array: the pad is inside its stride
+  if (lane == 0) {
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(c.sm.mbar());
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(c.sm.spel());
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(pel_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(dst), "l"(c.pel_()), "r"(pel_bytes), "r"(mb), "l"(l2_evict_last()) : "memory");
+  }
   agarcl_inst_hdr* hdr = reinterpret_cast<agarcl_inst_hdr*>(c.blob + P.L.off_hdr);
   c.tick = hdr->tick; c.next_id = hdr->next_cell_id;
   c.n_pellets = hdr->n_pellets; c.n_viruses = hdr->n_viruses; c.n_foods = hdr->n_foods;
@@ -2050,6 +2021,7 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
   c.done_sticky = hdr->done_sticky;
   c.nprem = 0; c.nvrem = 0;
   c.emitted = 0; c.hash_valid = false; c.vc_valid = false; c.lanes_dirty = false; c.min_vmass = 0xffffffffu;
+  c.pel_dirty = false;
   c.W = P.W;
   const int Pn = P.L.P, A = P.L.A;
 
@@ -2090,6 +2062,15 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
     // last pieces cost the finish in waiting (measured, tools/exp_chunks.sh)
     const uint32_t chunks = P.zero_chunks > 0 ? (uint32_t)P.zero_chunks : (uint32_t)(4 * (P.n_ticks > 0 ? P.n_ticks : 1));
     c.zchunk = (total + chunks - 1u) / chunks;
+  }
+  {  // the pellets have arrived (all lanes observe the phase flip: their later reads are ordered behind it)
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(c.sm.mbar());
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(mb), "r"(mbar_phase) : "memory");
+    }
+    mbar_phase ^= 1u;
   }
   LaneState ls;
   ls.fresh = false;
@@ -2148,7 +2129,20 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
   }
 
   c.flags = __reduce_or_sync(AG_FULL, c.flags);
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the source tiles / rows outlive their readers
+  if (c.pel_dirty) {  // pellets eaten / spawned: the shared-memory array is the truth, one bulk store puts it back
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t src = (uint32_t)__cvta_generic_to_shared(c.sm.spel());
+      const uint32_t bytes = min(((uint32_t)c.n_pellets * 8u + 15u) & ~15u, pel_bytes);
+      if (bytes > 0u) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                     :: "l"(c.pel_()), "r"(src), "r"(bytes), "l"(l2_evict_last()) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the source tiles / rows / pellets outlive their readers
   if (lane == 0) {
     hdr->tick = c.tick; hdr->next_cell_id = c.next_id;
     hdr->n_pellets = c.n_pellets; hdr->n_viruses = c.n_viruses; hdr->n_foods = c.n_foods;
@@ -2163,47 +2157,54 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
 // another instance instead of idling until the slowest warp of its CTA is done, and there is no tail wave.
 // tickets[0] = next instance, tickets[1] = warps that have left; the last warp to leave rewinds both,
 // so the next launch on the stream (stream order) starts from zero again without a memset.
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_step(const __grid_constant__ SimParams P) {
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_constant__ SimParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // the CTA's all-zero tile (first kZeroTileBytes of shared memory), made visible to the async proxy
   // ... and its all-ones (-1) tile right behind it, source of the out-of-bounds rows of channel 0
-  for (int i = threadIdx.x; i < kZeroTileBytes / 16; i += kWarpsPerCta * 32) {
+  for (int i = threadIdx.x; i < kZeroTileBytes / 16; i += blockDim.x) {
     reinterpret_cast<int4*>(smem_raw)[i] = make_int4(0, 0, 0, 0);
     reinterpret_cast<int4*>(smem_raw + kZeroTileBytes)[i] = make_int4(-1, -1, -1, -1);
   }
+  if (lane == 0) {  // this warp's mbarrier (one arrival: the lane that queues the pellet load)
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(smem_raw + 2 * kZeroTileBytes + (size_t)warp * P.smem_per_warp + P.so.mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
+  uint32_t mbar_phase = 0u;
   while (true) {
     uint32_t t = 0;
     if (lane == 0) t = atomicAdd(P.tickets, 1u);
     t = __shfl_sync(AG_FULL, t, 0);
     if (t >= (uint32_t)P.N) break;
-    step_instance(P, smem_raw, (int)t, warp, lane);
+    step_instance(P, smem_raw, (int)t, warp, lane, mbar_phase);
   }
   if (lane == 0) {
     const uint32_t left = atomicAdd(P.tickets + 1, 1u);
-    if (left == gridDim.x * (uint32_t)kWarpsPerCta - 1u) { P.tickets[0] = 0u; P.tickets[1] = 0u; }
+    if (left == gridDim.x * (blockDim.x >> 5) - 1u) { P.tickets[0] = 0u; P.tickets[1] = 0u; }
   }
 }
 
+// One CTA per SM, as many warps (= concurrent instances) as the shared memory holds, at most kMaxWarpsPerCta.
 cudaError_t launch_step(const SimParams& P, cudaStream_t stream) {
-  size_t smem = (size_t)2 * kZeroTileBytes + (size_t)P.smem_per_warp * kWarpsPerCta;
-  static size_t configured = 0;
-  static int resident = 0;  // CTAs the device holds at once (SMs x CTAs per SM) for `configured` bytes of shared memory
-  if (smem > configured || resident == 0) {
-    cudaError_t e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-    int dev = 0, sms = 0, per_sm = 0;
+  static int sms = 0, smem_max = 0;
+  cudaError_t e;
+  if (sms == 0) {
+    int dev = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step, kWarpsPerCta * 32, smem)) != cudaSuccess) return e;
-    resident = sms * (per_sm > 0 ? per_sm : 1);
+    if ((e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) return e;
   }
-  int ctas = (P.N + kWarpsPerCta - 1) / kWarpsPerCta;
-  if (ctas > resident) ctas = resident;
-  k_step<<<ctas, kWarpsPerCta * 32, smem, stream>>>(P);
+  int warps = (int)(((size_t)smem_max - 2 * kZeroTileBytes) / P.smem_per_warp);
+  if (warps > kMaxWarpsPerCta) warps = kMaxWarpsPerCta;
+  if (warps < 1) return cudaErrorInvalidConfiguration;
+  const size_t smem = (size_t)2 * kZeroTileBytes + (size_t)P.smem_per_warp * warps;
+  int ctas = (P.N + warps - 1) / warps;
+  if (ctas > sms) ctas = sms;
+  k_step<<<ctas, warps * 32, smem, stream>>>(P);
   return cudaGetLastError();
 }
 

@@ -7,7 +7,8 @@
 
 namespace ag {
 
-constexpr int kWarpsPerCta = 7;       // one warp owns one game instance; a CTA is 7 independent warps, 2 CTAs / SM (14 warps, 144 registers)
+constexpr int kMaxWarpsPerCta = 13;   // one warp owns one game instance; ONE persistent CTA per SM of as many independent warps as the
+                                      // shared memory holds (13 x 16.9 KB at 1000 pellets), <= 157 registers per thread
 constexpr int kPremCap = 192;         // pellets_to_remove entries per tick (Engine.hpp:212)
 constexpr int kVremCap = 32;          // viruses_to_remove entries per tick (Engine.hpp:213)
 constexpr int kCandCap = 32;          // pellet candidates resolved in registers per cell
@@ -19,7 +20,7 @@ constexpr int kCellRefCap = 256;      // total live cells per instance handled b
 
 // byte offsets of one warp's shared-memory arrays (sim_shared.cuh)
 struct SmemOff {
-  uint32_t hcnt, hsorted, hq, cellref, rows, strip, hitq, snap, vcache, psum, pcell, pairs, reskeys, resorder, cand, prem, vrem, lprem;
+  uint32_t hcnt, hsorted, spel, mbar, cellref, rows, strip, hitq, snap, vcache, psum, pcell, pairs, reskeys, resorder, cand, prem, vrem, lprem;
 };
 
 struct SimParams {
@@ -43,7 +44,6 @@ struct SimParams {
   int32_t HG;              // spatial hash is HG x HG over the arena
   float W;                 // arena width == height
   float hash_scale;        // HG / W
-  float q_scale, q_inv;    // pellet quantisation: q = int(x * q_scale), x ~ (q + 0.5) * q_inv, |error| < q_inv per axis
   int32_t gw_pellet;       // reference pellet bucket grid width (bucket 510, Engine.hpp:962-965)
   int32_t gw_virus;        // reference virus bucket grid width (bucket 25, Engine.hpp:1207-1211)
   uint32_t smem_per_warp;  // bytes

@@ -22,7 +22,11 @@ inline uint32_t make_smem_offsets(const agarcl_layout& L, int HG, SmemOff& o) {
   // pellet spatial hash: persists across the ticks of a launch, patched on removals
   o.hcnt = p;    p += ag_align16((uint32_t)(HG * HG) * 4u);        // u32 [HG*HG]   counts -> offsets -> cell ends
   o.hsorted = p; p += ag_align16((uint32_t)L.cap_pellets * 2u);    // u16 [cap_pellets] pellet indices grouped by hash cell
-  o.hq = p;      p += ag_align16((uint32_t)L.cap_pellets * 4u);    // u32 [cap_pellets] same order: position quantised to 2 x 16 bits
+  // the instance's pellet array itself (index order), brought in by ONE TMA bulk load when the warp takes the
+  // instance and written back by one bulk store if a pellet was eaten or spawned: every pellet access of the
+  // ticks and of the observation scatter is a shared-memory access, not a trip to L2 / HBM behind the obs stores
+  o.spel = p;    p += ag_align16((uint32_t)L.cap_pellets * 8u);    // float2 [cap_pellets]
+  o.mbar = p;    p += 16u;                                         // u64 mbarrier of the bulk load
   // players_collision
   o.cellref = p; p += ag_align16(kCellRefCap * 2u);                // u16 [kCellRefCap] (player << 8 | cell) in snapshot order
   o.rows = p;    p += ag_align16(kCellRefCap * 2u);                // i16 [kCellRefCap] strip id
@@ -49,7 +53,7 @@ struct WarpSmem {
   uint8_t* base;
   const SmemOff* o;
 #define AG_SM(name, type) __device__ __forceinline__ type* name() const { return reinterpret_cast<type*>(base + o->name); }
-  AG_SM(hcnt, uint32_t) AG_SM(hsorted, uint16_t) AG_SM(hq, uint32_t)
+  AG_SM(hcnt, uint32_t) AG_SM(hsorted, uint16_t) AG_SM(spel, float2) AG_SM(mbar, uint64_t)
   AG_SM(cellref, uint16_t) AG_SM(rows, int16_t) AG_SM(strip, uint16_t) AG_SM(hitq, uint16_t) AG_SM(snap, float4)
   AG_SM(vcache, float4) AG_SM(psum, float4) AG_SM(pcell, float4)
   AG_SM(pairs, uint4) AG_SM(reskeys, uint16_t) AG_SM(resorder, uint16_t)
