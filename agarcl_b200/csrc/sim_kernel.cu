@@ -1795,6 +1795,7 @@ __device__ void obs_finish_warp(Ctx& c) {
   const int G = P.obs_G, lane = c.lane, A = P.L.A, Pn = P.L.P;
   const size_t plane = (size_t)G * G;
   int32_t* yrow = reinterpret_cast<int32_t*>(c.sm.cellref());  // [G]: the collision scratch is free now
+  if (!c.vc_valid && P.observe_viruses) { build_virus_cache(c); c.vc_valid = true; }
   // the zero vectors of this instance must have landed before anything is scattered onto them
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   __syncwarp();
@@ -1802,7 +1803,6 @@ __device__ void obs_finish_warp(Ctx& c) {
   const float W = c.W;
   const float centering = (float)(G / 2.0);
   const float2* pel = c.sm.spel();
-  const agarcl_virus* vir = c.vir_();
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t ones_tile = (uint32_t)__cvta_generic_to_shared(smem_raw + kZeroTileBytes);
   const uint32_t yrow_s = (uint32_t)__cvta_generic_to_shared(yrow);
@@ -1881,27 +1881,35 @@ __device__ void obs_finish_warp(Ctx& c) {
       int32_t* ch3 = out + (size_t)(channel + 1) * plane;
       int32_t* ch4 = out + (size_t)(channel + 2) * plane;
       const int nv = c.n_viruses;
+      const float4* vc = c.sm.vcache();  // x, y, radius, mass bits: valid (rebuilt above if a virus changed in the last tick)
       for (int k = lane; k < nv; k += 32) {
         int gx, gy;
-        if (grid_of(vir[k].x, vir[k].y, gx, gy)) {
-          atomicAdd(ch4 + (size_t)gx * G + gy, (int)vir[k].mass);
+        const float4 vk = vc[k];
+        if (grid_of(vk.x, vk.y, gx, gy)) {
+          atomicAdd(ch4 + (size_t)gx * G + gy, (int)__float_as_uint(vk.w));
           // at_least_ keeps the LAST writer in index order: write only if no later virus shares the cell
           bool last = true;
           for (int k2 = k + 1; k2 < nv; k2++) {
             int hx, hy;
-            if (grid_of(vir[k2].x, vir[k2].y, hx, hy) && hx == gx && hy == gy) { last = false; break; }
+            if (grid_of(vc[k2].x, vc[k2].y, hx, hy) && hx == gx && hy == gy) { last = false; break; }
           }
-          if (last) ch3[(size_t)gx * G + gy] = (int)vir[k].mass;
+          if (last) ch3[(size_t)gx * G + gy] = (int)__float_as_uint(vk.w);
         }
       }
       channel += 2;
     }
     if (P.observe_cells) {
       int32_t* ch5 = out + (size_t)(channel + 1) * plane;
-      const agarcl_cell* pc = c.pcells(a);
-      for (int k = lane; k < n; k += 32) {
+      const float4 pcv = c.sm.pcell()[a];
+      if (n == 1 && pcv.w >= 0.0f) {  // lane-ticked one-cell agent: its cell is in shared memory
         int gx, gy;
-        if (grid_of(pc[k].x, pc[k].y, gx, gy)) atomicAdd(ch5 + (size_t)gx * G + gy, (int)pc[k].mass);
+        if (lane == 0 && grid_of(pcv.x, pcv.y, gx, gy)) atomicAdd(ch5 + (size_t)gx * G + gy, (int)__float_as_uint(pcv.z));
+      } else {
+        const agarcl_cell* pc = c.pcells(a);
+        for (int k = lane; k < n; k += 32) {
+          int gx, gy;
+          if (grid_of(pc[k].x, pc[k].y, gx, gy)) atomicAdd(ch5 + (size_t)gx * G + gy, (int)pc[k].mass);
+        }
       }
       channel += 1;
     }
@@ -2015,23 +2023,87 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
                  :: "r"(dst), "l"(c.pel_()), "r"(pel_bytes), "r"(mb), "l"(l2_evict_last()) : "memory");
   }
   agarcl_inst_hdr* hdr = reinterpret_cast<agarcl_inst_hdr*>(c.blob + P.L.off_hdr);
-  c.tick = hdr->tick; c.next_id = hdr->next_cell_id;
-  c.n_pellets = hdr->n_pellets; c.n_viruses = hdr->n_viruses; c.n_foods = hdr->n_foods;
-  c.cursor = hdr->rng_cursor; c.flags = hdr->flags;
-  c.done_sticky = hdr->done_sticky;
+  const int Pn = P.L.P, A = P.L.A;
+  // ---- ONE round trip to memory for everything else the step starts from.  Under the observation's store
+  // stream a trip to HBM costs microseconds, so nothing here may depend on the value of another load: the
+  // header, this lane's player record + first cell (block 0 of the player order), two virus records per
+  // lane and the agents' actions are all requested before the first of them is used.
+  LaneState ls;
+  const int k0 = lane;
+  const bool valid0 = k0 < Pn;
+  const int p0 = valid0 ? P.L.order[k0] : 0;
+  {
+    const int4* rec = reinterpret_cast<const int4*>(c.players_() + p0);
+    ls.w0 = ldg_keep(rec); ls.w1 = ldg_keep(rec + 1); ls.w2 = ldg_keep(rec + 2); ls.w3 = ldg_keep(rec + 3);
+    ls.me = cell_load(c.pcells(p0));
+    ls.fresh = valid0;
+  }
+  float4 vpre[2];
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const int v = lane + 32 * j;
+    vpre[j] = v < P.L.cap_viruses ? ldg_keep(reinterpret_cast<const float4*>(c.vir_() + v)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // actions: for agent `lane` (take_actions below) and for the agent this lane holds in registers
+  float adx = 0.f, ady = 0.f, hdx = 0.f, hdy = 0.f;
+  int aact = 0, hact = 0;
+  if (P.do_begin) {
+    if (lane < A) {
+      const size_t gi = (size_t)inst * A + lane;
+      adx = P.dxdy[2 * gi]; ady = P.dxdy[2 * gi + 1]; aact = P.act[gi];
+    }
+    if (valid0 && p0 < A) {
+      const size_t gi = (size_t)inst * A + p0;
+      hdx = P.dxdy[2 * gi]; hdy = P.dxdy[2 * gi + 1]; hact = P.act[gi];
+    }
+  }
+  {
+    const int4 h0 = ldg_keep(reinterpret_cast<const int4*>(hdr));
+    const int4 h1 = ldg_keep(reinterpret_cast<const int4*>(hdr) + 1);
+    const int4 h2 = ldg_keep(reinterpret_cast<const int4*>(hdr) + 2);
+    c.tick = (uint32_t)h0.x; c.next_id = (uint32_t)h0.y; c.n_pellets = h0.z; c.n_viruses = h0.w;
+    c.n_foods = h1.x; c.cursor = (uint32_t)h1.y; c.flags = (uint32_t)h1.z; c.done_sticky = (uint32_t)h2.y;
+  }
   c.nprem = 0; c.nvrem = 0;
   c.emitted = 0; c.hash_valid = false; c.vc_valid = false; c.lanes_dirty = false; c.min_vmass = 0xffffffffu;
   c.pel_dirty = false;
   c.W = P.W;
-  const int Pn = P.L.P, A = P.L.A;
 
-  // player summaries (centroid, mass, count)
-  for (int base = 0; base < Pn; base += 32) {
-    int p = base + lane;
-    if (p < Pn) {
+  // player summaries (centroid, mass, count): from the registers for a one-cell player
+  if (valid0) {
+    const int n = ls.w0.x;
+    float4 sum;
+    if (n == 1) {
+      const float fm = (float)ls.me.mass;
+      sum = make_float4((0.0f + ls.me.x * fm) / fm, (0.0f + ls.me.y * fm) / fm, __uint_as_float(ls.me.mass), __int_as_float(1));
+    } else {
+      sum = centroid_from_global(c.pcells(p0), n);
+    }
+    c.sm.psum()[p0] = sum;
+    c.sm.pcell()[p0] = make_float4(0.f, 0.f, 0.f, -1.0f);
+  }
+  for (int base = 32; base < Pn; base += 32) {
+    const int k = base + lane;
+    if (k < Pn) {
+      const int p = P.L.order[k];
       c.sm.psum()[p] = centroid_from_global(c.pcells(p), c.players_()[p].n_cells);
       c.sm.pcell()[p] = make_float4(0.f, 0.f, 0.f, -1.0f);
     }
+  }
+  // virus cache straight from the prefetched records (build_virus_cache redoes it whenever a virus changes)
+  if (c.n_viruses <= 64) {
+    uint32_t mn = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int v = lane + 32 * j;
+      if (v < c.n_viruses) {
+        const uint32_t vm = __float_as_uint(vpre[j].z);
+        mn = min(mn, vm);
+        c.sm.vcache()[v] = make_float4(vpre[j].x, vpre[j].y, radius_of(P.T, vm), vpre[j].z);
+      }
+    }
+    c.min_vmass = warp_min_u32(mn);
+    c.vc_valid = true;
   }
   __syncwarp();
 
@@ -2045,11 +2117,19 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
       P.before[gi] = (float)m;
       if (__float_as_int(s.w) > 0) {
         agarcl_player* pl = c.players_() + a;
-        pl->target_x = s.x + P.dxdy[2 * gi] * 10.0f;
-        pl->target_y = s.y + P.dxdy[2 * gi + 1] * 10.0f;
-        pl->action = P.act[gi];
+        if (a >= 32) { adx = P.dxdy[2 * gi]; ady = P.dxdy[2 * gi + 1]; aact = P.act[gi]; }
+        pl->target_x = s.x + adx * 10.0f;
+        pl->target_y = s.y + ady * 10.0f;
+        pl->action = aact;
       }
       if (P.mode == 3 && m >= 23000u) c.done_sticky = 1u;
+    }
+    // the lane that holds an agent's record in registers applies the same action to its copy
+    if (valid0 && p0 < A && ls.w0.x > 0) {
+      const float4 s = c.sm.psum()[p0];
+      ls.w0.y = __float_as_int(s.x + hdx * 10.0f);
+      ls.w0.z = __float_as_int(s.y + hdy * 10.0f);
+      ls.w0.w = hact;
     }
     c.done_sticky = __reduce_or_sync(AG_FULL, c.done_sticky);
     __syncwarp();
@@ -2072,11 +2152,6 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
     }
     mbar_phase ^= 1u;
   }
-  LaneState ls;
-  ls.fresh = false;
-  ls.w0 = ls.w1 = ls.w2 = ls.w3 = make_int4(0, 0, 0, 0);
-  ls.me.x = ls.me.y = ls.me.vx = ls.me.vy = ls.me.svx = ls.me.svy = 0.0f;
-  ls.me.mass = 0; ls.me.id = 0; ls.me.rec = 0;
   for (int t = 0; t < P.n_ticks; t++) engine_tick(c, ls);
   zero_chunk(c, 0xffffffffu);  // whatever is left (n_ticks == 0, rounding)
 
