@@ -187,7 +187,7 @@ def _ref_pool():
     return lib, make_cfg(**WORKLOAD)
 
 
-def cpu_reference_rate(seconds_target=12.0, threads=None):
+def _cpu_reference_rate_inproc(seconds_target=12.0, threads=None):
     """Times the reference's own CPU implementation of the path on a bounded sample of the workload."""
     lib, cfg = _ref_pool()
     if lib is None:
@@ -201,39 +201,73 @@ def cpu_reference_rate(seconds_target=12.0, threads=None):
     sec = lib.ref_pool_run(pool, threads, steps, 1)
     lib.ref_pool_destroy(pool)
     return dict(value=inst * steps / sec, unit=UNIT, cores=threads, kind="reference",
-                sample=f"{inst} instances x {steps} env-steps each (forced add_frame per step) on {threads} threads of the "
-                       f"reference ThreadPool, {sec:.1f} s")
+                sample=f"{inst} instances x {steps} env-steps each (forced add_frame per step), one reference engine per "
+                       f"thread on {threads} host threads, {sec:.1f} s")
+
+
+def _reference_arm_inproc(steps, warmup, gpus, threads=None):
+    lib, cfg = _ref_pool()
+    if lib is None:
+        return {"impl": "reference", "unavailable": "oracle/_ref/libagarcl_ref.so missing and /root/reference absent"}
+    threads = threads or (os.cpu_count() or 1)
+    inst = 2 * threads
+    pool = C.c_void_p(lib.ref_pool_create(C.byref(cfg), inst, 1234))
+    sec = lib.ref_pool_run(pool, threads, 3, 1)
+    rate = inst * 3 / sec
+    per_step = max(2, int(0.5 * rate / inst))  # env-steps per instance in one bench "step" (about 0.5 s)
+    for _ in range(warmup):
+        lib.ref_pool_run(pool, threads, per_step, 1)
+    t = 0.0
+    for _ in range(steps):
+        t += lib.ref_pool_run(pool, threads, per_step, 1)
+    lib.ref_pool_destroy(pool)
+    value = inst * per_step * steps / t
+    sample = (f"each step = {inst} instances x {per_step} env-steps (forced add_frame per step), one reference engine per thread "
+              f"on {threads} host threads")
+    return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": 1e3 * t / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def _ref_child(what, steps, warmup, gpus, threads, budget_s):
+    """The reference engine is third-party code with process-wide globals (Ball::global_id, libc rand()): it runs in a
+    CHILD process under a watchdog so that a hang or crash in it can never take the bench line down; one retry on
+    half the threads."""
+    last = "no attempt"
+    for attempt in range(2):
+        cmd = [sys.executable, os.path.abspath(__file__), "--_refchild", what, "--steps", str(steps), "--warmup", str(warmup),
+               "--gpus", str(gpus), "--_threads", str(threads)]
+        try:
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=budget_s)
+            lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+            if out.returncode == 0 and lines:
+                return json.loads(lines[-1])
+            last = f"child rc={out.returncode}: {out.stderr.strip()[-200:]}"
+        except subprocess.TimeoutExpired:
+            last = f"child exceeded {budget_s}s on {threads} threads"
+        threads = max(1, threads // 2)
+    return {"failed": last}
+
+
+def cpu_reference_rate():
+    r = _ref_child("cpu_baseline", 0, 0, 1, os.cpu_count() or 1, 120)
+    if r is None or "failed" in r:
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {r and r['failed']}"}
+    return r
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    lib, cfg = _ref_pool()
-    if lib is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libagarcl_ref.so missing and /root/reference absent"}))
-        return 0
-    threads = os.cpu_count() or 1
-    inst = 2 * threads
-    pool = C.c_void_p(lib.ref_pool_create(C.byref(cfg), inst, 1234))
-    sec = lib.ref_pool_run(pool, threads, 3, 1)
-    rate = inst * 3 / sec
-    per_step = max(2, int(0.5 * rate / inst))  # env-steps per instance in one bench "step" (about 0.5 s)
-    for _ in range(args.warmup):
-        lib.ref_pool_run(pool, threads, per_step, 1)
-    t = 0.0
-    for _ in range(args.steps):
-        t += lib.ref_pool_run(pool, threads, per_step, 1)
-    lib.ref_pool_destroy(pool)
-    value = inst * per_step * args.steps / t
-    sample = f"each step = {inst} instances x {per_step} env-steps on {threads} host threads (reference ThreadPool)"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME, "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+    budget = 60 + 2 * (args.steps + args.warmup + 3)  # each step is sized to about 0.5 s
+    line = _ref_child("arm", args.steps, args.warmup, args.gpus, os.cpu_count() or 1, budget)
+    if "failed" in line:
+        line = {"impl": "reference", "unavailable": line["failed"]}
     print(json.dumps(line))
     return 0
 
@@ -378,10 +412,7 @@ def run_ours(args):
                         "steps": Ke, "note": "agarcl_batch_step_host: pinned host actions in, int32 obs + rewards + dones out"},
                 "gpu_launches": launches, "clocks": clocks}
         if not args.no_cpu_baseline and world == 1:
-            try:
-                line["cpu_baseline"] = cpu_reference_rate()
-            except Exception as ex:  # the checker must never take the bench down
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+            line["cpu_baseline"] = cpu_reference_rate()  # child process under a watchdog: never takes the bench down
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))
@@ -402,7 +433,15 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tps", type=int, default=None, help="diagnostic only: ticks per env-step (the workload's is 4)")
+    ap.add_argument("--_refchild", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--_threads", type=int, default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args._refchild == "cpu_baseline":
+        print(json.dumps(_cpu_reference_rate_inproc(threads=args._threads)))
+        return 0
+    if args._refchild == "arm":
+        print(json.dumps(_reference_arm_inproc(args.steps, args.warmup, args.gpus, threads=args._threads)))
+        return 0
     if args.warmup < 3:
         args.warmup = 3
     if args.tps is not None:

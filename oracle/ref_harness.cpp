@@ -73,7 +73,6 @@
 #include <atomic>
 
 #include "../include/agarcl_b200.h"
-#include <utils/thread-pool.h> /* the reference's own pool (utils/thread-pool.h:21), CPU baseline only */
 
 /* ---- deviation 2: simulation clock standing in for steady_clock ------------------------- */
 namespace std { namespace chrono {
@@ -418,9 +417,13 @@ void ref_umap_order(const int* keys, int n, int* out) {
 }
 
 /* ------------------------------------------------------------------------------------------
- * CPU baseline: M independent GridEnvironment instances over the reference's own ThreadPool
- * (utils/thread-pool.h:21), the pattern of BotEvaluator::run (agario/bots/benchmark.cpp:146-168):
- * one thunk per instance runs `steps` env-steps of (random actions, step(), forced add_frame).
+ * CPU baseline: M independent GridEnvironment instances, one engine per worker thread with no
+ * exchange — the pattern of BotEvaluator::run (agario/bots/benchmark.cpp:146-168): each work item
+ * runs `steps` env-steps of (random actions, step(), forced add_frame) of one instance.
+ * The workers are plain std::threads drawing instances from an atomic counter, NOT the reference's
+ * utils/thread-pool.h: that pool starts its workers while the constructor is still growing the
+ * vectors they index (thread-pool.cpp:18-26) and its destructor signals the dispatcher without the
+ * mutex (:112-114, a lost wake-up) — it hung a whole bench run on a 16-thread box.
  * Environments are built once (ref_pool_create) so that only stepping is timed.
  * ------------------------------------------------------------------------------------------ */
 struct RefPool {
@@ -472,9 +475,14 @@ double ref_pool_run(void* h, int threads, int steps, int with_obs) {
   };
   auto t0 = std::chrono::high_resolution_clock::now();
   {
-    ThreadPool pool((size_t)threads);
-    for (int i = 0; i < (int)p->envs.size(); i++) pool.schedule([&work, i]() { work(i); });
-    pool.wait();
+    std::atomic<int> next(0);
+    const int n = (int)p->envs.size();
+    std::vector<std::thread> workers;
+    for (int t = 0; t < threads; t++)
+      workers.emplace_back([&work, &next, n]() {
+        for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) work(i);
+      });
+    for (auto& w : workers) w.join();
   }
   auto t1 = std::chrono::high_resolution_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
