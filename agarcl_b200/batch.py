@@ -46,6 +46,7 @@ class Batch:
 
     def close(self):
         if self._h:
+            self._mirror = None
             _lib.lib().agarcl_batch_destroy(self._h)
             self._h = _vp()
 
@@ -96,6 +97,36 @@ class Batch:
     def step_host(self, dxdy, act, obs_out=None, rewards_out=None, dones_out=None):
         f = lambda a: a.ctypes.data_as(_vp) if a is not None else None
         _lib.check(_lib.lib().agarcl_batch_step_host(self._h, f(dxdy), f(act), f(obs_out), f(rewards_out), f(dones_out)))
+
+    # ---- host-resident observation mirror (include/agarcl_b200.h, mirror.cu)
+    def mirror(self):
+        """numpy view [N*A, C*frames, G, G] of the library-owned pinned host mirror of the observation (read-only)"""
+        if getattr(self, "_mirror", None) is None:
+            p, shape, dt = _vp(), (C.c_int64 * 4)(), C.c_int32()
+            _lib.check(_lib.lib().agarcl_batch_mirror(self._h, C.byref(p), C.byref(shape), C.byref(dt)))
+            n = int(np.prod(list(shape)))
+            ct = C.c_int16 if dt.value == OBS_I16 else C.c_int32
+            a = np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), shape=(n,)).reshape(tuple(int(x) for x in shape))
+            a.flags.writeable = False
+            self._mirror = a
+        return self._mirror
+
+    def sync_mirror(self, stream=0):
+        self.mirror()
+        _lib.check(_lib.lib().agarcl_batch_sync_mirror(self._h, _vp(stream)))
+        return self._mirror
+
+    def step_mirror(self, dxdy, act, rewards_out=None, dones_out=None):
+        """take_actions (host arrays) + step + mirror sync; returns the mirror view"""
+        f = lambda a: a.ctypes.data_as(_vp) if a is not None else None
+        self.mirror()
+        _lib.check(_lib.lib().agarcl_batch_step_mirror(self._h, f(dxdy), f(act), f(rewards_out), f(dones_out)))
+        return self._mirror
+
+    def mirror_stats(self):
+        out = (C.c_uint64 * 4)()
+        _lib.check(_lib.lib().agarcl_batch_mirror_stats(self._h, C.byref(out)))
+        return dict(entries=int(out[0]), dense_images=int(out[1]), d2h_bytes=int(out[2]), host_threads=int(out[3]))
 
     def set_timing(self, enable=True):
         _lib.check(_lib.lib().agarcl_batch_set_timing(self._h, int(enable)))

@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libagarcl_b200.so")
-SOURCES = ["sim_kernel.cu", "obs_kernel.cu", "ram_kernel.cu", "reset_kernel.cu", "batch.cu", "layout.cpp", "host_util.cpp", "snapshot.cpp"]
-HEADERS = ["device_math.cuh", "sim_params.h", "sim_shared.cuh", "host_util.h", os.path.join("..", "..", "include", "agarcl_b200.h")]
+SOURCES = ["sim_kernel.cu", "obs_kernel.cu", "ram_kernel.cu", "reset_kernel.cu", "batch.cu", "mirror.cu", "layout.cpp", "host_util.cpp", "snapshot.cpp"]
+HEADERS = ["device_math.cuh", "sim_params.h", "sim_shared.cuh", "host_util.h", "mirror.h", os.path.join("..", "..", "include", "agarcl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false",  # the reference host build has no FMA contraction
               "-ccbin", "g++", "-Xcompiler", "-fPIC", "-shared"]

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "host_util.h"
+#include "mirror.h"
 #include "sim_params.h"
 #include "sim_shared.cuh"
 
@@ -53,6 +54,7 @@ struct agarcl_batch {
   int fuse_clear = 2;  // 0: k_obs writes everything; 1: the engine-tick kernel clears channels 1..C-1 while ticking;
                        // 2: it also writes channel 0 and scatters the entities (one kernel per step).  AGARCL_FUSE_CLEAR overrides (A/B timing)
   int launches_last_step = 0;
+  ag::HostMirror* mirror = nullptr;  // host-resident observation mirror (mirror.cu), created on first use
   // optional per-kernel timing: (start, after sim, after obs) event triples of steps not yet collected
   bool timing = false;
   std::vector<cudaEvent_t> ev;
@@ -164,6 +166,7 @@ static void fill_obs_params(const agarcl_batch* b, ag::ObsParams& P, int frame, 
 
 extern "C" int agarcl_batch_destroy(agarcl_batch* b) {
   if (!b) return AGARCL_OK;
+  ag::mirror_destroy(b->mirror);
   cudaFree(b->d_ram);
   cudaFree(b->d_state); cudaFree(b->d_obs); cudaFree(b->d_rewards); cudaFree(b->d_dones); cudaFree(b->d_before);
   cudaFree(b->d_dxdy); cudaFree(b->d_act); cudaFree(b->d_replay); cudaFree(b->d_seeds); cudaFree(b->d_mask); cudaFree(b->d_tickets);
@@ -510,6 +513,63 @@ extern "C" int agarcl_batch_step_host(agarcl_batch* b, const float* dxdy, const 
   if (rewards_out) CK(cudaMemcpyAsync(rewards_out, b->d_rewards, NA * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
   if (dones_out) CK(cudaMemcpyAsync(dones_out, b->d_dones, NA, cudaMemcpyDeviceToHost, nullptr));
   CK(cudaStreamSynchronize(nullptr));
+  return AGARCL_OK;
+}
+
+// ---- host-resident observation mirror (mirror.cu)
+static int ensure_mirror(agarcl_batch* b) {
+  if (b->mirror) return AGARCL_OK;
+  CK(cudaSetDevice(b->cfg.device));
+  b->mirror = ag::mirror_create(b->N * b->A, b->frames * b->C, b->C, b->G, b->cfg.obs_dtype);
+  return b->mirror ? AGARCL_OK : AGARCL_ERR_NOMEM;
+}
+
+extern "C" int agarcl_batch_sync_mirror(agarcl_batch* b, void* stream) {
+  if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");
+  int rc = ensure_mirror(b);
+  if (rc) return rc;
+  CK(cudaSetDevice(b->cfg.device));
+  return ag::mirror_sync(b->mirror, b->d_obs, (cudaStream_t)stream);
+}
+
+extern "C" int agarcl_batch_mirror(agarcl_batch* b, void** host_ptr, int64_t shape[4], int32_t* dtype) {
+  if (!b || !host_ptr) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  const bool fresh = b->mirror == nullptr;
+  int rc = ensure_mirror(b);
+  if (rc) return rc;
+  if (fresh) {
+    rc = ag::mirror_sync(b->mirror, b->d_obs, nullptr);
+    if (rc) return rc;
+  }
+  *host_ptr = ag::mirror_ptr(b->mirror);
+  if (shape) { shape[0] = (int64_t)b->N * b->A; shape[1] = (int64_t)b->frames * b->C; shape[2] = b->G; shape[3] = b->G; }
+  if (dtype) *dtype = b->cfg.obs_dtype;
+  return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_step_mirror(agarcl_batch* b, const float* dxdy, const int32_t* act, double* rewards_out,
+                                        uint8_t* dones_out) {
+  if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");
+  int rc = ensure_mirror(b);
+  if (rc) return rc;
+  rc = agarcl_batch_set_actions(b, dxdy, act, 0, nullptr);
+  if (rc) return rc;
+  rc = agarcl_batch_step(b, nullptr);
+  if (rc) return rc;
+  const size_t NA = (size_t)b->N * b->A;
+  if (rewards_out) CK(cudaMemcpyAsync(rewards_out, b->d_rewards, NA * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+  if (dones_out) CK(cudaMemcpyAsync(dones_out, b->d_dones, NA, cudaMemcpyDeviceToHost, nullptr));
+  rc = ag::mirror_sync(b->mirror, b->d_obs, nullptr);
+  b->launches_last_step += 1;  // k_pack
+  return rc;
+}
+
+extern "C" int agarcl_batch_mirror_stats(const agarcl_batch* b, uint64_t out[4]) {
+  if (!b || !out) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  if (!b->mirror) return agarcl_set_error(AGARCL_ERR_STATE, "no host mirror yet (agarcl_batch_mirror)");
+  ag::MirrorStats st;
+  ag::mirror_stats(b->mirror, &st);
+  out[0] = st.entries; out[1] = st.dense_images; out[2] = st.d2h_bytes; out[3] = st.host_threads;
   return AGARCL_OK;
 }
 

@@ -14,8 +14,9 @@ instances with no collective on the step path ("weak" scaling); torch.distribute
 the barrier and the max-over-ranks of the device time.
 
 `value` is timed with inputs (per-step action tensors) resident in HBM; `e2e` goes through the
-reference-facing C-ABI call agarcl_batch_step_host with pinned HOST buffers: actions H2D and the
-observations / rewards / dones D2H are inside the timed region.
+reference-facing C-ABI call agarcl_batch_step_mirror with pinned HOST buffers: actions H2D, rewards / dones D2H and
+the update of the dense host observation mirror are inside the timed region (the dense-copy call
+agarcl_batch_step_host is timed beside it as e2e.dense_copy).
 """
 import argparse
 import ctypes as C
@@ -289,6 +290,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    if world > 1:  # the mirror's host threads: share the box's cores between the ranks
+        os.environ.setdefault("AGARCL_HOST_THREADS", str(max(2, (os.cpu_count() or 2) // world)))
     N = args.instances
     cfg = make_cfg(n_instances=N, device=local_rank, instance_base=rank * N, **WORKLOAD)
     b = Batch(cfg)
@@ -349,29 +352,50 @@ def run_ours(args):
     h_act.numpy()[:] = rng.integers(0, 3, size=N * A).astype(np.int32)
     vp = C.c_void_p
 
-    def host_step():
+    def host_step_dense():
         from agarcl_b200 import _lib
         _lib.check(_lib.lib().agarcl_batch_step_host(b._h, vp(h_dxdy.data_ptr()), vp(h_act.data_ptr()), vp(h_obs.data_ptr()),
                                                      vp(h_rew.data_ptr()), vp(h_done.data_ptr())))
-    for _ in range(2):
-        host_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(Ke):
-        host_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+
+    def host_step_mirror():
+        from agarcl_b200 import _lib
+        _lib.check(_lib.lib().agarcl_batch_step_mirror(b._h, vp(h_dxdy.data_ptr()), vp(h_act.data_ptr()),
+                                                       vp(h_rew.data_ptr()), vp(h_done.data_ptr())))
+
+    def time_host(fn, n):
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    # (a) dense copy: the whole int32 observation crosses PCIe every step (kept for comparison)
+    Kd = max(3, min(Ke, 5))
+    dense_s = time_host(host_step_dense, Kd) / Kd
     h2d = N * A * (2 * 4 + 4)
-    d2h = int(np.prod(b.obs_shape)) * 4 + N * A * (8 + 1)
+    d2h_dense = int(np.prod(b.obs_shape)) * 4 + N * A * (8 + 1)
+    del h_obs
+    # (b) host-resident mirror: same result in host memory (the full dense int32 tensor, kept identical to the device's by
+    # moving the out-of-bounds masks + the non-zero lists and patching the mirror in place) -- this is `e2e`
+    mirror = b.mirror()
+    Km = max(Ke, min(K, 50))
+    e2e_s = time_host(host_step_mirror, Km)
+    mstats = b.mirror_stats()
+    d2h = mstats["d2h_bytes"] + N * A * (8 + 1)
+    mirror_ok = bool(torch.equal(torch.from_numpy(mirror[:64].copy()).cuda(), b.obs_tensor()[:64]))
+    Ke = Km
     flags_seen = 0
     for i in (0, N // 2, N - 1):
         flags_seen |= int(b.download_state(i).hdr["flags"])
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms, e2e_s, sim_ms, obs_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, sim_ms, obs_ms, dense_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, sim_ms, obs_ms = [float(x) for x in t.tolist()]
+        ms, e2e_s, sim_ms, obs_ms, dense_s = [float(x) for x in t.tolist()]
     if rank == 0:
         peak, peak_src = measured_peaks()
         sv = b.download_state(0)
@@ -409,7 +433,15 @@ def run_ours(args):
                                  "whole_step": {"achieved": whole, "peak": peak, "unit": "GB/s", "frac": whole / peak,
                                                 "algorithmic_bytes_per_env_step": ab["step"]}},
                 "e2e": {"value": world * N * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": Ke, "note": "agarcl_batch_step_host: pinned host actions in, int32 obs + rewards + dones out"},
+                        "steps": Ke,
+                        "note": "agarcl_batch_step_mirror: pinned host actions in; rewards + dones out; the dense int32 observation "
+                                "[N*A,8,128,128] is left in the library-owned pinned HOST mirror, kept identical to the device tensor by "
+                                "copying only the out-of-bounds masks and non-zero lists (k_pack) and patching the mirror on "
+                                f"{mstats['host_threads']} host threads; d2h_bytes_per_step is what crossed PCIe in the last step",
+                        "mirror_equals_device": mirror_ok, "mirror_entries_per_step": mstats["entries"],
+                        "mirror_dense_images": mstats["dense_images"],
+                        "dense_copy": {"value": world * N / dense_s, "unit": UNIT, "d2h_bytes_per_step": d2h_dense,
+                                       "note": "agarcl_batch_step_host: the whole int32 observation copied D2H every step (PCIe bound)"}},
                 "gpu_launches": launches, "clocks": clocks}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_reference_rate()  # child process under a watchdog: never takes the bench down

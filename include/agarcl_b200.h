@@ -186,6 +186,27 @@ int agarcl_batch_dones(agarcl_batch* b, uint8_t** dev_ptr);  /* dones(), u8[N*A]
 int agarcl_batch_step_host(agarcl_batch* b, const float* dxdy, const int32_t* act,
                            void* obs_out, double* rewards_out, uint8_t* dones_out);
 
+/* ---------------------------------------------------- host-resident observation mirror
+ * get_state (bindings.cpp:67-91) hands every agent's frame to HOST memory; for a batch that is 512 KB per agent
+ * per step, and the dense copy above is bound by PCIe.  The mirror is a library-owned, pinned host tensor
+ * [N*A, C*num_frames, G, G] of the observation dtype that the library keeps IDENTICAL to the device observation
+ * while moving only what a grid observation really contains: per frame the row/column bit masks of the
+ * out-of-bounds channel (GridEnvironment.hpp:235-248) and the (offset, value) list of the few hundred non-zero
+ * elements of the other channels (:212-232).  Host threads undo the previous step's list, patch the mask rows /
+ * columns that changed and store the new list.  Images that do not fit the scheme are copied densely, so the
+ * result never depends on it.  The caller reads the mirror and must not write to it.
+ *   agarcl_batch_mirror       creates the mirror on first use, syncs it, returns the host pointer (stable).
+ *   agarcl_batch_sync_mirror  brings it up to date with the current device observation (after a reset, a
+ *                             render, or agarcl_batch_step); synchronises `stream`.
+ *   agarcl_batch_step_mirror  = take_actions (host) + step + sync_mirror + rewards/dones to host: the
+ *                             reference-facing call `e2e` in bench.py times.
+ *   agarcl_batch_mirror_stats out[0] entries moved by the last sync, [1] images copied densely, [2] bytes copied
+ *                             device->host, [3] host threads.                                                  */
+int agarcl_batch_mirror(agarcl_batch* b, void** host_ptr, int64_t shape[4], int32_t* dtype);
+int agarcl_batch_sync_mirror(agarcl_batch* b, void* stream);
+int agarcl_batch_step_mirror(agarcl_batch* b, const float* dxdy, const int32_t* act, double* rewards_out, uint8_t* dones_out);
+int agarcl_batch_mirror_stats(const agarcl_batch* b, uint64_t out[4]);
+
 /* ---------------------------------------------------- structured ("ram") observation
  * GoBiggerObservation::add_frame (environment/envs/GoBiggerEnvironment.hpp:515-548, _store_entities
  * 446-513): for EVERY player of the instance, the in-view viruses, pellets ("food"), ejected foods
