@@ -125,6 +125,8 @@ static void fill_sim_params(const agarcl_batch* b, ag::SimParams& P) {
   if (const char* e = std::getenv("AGARCL_ZERO_CHUNKS")) P.zero_chunks = std::atoi(e);
   P.observe_cells = b->cfg.observe_cells; P.observe_others = b->cfg.observe_others;
   P.observe_viruses = b->cfg.observe_viruses; P.observe_pellets = b->cfg.observe_pellets;
+  std::memset(&P.pk, 0, sizeof(P.pk));
+  P.inst_first = 0;
 }
 
 // Lets the engine-tick kernel clear channels 1..C-1 of frame slot `frame` (see SimParams); false when
@@ -420,11 +422,12 @@ extern "C" int agarcl_batch_set_actions(agarcl_batch* b, const float* dxdy, cons
   return AGARCL_OK;
 }
 
-extern "C" int agarcl_batch_step(agarcl_batch* b, void* stream) {
-  if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");
+// One env-step of every instance.  `want_lists`: the caller is agarcl_batch_step_mirror; when the step is the single
+// fused kernel, it also leaves the host mirror's transfer lists (*lists_made = true) and the k_pack pass is not needed.
+static int step_impl(agarcl_batch* b, cudaStream_t s, bool want_lists, bool* lists_made) {
+  if (lists_made) *lists_made = false;
   if (!b->was_reset) return agarcl_set_error(AGARCL_ERR_STATE, "step() before reset()");
   CK(cudaSetDevice(b->cfg.device));
-  cudaStream_t s = (cudaStream_t)stream;
   ag::SimParams P;
   fill_sim_params(b, P);
   const int tps = b->cfg.ticks_per_step;
@@ -439,6 +442,10 @@ extern "C" int agarcl_batch_step(agarcl_batch* b, void* stream) {
   } else if (b->frames == 1) {
     P.n_ticks = tps; P.do_begin = 1; P.do_end = 1;
     const int fused = fuse_obs_clear(b, P, 0) ? 1 : 0;
+    if (want_lists && P.obs_finish && b->mirror && !b->d_ram) {
+      P.pk = ag::mirror_pack_out(b->mirror);
+      *lists_made = true;
+    }
     if (b->timing) { if (b->ev_used >= 3 * 2048) collect_timing(b); CK(cudaEventRecord(next_event(b), s)); }
     CK(ag::launch_step(P, s)); launches++;
     if (b->timing) CK(cudaEventRecord(next_event(b), s));
@@ -460,6 +467,11 @@ extern "C" int agarcl_batch_step(agarcl_batch* b, void* stream) {
   if (b->d_ram) { int rc = render_ram(b, s, 1); if (rc) return rc; launches++; }
   b->launches_last_step = launches;
   return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_step(agarcl_batch* b, void* stream) {
+  if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");
+  return step_impl(b, (cudaStream_t)stream, false, nullptr);
 }
 
 extern "C" int agarcl_batch_set_timing(agarcl_batch* b, int enable) {
@@ -520,7 +532,7 @@ extern "C" int agarcl_batch_step_host(agarcl_batch* b, const float* dxdy, const 
 static int ensure_mirror(agarcl_batch* b) {
   if (b->mirror) return AGARCL_OK;
   CK(cudaSetDevice(b->cfg.device));
-  b->mirror = ag::mirror_create(b->N * b->A, b->frames * b->C, b->C, b->G, b->cfg.obs_dtype);
+  b->mirror = ag::mirror_create(b->N * b->A, b->A, b->frames * b->C, b->C, b->G, b->cfg.obs_dtype);
   return b->mirror ? AGARCL_OK : AGARCL_ERR_NOMEM;
 }
 
@@ -554,11 +566,13 @@ extern "C" int agarcl_batch_step_mirror(agarcl_batch* b, const float* dxdy, cons
   if (rc) return rc;
   rc = agarcl_batch_set_actions(b, dxdy, act, 0, nullptr);
   if (rc) return rc;
-  rc = agarcl_batch_step(b, nullptr);
+  bool lists_made = false;
+  rc = step_impl(b, nullptr, true, &lists_made);
   if (rc) return rc;
   const size_t NA = (size_t)b->N * b->A;
   if (rewards_out) CK(cudaMemcpyAsync(rewards_out, b->d_rewards, NA * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
   if (dones_out) CK(cudaMemcpyAsync(dones_out, b->d_dones, NA, cudaMemcpyDeviceToHost, nullptr));
+  if (lists_made) return ag::mirror_collect(b->mirror, b->d_obs, nullptr);  // k_step listed what it scattered
   rc = ag::mirror_sync(b->mirror, b->d_obs, nullptr);
   b->launches_last_step += 1;  // k_pack
   return rc;
@@ -570,6 +584,15 @@ extern "C" int agarcl_batch_mirror_stats(const agarcl_batch* b, uint64_t out[4])
   ag::MirrorStats st;
   ag::mirror_stats(b->mirror, &st);
   out[0] = st.entries; out[1] = st.dense_images; out[2] = st.d2h_bytes; out[3] = st.host_threads;
+  return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_mirror_timing(const agarcl_batch* b, uint64_t out[2]) {
+  if (!b || !out) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  if (!b->mirror) return agarcl_set_error(AGARCL_ERR_STATE, "no host mirror yet (agarcl_batch_mirror)");
+  ag::MirrorStats st;
+  ag::mirror_stats(b->mirror, &st);
+  out[0] = st.wait_us; out[1] = st.total_us;
   return AGARCL_OK;
 }
 

@@ -6,19 +6,26 @@
 // is the union of whole rows and whole columns (GridObservation::_mark_out_of_bounds,
 // environment/envs/GridEnvironment.hpp:235-248: a grid point is marked iff its x or its y leaves the arena),
 // and the other channels hold a few hundred non-zero elements (one per in-view entity,
-// _store_entities :212-232).  So after every step
-//   1. k_pack (one CTA per agent image) reads the dense device observation once and emits, per image,
-//      the row/column bit masks of every mask channel and the (offset, value) list of all other non-zeros,
-//      packed into one device array through a single atomic cursor;
-//   2. the lists (a few MB instead of 2.1 GB at configs[1]) are copied to pinned host memory;
-//   3. a pool of host threads brings the library-owned dense mirror [N*A, frames*C, G, G] up to date in place:
-//      zero the previous step's entries, rewrite only the mask rows/columns that changed, store the new entries.
+// _store_entities :212-232).  So per step
+//   1. the device produces, per image, the row/column bit masks of every mask channel and the (offset, value)
+//      list of all other non-zeros, grouped into chunks of consecutive images (PackOut, sim_params.h):
+//      - agarcl_batch_step_mirror: the fused observation finish of k_step lists what it scatters while it
+//        scatters it (sim_kernel.cu, obs_finish_warp) -- the dense tensor is never read back;
+//      - agarcl_batch_sync_mirror (after a reset / render, or a configuration k_step does not finish itself):
+//        k_pack, one CTA per image, reads the dense device observation once;
+//   2. every finished chunk (a few hundred KB instead of 2.1 GB at configs[1]) is copied to pinned host memory
+//      by ONE copy -- in the fused path as soon as the kernel flags the chunk in host-mapped memory, while it is
+//      still stepping the instances of the next chunks;
+//   3. a pool of host threads brings the library-owned dense mirror [N*A, frames*C, G, G] up to date in place,
+//      chunk by chunk as they arrive: zero the previous step's entries, rewrite only the mask rows/columns that
+//      changed, store the new entries.
 // An image that does not fit the scheme (entry capacity exceeded, or a mask channel that is not a row/column
 // union) is copied densely instead, so the mirror is ALWAYS identical to the device tensor — the parity test
 // tests/test_gpu_mirror.py compares them element for element after every step.
 #include "mirror.h"
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -33,17 +40,12 @@
 namespace ag {
 
 constexpr int kPackThreads = 256;
-constexpr uint32_t kDense = 0xFFFFFFFFu;  // img_count marker: this image takes the dense copy
 
 struct PackParams {
   const void* obs;
-  int32_t n_img, CH, C, G, MW;  // MW: 32-bit words per row (or column) mask
-  uint32_t cap_img, cap_total;
-  uint2* entries;               // [cap_total] (offset inside the image, value)
-  uint32_t* img_count;          // [n_img] entries of the image, or kDense
-  uint32_t* img_base;           // [n_img] first entry of the image
-  uint32_t* total;              // atomic cursor into entries
-  uint32_t* masks;              // [n_img][frames][2][MW]: bit i of the row mask = row i is out of bounds
+  int32_t CH, C, G;
+  uint32_t cap_img;  // entries staged in shared memory per image
+  PackOut pk;
 };
 
 template <typename T> struct Vec;
@@ -75,6 +77,9 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const PackParams P) {
   __shared__ uint32_t s_cnt, s_bad, s_base;
   const uint32_t tid = threadIdx.x, img = blockIdx.x;
   const uint32_t G = (uint32_t)P.G, plane = G * G, pv = plane / VE;
+  const uint32_t MW = (uint32_t)P.pk.MW;
+  const uint32_t chunk = img / P.pk.ipc, li = img - chunk * P.pk.ipc;
+  uint32_t* blk = P.pk.chunks + (size_t)chunk * P.pk.chunk_words;
   const T* base = reinterpret_cast<const T*>(P.obs) + (size_t)img * P.CH * plane;
   if (tid == 0) { s_cnt = 0; s_bad = 0; }
   for (uint32_t i = tid; i < 2 * G; i += kPackThreads) row_any[i] = 0;
@@ -106,10 +111,10 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const PackParams P) {
       }
     }
     if (bad) s_bad = 1;
-    uint32_t* mk = P.masks + ((size_t)img * frames + f) * 2 * P.MW;
-    for (uint32_t w = tid; w < 2u * P.MW; w += kPackThreads) {
-      const uint8_t* any = w < (uint32_t)P.MW ? row_any : col_any;
-      const uint32_t w0 = (w % P.MW) * 32;
+    uint32_t* mk = blk + pk_off_masks(P.pk) + (size_t)li * P.pk.mask_words + (size_t)f * 2 * MW;
+    for (uint32_t w = tid; w < 2u * MW; w += kPackThreads) {
+      const uint8_t* any = w < MW ? row_any : col_any;
+      const uint32_t w0 = (w % MW) * 32;
       uint32_t bits = 0;
       for (uint32_t b = 0; b < 32 && w0 + b < G; b++)
         if (!any[w0 + b]) bits |= 1u << b;
@@ -147,24 +152,41 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const PackParams P) {
   __syncthreads();
   if (tid == 0) {
     uint32_t cnt = s_cnt, b0 = 0;
-    if (s_bad || cnt > P.cap_img) cnt = kDense;
+    if (s_bad || cnt > P.cap_img) cnt = kPackDense;
     else if (cnt) {
-      b0 = atomicAdd(P.total, cnt);
-      if (b0 + cnt > P.cap_total) cnt = kDense;
+      b0 = atomicAdd(P.pk.cursor + chunk, cnt);
+      if (b0 + cnt > P.pk.cap_chunk) cnt = kPackDense;
     }
-    P.img_count[img] = cnt;
-    P.img_base[img] = b0;
+    blk[pk_off_count(P.pk) + li] = cnt;
+    blk[pk_off_base(P.pk) + li] = b0;
     s_cnt = cnt;
     s_base = b0;
   }
   __syncthreads();
   const uint32_t cnt = s_cnt;
-  if (cnt == kDense) return;
-  for (uint32_t k = tid; k < cnt; k += kPackThreads) P.entries[s_base + k] = s_ent[k];
+  if (cnt != kPackDense) {
+    uint2* ent = reinterpret_cast<uint2*>(blk + pk_off_entries(P.pk));
+    for (uint32_t k = tid; k < cnt; k += kPackThreads) ent[s_base + k] = s_ent[k];
+  }
+  // the CTA that finishes the last image of the chunk publishes the entry count and rewinds the counters
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t in_chunk = min(P.pk.ipc, P.pk.n_img - chunk * P.pk.ipc);
+    if (atomicAdd(P.pk.done + chunk, 1u) + 1u == in_chunk) {
+      __threadfence();
+      blk[0] = atomicExch(P.pk.cursor + chunk, 0u);
+      P.pk.done[chunk] = 0u;
+      if (P.pk.flags) {
+        __threadfence_system();
+        P.pk.flags[chunk] = P.pk.seq;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host pool
-// Every worker and the caller run the same job, which pulls chunks from an atomic counter.
+// Every worker (and, from join() on, the caller) runs the same job, which pulls work from atomic counters.
 class Pool {
  public:
   explicit Pool(int workers) {
@@ -179,7 +201,7 @@ class Pool {
     for (auto& t : th_) t.join();
   }
   int threads() const { return (int)th_.size() + 1; }
-  void run(const std::function<void()>& job) {
+  void start(const std::function<void()>& job) {  // wakes the workers; the job object must live until join() returns
     {
       std::lock_guard<std::mutex> g(mu_);
       job_ = &job;
@@ -187,10 +209,16 @@ class Pool {
       gen_++;
     }
     cv_start_.notify_all();
-    job();
+  }
+  void join() {  // the caller works too, then waits for the workers
+    (*job_)();
     std::unique_lock<std::mutex> g(mu_);
     cv_done_.wait(g, [this] { return pending_ == 0; });
     job_ = nullptr;
+  }
+  void run(const std::function<void()>& job) {
+    start(job);
+    join();
   }
 
  private:
@@ -221,24 +249,34 @@ class Pool {
   bool stop_ = false;
 };
 
+static inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#else
+  std::this_thread::yield();
+#endif
+}
+
 struct HostMirror {
   int n_img = 0, CH = 0, C = 0, G = 0, frames = 0, MW = 0, dtype = 0;
   size_t esz = 4, img_elems = 0, img_bytes = 0;
-  uint32_t cap_img = 0, cap_total = 0;
+  uint32_t cap_img = 0;
+  int n_chunks = 1;
+  PackOut pk{};                   // device side of the chunk blocks (flags / seq filled per use)
+  size_t meta_words = 0;          // words of a chunk block in front of its entries
   void* h_obs = nullptr;          // pinned [n_img][CH][G][G]
-  uint2* d_entries = nullptr;
-  uint32_t* d_meta = nullptr;     // [count n_img][base n_img][total, pad x3][masks n_img*frames*2*MW]
-  size_t meta_words = 0;
-  uint2* h_entries[2] = {nullptr, nullptr};  // pinned staging; [cur] = this step's lists, [cur^1] = the previous step's
-  uint32_t* h_meta[2] = {nullptr, nullptr};
+  uint32_t* d_chunks = nullptr;
+  uint32_t* d_counters = nullptr; // [2][n_chunks] cursor, done
+  uint32_t* h_chunks[2] = {nullptr, nullptr};  // pinned staging, same block layout; [cur] = this step's lists, [cur^1] = the previous step's
+  volatile uint32_t* h_flags = nullptr;        // host-mapped [n_chunks]
+  uint32_t* d_flags = nullptr;                 // its device address
+  uint32_t seq = 0;
   int cur = 0;
-  size_t guess = 0;               // entries fetched together with the counts (the remainder, if any, in a second copy)
+  std::vector<size_t> guess;      // per chunk: entries fetched together with the meta words (the remainder, if any, in a second copy)
+  cudaStream_t copy_stream = nullptr;          // non-blocking: copies chunks while the step kernel runs
   Pool* pool = nullptr;
   MirrorStats stats{};
-  uint32_t* count(int w) const { return h_meta[w]; }
-  uint32_t* base(int w) const { return h_meta[w] + n_img; }
-  uint32_t* total(int w) const { return h_meta[w] + 2 * (size_t)n_img; }
-  uint32_t* masks(int w) const { return h_meta[w] + 2 * (size_t)n_img + 4; }
+  uint32_t* blk(int w, int chunk) const { return h_chunks[w] + (size_t)chunk * pk.chunk_words; }
 };
 
 static inline bool bit(const uint32_t* m, int i) { return (m[i >> 5] >> (i & 31)) & 1u; }
@@ -271,46 +309,57 @@ static void apply_mask_delta(T* p, const uint32_t* om, const uint32_t* nm, int G
 template <typename T>
 static void expand_range(HostMirror* m, int lo, int hi, const uint32_t* zero_masks) {
   const int cur = m->cur, prev = cur ^ 1;
+  const PackOut& k = m->pk;
   const size_t mw2 = 2 * (size_t)m->MW, plane = (size_t)m->G * m->G;
   for (int img = lo; img < hi; img++) {
-    const uint32_t cnt = m->count(cur)[img];
-    if (cnt == kDense) continue;  // the dense copy of this image is already in flight
+    const int chunk = img / (int)k.ipc, li = img - chunk * (int)k.ipc;
+    const uint32_t *cb = m->blk(cur, chunk), *pb = m->blk(prev, chunk);
+    const uint32_t cnt = cb[pk_off_count(k) + li];
+    if (cnt == kPackDense) continue;  // the dense copy of this image is already in flight
     T* p = reinterpret_cast<T*>(m->h_obs) + (size_t)img * m->img_elems;
-    const uint32_t pcnt = m->count(prev)[img];
-    const uint32_t* om = m->masks(prev) + (size_t)img * m->frames * mw2;
-    const uint32_t* nm = m->masks(cur) + (size_t)img * m->frames * mw2;
-    if (pcnt == kDense) {
+    const uint32_t pcnt = pb[pk_off_count(k) + li];
+    const uint32_t* om = pb + pk_off_masks(k) + (size_t)li * k.mask_words;
+    const uint32_t* nm = cb + pk_off_masks(k) + (size_t)li * k.mask_words;
+    if (pcnt == kPackDense) {
       std::memset(p, 0, m->img_bytes);
       om = nullptr;
     } else {
-      const uint2* pe = m->h_entries[prev] + m->base(prev)[img];
-      for (uint32_t k = 0; k < pcnt; k++) p[pe[k].x] = 0;
+      const uint2* pe = reinterpret_cast<const uint2*>(pb + pk_off_entries(k)) + pb[pk_off_base(k) + li];
+      for (uint32_t e = 0; e < pcnt; e++) p[pe[e].x & kPkOffMask] = 0;
     }
     for (int f = 0; f < m->frames; f++) {
       const uint32_t* o = om ? om + f * mw2 : zero_masks;
       if (std::memcmp(o, nm + f * mw2, mw2 * 4) != 0) apply_mask_delta<T>(p + (size_t)f * m->C * plane, o, nm + f * mw2, m->G, m->MW);
     }
-    const uint2* ne = m->h_entries[cur] + m->base(cur)[img];
-    for (uint32_t k = 0; k < cnt; k++) p[ne[k].x] = (T)(int32_t)ne[k].y;
+    const uint2* ne = reinterpret_cast<const uint2*>(cb + pk_off_entries(k)) + cb[pk_off_base(k) + li];
+    for (uint32_t e = 0; e < cnt; e++) {
+      T& x = p[ne[e].x & kPkOffMask];
+      const T v = (T)(int32_t)ne[e].y;
+      switch (ne[e].x >> 29) {
+        case kPkSet: x = v; break;
+        case kPkAdd: x = (T)(x + v); break;
+        case kPkMinNz: x = (x != 0 && x < v) ? x : v; break;
+        default: x = x > v ? x : v; break;
+      }
+    }
   }
 }
 
 void mirror_destroy(HostMirror* m) {
   if (!m) return;
   delete m->pool;
-  cudaFree(m->d_entries);
-  cudaFree(m->d_meta);
-  for (int w = 0; w < 2; w++) {
-    cudaFreeHost(m->h_entries[w]);
-    cudaFreeHost(m->h_meta[w]);
-  }
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  cudaFree(m->d_chunks);
+  cudaFree(m->d_counters);
+  for (int w = 0; w < 2; w++) cudaFreeHost(m->h_chunks[w]);
+  cudaFreeHost((void*)m->h_flags);
   cudaFreeHost(m->h_obs);
   delete m;
 }
 
-HostMirror* mirror_create(int n_img, int CH, int C, int G, int dtype) {
+HostMirror* mirror_create(int n_img, int agents, int CH, int C, int G, int dtype) {
   const size_t esz = dtype == AGARCL_OBS_I16 ? 2 : 4;
-  if (((size_t)G * G * esz) % 16 != 0 || G > 4096) {
+  if (((size_t)G * G * esz) % 16 != 0 || G > 4096 || (uint64_t)CH * G * G > kPkOffMask) {
     agarcl_set_error(AGARCL_ERR_INVALID, "the host mirror needs grid planes that are multiples of 16 bytes (grid_size %d)", G);
     return nullptr;
   }
@@ -325,17 +374,38 @@ HostMirror* mirror_create(int n_img, int CH, int C, int G, int dtype) {
   m->img_bytes = m->img_elems * esz;
   m->cap_img = 2048;
   if (const char* e = std::getenv("AGARCL_MIRROR_CAP_IMG")) m->cap_img = (uint32_t)std::atoi(e);
-  uint64_t ct = (uint64_t)n_img * (m->cap_img < 1024 ? m->cap_img : 1024);
-  if (ct < 4096) ct = 4096;
-  m->cap_total = (uint32_t)(ct > 0x7FFFFFFFull ? 0x7FFFFFFFull : ct);
-  m->meta_words = 2 * (size_t)n_img + 4 + (size_t)n_img * m->frames * 2 * m->MW;
+  // chunks: whole instances, about 8 per batch but not smaller than 64 images
+  if (agents < 1) agents = 1;
+  int want = 8;
+  if (const char* e = std::getenv("AGARCL_MIRROR_CHUNKS")) want = std::atoi(e);
+  if (want < 1) want = 1;
+  const int inst = n_img / agents;
+  int ipc_inst = (inst + want - 1) / want;
+  if (ipc_inst * agents < 64) ipc_inst = (64 + agents - 1) / agents;
+  if (ipc_inst < 1) ipc_inst = 1;
+  PackOut& k = m->pk;
+  k.ipc = (uint32_t)ipc_inst * (uint32_t)agents;
+  m->n_chunks = (n_img + (int)k.ipc - 1) / (int)k.ipc;
+  k.mask_words = (uint32_t)(m->frames * 2 * m->MW);
+  k.MW = m->MW;
+  k.n_img = (uint32_t)n_img;
+  uint64_t cc = (uint64_t)k.ipc * (m->cap_img < 1024 ? m->cap_img : 1024);
+  if (cc < 16) cc = 16;
+  k.cap_chunk = (uint32_t)(cc > 0x3FFFFFFFull ? 0x3FFFFFFFull : cc);
+  m->meta_words = pk_off_entries(k);
+  k.chunk_words = (uint32_t)(m->meta_words + 2 * (size_t)k.cap_chunk);
+  const size_t all_words = (size_t)m->n_chunks * k.chunk_words;
   bool ok = cudaHostAlloc(&m->h_obs, (size_t)n_img * m->img_bytes, cudaHostAllocDefault) == cudaSuccess;
-  ok = ok && cudaMalloc((void**)&m->d_entries, (size_t)m->cap_total * sizeof(uint2)) == cudaSuccess;
-  ok = ok && cudaMalloc((void**)&m->d_meta, m->meta_words * 4) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&m->d_chunks, all_words * 4) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&m->d_counters, 2 * (size_t)m->n_chunks * 4) == cudaSuccess;
+  ok = ok && cudaMemset(m->d_counters, 0, 2 * (size_t)m->n_chunks * 4) == cudaSuccess;
+  ok = ok && cudaHostAlloc((void**)&m->h_flags, (size_t)m->n_chunks * 4, cudaHostAllocMapped) == cudaSuccess;
+  ok = ok && cudaHostGetDevicePointer((void**)&m->d_flags, (void*)m->h_flags, 0) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int w = 0; w < 2 && ok; w++) {
-    ok = ok && cudaHostAlloc((void**)&m->h_entries[w], (size_t)m->cap_total * sizeof(uint2), cudaHostAllocDefault) == cudaSuccess;
-    ok = ok && cudaHostAlloc((void**)&m->h_meta[w], m->meta_words * 4, cudaHostAllocDefault) == cudaSuccess;
-    if (ok) std::memset(m->h_meta[w], 0, m->meta_words * 4);  // no entries, nothing out of bounds == the all-zero mirror
+    ok = ok && cudaHostAlloc((void**)&m->h_chunks[w], all_words * 4, cudaHostAllocDefault) == cudaSuccess;
+    if (ok)  // no entries, nothing out of bounds == the all-zero mirror
+      for (int c = 0; c < m->n_chunks; c++) std::memset(m->blk(w, c), 0, m->meta_words * 4);
   }
   if (!ok) {
     agarcl_set_error(AGARCL_ERR_NOMEM, "host mirror allocation failed (%zu B pinned): %s", (size_t)n_img * m->img_bytes,
@@ -343,13 +413,19 @@ HostMirror* mirror_create(int n_img, int CH, int C, int G, int dtype) {
     mirror_destroy(m);
     return nullptr;
   }
+  for (int c = 0; c < m->n_chunks; c++) m->h_flags[c] = 0u;
+  k.chunks = m->d_chunks;
+  k.cursor = m->d_counters;
+  k.done = m->d_counters + m->n_chunks;
+  k.flags = nullptr;
+  k.seq = 0;
   int nt = (int)std::thread::hardware_concurrency();
   if (const char* e = std::getenv("AGARCL_HOST_THREADS")) nt = std::atoi(e);
   nt = nt < 1 ? 1 : (nt > 64 ? 64 : nt);
   if (nt > n_img) nt = n_img;
   m->pool = new Pool(nt - 1);
   m->stats.host_threads = (uint64_t)nt;
-  m->guess = (size_t)n_img * 64;
+  m->guess.assign((size_t)m->n_chunks, (size_t)k.ipc * 64);
   // first touch of the mirror by the threads that will write it
   {
     std::atomic<int> next{0};
@@ -366,6 +442,13 @@ HostMirror* mirror_create(int n_img, int CH, int C, int G, int dtype) {
 void* mirror_ptr(HostMirror* m) { return m->h_obs; }
 void mirror_stats(const HostMirror* m, MirrorStats* out) { *out = m->stats; }
 
+PackOut mirror_pack_out(HostMirror* m) {
+  PackOut k = m->pk;
+  k.flags = m->d_flags;
+  k.seq = ++m->seq;
+  return k;
+}
+
 #define MCK(call)                                                                                  \
   do {                                                                                             \
     cudaError_t e__ = (call);                                                                      \
@@ -373,19 +456,113 @@ void mirror_stats(const HostMirror* m, MirrorStats* out) { *out = m->stats; }
       return agarcl_set_error(AGARCL_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));   \
   } while (0)
 
-int mirror_sync(HostMirror* m, const void* d_obs, cudaStream_t s) {
+// Fetches the chunks as they become complete and expands them into the mirror.  `flagged`: a kernel launched on
+// `s` with mirror_pack_out() raises the flags (the chunks are fetched on the copy stream while it runs);
+// otherwise everything on `s` is complete already.
+static int collect(HostMirror* m, const void* d_obs, cudaStream_t s, bool flagged) {
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
   m->cur ^= 1;
-  const int cur = m->cur;
+  const int cur = m->cur, K = m->n_chunks;
+  const PackOut& k = m->pk;
+  std::vector<uint32_t> zero_masks(2 * (size_t)m->MW, 0u);
+  std::atomic<int> next{0}, avail{0};
+  std::atomic<bool> abort{false};
+  const int grab = 8;
+  const std::function<void()> job = [&] {
+    for (;;) {
+      int i = next.load(std::memory_order_relaxed);
+      if (i >= m->n_img || abort.load(std::memory_order_relaxed)) break;
+      const int av = avail.load(std::memory_order_acquire);
+      if (i >= av) { cpu_relax(); continue; }
+      const int hi = i + grab < av ? i + grab : av;
+      if (!next.compare_exchange_weak(i, hi, std::memory_order_relaxed)) continue;
+      if (m->dtype == AGARCL_OBS_I16) expand_range<int16_t>(m, i, hi, zero_masks.data());
+      else expand_range<int32_t>(m, i, hi, zero_masks.data());
+    }
+  };
+  m->pool->start(job);
+  uint64_t d2h = 0, dense = 0, entries = 0;
+  double wait_s = 0.0;
+  int rc = AGARCL_OK;
+  auto fail = [&](cudaError_t e, const char* what) {
+    rc = agarcl_set_error(AGARCL_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+  };
+  for (int c = 0; c < K && rc == AGARCL_OK; c++) {
+    const auto w0 = clk::now();
+    if (flagged) {
+      // the kernel flags chunk c in host-mapped memory; keep an eye on the stream so that a failed launch cannot hang us
+      uint32_t spins = 0;
+      while (m->h_flags[c] != m->seq) {
+        cpu_relax();
+        if ((++spins & 0xFFFu) == 0u) {
+          const cudaError_t q = cudaStreamQuery(s);
+          if (q == cudaSuccess) {
+            if (m->h_flags[c] != m->seq) rc = agarcl_set_error(AGARCL_ERR_STATE, "step kernel finished without completing mirror chunk %d", c);
+            break;
+          }
+          if (q != cudaErrorNotReady) { fail(q, "cudaStreamQuery"); break; }
+        }
+      }
+      if (rc != AGARCL_OK) break;
+    }
+    const cudaStream_t cs = flagged ? m->copy_stream : s;
+    uint32_t* hb = m->blk(cur, c);
+    const uint32_t* db = m->d_chunks + (size_t)c * k.chunk_words;
+    size_t got = m->guess[c] < k.cap_chunk ? m->guess[c] : k.cap_chunk;
+    cudaError_t e = cudaMemcpyAsync(hb, db, (m->meta_words + 2 * got) * 4, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+    if (e != cudaSuccess) { fail(e, "chunk copy"); break; }
+    d2h += (m->meta_words + 2 * got) * 4;
+    size_t total = hb[0];
+    if (total > k.cap_chunk) total = k.cap_chunk;
+    if (total > got) {
+      e = cudaMemcpyAsync(hb + m->meta_words + 2 * got, db + m->meta_words + 2 * got, (total - got) * 8, cudaMemcpyDeviceToHost, cs);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+      if (e != cudaSuccess) { fail(e, "chunk copy (remainder)"); break; }
+      d2h += (total - got) * 8;
+    }
+    m->guess[c] = total + total / 8 + 1024;
+    entries += total;
+    // dense copies (asynchronous into the pinned mirror), they overlap the list expansion
+    const int lo = c * (int)k.ipc, hi = lo + (int)k.ipc < m->n_img ? lo + (int)k.ipc : m->n_img;
+    const uint32_t* cnt = hb + pk_off_count(k);
+    for (int i = lo; i < hi; i++)
+      if (cnt[i - lo] == kPackDense) {
+        e = cudaMemcpyAsync((uint8_t*)m->h_obs + (size_t)i * m->img_bytes, (const uint8_t*)d_obs + (size_t)i * m->img_bytes,
+                            m->img_bytes, cudaMemcpyDeviceToHost, cs);
+        if (e != cudaSuccess) { fail(e, "dense image copy"); break; }
+        dense++;
+      }
+    wait_s += std::chrono::duration<double>(clk::now() - w0).count();
+    avail.store(hi, std::memory_order_release);
+  }
+  if (rc != AGARCL_OK) abort.store(true);
+  m->pool->join();
+  if (rc == AGARCL_OK && dense) {
+    const cudaError_t e = cudaStreamSynchronize(flagged ? m->copy_stream : s);
+    if (e != cudaSuccess) fail(e, "dense image copies");
+  }
+  if (rc == AGARCL_OK && flagged) {  // rewards / dones copies and the kernel itself
+    const cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) fail(e, "cudaStreamSynchronize");
+  }
+  m->stats.entries = entries;
+  m->stats.dense_images = dense;
+  m->stats.d2h_bytes = d2h + dense * m->img_bytes;
+  m->stats.wait_us = (uint64_t)(wait_s * 1e6);
+  m->stats.total_us = (uint64_t)(std::chrono::duration<double>(clk::now() - t0).count() * 1e6);
+  return rc;
+}
+
+int mirror_collect(HostMirror* m, const void* d_obs, cudaStream_t s) { return collect(m, d_obs, s, true); }
+
+int mirror_sync(HostMirror* m, const void* d_obs, cudaStream_t s) {
   PackParams P;
   P.obs = d_obs;
-  P.n_img = m->n_img; P.CH = m->CH; P.C = m->C; P.G = m->G; P.MW = m->MW;
-  P.cap_img = m->cap_img; P.cap_total = m->cap_total;
-  P.entries = m->d_entries;
-  P.img_count = m->d_meta;
-  P.img_base = m->d_meta + m->n_img;
-  P.total = m->d_meta + 2 * (size_t)m->n_img;
-  P.masks = m->d_meta + 2 * (size_t)m->n_img + 4;
-  MCK(cudaMemsetAsync(P.total, 0, 16, s));
+  P.CH = m->CH; P.C = m->C; P.G = m->G;
+  P.cap_img = m->cap_img;
+  P.pk = m->pk;  // no flags: the host waits for the stream
   const size_t smem = (size_t)m->cap_img * sizeof(uint2) + 2 * (size_t)m->G + 16;
   if (m->dtype == AGARCL_OBS_I16) {
     if (smem > 48 * 1024) MCK(cudaFuncSetAttribute(k_pack<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -395,43 +572,8 @@ int mirror_sync(HostMirror* m, const void* d_obs, cudaStream_t s) {
     k_pack<int32_t><<<m->n_img, kPackThreads, smem, s>>>(P);
   }
   MCK(cudaGetLastError());
-  MCK(cudaMemcpyAsync(m->h_meta[cur], m->d_meta, m->meta_words * 4, cudaMemcpyDeviceToHost, s));
-  size_t got = m->guess < m->cap_total ? m->guess : m->cap_total;
-  MCK(cudaMemcpyAsync(m->h_entries[cur], m->d_entries, got * sizeof(uint2), cudaMemcpyDeviceToHost, s));
   MCK(cudaStreamSynchronize(s));
-  uint64_t d2h = m->meta_words * 4 + got * sizeof(uint2);
-  size_t total = *m->total(cur);
-  if (total > m->cap_total) total = m->cap_total;
-  if (total > got) {
-    MCK(cudaMemcpyAsync(m->h_entries[cur] + got, m->d_entries + got, (total - got) * sizeof(uint2), cudaMemcpyDeviceToHost, s));
-    d2h += (total - got) * sizeof(uint2);
-    MCK(cudaStreamSynchronize(s));
-  }
-  m->guess = total + total / 8 + 4096;
-  // dense copies first (asynchronous into the pinned mirror), they overlap the list expansion below
-  uint64_t dense = 0;
-  const uint32_t* cnt = m->count(cur);
-  for (int i = 0; i < m->n_img; i++)
-    if (cnt[i] == kDense) {
-      MCK(cudaMemcpyAsync((uint8_t*)m->h_obs + (size_t)i * m->img_bytes, (const uint8_t*)d_obs + (size_t)i * m->img_bytes,
-                          m->img_bytes, cudaMemcpyDeviceToHost, s));
-      dense++;
-    }
-  std::vector<uint32_t> zero_masks(2 * (size_t)m->MW, 0u);
-  std::atomic<int> next{0};
-  const int chunk = 8;
-  m->pool->run([&] {
-    for (int i; (i = next.fetch_add(chunk)) < m->n_img;) {
-      const int hi = i + chunk < m->n_img ? i + chunk : m->n_img;
-      if (m->dtype == AGARCL_OBS_I16) expand_range<int16_t>(m, i, hi, zero_masks.data());
-      else expand_range<int32_t>(m, i, hi, zero_masks.data());
-    }
-  });
-  if (dense) MCK(cudaStreamSynchronize(s));
-  m->stats.entries = total;
-  m->stats.dense_images = dense;
-  m->stats.d2h_bytes = d2h + dense * m->img_bytes;
-  return AGARCL_OK;
+  return collect(m, d_obs, s, false);
 }
 
 }  // namespace ag

@@ -5,6 +5,8 @@
 
 #include <cstdint>
 
+#include "sim_params.h"
+
 namespace ag {
 
 struct HostMirror;
@@ -14,15 +16,22 @@ struct MirrorStats {
   uint64_t dense_images; // images that took the dense copy (entry capacity exceeded or a non-separable mask)
   uint64_t d2h_bytes;    // bytes copied device -> host by the last sync
   uint64_t host_threads; // threads that expand the lists into the mirror
+  uint64_t wait_us;      // last sync: time the calling thread waited for the device (chunk flags + chunk copies)
+  uint64_t total_us;     // last sync: first chunk wait to mirror complete
 };
 
-// n_img images of CH = frames*C channels of G x G elements; dtype: agarcl_obs_dtype.  nullptr + agarcl_set_error on failure.
-HostMirror* mirror_create(int n_img, int CH, int C, int G, int dtype);
+// n_img = instances * agents images of CH = frames*C channels of G x G elements; dtype: agarcl_obs_dtype.
+// nullptr + agarcl_set_error on failure.
+HostMirror* mirror_create(int n_img, int agents, int CH, int C, int G, int dtype);
 void mirror_destroy(HostMirror* m);
 void* mirror_ptr(HostMirror* m);
-// Makes the host mirror identical to the device observation `d_obs` (work enqueued on `s`, then synchronised;
-// everything enqueued on `s` before the call is complete when it returns).
+// Makes the host mirror identical to the device observation `d_obs`: k_pack enqueued on `s`, then synchronised;
+// everything enqueued on `s` before the call is complete when it returns.
 int mirror_sync(HostMirror* m, const void* d_obs, cudaStream_t s);
+// The fused path: hand mirror_pack_out() to ONE k_step launch on `s` (SimParams::pk), then call mirror_collect(m, d_obs, s):
+// chunks are fetched and expanded while the kernel runs; `s` is synchronised when it returns.
+PackOut mirror_pack_out(HostMirror* m);
+int mirror_collect(HostMirror* m, const void* d_obs, cudaStream_t s);
 void mirror_stats(const HostMirror* m, MirrorStats* out);
 
 }  // namespace ag

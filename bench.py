@@ -382,7 +382,10 @@ def run_ours(args):
     # moving the out-of-bounds masks + the non-zero lists and patching the mirror in place) -- this is `e2e`
     mirror = b.mirror()
     Km = max(Ke, min(K, 50))
+    b.set_timing(True)
     e2e_s = time_host(host_step_mirror, Km)
+    e2e_kernel_ms, _, e2e_ksteps = b.get_timing()
+    b.set_timing(False)
     mstats = b.mirror_stats()
     d2h = mstats["d2h_bytes"] + N * A * (8 + 1)
     mirror_ok = bool(torch.equal(torch.from_numpy(mirror[:64].copy()).cuda(), b.obs_tensor()[:64]))
@@ -436,9 +439,12 @@ def run_ours(args):
                         "steps": Ke,
                         "note": "agarcl_batch_step_mirror: pinned host actions in; rewards + dones out; the dense int32 observation "
                                 "[N*A,8,128,128] is left in the library-owned pinned HOST mirror, kept identical to the device tensor by "
-                                "copying only the out-of-bounds masks and non-zero lists (k_pack) and patching the mirror on "
-                                f"{mstats['host_threads']} host threads; d2h_bytes_per_step is what crossed PCIe in the last step",
+                                "copying only the out-of-bounds masks and non-zero lists (listed by k_step itself while it scatters, fetched chunk by chunk "
+                                f"while the kernel runs) and patching the mirror on {mstats['host_threads']} host threads; d2h_bytes_per_step is "
+                                "what crossed PCIe in the last step",
                         "mirror_equals_device": mirror_ok, "mirror_entries_per_step": mstats["entries"],
+                        "mirror_last_step_us": {"device_wait": mstats["wait_us"], "collect_total": mstats["total_us"]},
+                        "k_step_ms_in_e2e": e2e_kernel_ms / max(e2e_ksteps, 1),
                         "mirror_dense_images": mstats["dense_images"],
                         "dense_copy": {"value": world * N / dense_s, "unit": UNIT, "d2h_bytes_per_step": d2h_dense,
                                        "note": "agarcl_batch_step_host: the whole int32 observation copied D2H every step (PCIe bound)"}},

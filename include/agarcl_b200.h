@@ -199,13 +199,19 @@ int agarcl_batch_step_host(agarcl_batch* b, const float* dxdy, const int32_t* ac
  *   agarcl_batch_sync_mirror  brings it up to date with the current device observation (after a reset, a
  *                             render, or agarcl_batch_step); synchronises `stream`.
  *   agarcl_batch_step_mirror  = take_actions (host) + step + sync_mirror + rewards/dones to host: the
- *                             reference-facing call `e2e` in bench.py times.
+ *                             reference-facing call `e2e` in bench.py times.  When the step is the single fused
+ *                             kernel (int32, one frame) that kernel lists what it scatters itself and flags
+ *                             finished chunks of instances in host-mapped memory, so the host fetches and
+ *                             expands chunk k while the device still steps chunk k+1.
  *   agarcl_batch_mirror_stats out[0] entries moved by the last sync, [1] images copied densely, [2] bytes copied
  *                             device->host, [3] host threads.                                                  */
 int agarcl_batch_mirror(agarcl_batch* b, void** host_ptr, int64_t shape[4], int32_t* dtype);
 int agarcl_batch_sync_mirror(agarcl_batch* b, void* stream);
 int agarcl_batch_step_mirror(agarcl_batch* b, const float* dxdy, const int32_t* act, double* rewards_out, uint8_t* dones_out);
 int agarcl_batch_mirror_stats(const agarcl_batch* b, uint64_t out[4]);
+/* last sync: out[0] microseconds the calling thread waited for the device (chunk flags and list copies),
+ * out[1] microseconds from the start of the collection to the mirror being complete. */
+int agarcl_batch_mirror_timing(const agarcl_batch* b, uint64_t out[2]);
 
 /* ---------------------------------------------------- structured ("ram") observation
  * GoBiggerObservation::add_frame (environment/envs/GoBiggerEnvironment.hpp:515-548, _store_entities

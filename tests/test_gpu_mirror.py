@@ -83,10 +83,10 @@ def test_mirror_int16_frames_and_small_grid():
 
 
 def test_mirror_dense_fallback_is_exact():
-    """Entry capacity 4 per image: almost every image overflows and takes the dense copy, and images move between the
-    sparse and the dense path from step to step; the mirror must not notice."""
+    """Entry capacity 1 per image (64 per chunk of images on the fused path): the lists overflow, images take the dense
+    copy and move between the sparse and the dense path from step to step; the mirror must not notice."""
     from agarcl_b200.env import BatchedGridEnvironment
-    os.environ["AGARCL_MIRROR_CAP_IMG"] = "4"
+    os.environ["AGARCL_MIRROR_CAP_IMG"] = "1"
     try:
         env = BatchedGridEnvironment(32, num_bots=4, arena_size=600, num_pellets=120, num_viruses=1)
         env.seed(8)
