@@ -52,7 +52,7 @@ def lib():
         L.agarcl_batch_sync_mirror.argtypes = [_vp, _vp]
         L.agarcl_batch_step_mirror.argtypes = [_vp, _vp, _vp, _vp, _vp]
         L.agarcl_batch_mirror_stats.argtypes = [_vp, C.POINTER(C.c_uint64 * 4)]
-        L.agarcl_batch_mirror_timing.argtypes = [_vp, C.POINTER(C.c_uint64 * 2)]
+        L.agarcl_batch_mirror_timing.argtypes = [_vp, C.POINTER(C.c_uint64 * 4)]
         L.agarcl_batch_download_state.argtypes = [_vp, C.c_int32, _vp]
         L.agarcl_batch_upload_state.argtypes = [_vp, C.c_int32, _vp]
         L.agarcl_batch_save_env_state.argtypes = [_vp, C.c_int32, C.c_char_p]

@@ -126,10 +126,10 @@ class Batch:
     def mirror_stats(self):
         out = (C.c_uint64 * 4)()
         _lib.check(_lib.lib().agarcl_batch_mirror_stats(self._h, C.byref(out)))
-        t = (C.c_uint64 * 2)()
+        t = (C.c_uint64 * 4)()
         _lib.check(_lib.lib().agarcl_batch_mirror_timing(self._h, C.byref(t)))
         return dict(entries=int(out[0]), dense_images=int(out[1]), d2h_bytes=int(out[2]), host_threads=int(out[3]),
-                    wait_us=int(t[0]), total_us=int(t[1]))
+                    wait_us=int(t[0]), total_us=int(t[1]), launch_us=int(t[2]), call_us=int(t[3]))
 
     def set_timing(self, enable=True):
         _lib.check(_lib.lib().agarcl_batch_set_timing(self._h, int(enable)))

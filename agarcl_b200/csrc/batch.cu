@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -55,6 +56,7 @@ struct agarcl_batch {
                        // 2: it also writes channel 0 and scatters the entities (one kernel per step).  AGARCL_FUSE_CLEAR overrides (A/B timing)
   int launches_last_step = 0;
   ag::HostMirror* mirror = nullptr;  // host-resident observation mirror (mirror.cu), created on first use
+  uint64_t mirror_launch_us = 0, mirror_call_us = 0;  // last agarcl_batch_step_mirror: staging + launch, whole call
   // optional per-kernel timing: (start, after sim, after obs) event triples of steps not yet collected
   bool timing = false;
   std::vector<cudaEvent_t> ev;
@@ -442,7 +444,7 @@ static int step_impl(agarcl_batch* b, cudaStream_t s, bool want_lists, bool* lis
   } else if (b->frames == 1) {
     P.n_ticks = tps; P.do_begin = 1; P.do_end = 1;
     const int fused = fuse_obs_clear(b, P, 0) ? 1 : 0;
-    if (want_lists && P.obs_finish && b->mirror && !b->d_ram) {
+    if (want_lists && P.obs_finish && b->mirror && 5 + 2 * ((b->G + 31) / 32) <= 32) {  // (the image's record is one warp store)
       P.pk = ag::mirror_pack_out(b->mirror);
       *lists_made = true;
     }
@@ -564,17 +566,25 @@ extern "C" int agarcl_batch_step_mirror(agarcl_batch* b, const float* dxdy, cons
   if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");
   int rc = ensure_mirror(b);
   if (rc) return rc;
-  rc = agarcl_batch_set_actions(b, dxdy, act, 0, nullptr);
-  if (rc) return rc;
+  if (!dxdy || !act) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  // the kernel reads the actions straight from host-mapped staging: no H2D copy in front of the launch
+  const auto t0 = std::chrono::steady_clock::now();
+  ag::mirror_stage_actions(b->mirror, dxdy, act, &b->cur_dxdy, &b->cur_act);
   bool lists_made = false;
   rc = step_impl(b, nullptr, true, &lists_made);
   if (rc) return rc;
+  b->mirror_launch_us = (uint64_t)(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e6);
+  if (lists_made) {  // k_step lists what it scatters (and reward / done) into pinned host memory while it runs
+    rc = ag::mirror_collect(b->mirror, b->d_obs, nullptr, rewards_out, dones_out);
+    b->mirror_call_us = (uint64_t)(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e6);
+    return rc;
+  }
   const size_t NA = (size_t)b->N * b->A;
   if (rewards_out) CK(cudaMemcpyAsync(rewards_out, b->d_rewards, NA * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
   if (dones_out) CK(cudaMemcpyAsync(dones_out, b->d_dones, NA, cudaMemcpyDeviceToHost, nullptr));
-  if (lists_made) return ag::mirror_collect(b->mirror, b->d_obs, nullptr);  // k_step listed what it scattered
   rc = ag::mirror_sync(b->mirror, b->d_obs, nullptr);
   b->launches_last_step += 1;  // k_pack
+  b->mirror_call_us = (uint64_t)(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e6);
   return rc;
 }
 
@@ -587,12 +597,12 @@ extern "C" int agarcl_batch_mirror_stats(const agarcl_batch* b, uint64_t out[4])
   return AGARCL_OK;
 }
 
-extern "C" int agarcl_batch_mirror_timing(const agarcl_batch* b, uint64_t out[2]) {
+extern "C" int agarcl_batch_mirror_timing(const agarcl_batch* b, uint64_t out[4]) {
   if (!b || !out) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
   if (!b->mirror) return agarcl_set_error(AGARCL_ERR_STATE, "no host mirror yet (agarcl_batch_mirror)");
   ag::MirrorStats st;
   ag::mirror_stats(b->mirror, &st);
-  out[0] = st.wait_us; out[1] = st.total_us;
+  out[0] = st.wait_us; out[1] = st.total_us; out[2] = b->mirror_launch_us; out[3] = b->mirror_call_us;
   return AGARCL_OK;
 }
 

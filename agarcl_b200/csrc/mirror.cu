@@ -24,6 +24,8 @@
 // tests/test_gpu_mirror.py compares them element for element after every step.
 #include "mirror.h"
 
+#include <sys/mman.h>
+
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const PackParams P) {
       }
     }
     if (bad) s_bad = 1;
-    uint32_t* mk = blk + pk_off_masks(P.pk) + (size_t)li * P.pk.mask_words + (size_t)f * 2 * MW;
+    uint32_t* mk = blk + pk_off_rec(P.pk) + (size_t)li * P.pk.rec_words + 2 + (size_t)f * 2 * MW;
     for (uint32_t w = tid; w < 2u * MW; w += kPackThreads) {
       const uint8_t* any = w < MW ? row_any : col_any;
       const uint32_t w0 = (w % MW) * 32;
@@ -157,8 +159,9 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const PackParams P) {
       b0 = atomicAdd(P.pk.cursor + chunk, cnt);
       if (b0 + cnt > P.pk.cap_chunk) cnt = kPackDense;
     }
-    blk[pk_off_count(P.pk) + li] = cnt;
-    blk[pk_off_base(P.pk) + li] = b0;
+    uint32_t* rec = blk + pk_off_rec(P.pk) + (size_t)li * P.pk.rec_words;
+    rec[0] = cnt;
+    rec[1] = b0;
     s_cnt = cnt;
     s_base = b0;
   }
@@ -187,6 +190,8 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const PackParams P) {
 
 // ------------------------------------------------------------------------------------------------ host pool
 // Every worker (and, from join() on, the caller) runs the same job, which pulls work from atomic counters.
+// Workers sleep on a condition variable between jobs; the END of a job is awaited by spinning on an atomic
+// (a futex wake-up of the caller would add tens of microseconds to every step).
 class Pool {
  public:
   explicit Pool(int workers) {
@@ -205,15 +210,20 @@ class Pool {
     {
       std::lock_guard<std::mutex> g(mu_);
       job_ = &job;
-      pending_ = (int)th_.size();
+      pending_.store((int)th_.size(), std::memory_order_relaxed);
       gen_++;
     }
     cv_start_.notify_all();
   }
   void join() {  // the caller works too, then waits for the workers
     (*job_)();
-    std::unique_lock<std::mutex> g(mu_);
-    cv_done_.wait(g, [this] { return pending_ == 0; });
+    while (pending_.load(std::memory_order_acquire) != 0) {
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#else
+      std::this_thread::yield();
+#endif
+    }
     job_ = nullptr;
   }
   void run(const std::function<void()>& job) {
@@ -234,18 +244,15 @@ class Pool {
         job = job_;
       }
       (*job)();
-      {
-        std::lock_guard<std::mutex> g(mu_);
-        if (--pending_ == 0) cv_done_.notify_one();
-      }
+      pending_.fetch_sub(1, std::memory_order_release);
     }
   }
   std::vector<std::thread> th_;
   std::mutex mu_;
-  std::condition_variable cv_start_, cv_done_;
+  std::condition_variable cv_start_;
   const std::function<void()>* job_ = nullptr;
   uint64_t gen_ = 0;
-  int pending_ = 0;
+  std::atomic<int> pending_{0};
   bool stop_ = false;
 };
 
@@ -265,15 +272,20 @@ struct HostMirror {
   PackOut pk{};                   // device side of the chunk blocks (flags / seq filled per use)
   size_t meta_words = 0;          // words of a chunk block in front of its entries
   void* h_obs = nullptr;          // pinned [n_img][CH][G][G]
+  bool obs_malloced = false, obs_registered = false;
   uint32_t* d_chunks = nullptr;
   uint32_t* d_counters = nullptr; // [2][n_chunks] cursor, done
-  uint32_t* h_chunks[2] = {nullptr, nullptr};  // pinned staging, same block layout; [cur] = this step's lists, [cur^1] = the previous step's
+  uint32_t* h_chunks[2] = {nullptr, nullptr};  // pinned + host-mapped, same block layout; [cur] = this step's lists, [cur^1] = the previous step's
+  uint32_t* dh_chunks[2] = {nullptr, nullptr}; // their device addresses (k_step writes its lists straight into them)
+  float* h_dxdy = nullptr;                     // host-mapped action staging [n_img][2], [n_img]: k_step reads the step's
+  int32_t* h_act = nullptr;                    // actions straight from host memory
+  float* d_dxdy = nullptr;
+  int32_t* d_act = nullptr;
   volatile uint32_t* h_flags = nullptr;        // host-mapped [n_chunks]
   uint32_t* d_flags = nullptr;                 // its device address
   uint32_t seq = 0;
   int cur = 0;
   std::vector<size_t> guess;      // per chunk: entries fetched together with the meta words (the remainder, if any, in a second copy)
-  cudaStream_t copy_stream = nullptr;          // non-blocking: copies chunks while the step kernel runs
   Pool* pool = nullptr;
   MirrorStats stats{};
   uint32_t* blk(int w, int chunk) const { return h_chunks[w] + (size_t)chunk * pk.chunk_words; }
@@ -306,32 +318,52 @@ static void apply_mask_delta(T* p, const uint32_t* om, const uint32_t* nm, int G
   }
 }
 
+// The elements an image's two lists touch are scattered over its 512 KB: ask for their cache lines (for writing)
+// one image ahead, so that the misses of image i+1 overlap the read-modify-writes of image i.
+template <typename T>
+static void prefetch_image(const HostMirror* m, int img) {
+  const int cur = m->cur, prev = cur ^ 1;
+  const PackOut& k = m->pk;
+  const int chunk = img / (int)k.ipc, li = img - chunk * (int)k.ipc;
+  const T* p = reinterpret_cast<const T*>(m->h_obs) + (size_t)img * m->img_elems;
+  for (int w = 0; w < 2; w++) {
+    const uint32_t* b = m->blk(w ? prev : cur, chunk);
+    const uint32_t* rec = b + pk_off_rec(k) + (size_t)li * k.rec_words;
+    if (rec[0] == kPackDense) continue;
+    const uint2* e = reinterpret_cast<const uint2*>(b + pk_off_entries(k)) + rec[1];
+    for (uint32_t i = 0; i < rec[0]; i++) __builtin_prefetch(p + (e[i].x & kPkOffMask), 1, 1);
+  }
+}
+
 template <typename T>
 static void expand_range(HostMirror* m, int lo, int hi, const uint32_t* zero_masks) {
   const int cur = m->cur, prev = cur ^ 1;
   const PackOut& k = m->pk;
   const size_t mw2 = 2 * (size_t)m->MW, plane = (size_t)m->G * m->G;
+  prefetch_image<T>(m, lo);
   for (int img = lo; img < hi; img++) {
+    if (img + 1 < hi) prefetch_image<T>(m, img + 1);
     const int chunk = img / (int)k.ipc, li = img - chunk * (int)k.ipc;
     const uint32_t *cb = m->blk(cur, chunk), *pb = m->blk(prev, chunk);
-    const uint32_t cnt = cb[pk_off_count(k) + li];
-    if (cnt == kPackDense) continue;  // the dense copy of this image is already in flight
+    const uint32_t *crec = cb + pk_off_rec(k) + (size_t)li * k.rec_words, *prec = pb + pk_off_rec(k) + (size_t)li * k.rec_words;
+    const uint32_t cnt = crec[0];
+    if (cnt == kPackDense) continue;  // the dense copy of this image is made by the calling thread
     T* p = reinterpret_cast<T*>(m->h_obs) + (size_t)img * m->img_elems;
-    const uint32_t pcnt = pb[pk_off_count(k) + li];
-    const uint32_t* om = pb + pk_off_masks(k) + (size_t)li * k.mask_words;
-    const uint32_t* nm = cb + pk_off_masks(k) + (size_t)li * k.mask_words;
+    const uint32_t pcnt = prec[0];
+    const uint32_t* om = prec + 2;
+    const uint32_t* nm = crec + 2;
     if (pcnt == kPackDense) {
       std::memset(p, 0, m->img_bytes);
       om = nullptr;
     } else {
-      const uint2* pe = reinterpret_cast<const uint2*>(pb + pk_off_entries(k)) + pb[pk_off_base(k) + li];
+      const uint2* pe = reinterpret_cast<const uint2*>(pb + pk_off_entries(k)) + prec[1];
       for (uint32_t e = 0; e < pcnt; e++) p[pe[e].x & kPkOffMask] = 0;
     }
     for (int f = 0; f < m->frames; f++) {
       const uint32_t* o = om ? om + f * mw2 : zero_masks;
       if (std::memcmp(o, nm + f * mw2, mw2 * 4) != 0) apply_mask_delta<T>(p + (size_t)f * m->C * plane, o, nm + f * mw2, m->G, m->MW);
     }
-    const uint2* ne = reinterpret_cast<const uint2*>(cb + pk_off_entries(k)) + cb[pk_off_base(k) + li];
+    const uint2* ne = reinterpret_cast<const uint2*>(cb + pk_off_entries(k)) + crec[1];
     for (uint32_t e = 0; e < cnt; e++) {
       T& x = p[ne[e].x & kPkOffMask];
       const T v = (T)(int32_t)ne[e].y;
@@ -348,12 +380,18 @@ static void expand_range(HostMirror* m, int lo, int hi, const uint32_t* zero_mas
 void mirror_destroy(HostMirror* m) {
   if (!m) return;
   delete m->pool;
-  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   cudaFree(m->d_chunks);
   cudaFree(m->d_counters);
   for (int w = 0; w < 2; w++) cudaFreeHost(m->h_chunks[w]);
   cudaFreeHost((void*)m->h_flags);
-  cudaFreeHost(m->h_obs);
+  cudaFreeHost(m->h_dxdy);
+  cudaFreeHost(m->h_act);
+  if (m->obs_malloced) {
+    if (m->obs_registered) cudaHostUnregister(m->h_obs);
+    std::free(m->h_obs);
+  } else {
+    cudaFreeHost(m->h_obs);
+  }
   delete m;
 }
 
@@ -386,24 +424,45 @@ HostMirror* mirror_create(int n_img, int agents, int CH, int C, int G, int dtype
   PackOut& k = m->pk;
   k.ipc = (uint32_t)ipc_inst * (uint32_t)agents;
   m->n_chunks = (n_img + (int)k.ipc - 1) / (int)k.ipc;
-  k.mask_words = (uint32_t)(m->frames * 2 * m->MW);
+  k.rec_words = (uint32_t)(2 + m->frames * 2 * m->MW + 3);
   k.MW = m->MW;
   k.n_img = (uint32_t)n_img;
-  uint64_t cc = (uint64_t)k.ipc * (m->cap_img < 1024 ? m->cap_img : 1024);
-  if (cc < 16) cc = 16;
-  k.cap_chunk = (uint32_t)(cc > 0x3FFFFFFFull ? 0x3FFFFFFFull : cc);
+  uint32_t per_img = (m->cap_img < 1024 ? m->cap_img : 1024) & ~1u;  // entries per image (k_step: the image's slot)
+  if (per_img < 2) per_img = 2;
+  k.slot = per_img;
+  k.cap_chunk = k.ipc * per_img;
   m->meta_words = pk_off_entries(k);
   k.chunk_words = (uint32_t)(m->meta_words + 2 * (size_t)k.cap_chunk);
   const size_t all_words = (size_t)m->n_chunks * k.chunk_words;
-  bool ok = cudaHostAlloc(&m->h_obs, (size_t)n_img * m->img_bytes, cudaHostAllocDefault) == cudaSuccess;
+  // the mirror itself: 2 MB-aligned, transparent huge pages requested (random element updates over gigabytes are
+  // TLB-bound with 4 KB pages), then page-locked; plain cudaHostAlloc if that does not work
+  bool ok = true;
+  {
+    const size_t bytes = (size_t)n_img * m->img_bytes, two_mb = (size_t)2 << 20;
+    void* p = nullptr;
+    if (!std::getenv("AGARCL_MIRROR_NO_THP") && posix_memalign(&p, two_mb, (bytes + two_mb - 1) / two_mb * two_mb) == 0 && p) {
+#ifdef MADV_HUGEPAGE
+      madvise(p, (bytes + two_mb - 1) / two_mb * two_mb, MADV_HUGEPAGE);
+#endif
+      m->h_obs = p;
+      m->obs_registered = false;  // registered after the first touch below
+      m->obs_malloced = true;
+    } else {
+      ok = cudaHostAlloc(&m->h_obs, bytes, cudaHostAllocDefault) == cudaSuccess;
+    }
+  }
   ok = ok && cudaMalloc((void**)&m->d_chunks, all_words * 4) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&m->d_counters, 2 * (size_t)m->n_chunks * 4) == cudaSuccess;
   ok = ok && cudaMemset(m->d_counters, 0, 2 * (size_t)m->n_chunks * 4) == cudaSuccess;
   ok = ok && cudaHostAlloc((void**)&m->h_flags, (size_t)m->n_chunks * 4, cudaHostAllocMapped) == cudaSuccess;
   ok = ok && cudaHostGetDevicePointer((void**)&m->d_flags, (void*)m->h_flags, 0) == cudaSuccess;
-  ok = ok && cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaHostAlloc((void**)&m->h_dxdy, (size_t)n_img * 2 * sizeof(float), cudaHostAllocMapped) == cudaSuccess;
+  ok = ok && cudaHostGetDevicePointer((void**)&m->d_dxdy, m->h_dxdy, 0) == cudaSuccess;
+  ok = ok && cudaHostAlloc((void**)&m->h_act, (size_t)n_img * sizeof(int32_t), cudaHostAllocMapped) == cudaSuccess;
+  ok = ok && cudaHostGetDevicePointer((void**)&m->d_act, m->h_act, 0) == cudaSuccess;
   for (int w = 0; w < 2 && ok; w++) {
-    ok = ok && cudaHostAlloc((void**)&m->h_chunks[w], all_words * 4, cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaHostAlloc((void**)&m->h_chunks[w], all_words * 4, cudaHostAllocMapped) == cudaSuccess;
+    ok = ok && cudaHostGetDevicePointer((void**)&m->dh_chunks[w], m->h_chunks[w], 0) == cudaSuccess;
     if (ok)  // no entries, nothing out of bounds == the all-zero mirror
       for (int c = 0; c < m->n_chunks; c++) std::memset(m->blk(w, c), 0, m->meta_words * 4);
   }
@@ -436,14 +495,26 @@ HostMirror* mirror_create(int n_img, int agents, int CH, int C, int G, int dtype
       }
     });
   }
+  if (m->obs_malloced) {  // page-lock it (dense fallback copies land here; callers may copy it to a device)
+    if (cudaHostRegister(m->h_obs, (size_t)n_img * m->img_bytes, cudaHostRegisterDefault) == cudaSuccess) m->obs_registered = true;
+    else cudaGetLastError();  // stays pageable: only the rare dense copies get slower
+  }
   return m;
 }
 
 void* mirror_ptr(HostMirror* m) { return m->h_obs; }
 void mirror_stats(const HostMirror* m, MirrorStats* out) { *out = m->stats; }
 
+void mirror_stage_actions(HostMirror* m, const float* dxdy, const int32_t* act, const float** d_dxdy, const int32_t** d_act) {
+  std::memcpy(m->h_dxdy, dxdy, (size_t)m->n_img * 2 * sizeof(float));
+  std::memcpy(m->h_act, act, (size_t)m->n_img * sizeof(int32_t));
+  *d_dxdy = m->d_dxdy;
+  *d_act = m->d_act;
+}
+
 PackOut mirror_pack_out(HostMirror* m) {
   PackOut k = m->pk;
+  k.chunks = m->dh_chunks[m->cur ^ 1];  // mirror_collect flips `cur`: the kernel writes what the host then reads as [cur]
   k.flags = m->d_flags;
   k.seq = ++m->seq;
   return k;
@@ -459,7 +530,8 @@ PackOut mirror_pack_out(HostMirror* m) {
 // Fetches the chunks as they become complete and expands them into the mirror.  `flagged`: a kernel launched on
 // `s` with mirror_pack_out() raises the flags (the chunks are fetched on the copy stream while it runs);
 // otherwise everything on `s` is complete already.
-static int collect(HostMirror* m, const void* d_obs, cudaStream_t s, bool flagged) {
+static int collect(HostMirror* m, const void* d_obs, cudaStream_t s, bool flagged, double* rewards_out = nullptr,
+                   uint8_t* dones_out = nullptr) {
   using clk = std::chrono::steady_clock;
   const auto t0 = clk::now();
   m->cur ^= 1;
@@ -482,7 +554,8 @@ static int collect(HostMirror* m, const void* d_obs, cudaStream_t s, bool flagge
     }
   };
   m->pool->start(job);
-  uint64_t d2h = 0, dense = 0, entries = 0;
+  uint64_t d2h = 0, entries = 0;
+  std::vector<int> dense_imgs;
   double wait_s = 0.0;
   int rc = AGARCL_OK;
   auto fail = [&](cudaError_t e, const char* what) {
@@ -506,44 +579,57 @@ static int collect(HostMirror* m, const void* d_obs, cudaStream_t s, bool flagge
       }
       if (rc != AGARCL_OK) break;
     }
-    const cudaStream_t cs = flagged ? m->copy_stream : s;
     uint32_t* hb = m->blk(cur, c);
-    const uint32_t* db = m->d_chunks + (size_t)c * k.chunk_words;
-    size_t got = m->guess[c] < k.cap_chunk ? m->guess[c] : k.cap_chunk;
-    cudaError_t e = cudaMemcpyAsync(hb, db, (m->meta_words + 2 * got) * 4, cudaMemcpyDeviceToHost, cs);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
-    if (e != cudaSuccess) { fail(e, "chunk copy"); break; }
-    d2h += (m->meta_words + 2 * got) * 4;
-    size_t total = hb[0];
-    if (total > k.cap_chunk) total = k.cap_chunk;
-    if (total > got) {
-      e = cudaMemcpyAsync(hb + m->meta_words + 2 * got, db + m->meta_words + 2 * got, (total - got) * 8, cudaMemcpyDeviceToHost, cs);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
-      if (e != cudaSuccess) { fail(e, "chunk copy (remainder)"); break; }
-      d2h += (total - got) * 8;
-    }
-    m->guess[c] = total + total / 8 + 1024;
-    entries += total;
-    // dense copies (asynchronous into the pinned mirror), they overlap the list expansion
     const int lo = c * (int)k.ipc, hi = lo + (int)k.ipc < m->n_img ? lo + (int)k.ipc : m->n_img;
-    const uint32_t* cnt = hb + pk_off_count(k);
-    for (int i = lo; i < hi; i++)
-      if (cnt[i - lo] == kPackDense) {
-        e = cudaMemcpyAsync((uint8_t*)m->h_obs + (size_t)i * m->img_bytes, (const uint8_t*)d_obs + (size_t)i * m->img_bytes,
-                            m->img_bytes, cudaMemcpyDeviceToHost, cs);
-        if (e != cudaSuccess) { fail(e, "dense image copy"); break; }
-        dense++;
+    if (!flagged) {  // k_pack left a compact block in device memory: one copy (a second one if the guess was short)
+      const uint32_t* db = m->d_chunks + (size_t)c * k.chunk_words;
+      size_t got = m->guess[c] < k.cap_chunk ? m->guess[c] : k.cap_chunk;
+      cudaError_t e = cudaMemcpyAsync(hb, db, (m->meta_words + 2 * got) * 4, cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) { fail(e, "chunk copy"); break; }
+      d2h += (m->meta_words + 2 * got) * 4;
+      size_t total = hb[0];
+      if (total > k.cap_chunk) total = k.cap_chunk;
+      if (total > got) {
+        e = cudaMemcpyAsync(hb + m->meta_words + 2 * got, db + m->meta_words + 2 * got, (total - got) * 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { fail(e, "chunk copy (remainder)"); break; }
+        d2h += (total - got) * 8;
       }
+      m->guess[c] = total + total / 8 + 1024;
+    }
+    for (int i = lo; i < hi; i++) {
+      const uint32_t* rec = hb + pk_off_rec(k) + (size_t)(i - lo) * k.rec_words;
+      if (rec[0] == kPackDense) dense_imgs.push_back(i);
+      else entries += rec[0];
+      if (flagged) {  // reward and done flag of the step came with the record
+        if (rewards_out) std::memcpy(rewards_out + i, rec + k.rec_words - 3, sizeof(double));
+        if (dones_out) dones_out[i] = (uint8_t)rec[k.rec_words - 1];
+      }
+    }
+    if (flagged) d2h += (size_t)(hi - lo) * k.rec_words * 4 + 4;  // what the kernel wrote over PCIe: records + flag (entries below)
     wait_s += std::chrono::duration<double>(clk::now() - w0).count();
     avail.store(hi, std::memory_order_release);
   }
+  if (flagged) d2h += entries * 8;
+  // images that do not fit the scheme: dense copies into the pinned mirror (the workers skip them); in the fused
+  // path the frames are only known to be complete in device memory once the kernel has ended
+  if (rc == AGARCL_OK && !dense_imgs.empty()) {
+    cudaError_t e = flagged ? cudaStreamSynchronize(s) : cudaSuccess;
+    for (size_t j = 0; j < dense_imgs.size() && e == cudaSuccess; j++) {
+      const size_t i = (size_t)dense_imgs[j];
+      e = cudaMemcpyAsync((uint8_t*)m->h_obs + i * m->img_bytes, (const uint8_t*)d_obs + i * m->img_bytes, m->img_bytes,
+                          cudaMemcpyDeviceToHost, s);
+    }
+    if (e != cudaSuccess) fail(e, "dense image copy");
+  }
+  const uint64_t dense = dense_imgs.size();
   if (rc != AGARCL_OK) abort.store(true);
   m->pool->join();
+  // Every chunk flag is up: all instances have been stepped and everything the caller reads is in host memory.  The
+  // kernel's last warps may still be leaving; whatever is enqueued on `s` next is ordered behind them, so only the
+  // dense copies (if any) need the stream.
   if (rc == AGARCL_OK && dense) {
-    const cudaError_t e = cudaStreamSynchronize(flagged ? m->copy_stream : s);
-    if (e != cudaSuccess) fail(e, "dense image copies");
-  }
-  if (rc == AGARCL_OK && flagged) {  // rewards / dones copies and the kernel itself
     const cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) fail(e, "cudaStreamSynchronize");
   }
@@ -555,7 +641,9 @@ static int collect(HostMirror* m, const void* d_obs, cudaStream_t s, bool flagge
   return rc;
 }
 
-int mirror_collect(HostMirror* m, const void* d_obs, cudaStream_t s) { return collect(m, d_obs, s, true); }
+int mirror_collect(HostMirror* m, const void* d_obs, cudaStream_t s, double* rewards_out, uint8_t* dones_out) {
+  return collect(m, d_obs, s, true, rewards_out, dones_out);
+}
 
 int mirror_sync(HostMirror* m, const void* d_obs, cudaStream_t s) {
   PackParams P;

@@ -30,8 +30,12 @@ void* mirror_ptr(HostMirror* m);
 int mirror_sync(HostMirror* m, const void* d_obs, cudaStream_t s);
 // The fused path: hand mirror_pack_out() to ONE k_step launch on `s` (SimParams::pk), then call mirror_collect(m, d_obs, s):
 // chunks are fetched and expanded while the kernel runs; `s` is synchronised when it returns.
+// mirror_collect returns when every chunk has been flagged and expanded: the mirror and rewards_out / dones_out (from the
+// records, may be null) are complete; the kernel itself may still be retiring on `s`.
+// mirror_stage_actions copies the step's actions into host-mapped staging the kernel reads directly (no H2D copy).
 PackOut mirror_pack_out(HostMirror* m);
-int mirror_collect(HostMirror* m, const void* d_obs, cudaStream_t s);
+int mirror_collect(HostMirror* m, const void* d_obs, cudaStream_t s, double* rewards_out, uint8_t* dones_out);
+void mirror_stage_actions(HostMirror* m, const float* dxdy, const int32_t* act, const float** d_dxdy, const int32_t** d_act);
 void mirror_stats(const HostMirror* m, MirrorStats* out);
 
 }  // namespace ag

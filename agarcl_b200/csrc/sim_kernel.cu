@@ -1838,72 +1838,58 @@ __device__ void obs_finish_warp(Ctx& c) {
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    // host-mirror lists (PackOut): the row / column bit masks of channel 0 straight from the predicates above
+    // host-mirror lists (PackOut, sim_params.h): this image's record and entry slot in pinned host memory
     bool emit = P.pk.chunks != nullptr;
-    uint32_t* pk_blk = nullptr;  // this image's chunk block and its index inside the chunk
-    uint32_t pk_li = 0, pk_chunk = 0;
+    uint32_t* pk_rec = nullptr;
+    uint4* pk_ent = nullptr;     // the image's slot, two entries per 16-byte store
+    uint32_t pk_mine = 0u;       // lane l holds word l of the record: count, base, row masks, column masks
+    uint32_t wq = 0u;            // entries listed so far (warp-uniform, even)
     if (emit) {
       const uint32_t img = (uint32_t)c.inst_local * (uint32_t)A + (uint32_t)a;
-      pk_chunk = img / P.pk.ipc;
-      pk_li = img - pk_chunk * P.pk.ipc;
-      pk_blk = P.pk.chunks + (size_t)pk_chunk * P.pk.chunk_words;
+      const uint32_t chunk = img / P.pk.ipc, li = img - chunk * P.pk.ipc;
+      uint32_t* blk = P.pk.chunks + (size_t)chunk * P.pk.chunk_words;
+      pk_rec = blk + pk_off_rec(P.pk) + (size_t)li * P.pk.rec_words;
+      pk_ent = reinterpret_cast<uint4*>(blk + pk_off_entries(P.pk)) + (size_t)li * (P.pk.slot / 2u);
+      if (lane == 1) pk_mine = li * P.pk.slot;
       const int MW = P.pk.MW;
-      uint32_t* mk = pk_blk + pk_off_masks(P.pk) + (size_t)pk_li * P.pk.mask_words;
-      for (int i0 = 0, w = 0; i0 < G; i0 += 32, w++) {
+      for (int i0 = 0, w = 0; i0 < G; i0 += 32, w++) {  // the row / column bit masks of channel 0 from the predicates above
         const int i = i0 + lane;
         const float wx = px + ((float)i - centering) * view / (float)G;
         const float wy = py + ((float)i - centering) * view / (float)G;
         const unsigned rb = __ballot_sync(AG_FULL, i < G && !(0 <= wx && wx < W));
         const unsigned cb = __ballot_sync(AG_FULL, i < G && !(0 <= wy && wy < W));
-        if (lane == 0) { mk[w] = rb; mk[MW + w] = cb; }
+        if (lane == 2 + w) pk_mine = rb;
+        if (lane == 2 + MW + w) pk_mine = cb;
       }
-      if (n == 0 && lane == 0) { pk_blk[pk_off_count(P.pk) + pk_li] = 0u; pk_blk[pk_off_base(P.pk) + pk_li] = 0u; }
     }
-    if (n == 0) continue;  // dead agent: nothing lands inside the grid
     auto grid_of = [&](float x, float y, int& gx, int& gy) -> bool {
       gx = to_int_x86((float)G * (x - px) / view + centering);
       gy = to_int_x86((float)G * (y - py) / view + centering);
       return 0 <= gx && gx < G && 0 <= gy && gy < G;
     };
-    // The scatter.  For the host mirror it is preceded by a counting pass over the same entities (pass 0: no memory
-    // traffic), so that the image's entries can be reserved in one piece; pass 1 then lists every operation it
-    // applies as (op << 29 | element offset, operand) -- the host replays the same integer operations on its copy.
-    uint32_t q = 0;  // pass 0: entries this lane will list; pass 1: its cursor into the chunk's entries
-    uint2* pk_ent = emit ? reinterpret_cast<uint2*>(pk_blk + pk_off_entries(P.pk)) : nullptr;
-    auto list = [&](uint32_t op, uint32_t off, uint32_t v) { if (emit) pk_ent[q++] = make_uint2(op << 29 | off, v); };
-    for (int pass = emit ? 0 : 1; pass < 2; pass++) {
-      if (pass == 1 && emit) {
-        uint32_t incl = q;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t t = __shfl_up_sync(AG_FULL, incl, o);
-          if (lane >= o) incl += t;
-        }
-        const uint32_t total = __shfl_sync(AG_FULL, incl, 31);
-        uint32_t base = 0;
-        if (lane == 0 && total) base = atomicAdd(P.pk.cursor + pk_chunk, total);
-        base = __shfl_sync(AG_FULL, base, 0);
-        const bool fits = base + total <= P.pk.cap_chunk;
-        if (lane == 0) {
-          pk_blk[pk_off_count(P.pk) + pk_li] = fits ? total : kPackDense;
-          pk_blk[pk_off_base(P.pk) + pk_li] = base;
-        }
-        if (!fits) { emit = false; pk_ent = nullptr; }  // the host copies this image densely
-        q = base + incl - q;
-      }
+    // Appends two entries for every lane with `hit` (warp-uniform call): the hit lanes' entries are consecutive, so
+    // the warp's stores coalesce into a few PCIe writes.  Entry = (op << 29 | element offset, operand).
+    auto list2 = [&](bool hit, uint32_t op0, uint32_t off0, uint32_t v0, uint32_t op1, uint32_t off1, uint32_t v1) {
+      if (!emit) return;
+      const unsigned m = __ballot_sync(AG_FULL, hit);
+      if (m == 0u) return;
+      const uint32_t k = wq + 2u * (uint32_t)__popc(m & lanemask_lt(lane));
+      wq += 2u * (uint32_t)__popc(m);
+      if (hit && k + 2u <= P.pk.slot) pk_ent[k >> 1] = make_uint4(op0 << 29 | off0, v0, op1 << 29 | off1, v1);
+    };
+    if (n > 0) {  // (a dead agent: nothing lands inside the grid)
       int channel = 0;
       if (P.observe_pellets) {
         const uint32_t o1 = (uint32_t)((channel + 1) * plane), o2 = (uint32_t)((channel + 2) * plane);
-        auto put_pellet = [&](float2 pq) {
-          int gx, gy;
-          if (grid_of(pq.x, pq.y, gx, gy)) {
-            const uint32_t o = (uint32_t)gx * G + gy;
-            if (pass == 0) { q += 2u; return; }
+        auto put_pellet = [&](bool valid, float2 pq) {
+          int gx = 0, gy = 0;
+          const bool hit = valid && grid_of(pq.x, pq.y, gx, gy);
+          const uint32_t o = (uint32_t)gx * G + gy;
+          if (hit) {
             __stcs(out + o1 + o, 1);           // at_least_: data = mass (1)
             red_add_stream(out + o2 + o, 1);  // total_mass_
-            list(kPkSet, o1 + o, 1u);
-            list(kPkAdd, o2 + o, 1u);
           }
+          list2(hit, kPkSet, o1 + o, 1u, kPkAdd, o2 + o, 1u);
         };
         if (c.hash_valid) {
           // only the hash cells under the view: grid_of truncates towards zero, so column 0 reaches one grid
@@ -1915,15 +1901,18 @@ __device__ void obs_finish_warp(Ctx& c) {
           for (int hy = hy0; hy <= hy1; hy++) {
             int s0, e0;
             hash_range(c, hy * HG + hx0, hy * HG + hx1, s0, e0);
-#pragma unroll 2
-            for (int j = s0 + lane; j < e0; j += 32) {
-              uint32_t idx = c.sm.hsorted()[j];
-              if (idx != (uint32_t)kHashDead) put_pellet(pel[idx]);
+            for (int j0 = s0; j0 < e0; j0 += 32) {
+              const int j = j0 + lane;
+              const uint32_t idx = j < e0 ? (uint32_t)c.sm.hsorted()[j] : (uint32_t)kHashDead;
+              const bool valid = idx != (uint32_t)kHashDead;
+              put_pellet(valid, valid ? pel[idx] : make_float2(0.f, 0.f));
             }
           }
         } else {
-#pragma unroll 4
-          for (int k = lane; k < c.n_pellets; k += 32) put_pellet(pel[k]);
+          for (int k0 = 0; k0 < c.n_pellets; k0 += 32) {
+            const int k = k0 + lane;
+            put_pellet(k < c.n_pellets, k < c.n_pellets ? pel[k] : make_float2(0.f, 0.f));
+          }
         }
         channel += 2;
       }
@@ -1931,70 +1920,77 @@ __device__ void obs_finish_warp(Ctx& c) {
         const uint32_t o3 = (uint32_t)((channel + 1) * plane), o4 = (uint32_t)((channel + 2) * plane);
         const int nv = c.n_viruses;
         const float4* vc = c.sm.vcache();  // x, y, radius, mass bits: valid (rebuilt above if a virus changed in the last tick)
-        for (int k = lane; k < nv; k += 32) {
-          int gx, gy;
-          const float4 vk = vc[k];
-          if (grid_of(vk.x, vk.y, gx, gy)) {
-            const uint32_t o = (uint32_t)gx * G + gy;
-            if (pass == 0) { q += 2u; continue; }
-            const uint32_t vm = __float_as_uint(vk.w);
+        for (int k0 = 0; k0 < nv; k0 += 32) {
+          const int k = k0 + lane;
+          int gx = 0, gy = 0;
+          const float4 vk = k < nv ? vc[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool hit = k < nv && grid_of(vk.x, vk.y, gx, gy);
+          const uint32_t o = (uint32_t)gx * G + gy;
+          const uint32_t vm = __float_as_uint(vk.w);
+          bool last = true;
+          if (hit) {
             atomicAdd(out + o4 + o, (int)vm);
-            list(kPkAdd, o4 + o, vm);
             // at_least_ keeps the LAST writer in index order: write only if no later virus shares the cell
-            bool last = true;
             for (int k2 = k + 1; k2 < nv; k2++) {
               int hx, hy;
               if (grid_of(vc[k2].x, vc[k2].y, hx, hy) && hx == gx && hy == gy) { last = false; break; }
             }
             if (last) out[o3 + o] = (int)vm;
-            list(last ? kPkSet : kPkAdd, last ? o3 + o : o4 + o, last ? vm : 0u);  // (not last: a no-op keeps the count)
           }
+          list2(hit, kPkAdd, o4 + o, vm, last ? kPkSet : kPkAdd, last ? o3 + o : o4 + o, last ? vm : 0u);  // (not last: a no-op)
         }
         channel += 2;
       }
       if (P.observe_cells) {
         const uint32_t o5 = (uint32_t)((channel + 1) * plane);
-        auto put_own = [&](float x, float y, uint32_t m) {
-          int gx, gy;
-          if (grid_of(x, y, gx, gy)) {
-            const uint32_t o = (uint32_t)gx * G + gy;
-            if (pass == 0) { q += 1u; return; }
-            atomicAdd(out + o5 + o, (int)m);
-            list(kPkAdd, o5 + o, m);
-          }
+        auto put_own = [&](bool valid, float x, float y, uint32_t m) {
+          int gx = 0, gy = 0;
+          const bool hit = valid && grid_of(x, y, gx, gy);
+          const uint32_t o = (uint32_t)gx * G + gy;
+          if (hit) atomicAdd(out + o5 + o, (int)m);
+          list2(hit, kPkAdd, o5 + o, m, kPkAdd, o5 + o, 0u);  // (entries come in pairs: the second is a no-op)
         };
         const float4 pcv = c.sm.pcell()[a];
         if (n == 1 && pcv.w >= 0.0f) {  // lane-ticked one-cell agent: its cell is in shared memory
-          if (lane == 0) put_own(pcv.x, pcv.y, __float_as_uint(pcv.z));
+          put_own(lane == 0, pcv.x, pcv.y, __float_as_uint(pcv.z));
         } else {
           const agarcl_cell* pc = c.pcells(a);
-          for (int k = lane; k < n; k += 32) put_own(pc[k].x, pc[k].y, pc[k].mass);
+          for (int k0 = 0; k0 < n; k0 += 32) {
+            const int k = k0 + lane;
+            const bool v = k < n;
+            put_own(v, v ? pc[k].x : 0.f, v ? pc[k].y : 0.f, v ? pc[k].mass : 0u);
+          }
         }
         channel += 1;
       }
       if (P.observe_others) {
         const uint32_t o6 = (uint32_t)((channel + 1) * plane);  // min over non-empty
         const uint32_t o7 = (uint32_t)((channel + 2) * plane);  // max
-        auto put = [&](float x, float y, uint32_t m) {
-          int gx, gy;
-          if (grid_of(x, y, gx, gy)) {
-            const uint32_t o = (uint32_t)gx * G + gy;
-            if (pass == 0) { q += 2u; return; }
+        auto put = [&](bool valid, float x, float y, uint32_t m) {
+          int gx = 0, gy = 0;
+          const bool hit = valid && grid_of(x, y, gx, gy);
+          const uint32_t o = (uint32_t)gx * G + gy;
+          if (hit) {
             int32_t* p6 = out + o6 + o;
             int old = atomicCAS(p6, 0, (int)m);  // empty cell: take the mass; otherwise minimum (masses are > 0)
             if (old != 0) atomicMin(p6, (int)m);
             atomicMax(out + o7 + o, (int)m);
-            list(kPkMinNz, o6 + o, m);
-            list(kPkMax, o7 + o, m);
           }
+          list2(hit, kPkMinNz, o6 + o, m, kPkMax, o7 + o, m);
         };
         for (int base = 0; base < Pn; base += 32) {
           const int p = base + lane;
           const int np = p < Pn ? __float_as_int(c.sm.psum()[p].w) : 0;
-          if (p != a && np >= 1) {  // first cells: one player per lane
-            float4 pcv = c.sm.pcell()[p];
-            if (pcv.w >= 0.0f) put(pcv.x, pcv.y, __float_as_uint(pcv.z));
-            else { const agarcl_cell* oc = c.pcells(p); put(oc->x, oc->y, oc->mass); }
+          {  // first cells: one player per lane
+            const bool v = p != a && np >= 1;
+            float x = 0.f, y = 0.f;
+            uint32_t m = 0u;
+            if (v) {
+              const float4 pcv = c.sm.pcell()[p];
+              if (pcv.w >= 0.0f) { x = pcv.x; y = pcv.y; m = __float_as_uint(pcv.z); }
+              else { const agarcl_cell* oc = c.pcells(p); x = oc->x; y = oc->y; m = oc->mass; }
+            }
+            put(v, x, y, m);
           }
           unsigned multi = __ballot_sync(AG_FULL, p != a && np >= 2);
           while (multi) {  // further cells of split players: one cell per lane
@@ -2002,10 +1998,15 @@ __device__ void obs_finish_warp(Ctx& c) {
             multi &= multi - 1;
             const int mp = base + src, mn = __shfl_sync(AG_FULL, np, src);
             const agarcl_cell* oc = c.pcells(mp);
-            if (lane + 1 < mn) put(oc[lane + 1].x, oc[lane + 1].y, oc[lane + 1].mass);
+            const bool v = lane + 1 < mn;
+            put(v, v ? oc[lane + 1].x : 0.f, v ? oc[lane + 1].y : 0.f, v ? oc[lane + 1].mass : 0u);
           }
         }
       }
+    }
+    if (emit) {  // the image's record in one store: count (or "copy me densely"), base, masks
+      if (lane == 0) pk_mine = wq <= P.pk.slot ? wq : kPackDense;
+      if (lane < (int)P.pk.rec_words - 3) pk_rec[lane] = pk_mine;  // (the last three words: reward and done, at the end of the step)
     }
   }
 }
@@ -2263,7 +2264,14 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
       double r = (double)m;
       if (P.reward_type) r -= (double)(P.before[gi] - 0.0f);
       P.rewards[gi] = r;
-      P.dones[gi] = (a == 0) ? (uint8_t)(c.done_sticky != 0u) : (uint8_t)0;
+      const uint8_t dn = (a == 0) ? (uint8_t)(c.done_sticky != 0u) : (uint8_t)0;
+      P.dones[gi] = dn;
+      if (P.pk.chunks != nullptr && P.obs_finish) {  // host mirror: reward and done travel in the image's record
+        const uint32_t img = (uint32_t)gi, chunk = img / P.pk.ipc, li = img - chunk * P.pk.ipc;
+        uint32_t* tail = P.pk.chunks + (size_t)chunk * P.pk.chunk_words + pk_off_rec(P.pk) + (size_t)li * P.pk.rec_words + (P.pk.rec_words - 3u);
+        const unsigned long long rb = (unsigned long long)__double_as_longlong(r);
+        tail[0] = (uint32_t)rb; tail[1] = (uint32_t)(rb >> 32); tail[2] = (uint32_t)dn;
+      }
     }
   }
 
@@ -2281,30 +2289,25 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
       }
     }
   }
-  const bool pk_on = P.pk.chunks != nullptr && P.do_end && P.obs_finish;
-  if (pk_on) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // host mirror: the frames are complete in memory before their chunk is flagged
-  else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the source tiles / rows / pellets outlive their readers
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the source tiles / rows / pellets outlive their readers
   if (lane == 0) {
     hdr->tick = c.tick; hdr->next_cell_id = c.next_id;
     hdr->n_pellets = c.n_pellets; hdr->n_viruses = c.n_viruses; hdr->n_foods = c.n_foods;
     hdr->rng_cursor = c.cursor; hdr->flags = c.flags; hdr->done_sticky = c.done_sticky;
   }
-  if (pk_on) {
-    // the warp that finishes the last image of a chunk publishes its entry count, rewinds the chunk's
-    // counters for the next launch and raises the flag the host polls (PackOut, sim_params.h)
-    __threadfence();
+  if (P.pk.chunks != nullptr && P.do_end && P.obs_finish) {
+    // host mirror: the warp that finishes the last instance of a chunk rewinds the chunk's counter for the next
+    // launch and raises the flag the host polls; the system-scope fences order every warp's list stores (pinned
+    // host memory) before the flag (PackOut, sim_params.h)
+    __threadfence_system();
     __syncwarp();
     if (lane == 0) {
       const uint32_t chunk = ((uint32_t)inst * (uint32_t)A) / P.pk.ipc;
       const uint32_t in_chunk = min(P.pk.ipc, P.pk.n_img - chunk * P.pk.ipc);
       if (atomicAdd(P.pk.done + chunk, (uint32_t)A) + (uint32_t)A == in_chunk) {
-        __threadfence();
-        P.pk.chunks[(size_t)chunk * P.pk.chunk_words] = atomicExch(P.pk.cursor + chunk, 0u);
         P.pk.done[chunk] = 0u;
-        if (P.pk.flags) {
-          __threadfence_system();
-          P.pk.flags[chunk] = P.pk.seq;
-        }
+        __threadfence_system();
+        P.pk.flags[chunk] = P.pk.seq;
       }
     }
   }

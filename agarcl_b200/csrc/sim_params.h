@@ -23,27 +23,33 @@ struct SmemOff {
   uint32_t hcnt, hsorted, spel, mbar, cellref, rows, strip, hitq, snap, vcache, psum, pcell, pairs, reskeys, resorder, cand, prem, vrem, lprem;
 };
 
-// Transfer lists of the host-resident observation mirror (mirror.cu), filled on the device either by the fused
+// Transfer lists of the host-resident observation mirror (mirror.cu), produced on the device either by the fused
 // observation finish of k_step (no second pass over the dense tensor) or by k_pack.  The agent images are grouped
 // into CHUNKS of `ipc` consecutive images; one chunk = one contiguous block of 32-bit words
-//   [0] entries of the chunk (published when its last image is finished)   [1..3] pad
-//   count[ipc]   entries of the image, or 0xFFFFFFFF: does not fit the scheme, copy the image densely
-//   base[ipc]    first entry of the image (index into the chunk's entry array)
-//   masks[ipc][mask_words]   per frame: row bit mask, then column bit mask, of the out-of-bounds channel
-//   entries[cap_chunk]       uint2 (op << 29 | element offset inside the image, operand): the integer operation
-//                            the host replays on its copy of the element (kPkSet .. kPkMax)
-// so that the host fetches a finished chunk with ONE copy while the kernel is still working on the next chunks:
-// the warp (k_step) / CTA (k_pack) that finishes the last image of a chunk publishes the count, rewinds the
-// cursor and raises the chunk's flag in host-mapped memory.
+//   [0] entries used in the chunk (k_pack only)   [1..3] pad
+//   rec[ipc][rec_words]   per image: count (entries of the image, or 0xFFFFFFFF: does not fit the scheme, copy the
+//                         image densely), base (its first entry in the chunk's entry array), then per frame the row
+//                         bit mask and the column bit mask of the out-of-bounds channel (bit i: row i out of bounds),
+//                         then the agent's reward (f64, two words) and done flag of the step (k_step only)
+//   entries[cap_chunk]    uint2 (op << 29 | element offset inside the image, operand): the integer operation the
+//                         host replays on its copy of the element (kPkSet .. kPkMax)
+// k_step writes its blocks STRAIGHT INTO PINNED HOST MEMORY (`chunks` is then the device address of a host-mapped
+// buffer): every image owns the fixed slot [li * slot, (li + 1) * slot) of its chunk's entry array -- slack costs
+// nothing because only the bytes written cross PCIe -- and the warp writes its entries as coalesced 16-byte
+// stores while it scatters.  The warp that finishes the last instance of a chunk raises the chunk's flag in
+// host-mapped memory, so the host expands chunk k while the kernel is still stepping the instances of chunk k+1
+// and nothing is left to copy when the kernel ends.  k_pack writes compact blocks in device memory (one cursor per
+// chunk), which the host fetches with one copy per chunk.
 struct PackOut {
   uint32_t* chunks;          // nullptr: no lists wanted
-  uint32_t* cursor;          // [n_chunks] running entry count (self-rewinding)
+  uint32_t* cursor;          // [n_chunks] running entry count (k_pack; self-rewinding)
   uint32_t* done;            // [n_chunks] images finished (self-rewinding)
   volatile uint32_t* flags;  // [n_chunks] host-mapped: last step sequence number whose chunk is complete; may be nullptr
   uint32_t chunk_words;      // words between consecutive chunk blocks
   uint32_t ipc;              // images per chunk (a multiple of the agents per instance)
-  uint32_t mask_words;       // frames * 2 * MW
+  uint32_t rec_words;        // 2 + frames * 2 * MW + 3
   uint32_t cap_chunk;        // entry capacity of a chunk
+  uint32_t slot;             // k_step: entries per image slot (even; ipc * slot <= cap_chunk)
   uint32_t n_img;
   uint32_t seq;
   int32_t MW;                // 32-bit words per row (or column) mask
@@ -53,10 +59,8 @@ constexpr uint32_t kPackDense = 0xFFFFFFFFu;
 // min / max channel rules, environment/envs/GridEnvironment.hpp:212-232); k_pack lists final values as kPkSet
 constexpr uint32_t kPkSet = 0u, kPkAdd = 1u, kPkMinNz = 2u, kPkMax = 3u;
 constexpr uint32_t kPkOffMask = 0x1FFFFFFFu;
-__host__ __device__ inline uint32_t pk_off_count(const PackOut&) { return 4u; }
-__host__ __device__ inline uint32_t pk_off_base(const PackOut& k) { return 4u + k.ipc; }
-__host__ __device__ inline uint32_t pk_off_masks(const PackOut& k) { return 4u + 2u * k.ipc; }
-__host__ __device__ inline uint32_t pk_off_entries(const PackOut& k) { return (4u + 2u * k.ipc + k.ipc * k.mask_words + 3u) & ~3u; }
+__host__ __device__ inline uint32_t pk_off_rec(const PackOut&) { return 4u; }
+__host__ __device__ inline uint32_t pk_off_entries(const PackOut& k) { return (4u + k.ipc * k.rec_words + 3u) & ~3u; }
 
 struct SimParams {
   agarcl_layout L;

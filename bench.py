@@ -443,7 +443,8 @@ def run_ours(args):
                                 f"while the kernel runs) and patching the mirror on {mstats['host_threads']} host threads; d2h_bytes_per_step is "
                                 "what crossed PCIe in the last step",
                         "mirror_equals_device": mirror_ok, "mirror_entries_per_step": mstats["entries"],
-                        "mirror_last_step_us": {"device_wait": mstats["wait_us"], "collect_total": mstats["total_us"]},
+                        "mirror_last_step_us": {"stage_and_launch": mstats["launch_us"], "device_wait": mstats["wait_us"],
+                                                "collect_total": mstats["total_us"], "whole_call": mstats["call_us"]},
                         "k_step_ms_in_e2e": e2e_kernel_ms / max(e2e_ksteps, 1),
                         "mirror_dense_images": mstats["dense_images"],
                         "dense_copy": {"value": world * N / dense_s, "unit": UNIT, "d2h_bytes_per_step": d2h_dense,

@@ -209,9 +209,9 @@ int agarcl_batch_mirror(agarcl_batch* b, void** host_ptr, int64_t shape[4], int3
 int agarcl_batch_sync_mirror(agarcl_batch* b, void* stream);
 int agarcl_batch_step_mirror(agarcl_batch* b, const float* dxdy, const int32_t* act, double* rewards_out, uint8_t* dones_out);
 int agarcl_batch_mirror_stats(const agarcl_batch* b, uint64_t out[4]);
-/* last sync: out[0] microseconds the calling thread waited for the device (chunk flags and list copies),
- * out[1] microseconds from the start of the collection to the mirror being complete. */
-int agarcl_batch_mirror_timing(const agarcl_batch* b, uint64_t out[2]);
+/* last agarcl_batch_step_mirror, microseconds: out[0] the calling thread waiting for the device (chunk flags, list
+ * copies), out[1] first wait to mirror complete, out[2] action staging + kernel launch, out[3] the whole call. */
+int agarcl_batch_mirror_timing(const agarcl_batch* b, uint64_t out[4]);
 
 /* ---------------------------------------------------- structured ("ram") observation
  * GoBiggerObservation::add_frame (environment/envs/GoBiggerEnvironment.hpp:515-548, _store_entities
