@@ -109,6 +109,7 @@ struct Ctx {
   uint32_t zagent, zoff, zchunk;  // fused observation clear: cursor (agent, vector) and vectors per chunk
   bool vc_valid;        // the virus cache in shared memory matches the virus array
   bool lanes_dirty;     // players_collision changed players: lanes must reload their registers
+  uint32_t pre_lo, pre_hi;  // players whose move + self-collisions of this tick are already done (premove_players)
   int inst_local;
   float W;
   static constexpr float dt = (float)(1.0 / 30.0);
@@ -151,12 +152,22 @@ __device__ __forceinline__ void cell_move(Cell& k, float dt) {  // Cell::move, E
 }
 
 // ------------------------------------------------------------------------------------------------
-// pair routines of the self-collision solver; operate on broadcast copies (uniform in all lanes)
+// pair routines of the self-collision solver; operate on broadcast copies (uniform within the lane group
+// that owns the player).  The radii come in as arguments: the masses do not change in this phase, so every
+// lane computes the radius of its cell once (radius_of is a table load) instead of once per use.
 // ------------------------------------------------------------------------------------------------
-__device__ void avoid_static_overlap(const Ctx& c, Cell& a, Cell& b) {  // Engine.hpp:701-749
+__device__ __forceinline__ bool touches_r(float ax, float ay, float ar, float bx, float by, float br) {  // Ball::touches, Ball.hpp:36-43
+  float s = ar + br;
+  return s * s >= sqr_dist(ax, ay, bx, by) + 0.0f;
+}
+__device__ __forceinline__ void bound_cell_r(const Ctx& c, Cell& k, float r) {
+  k.x = bound_axis(k.x, r, c.W);
+  k.y = bound_axis(k.y, r, c.W);
+}
+
+__device__ void avoid_static_overlap(const Ctx& c, Cell& a, Cell& b, float ra, float rb) {  // Engine.hpp:701-749
   float dx = b.x - a.x, dy = b.y - a.y;
   float dist = sqrtf(dx * dx + dy * dy);
-  float ra = radius_of(c.P.T, a.mass), rb = radius_of(c.P.T, b.mass);
   float target = ra + rb;
   if (dist > target) return;
   float xr = dx / (fabsf(dx) + fabsf(dy));
@@ -171,14 +182,14 @@ __device__ void avoid_static_overlap(const Ctx& c, Cell& a, Cell& b) {  // Engin
   a.y -= yr * depth * ary;
   b.x += xr * depth * brx;
   b.y += yr * depth * bry;
-  bound_cell(c, a);
-  bound_cell(c, b);
+  bound_cell_r(c, a, ra);
+  bound_cell_r(c, b, rb);
 }
 
-__device__ void separate_cells(const Ctx& c, Cell& a, Cell& b, float tx, float ty) {  // Engine.hpp:803-848
+__device__ void separate_cells(const Ctx& c, Cell& a, Cell& b, float ra, float rb, float tx, float ty) {  // Engine.hpp:803-848
   float dx = b.x - a.x, dy = b.y - a.y;
   float dist = sqrtf(dx * dx + dy * dy);
-  float target = radius_of(c.P.T, a.mass) + radius_of(c.P.T, b.mass);
+  float target = ra + rb;
   if (dist > target) return;
   float xr = dx / (fabsf(dx) + fabsf(dy));
   float yr = dy / (fabsf(dx) + fabsf(dy));
@@ -220,10 +231,10 @@ __device__ void elastic(Cell& a, Cell& b, float dx, float dy, float dist) {  // 
   }
 }
 
-__device__ void prevent_overlap(const Ctx& c, Cell& a, Cell& b, float tx, float ty) {  // Engine.hpp:857-888
+__device__ void prevent_overlap(const Ctx& c, Cell& a, Cell& b, float ra, float rb, float tx, float ty) {  // Engine.hpp:857-888
   float dx = b.x - a.x, dy = b.y - a.y;
   float dist = sqrtf(dx * dx + dy * dy);
-  float target = radius_of(c.P.T, a.mass) + radius_of(c.P.T, b.mass);
+  float target = ra + rb;
   if (dist > target) return;
   float dt = c.dt;
   a.x -= (a.vx + a.svx) * dt;
@@ -233,59 +244,66 @@ __device__ void prevent_overlap(const Ctx& c, Cell& a, Cell& b, float tx, float 
   elastic(a, b, dx, dy, dist);
   cell_move(a, dt);
   cell_move(b, dt);
-  if (touches(c.P.T, a.x, a.y, a.mass, b.x, b.y, b.mass)) {
+  if (touches_r(a.x, a.y, ra, b.x, b.y, rb)) {
     int diff = (int)(a.mass - b.mass);
-    if (abs(diff) <= 10) avoid_static_overlap(c, a, b);
-    else separate_cells(c, a, b, tx, ty);
+    if (abs(diff) <= 10) avoid_static_overlap(c, a, b, ra, rb);
+    else separate_cells(c, a, b, ra, rb, tx, ty);
   }
-  bound_cell(c, a);
-  bound_cell(c, b);
+  bound_cell_r(c, a, ra);
+  bound_cell_r(c, b, rb);
 }
 
-// Engine::check_player_self_collisions, Engine.hpp:763-794.  The reference walks pairs (a<b) in
-// index order and resolves the touching ones; here, for a fixed `a`, one ballot finds the next
-// touching b, the pair is resolved on broadcast copies, and the ballot is re-issued (a has moved).
-__device__ void self_collisions(const Ctx& c, Cell& me, int n, float tx, float ty) {
+// Engine::check_player_self_collisions, Engine.hpp:763-794, for up to 32 / gw players at once: the warp is cut
+// into groups of `gw` lanes (8, 16 or 32), every group owns one player with one cell per lane (gl = lane in the
+// group, gbase = first lane of the group, n = the group's cell count, 0 for an idle group).  The reference walks
+// the pairs (a < b) of a player in index order and resolves the touching ones, which is inherently sequential
+// PER PLAYER; the groups run that sequence side by side under one control flow (a group without a pair at the
+// current step is predicated off), so a tick costs the longest player's pair sequence instead of the sum.
+// For a fixed `a`, one ballot finds the next touching b, the pair is resolved on group-broadcast copies, and the
+// ballot is re-issued (a has moved).  static_pass: avoid_static_overlap instead of prevent_overlap.
+__device__ __forceinline__ bool self_pass(const Ctx& c, Cell& me, float myr, int n, bool on, float tx, float ty,
+                                         int gbase, int gl, unsigned gmask, bool static_pass) {
   bool overlap = false;
-  for (int iter = 0; iter < 5; iter++) {
-    overlap = false;
-    for (int a = 0; a + 1 < n; a++) {
-      int b_last = a;
-      while (true) {
-        float ax = __shfl_sync(AG_FULL, me.x, a), ay = __shfl_sync(AG_FULL, me.y, a);
-        uint32_t am = __shfl_sync(AG_FULL, me.mass, a);
-        bool t = c.lane > b_last && c.lane < n && touches(c.P.T, ax, ay, am, me.x, me.y, me.mass);
-        unsigned m = __ballot_sync(AG_FULL, t);
-        if (!m) break;
-        int b = __ffs(m) - 1;
+  const int nmax = (int)warp_max_u32(on ? (uint32_t)n : 0u);
+  for (int a = 0; a + 1 < nmax; a++) {
+    bool ga = on && a + 1 < n;
+    int b_last = a;
+    while (true) {
+      const int la = gbase + a;  // (an idle group may read a foreign lane here: predicated off below)
+      const float ax = __shfl_sync(AG_FULL, me.x, la), ay = __shfl_sync(AG_FULL, me.y, la);
+      const float ar = __shfl_sync(AG_FULL, myr, la);
+      const bool t = ga && gl > b_last && gl < n && touches_r(ax, ay, ar, me.x, me.y, myr);
+      const unsigned mg = (__ballot_sync(AG_FULL, t) & gmask) >> gbase;
+      const bool has = mg != 0u;
+      if (!__any_sync(AG_FULL, has)) break;
+      const int b = has ? __ffs(mg) - 1 : 0;
+      Cell A = cell_bcast(me, la), B = cell_bcast(me, gbase + b);
+      const float rb = __shfl_sync(AG_FULL, myr, gbase + b);
+      if (has) {
+        if (static_pass) avoid_static_overlap(c, A, B, ar, rb);
+        else prevent_overlap(c, A, B, ar, rb, tx, ty);
+        if (gl == a) me = A;
+        if (gl == b) me = B;
         overlap = true;
-        Cell A = cell_bcast(me, a), B = cell_bcast(me, b);
-        prevent_overlap(c, A, B, tx, ty);
-        if (c.lane == a) me = A;
-        if (c.lane == b) me = B;
         b_last = b;
-      }
-    }
-    if (!overlap) break;
-  }
-  if (overlap) {
-    for (int a = 0; a + 1 < n; a++) {
-      int b_last = a;
-      while (true) {
-        float ax = __shfl_sync(AG_FULL, me.x, a), ay = __shfl_sync(AG_FULL, me.y, a);
-        uint32_t am = __shfl_sync(AG_FULL, me.mass, a);
-        bool t = c.lane > b_last && c.lane < n && touches(c.P.T, ax, ay, am, me.x, me.y, me.mass);
-        unsigned m = __ballot_sync(AG_FULL, t);
-        if (!m) break;
-        int b = __ffs(m) - 1;
-        Cell A = cell_bcast(me, a), B = cell_bcast(me, b);
-        avoid_static_overlap(c, A, B);
-        if (c.lane == a) me = A;
-        if (c.lane == b) me = B;
-        b_last = b;
+      } else {
+        ga = false;  // this group is through with `a`
       }
     }
   }
+  return overlap;
+}
+__device__ void self_collisions(const Ctx& c, Cell& me, int n, float tx, float ty, int gbase, int gl, int gw) {
+  const unsigned gmask = (gw >= 32 ? 0xffffffffu : ((1u << gw) - 1u)) << gbase;
+  const float myr = radius_of(c.P.T, me.mass);
+  bool on = n >= 2, overlap = false;
+  for (int iter = 0; iter < 5; iter++) {
+    if (!__any_sync(AG_FULL, on)) break;
+    overlap = self_pass(c, me, myr, n, on, tx, ty, gbase, gl, gmask, false);
+    on = on && overlap;  // "if (!overlap) break" of the group's player
+  }
+  // the static pass only after five passes that all found an overlap
+  if (__any_sync(AG_FULL, on)) self_pass(c, me, myr, n, on, tx, ty, gbase, gl, gmask, true);
 }
 
 // Player::x / y / mass (Player.hpp:102-126): sequential fp32 accumulation in cell order
@@ -322,6 +340,7 @@ __device__ float4 centroid_from_global(const agarcl_cell* g, int n) {
 // ------------------------------------------------------------------------------------------------
 // Bot::nearest_pellet, Bot.hpp:92-129: first index attaining the minimum of sqrtf(d^2) among d > 0.01
 __device__ void lane_nearest_pellet(const Ctx& c, float lx, float ly, float& tx, float& ty);
+__device__ bool lane_eat_pellets(const Ctx& c, float cx, float cy, uint32_t& mass, int& ne, uint16_t* out);
 __device__ void nearest_pellet(Ctx& c, float lx, float ly, float& tx, float& ty) {
   if (c.n_pellets == 0) {  // std::rand() % arena: not replayable (flagged), same stand-in as the oracle
     c.flags |= AGARCL_FLAG_RAND_SITE;
@@ -484,6 +503,72 @@ __device__ void build_virus_cache(Ctx& c) {
 // ------------------------------------------------------------------------------------------------
 // Engine::tick_player
 // ------------------------------------------------------------------------------------------------
+// Engine::move_player for one cell (Engine.hpp:609-630)
+__device__ __forceinline__ void move_cell(Ctx& c, Cell& me, float tx, float ty) {
+  me.vx = 3.0f * (tx - me.x);
+  me.vy = 3.0f * (ty - me.y);
+  float limit = max_speed_of(c.P.T, me.mass, c.flags);
+  if (vmag(me.vx, me.vy) > limit) {  // Velocity::clamp_speed + set_speed (quirk Q8)
+    me.vx *= limit / vmag(me.vx, me.vy);
+    me.vy *= limit / vmag(me.vx, me.vy);
+  }
+  cell_move(me, c.dt);
+  decelerate(me.svx, me.svy, 80.0f, c.dt);
+  bound_cell(c, me);
+}
+
+// Engine::move_player + check_player_self_collisions of the multi-cell players, BEFORE the ordered player loop.
+// Both depend only on the player's own cells and its target, i.e. on nothing another player does in the same
+// tick (pellets, viruses and foods are touched by the later phases of tick_player; cells of other players only by
+// players_collision after the loop), so they can leave the serial order: four players of up to 8 cells (then two
+// of up to 16) are moved and resolved side by side in lane groups -- in mature games the pair sequences of split
+// and popped players are most of the work of a tick.  Not on bot-decision ticks (every 10th): there a target may
+// come out of the ordered loop itself.  The results go back to the cell arrays; tick_player skips what is done.
+__device__ void premove_players(Ctx& c) {
+  c.pre_lo = 0u; c.pre_hi = 0u;
+  if (c.tick % 10u == 0u) return;
+  const int Pn = c.P.L.P, lane = c.lane;
+  for (int base = 0; base < Pn; base += 32) {
+    const int k = base + lane;
+    const int p = k < Pn ? c.P.L.order[k] : 0;
+    const int np = k < Pn ? __float_as_int(c.sm.psum()[p].w) : 0;
+#pragma unroll 1
+    for (int wide = 0; wide < 2; wide++) {
+      const int gshift = wide ? 4 : 3, gw = 1 << gshift;
+      const int g = lane >> gshift, gl = lane & (gw - 1), gbase = g << gshift;
+      unsigned todo = __ballot_sync(AG_FULL, wide ? (np > 8 && np <= 16) : (np >= 2 && np <= 8));
+      while (todo) {
+        const unsigned src = __fns(todo, 0, g + 1);  // this group's player: the (g+1)-th one still to do
+        const bool have = src != 0xffffffffu;
+        const int gp = __shfl_sync(AG_FULL, p, (int)(src & 31u));
+        const int gn_src = __shfl_sync(AG_FULL, np, (int)(src & 31u));
+        const int gn = have ? gn_src : 0;
+        for (int i = 0; i < (32 >> gshift); i++) todo &= todo - 1u;
+        Cell me;
+        me.x = me.y = me.vx = me.vy = me.svx = me.svy = 0.0f;
+        me.mass = 0; me.id = 0; me.rec = 0;
+        float tx = 0.0f, ty = 0.0f;
+        const bool valid = have && gl < gn;
+        if (have) {
+          const agarcl_player* pl = c.players_() + gp;
+          tx = pl->target_x; ty = pl->target_y;
+        }
+        if (valid) {
+          me = cell_load(c.pcells(gp) + gl);
+          move_cell(c, me, tx, ty);
+        }
+        self_collisions(c, me, gn, tx, ty, gbase, gl, gw);
+        if (valid) cell_store(c.pcells(gp) + gl, me);
+        const bool mark = have && gl == 0;
+        c.pre_lo |= __reduce_or_sync(AG_FULL, (mark && gp < 32) ? 1u << gp : 0u);
+        c.pre_hi |= __reduce_or_sync(AG_FULL, (mark && gp >= 32) ? 1u << (gp - 32) : 0u);
+      }
+    }
+  }
+  c.flags = __reduce_or_sync(AG_FULL, c.flags);
+  __syncwarp();
+}
+
 __device__ void tick_player(Ctx& c, int p) {
   const Luts& T = c.P.T;
   agarcl_player* pl = c.players_() + p;
@@ -517,24 +602,16 @@ __device__ void tick_player(Ctx& c, int p) {
     }
   }
 
-  // ---- Engine::move_player
+  // ---- Engine::move_player + check_player_self_collisions (unless premove_players has done them for this tick)
+  const bool premoved = ((p < 32 ? c.pre_lo >> p : c.pre_hi >> (p - 32)) & 1u) != 0u;
   uint32_t smallest = 0xffffffffu;
   if (lane < n) {
-    me.vx = 3.0f * (tx - me.x);
-    me.vy = 3.0f * (ty - me.y);
     smallest = me.mass;
-    float limit = max_speed_of(T, me.mass, c.flags);
-    if (vmag(me.vx, me.vy) > limit) {  // Velocity::clamp_speed + set_speed (quirk Q8)
-      me.vx *= limit / vmag(me.vx, me.vy);
-      me.vy *= limit / vmag(me.vx, me.vy);
-    }
-    cell_move(me, c.dt);
-    decelerate(me.svx, me.svy, 80.0f, c.dt);
-    bound_cell(c, me);
+    if (!premoved) move_cell(c, me, tx, ty);
   }
   smallest = warp_min_u32(smallest);
   c.flags = __reduce_or_sync(AG_FULL, c.flags);
-  if (n >= 2) self_collisions(c, me, n, tx, ty);
+  if (n >= 2 && !premoved) self_collisions(c, me, n, tx, ty, 0, lane, 32);
 
   // ---- created cells accumulate in lanes [n, n+created) (they are inactive until add_cells)
   int created = 0;
@@ -545,7 +622,12 @@ __device__ void tick_player(Ctx& c, int p) {
 
   // ---- optimized_check_virus_collisions: first hit in (cell, dx, dy, virus index) order
   if (c.n_viruses > 0) {
-    for (int i = 0; i < n; i++) {
+    // only cells that could eat the smallest virus can touch one at all (mass > 1.1 * virus mass): the 25-mass
+    // fragments of a popped player are skipped wholesale
+    unsigned vcells = __ballot_sync(AG_FULL, lane < n && can_eat_mass(me.mass, c.min_vmass));
+    while (vcells) {
+      const int i = __ffs(vcells) - 1;
+      vcells &= vcells - 1u;
       float cx = __shfl_sync(AG_FULL, me.x, i), cy = __shfl_sync(AG_FULL, me.y, i);
       uint32_t cm = __shfl_sync(AG_FULL, me.mass, i);
       float cr = radius_of(T, cm);
@@ -613,7 +695,41 @@ __device__ void tick_player(Ctx& c, int p) {
 
   // ---- get_pellets_to_remove_and_increment_cells
   int pellets_eaten = 0;
-  if (c.n_pellets > 0) {
+  bool pellets_done = c.n_pellets == 0;
+  if (!pellets_done && n >= 2) {
+    // The cells of a player eat independently of each other within a tick (pellets only disappear after the
+    // player loop, Engine.hpp:221), so every lane resolves its own cell with the exact single-lane scan; the
+    // eaten indices then go to pellets_to_remove in cell order.  Any cell with too many candidates for the
+    // lane scan sends the whole player through the cell-by-cell warp scan below.
+    uint16_t mine[kLaneCand];
+    int ne = 0;
+    uint32_t nm = me.mass;
+    bool ok = true;
+    if (lane < n) ok = lane_eat_pellets(c, me.x, me.y, nm, ne, mine);
+    if (__all_sync(AG_FULL, ok)) {
+      int incl = ne;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(AG_FULL, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int total = __shfl_sync(AG_FULL, incl, 31);
+      if (total > 0) {
+        const int off = c.nprem + incl - ne;
+        for (int e = 0; e < ne; e++) {
+          if (off + e < kPremCap) c.sm.prem()[off + e] = mine[e];
+          else c.flags |= AGARCL_FLAG_REMOVE_OVERFLOW;
+        }
+        c.nprem = min(c.nprem + total, kPremCap);
+        c.flags = __reduce_or_sync(AG_FULL, c.flags);
+        me.mass = nm;
+        pellets_eaten = total;
+        __syncwarp();
+      }
+      pellets_done = true;
+    }
+  }
+  if (!pellets_done) {
     const int HG = c.P.HG;
     const float rp = radius_of(T, 1u);
     for (int i = 0; i < n; i++) {
@@ -2020,6 +2136,7 @@ __device__ void engine_tick(Ctx& c, LaneState& ls) {
   c.nvrem = 0;
   const int P = c.P.L.P;
   if (c.lanes_dirty) { ls.fresh = false; c.lanes_dirty = false; }
+  premove_players(c);
   tick_players_block(c, 0, ls);
   for (int base = 32; base < P; base += 32) {  // more than 32 players: the further blocks reload every tick
     LaneState tmp;

@@ -30,4 +30,11 @@ for w in range(total // 100):
         sv = b.download_state(k)
         cells.append(int(sv.players["n_cells"].sum())); pel.append(int(sv.hdr["n_pellets"])); flags |= int(sv.hdr["flags"])
     print(f"steps {w*100:5d}..{w*100+99:5d}  {e0.elapsed_time(e1)/100:.4f} ms/step  cells {cells} pellets {pel} flags {flags}", flush=True)
+hist = np.zeros(40, int); multi = []
+for k in range(0, N, 32):
+    nc = b.download_state(k).players["n_cells"]
+    for v in nc: hist[min(int(v), 39)] += 1
+    multi.append(int((nc >= 2).sum()))
+print("n_cells histogram over 128 instances:", {i: int(h) for i, h in enumerate(hist) if h})
+print("multi-cell players per instance: mean", np.mean(multi), "max", max(multi))
 b.close()
