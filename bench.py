@@ -13,6 +13,12 @@ regen/respawn + rewards/dones + one grid observation per agent.  Workload = BASE
 instances with no collective on the step path ("weak" scaling); torch.distributed is used only for
 the barrier and the max-over-ranks of the device time.
 
+Game age: the cost of a step grows with the age of the games (players split, get popped by viruses into up to
+16 cells, meet each other) and plateaus after about 1500 env-steps (tools/exp_age.py), so BOTH arms first settle
+their instances for --settle env-steps (default 2000) and measure the steady state that a continuing task
+(mode 0 never ends an episode) spends its life in; the young-game figure (age 100) is reported next to it as
+`age_profile`.
+
 `value` is timed with inputs (per-step action tensors) resident in HBM; `e2e` goes through the
 reference-facing C-ABI call agarcl_batch_step_mirror with pinned HOST buffers: actions H2D, rewards / dones D2H and
 the update of the dense host observation mirror are inside the timed region (the dense-copy call
@@ -188,7 +194,7 @@ def _ref_pool():
     return lib, make_cfg(**WORKLOAD)
 
 
-def _cpu_reference_rate_inproc(seconds_target=12.0, threads=None):
+def _cpu_reference_rate_inproc(seconds_target=12.0, threads=None, settle=2000):
     """Times the reference's own CPU implementation of the path on a bounded sample of the workload."""
     lib, cfg = _ref_pool()
     if lib is None:
@@ -196,26 +202,31 @@ def _cpu_reference_rate_inproc(seconds_target=12.0, threads=None):
     threads = threads or (os.cpu_count() or 1)
     inst = 2 * threads
     pool = C.c_void_p(lib.ref_pool_create(C.byref(cfg), inst, 1234))
-    sec = lib.ref_pool_run(pool, threads, 5, 1)  # calibration (also warms the instances up)
-    rate = inst * 5 / sec
+    if settle > 0:
+        lib.ref_pool_run(pool, threads, settle, 1)  # untimed: the same game age as the GPU arm measures at
+    sec = lib.ref_pool_run(pool, threads, 20, 1)  # calibration
+    rate = inst * 20 / sec
     steps = max(5, int(seconds_target * rate / inst))
     sec = lib.ref_pool_run(pool, threads, steps, 1)
     lib.ref_pool_destroy(pool)
     return dict(value=inst * steps / sec, unit=UNIT, cores=threads, kind="reference",
-                sample=f"{inst} instances x {steps} env-steps each (forced add_frame per step), one reference engine per "
-                       f"thread on {threads} host threads, {sec:.1f} s")
+                sample=f"{inst} instances settled for {settle} env-steps, then {steps} timed env-steps each (forced add_frame per "
+                       f"step), one reference engine per thread on {threads} host threads, {sec:.1f} s")
 
 
-def _reference_arm_inproc(steps, warmup, gpus, threads=None):
+def _reference_arm_inproc(steps, warmup, gpus, threads=None, settle=2000):
     lib, cfg = _ref_pool()
     if lib is None:
         return {"impl": "reference", "unavailable": "oracle/_ref/libagarcl_ref.so missing and /root/reference absent"}
     threads = threads or (os.cpu_count() or 1)
     inst = 2 * threads
     pool = C.c_void_p(lib.ref_pool_create(C.byref(cfg), inst, 1234))
-    sec = lib.ref_pool_run(pool, threads, 3, 1)
-    rate = inst * 3 / sec
+    if settle > 0:
+        lib.ref_pool_run(pool, threads, settle, 1)  # untimed: the same game age as the GPU arm measures at
+    sec = lib.ref_pool_run(pool, threads, 10, 1)
+    rate = inst * 10 / sec
     per_step = max(2, int(0.5 * rate / inst))  # env-steps per instance in one bench "step" (about 0.5 s)
+    per_step = min(per_step, max(2, int(150.0 * rate / inst / max(1, steps + warmup))))  # whole run within a few minutes
     for _ in range(warmup):
         lib.ref_pool_run(pool, threads, per_step, 1)
     t = 0.0
@@ -223,25 +234,25 @@ def _reference_arm_inproc(steps, warmup, gpus, threads=None):
         t += lib.ref_pool_run(pool, threads, per_step, 1)
     lib.ref_pool_destroy(pool)
     value = inst * per_step * steps / t
-    sample = (f"each step = {inst} instances x {per_step} env-steps (forced add_frame per step), one reference engine per thread "
-              f"on {threads} host threads")
+    sample = (f"{inst} instances settled for {settle} env-steps; each step = {inst} instances x {per_step} env-steps (forced add_frame "
+              f"per step), one reference engine per thread on {threads} host threads")
     return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": 1e3 * t / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME, "sample": sample},
+            "config": {"workload": WORKLOAD_NAME, "settle_steps": settle, "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
 
 
-def _ref_child(what, steps, warmup, gpus, threads, budget_s):
+def _ref_child(what, steps, warmup, gpus, threads, budget_s, settle=2000):
     """The reference engine is third-party code with process-wide globals (Ball::global_id, libc rand()): it runs in a
     CHILD process under a watchdog so that a hang or crash in it can never take the bench line down; one retry on
     half the threads."""
     last = "no attempt"
     for attempt in range(2):
         cmd = [sys.executable, os.path.abspath(__file__), "--_refchild", what, "--steps", str(steps), "--warmup", str(warmup),
-               "--gpus", str(gpus), "--_threads", str(threads)]
+               "--gpus", str(gpus), "--_threads", str(threads), "--settle", str(settle)]
         try:
             out = subprocess.run(cmd, capture_output=True, text=True, timeout=budget_s)
             lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
@@ -254,8 +265,8 @@ def _ref_child(what, steps, warmup, gpus, threads, budget_s):
     return {"failed": last}
 
 
-def cpu_reference_rate():
-    r = _ref_child("cpu_baseline", 0, 0, 1, os.cpu_count() or 1, 120)
+def cpu_reference_rate(settle):
+    r = _ref_child("cpu_baseline", 0, 0, 1, os.cpu_count() or 1, 180, settle)
     if r is None or "failed" in r:
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {r and r['failed']}"}
     return r
@@ -265,8 +276,8 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    budget = 60 + 2 * (args.steps + args.warmup + 3)  # each step is sized to about 0.5 s
-    line = _ref_child("arm", args.steps, args.warmup, args.gpus, os.cpu_count() or 1, budget)
+    budget = 240 + 2 * (args.steps + args.warmup + 3)  # settling + steps of at most about 0.5 s
+    line = _ref_child("arm", args.steps, args.warmup, args.gpus, os.cpu_count() or 1, budget, args.settle)
     if "failed" in line:
         line = {"impl": "reference", "unavailable": line["failed"]}
     print(json.dumps(line))
@@ -317,9 +328,24 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # let the games develop a little so the measured state is not the trivial post-reset one
-    for i in range(args.settle):
+    # let the games reach their steady state (see the module docstring); on the way, time the young games (age 100)
+    age_profile = []
+    young_at = 100
+    for i in range(min(args.settle, young_at)):
         one_step(i)
+    if args.settle > young_at:
+        for i in range(W_):
+            one_step(i)
+        barrier()
+        y0, y1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        y0.record()
+        for i in range(K):
+            one_step(i)
+        y1.record()
+        barrier()
+        age_profile.append({"age_env_steps": young_at + W_, "ms_per_step": y0.elapsed_time(y1) / K})
+        for i in range(max(0, args.settle - young_at - W_ - K)):
+            one_step(i)
     for i in range(W_):
         one_step(i)
     barrier()
@@ -424,13 +450,18 @@ def run_ours(args):
                     "avg_launch_ms": t_ms, "algorithmic_bytes_per_launch": byt, "traffic": traffic if k == dom else None,
                     "peak_source": peak_src}
         value = world * N * K / (ms * 1e-3)
+        for a in age_profile:
+            a["value"] = world * N / (a["ms_per_step"] * 1e-3)
+        age_profile.append({"age_env_steps": args.settle, "ms_per_step": ms / K, "value": value})
         whole = ab["step"] * value / 1e9 / world
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD_NAME, "instances_per_gpu": N, "settle_steps": args.settle,
                            "cache": "working set (state 235 MB + obs 2.1 GB per step) larger than the 126 MB L2; no flush needed",
+                           "game_age": f"steady state: instances settled for {args.settle} env-steps before the timed region (both arms)",
                            "rng": "philox4x32-10 per instance", "state_flags_seen": flags_seen},
+                "age_profile": age_profile,
                 "roofline": rf(dom),
                 "roofline_all": {"kernels": [rf(k) for k in kern],
                                  "whole_step": {"achieved": whole, "peak": peak, "unit": "GB/s", "frac": whole / peak,
@@ -451,7 +482,7 @@ def run_ours(args):
                                        "note": "agarcl_batch_step_host: the whole int32 observation copied D2H every step (PCIe bound)"}},
                 "gpu_launches": launches, "clocks": clocks}
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_reference_rate()  # child process under a watchdog: never takes the bench down
+            line["cpu_baseline"] = cpu_reference_rate(args.settle)  # child process under a watchdog: never takes the bench down
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))
@@ -468,7 +499,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--instances", type=int, default=INSTANCES_PER_GPU, help="instances per GPU")
-    ap.add_argument("--settle", type=int, default=100, help="untimed steps before warm-up so games are mid-play")
+    ap.add_argument("--settle", type=int, default=2000, help="untimed env-steps before the timed region: game age (both arms)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tps", type=int, default=None, help="diagnostic only: ticks per env-step (the workload's is 4)")
@@ -476,10 +507,10 @@ def main():
     ap.add_argument("--_threads", type=int, default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args._refchild == "cpu_baseline":
-        print(json.dumps(_cpu_reference_rate_inproc(threads=args._threads)))
+        print(json.dumps(_cpu_reference_rate_inproc(threads=args._threads, settle=args.settle)))
         return 0
     if args._refchild == "arm":
-        print(json.dumps(_reference_arm_inproc(args.steps, args.warmup, args.gpus, threads=args._threads)))
+        print(json.dumps(_reference_arm_inproc(args.steps, args.warmup, args.gpus, threads=args._threads, settle=args.settle)))
         return 0
     if args.warmup < 3:
         args.warmup = 3
