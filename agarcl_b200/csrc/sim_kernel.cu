@@ -67,21 +67,11 @@ __device__ __forceinline__ Cell cell_bcast(const Cell& c, int src) {
   r.rec = __shfl_sync(AG_FULL, c.rec, src);
   return r;
 }
-__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(AG_FULL, v, o);
-  return v;
-}
-__device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(AG_FULL, v, o));
-  return v;
-}
-__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(AG_FULL, v, o));
-  return v;
-}
+// warp reductions: one REDUX instruction each (sm_80+) instead of five shuffle/op pairs -- less latency and, as
+// they are inlined at dozens of sites, a good deal less code for the 32 KB instruction cache
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) { return __reduce_add_sync(AG_FULL, v); }
+__device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) { return __reduce_min_sync(AG_FULL, v); }
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) { return __reduce_max_sync(AG_FULL, v); }
 __device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
 constexpr int kHashDead = 0xffff;  // hash entry of a pellet removed since the hash was built
 
@@ -160,12 +150,12 @@ __device__ __forceinline__ bool touches_r(float ax, float ay, float ar, float bx
   float s = ar + br;
   return s * s >= sqr_dist(ax, ay, bx, by) + 0.0f;
 }
-__device__ __forceinline__ void bound_cell_r(const Ctx& c, Cell& k, float r) {
-  k.x = bound_axis(k.x, r, c.W);
-  k.y = bound_axis(k.y, r, c.W);
+__device__ __forceinline__ void bound_cell_r(float W, Cell& k, float r) {
+  k.x = bound_axis(k.x, r, W);
+  k.y = bound_axis(k.y, r, W);
 }
 
-__device__ void avoid_static_overlap(const Ctx& c, Cell& a, Cell& b, float ra, float rb) {  // Engine.hpp:701-749
+__device__ __forceinline__ void avoid_static_overlap(float W, Cell& a, Cell& b, float ra, float rb) {  // Engine.hpp:701-749
   float dx = b.x - a.x, dy = b.y - a.y;
   float dist = sqrtf(dx * dx + dy * dy);
   float target = ra + rb;
@@ -174,19 +164,19 @@ __device__ void avoid_static_overlap(const Ctx& c, Cell& a, Cell& b, float ra, f
   float yr = dy / (fabsf(dx) + fabsf(dy));
   float depth = target - dist;
   float arx = 0.5f, ary = 0.5f, brx = 0.5f, bry = 0.5f;
-  if (a.x == ra || a.x == c.W - ra) { arx = 1.0f; a.vx = 0.0f; }
-  if (a.y == ra || a.y == c.W - ra) { ary = 1.0f; a.vy = 0.0f; }
-  if (b.x == rb || b.x == c.W - rb) { brx = 1.0f; b.vx = 0.0f; }
-  if (b.y == rb || b.y == c.W - rb) { bry = 1.0f; b.vy = 0.0f; }
+  if (a.x == ra || a.x == W - ra) { arx = 1.0f; a.vx = 0.0f; }
+  if (a.y == ra || a.y == W - ra) { ary = 1.0f; a.vy = 0.0f; }
+  if (b.x == rb || b.x == W - rb) { brx = 1.0f; b.vx = 0.0f; }
+  if (b.y == rb || b.y == W - rb) { bry = 1.0f; b.vy = 0.0f; }
   a.x -= xr * depth * arx;
   a.y -= yr * depth * ary;
   b.x += xr * depth * brx;
   b.y += yr * depth * bry;
-  bound_cell_r(c, a, ra);
-  bound_cell_r(c, b, rb);
+  bound_cell_r(W, a, ra);
+  bound_cell_r(W, b, rb);
 }
 
-__device__ void separate_cells(const Ctx& c, Cell& a, Cell& b, float ra, float rb, float tx, float ty) {  // Engine.hpp:803-848
+__device__ __forceinline__ void separate_cells(Cell& a, Cell& b, float ra, float rb, float tx, float ty) {  // Engine.hpp:803-848
   float dx = b.x - a.x, dy = b.y - a.y;
   float dist = sqrtf(dx * dx + dy * dy);
   float target = ra + rb;
@@ -211,7 +201,7 @@ __device__ void separate_cells(const Ctx& c, Cell& a, Cell& b, float ra, float r
   if (move_a) { a.x = tx_; a.y = ty_; } else { b.x = tx_; b.y = ty_; }
 }
 
-__device__ void elastic(Cell& a, Cell& b, float dx, float dy, float dist) {  // Engine.hpp:893-938
+__device__ __forceinline__ void elastic(Cell& a, Cell& b, float dx, float dy, float dist) {  // Engine.hpp:893-938
   float nx = dx / dist, ny = dy / dist;
   float tx = -ny, ty = nx;
   float dpn1 = a.vx * nx + a.vy * ny;
@@ -231,12 +221,12 @@ __device__ void elastic(Cell& a, Cell& b, float dx, float dy, float dist) {  // 
   }
 }
 
-__device__ void prevent_overlap(const Ctx& c, Cell& a, Cell& b, float ra, float rb, float tx, float ty) {  // Engine.hpp:857-888
+__device__ __forceinline__ void prevent_overlap(float W, Cell& a, Cell& b, float ra, float rb, float tx, float ty) {  // Engine.hpp:857-888
   float dx = b.x - a.x, dy = b.y - a.y;
   float dist = sqrtf(dx * dx + dy * dy);
   float target = ra + rb;
   if (dist > target) return;
-  float dt = c.dt;
+  const float dt = Ctx::dt;
   a.x -= (a.vx + a.svx) * dt;
   a.y -= (a.vy + a.svy) * dt;
   b.x -= (b.vx + b.svx) * dt;
@@ -246,11 +236,11 @@ __device__ void prevent_overlap(const Ctx& c, Cell& a, Cell& b, float ra, float 
   cell_move(b, dt);
   if (touches_r(a.x, a.y, ra, b.x, b.y, rb)) {
     int diff = (int)(a.mass - b.mass);
-    if (abs(diff) <= 10) avoid_static_overlap(c, a, b, ra, rb);
-    else separate_cells(c, a, b, ra, rb, tx, ty);
+    if (abs(diff) <= 10) avoid_static_overlap(W, a, b, ra, rb);
+    else separate_cells(a, b, ra, rb, tx, ty);
   }
-  bound_cell_r(c, a, ra);
-  bound_cell_r(c, b, rb);
+  bound_cell_r(W, a, ra);
+  bound_cell_r(W, b, rb);
 }
 
 // Engine::check_player_self_collisions, Engine.hpp:763-794, for up to 32 / gw players at once: the warp is cut
@@ -260,50 +250,66 @@ __device__ void prevent_overlap(const Ctx& c, Cell& a, Cell& b, float ra, float 
 // PER PLAYER; the groups run that sequence side by side under one control flow (a group without a pair at the
 // current step is predicated off), so a tick costs the longest player's pair sequence instead of the sum.
 // For a fixed `a`, one ballot finds the next touching b, the pair is resolved on group-broadcast copies, and the
-// ballot is re-issued (a has moved).  static_pass: avoid_static_overlap instead of prevent_overlap.
-__device__ __forceinline__ bool self_pass(const Ctx& c, Cell& me, float myr, int n, bool on, float tx, float ty,
+// ballot is re-issued against the moved a.  static_pass: avoid_static_overlap instead of prevent_overlap.
+__device__ __forceinline__ bool self_pass(float W, Cell& me, float myr, int n, bool on, float tx, float ty,
                                          int gbase, int gl, unsigned gmask, bool static_pass) {
   bool overlap = false;
   const int nmax = (int)warp_max_u32(on ? (uint32_t)n : 0u);
+  // what a pair routine reads (position, both velocities, mass) / writes (position, velocity)
+  auto bcast = [&](int src) {
+    Cell r;
+    r.x = __shfl_sync(AG_FULL, me.x, src); r.y = __shfl_sync(AG_FULL, me.y, src);
+    r.vx = __shfl_sync(AG_FULL, me.vx, src); r.vy = __shfl_sync(AG_FULL, me.vy, src);
+    r.svx = __shfl_sync(AG_FULL, me.svx, src); r.svy = __shfl_sync(AG_FULL, me.svy, src);
+    r.mass = __shfl_sync(AG_FULL, me.mass, src); r.id = 0u; r.rec = 0u;
+    return r;
+  };
   for (int a = 0; a + 1 < nmax; a++) {
-    bool ga = on && a + 1 < n;
+    const bool mine_a = on && a + 1 < n;
+    bool ga = mine_a;
     int b_last = a;
+    // cell `a` stays in the group-uniform copy A for all its pairs and returns to its lane afterwards
+    // (an idle group reads a foreign lane here: never used, never written back)
+    Cell A = bcast(gbase + a);
+    const float ar = __shfl_sync(AG_FULL, myr, gbase + a);
     while (true) {
-      const int la = gbase + a;  // (an idle group may read a foreign lane here: predicated off below)
-      const float ax = __shfl_sync(AG_FULL, me.x, la), ay = __shfl_sync(AG_FULL, me.y, la);
-      const float ar = __shfl_sync(AG_FULL, myr, la);
-      const bool t = ga && gl > b_last && gl < n && touches_r(ax, ay, ar, me.x, me.y, myr);
+      const bool t = ga && gl > b_last && gl < n && touches_r(A.x, A.y, ar, me.x, me.y, myr);
       const unsigned mg = (__ballot_sync(AG_FULL, t) & gmask) >> gbase;
       const bool has = mg != 0u;
       if (!__any_sync(AG_FULL, has)) break;
       const int b = has ? __ffs(mg) - 1 : 0;
-      Cell A = cell_bcast(me, la), B = cell_bcast(me, gbase + b);
+      Cell B = bcast(gbase + b);
       const float rb = __shfl_sync(AG_FULL, myr, gbase + b);
       if (has) {
-        if (static_pass) avoid_static_overlap(c, A, B, ar, rb);
-        else prevent_overlap(c, A, B, ar, rb, tx, ty);
-        if (gl == a) me = A;
-        if (gl == b) me = B;
+        if (static_pass) avoid_static_overlap(W, A, B, ar, rb);
+        else prevent_overlap(W, A, B, ar, rb, tx, ty);
+        if (gl == b) { me.x = B.x; me.y = B.y; me.vx = B.vx; me.vy = B.vy; }
         overlap = true;
         b_last = b;
       } else {
         ga = false;  // this group is through with `a`
       }
     }
+    if (mine_a && gl == a) { me.x = A.x; me.y = A.y; me.vx = A.vx; me.vy = A.vy; }
   }
   return overlap;
 }
-__device__ void self_collisions(const Ctx& c, Cell& me, int n, float tx, float ty, int gbase, int gl, int gw) {
+// ONE out-of-line copy for both callers (premove_players and tick_player): the pair loop is the hottest code of
+// mature games and the instruction cache holds 32 KB; arguments and result by value, so nothing of the callers'
+// state is forced into local memory.
+__device__ __noinline__ Cell self_collisions_fn(Cell me, float myr, int n, float tx, float ty, int gbase, int gl, int gw, float W) {
   const unsigned gmask = (gw >= 32 ? 0xffffffffu : ((1u << gw) - 1u)) << gbase;
-  const float myr = radius_of(c.P.T, me.mass);
-  bool on = n >= 2, overlap = false;
-  for (int iter = 0; iter < 5; iter++) {
-    if (!__any_sync(AG_FULL, on)) break;
-    overlap = self_pass(c, me, myr, n, on, tx, ty, gbase, gl, gmask, false);
-    on = on && overlap;  // "if (!overlap) break" of the group's player
+  bool on = n >= 2;
+  int passes = 0;  // passes 0..4: prevent_overlap while the previous one found an overlap; pass 5: the static pass after five overlapping ones
+  while (__any_sync(AG_FULL, on)) {
+    const bool overlap = self_pass(W, me, myr, n, on, tx, ty, gbase, gl, gmask, passes == 5);
+    on = on && overlap && passes < 5;  // "if (!overlap) break" of the group's player
+    passes++;
   }
-  // the static pass only after five passes that all found an overlap
-  if (__any_sync(AG_FULL, on)) self_pass(c, me, myr, n, on, tx, ty, gbase, gl, gmask, true);
+  return me;
+}
+__device__ __forceinline__ void self_collisions(const Ctx& c, Cell& me, int n, float tx, float ty, int gbase, int gl, int gw) {
+  me = self_collisions_fn(me, radius_of(c.P.T, me.mass), n, tx, ty, gbase, gl, gw, c.W);
 }
 
 // Player::x / y / mass (Player.hpp:102-126): sequential fp32 accumulation in cell order
