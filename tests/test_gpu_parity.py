@@ -27,6 +27,22 @@ CASES = {
     "frames2": (dict(num_bots=4, num_frames=2, arena_size=200, num_pellets=100, num_viruses=2), dict(steps=40)),
 }
 
+# long horizons: the games of the bench workload grow into their steady state (players popped by viruses into 14
+# cells, lane groups of 8 and 16 in premove_players, lane-per-cell pellet eating); crowded arena for many multi-cell players
+LONG_CASES = {
+    "c2_default_bots_900_steps": (dict(), dict(steps=900, obs_every=30)),
+    "crowded_virus_field_500_steps": (dict(num_agents=2, num_bots=20, arena_size=400, num_pellets=600, num_viruses=30, cap_foods=2048,
+                                           cap_viruses=256), dict(steps=500, obs_every=25, boost=300, p_feed=0.2, p_split=0.2)),
+}
+
+
+@pytest.mark.parametrize("name", list(LONG_CASES))
+def test_cuda_matches_oracle_long_horizon(name):
+    cfg_kwargs, run_kwargs = LONG_CASES[name]
+    stats = run_parity(cfg_kwargs, seeds=[31, 32], **run_kwargs)
+    assert stats["viruses_eaten"] > 0 or stats["max_cells"] >= 2, stats  # the run must have produced multi-cell players
+    print(name, stats)
+
 
 RAM_CASES = {
     # BASELINE.json configs[2]: the structured ("ram") observation, continuous random actions
