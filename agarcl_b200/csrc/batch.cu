@@ -119,6 +119,7 @@ static void fill_sim_params(const agarcl_batch* b, ag::SimParams& P) {
   P.gw_pellet = (int)(((float)b->cfg.arena_size + 510.0f - 1.0f) / 510.0f);
   P.gw_virus = (int)(((float)b->cfg.arena_size + 25.0f - 1.0f) / 25.0f);
   P.smem_per_warp = b->smem_per_warp;
+  P.tiles_bytes = ag::kZeroTileBytes;  // (+ the all-ones tile when the kernel also finishes the observation, fuse_obs_clear)
   P.so = b->so;
   P.obs = nullptr;
   P.zero_vec_per_agent = 0; P.zero_skip_vec = 0; P.agent_stride_vec = 0;
@@ -145,6 +146,7 @@ static bool fuse_obs_clear(const agarcl_batch* b, ag::SimParams& P, int frame) {
   P.obs_finish = (b->fuse_clear >= 2 && b->cfg.obs_dtype == AGARCL_OBS_I32 && b->G % 4 == 0 &&
                   (size_t)b->G * 4 <= (size_t)ag::kZeroTileBytes &&  // one row of channel 0 = one bulk store from the ones tile
                   (size_t)b->G * 4 <= (size_t)(b->so.vcache - b->so.cellref)) ? 1 : 0;
+  if (P.obs_finish) P.tiles_bytes = ag::kZeroTileBytes + (((uint32_t)b->G * 4u + 127u) & ~127u);
   return true;
 }
 
@@ -209,7 +211,7 @@ extern "C" int agarcl_batch_create(const agarcl_cfg* cfg, agarcl_batch** out) {
   int hg = (int)std::floor(std::sqrt((double)L.cap_pellets / 3.0));
   b->HG = hg < 4 ? 4 : (hg > 64 ? 64 : hg);
   b->smem_per_warp = ag::make_smem_offsets(L, b->HG, b->so);
-  if ((size_t)b->smem_per_warp + 2 * ag::kZeroTileBytes > 227 * 1024) {
+  if ((size_t)b->smem_per_warp + 2 * ag::kZeroTileBytes > 227 * 1024) {  // (room for one warp with both tiles at full size)
     delete b;
     return agarcl_set_error(AGARCL_ERR_INVALID, "configuration needs %u B of shared memory per instance (too many pellets/viruses)", b->smem_per_warp);
   }

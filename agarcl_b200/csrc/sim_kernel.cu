@@ -463,36 +463,39 @@ __device__ __forceinline__ int hash_coord(const Ctx& c, float v) {
 }
 __device__ void build_pellet_hash(Ctx& c) {
   const int HG = c.P.HG, nc = HG * HG;
-  for (int i = c.lane; i < nc; i += 32) c.sm.hcnt()[i] = 0u;
+  uint32_t* cnt = c.sm.htmp();  // 32-bit counters for the shared-memory atomics (scratch that is dead at the start of a tick)
+  for (int i = c.lane; i < nc; i += 32) cnt[i] = 0u;
   __syncwarp();
   const float2* pel = c.sm.spel();
   for (int i = c.lane; i < c.n_pellets; i += 32) {
     float2 p = pel[i];
-    atomicAdd(&c.sm.hcnt()[hash_coord(c, p.y) * HG + hash_coord(c, p.x)], 1u);
+    atomicAdd(&cnt[hash_coord(c, p.y) * HG + hash_coord(c, p.x)], 1u);
   }
   __syncwarp();
   // exclusive scan over nc counters, 32 at a time
   uint32_t carry = 0;
   for (int base = 0; base < nc; base += 32) {
     int i = base + c.lane;
-    uint32_t v = i < nc ? c.sm.hcnt()[i] : 0u;
+    uint32_t v = i < nc ? cnt[i] : 0u;
     uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       uint32_t t = __shfl_up_sync(AG_FULL, incl, o);
       if (c.lane >= o) incl += t;
     }
-    if (i < nc) c.sm.hcnt()[i] = carry + incl - v;
+    if (i < nc) cnt[i] = carry + incl - v;
     carry += __shfl_sync(AG_FULL, incl, 31);
   }
   __syncwarp();
   for (int i = c.lane; i < c.n_pellets; i += 32) {
     float2 p = pel[i];
-    uint32_t pos = atomicAdd(&c.sm.hcnt()[hash_coord(c, p.y) * HG + hash_coord(c, p.x)], 1u);
+    uint32_t pos = atomicAdd(&cnt[hash_coord(c, p.y) * HG + hash_coord(c, p.x)], 1u);
     c.sm.hsorted()[pos] = (uint16_t)i;
   }
   __syncwarp();
-  // now hcnt[k] = end of cell k; start of cell k = (k ? hcnt[k-1] : 0)
+  // now cnt[k] = end of cell k; kept as 16-bit: start of cell k = (k ? hcnt[k-1] : 0)
+  for (int i = c.lane; i < nc; i += 32) c.sm.hcnt()[i] = (uint16_t)cnt[i];
+  __syncwarp();
 }
 __device__ void build_virus_cache(Ctx& c) {
   uint32_t mn = 0xffffffffu;
@@ -1721,6 +1724,7 @@ __device__ void players_collision(Ctx& c) {
     c.sm.rows()[g] = (int16_t)get_row(x, c.W);
   }
   __syncwarp();
+  if (c.P.so.sweep_in_hash) c.hash_valid = false;  // the sweep's scratch (rows above included) lies over the hash's index array
   if (lane == 0) players_collision_exact(c, total, nhit, staged);
   __syncwarp();
   c.flags = __shfl_sync(AG_FULL, c.flags, 0);
@@ -1926,7 +1930,7 @@ __device__ void obs_finish_warp(Ctx& c) {
   const float centering = (float)(G / 2.0);
   const float2* pel = c.sm.spel();
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const uint32_t ones_tile = (uint32_t)__cvta_generic_to_shared(smem_raw + kZeroTileBytes);
+  const uint32_t ones_tile = (uint32_t)__cvta_generic_to_shared(smem_raw + kZeroTileBytes);  // (present with obs_finish)
   const uint32_t yrow_s = (uint32_t)__cvta_generic_to_shared(yrow);
   for (int a = 0; a < A; a++) {
     int32_t* out = reinterpret_cast<int32_t*>(P.obs) + ((size_t)c.inst_local * A + a) * ((size_t)P.agent_stride_vec * 4u);
@@ -2198,7 +2202,7 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
   c.lane = lane;
   c.inst_local = inst;
   c.blob = P.state + (size_t)inst * P.L.stride;
-  c.sm.base = smem_raw + 2 * kZeroTileBytes + (size_t)warp * P.smem_per_warp;
+  c.sm.base = smem_raw + P.tiles_bytes + (size_t)warp * P.smem_per_warp;
   c.sm.o = &P.so;
   // the pellet array comes in by one TMA bulk load (whole capacity: the count is not known yet); everything
   // below that does not touch pellets overlaps with it, build_pellet_hash is its first consumer
@@ -2448,12 +2452,10 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // the CTA's all-zero tile (first kZeroTileBytes of shared memory), made visible to the async proxy
   // ... and its all-ones (-1) tile right behind it, source of the out-of-bounds rows of channel 0
-  for (int i = threadIdx.x; i < kZeroTileBytes / 16; i += blockDim.x) {
-    reinterpret_cast<int4*>(smem_raw)[i] = make_int4(0, 0, 0, 0);
-    reinterpret_cast<int4*>(smem_raw + kZeroTileBytes)[i] = make_int4(-1, -1, -1, -1);
-  }
+  for (int i = threadIdx.x; i < (int)P.tiles_bytes / 16; i += blockDim.x)
+    reinterpret_cast<int4*>(smem_raw)[i] = i < kZeroTileBytes / 16 ? make_int4(0, 0, 0, 0) : make_int4(-1, -1, -1, -1);
   if (lane == 0) {  // this warp's mbarrier (one arrival: the lane that queues the pellet load)
-    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(smem_raw + 2 * kZeroTileBytes + (size_t)warp * P.smem_per_warp + P.so.mbar);
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(smem_raw + P.tiles_bytes + (size_t)warp * P.smem_per_warp + P.so.mbar);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -2484,10 +2486,10 @@ cudaError_t launch_step(const SimParams& P, cudaStream_t stream) {
     if ((e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) return e;
   }
-  int warps = (int)(((size_t)smem_max - 2 * kZeroTileBytes) / P.smem_per_warp);
+  int warps = (int)(((size_t)smem_max - P.tiles_bytes) / P.smem_per_warp);
   if (warps > kMaxWarpsPerCta) warps = kMaxWarpsPerCta;
   if (warps < 1) return cudaErrorInvalidConfiguration;
-  const size_t smem = (size_t)2 * kZeroTileBytes + (size_t)P.smem_per_warp * warps;
+  const size_t smem = (size_t)P.tiles_bytes + (size_t)P.smem_per_warp * warps;
   int ctas = (P.N + warps - 1) / warps;
   if (ctas > sms) ctas = sms;
   k_step<<<ctas, warps * 32, smem, stream>>>(P);

@@ -7,8 +7,9 @@
 
 namespace ag {
 
-constexpr int kMaxWarpsPerCta = 13;   // one warp owns one game instance; ONE persistent CTA per SM of as many independent warps as the
-                                      // shared memory holds (13 x 16.9 KB at 1000 pellets), <= 157 registers per thread
+constexpr int kMaxWarpsPerCta = 16;   // one warp owns one game instance; ONE persistent CTA per SM of as many independent warps as the
+                                      // shared memory holds (16 x 13.9 KB at 1000 pellets) and the register file allows (4 per SM
+                                      // sub-partition x 128 registers per thread)
 constexpr int kPremCap = 192;         // pellets_to_remove entries per tick (Engine.hpp:212)
 constexpr int kVremCap = 32;          // viruses_to_remove entries per tick (Engine.hpp:213)
 constexpr int kCandCap = 32;          // pellet candidates resolved in registers per cell
@@ -20,7 +21,8 @@ constexpr int kCellRefCap = 256;      // total live cells per instance handled b
 
 // byte offsets of one warp's shared-memory arrays (sim_shared.cuh)
 struct SmemOff {
-  uint32_t hcnt, hsorted, spel, mbar, cellref, rows, strip, hitq, snap, vcache, psum, pcell, pairs, reskeys, resorder, cand, prem, vrem, lprem;
+  uint32_t hcnt, htmp, hsorted, spel, mbar, cellref, rows, strip, hitq, snap, vcache, psum, pcell, pairs, reskeys, resorder, cand, prem, vrem, lprem;
+  uint32_t sweep_in_hash;  // the exact collision sweep's scratch lies over hsorted: running it invalidates the pellet hash
 };
 
 // Transfer lists of the host-resident observation mirror (mirror.cu), produced on the device either by the fused
@@ -86,6 +88,7 @@ struct SimParams {
   int32_t gw_pellet;       // reference pellet bucket grid width (bucket 510, Engine.hpp:962-965)
   int32_t gw_virus;        // reference virus bucket grid width (bucket 25, Engine.hpp:1207-1211)
   uint32_t smem_per_warp;  // bytes
+  uint32_t tiles_bytes;    // CTA-wide tiles in front of the warps' carve-ups: the zero tile, then the all-ones tile (fused finish only)
   SmemOff so;
   // fused observation clear: the engine-tick kernel streams the zeros of channels 1..C-1 of every
   // agent frame (state independent, 7/8 of all bytes of the step) while it computes; k_obs then only
