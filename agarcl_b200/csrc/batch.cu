@@ -126,6 +126,8 @@ static void fill_sim_params(const agarcl_batch* b, ag::SimParams& P) {
   P.obs_finish = 0; P.obs_G = b->G; P.obs_C = b->C;
   P.zero_chunks = 0;
   if (const char* e = std::getenv("AGARCL_ZERO_CHUNKS")) P.zero_chunks = std::atoi(e);
+  P.tick_barrier = 2;
+  if (const char* e = std::getenv("AGARCL_TICK_BARRIER")) P.tick_barrier = std::atoi(e);  // (A/B timing)
   P.observe_cells = b->cfg.observe_cells; P.observe_others = b->cfg.observe_others;
   P.observe_viruses = b->cfg.observe_viruses; P.observe_pellets = b->cfg.observe_pellets;
   std::memset(&P.pk, 0, sizeof(P.pk));

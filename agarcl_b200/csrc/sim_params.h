@@ -102,6 +102,7 @@ struct SimParams {
   int32_t obs_finish, obs_G, obs_C;
   int32_t zero_chunks;          // > 0: the clear is queued in this many pieces (4 per tick); 0: spread over the ticks
   int32_t observe_cells, observe_others, observe_viruses, observe_pellets;
+  int32_t tick_barrier;         // instruction-fetch alignment (step_instance): 0 off, 1 CTA barrier at every tick start, 2 also behind the pair solver
   PackOut pk;                   // with obs_finish only
   int32_t inst_first;           // this launch steps instances [inst_first, inst_first + N) of the batch
 };
