@@ -72,6 +72,12 @@ __device__ __forceinline__ Cell cell_bcast(const Cell& c, int src) {
 __device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) { return __reduce_add_sync(AG_FULL, v); }
 __device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) { return __reduce_min_sync(AG_FULL, v); }
 __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) { return __reduce_max_sync(AG_FULL, v); }
+// Alignment barrier of the warp's group (step_instance): `ag` consecutive warps of the CTA, barrier 1 + group.
+__device__ __forceinline__ void align_barrier(int ag) {
+  const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5, g = warp / ag;
+  const int members = min(ag, nw - g * ag);
+  asm volatile("barrier.sync %0, %1;" :: "r"(1 + g), "r"(members * 32) : "memory");
+}
 __device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
 constexpr int kHashDead = 0xffff;  // hash entry of a pellet removed since the hash was built
 
@@ -2147,7 +2153,7 @@ __device__ void engine_tick(Ctx& c, LaneState& ls) {
   const int P = c.P.L.P;
   if (c.lanes_dirty) { ls.fresh = false; c.lanes_dirty = false; }
   premove_players(c);
-  if (c.P.tick_barrier >= 2) __syncthreads_or(1);  // ... and enter the player loop together (see step_instance)
+  if (c.P.tick_barrier >= 2) align_barrier(c.P.align_group);  // ... and enter the player loop together (see step_instance)
   tick_players_block(c, 0, ls);
   for (int base = 32; base < P; base += 32) {  // more than 32 players: the further blocks reload every tick
     LaneState tmp;
@@ -2354,7 +2360,7 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
     // warp waits for the slowest one is far less than what the shared fetch saves (2.22 -> 1.69 ms per steady-state
     // step).  Finer alignment (per phase, per solver batch) loses more to waiting than it gains (measured).
     // Warps that have run out of instances keep arriving (k_step) until every warp of the CTA is done.
-    if (P.tick_barrier) __syncthreads_or(1);
+    if (P.tick_barrier) align_barrier(P.align_group);
     engine_tick(c, ls);
   }
   zero_chunk(c, 0xffffffffu);  // whatever is left (n_ticks == 0, rounding)
@@ -2472,8 +2478,10 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // CTA-wide count of warps that have run out of instances (the spare half of warp 0's mbarrier slot)
-  volatile uint32_t* cta_done = reinterpret_cast<volatile uint32_t*>(smem_raw + P.tiles_bytes + P.so.mbar + 8);
-  if (threadIdx.x == 0) *cta_done = 0u;
+  // per alignment group: count of warps that have run out of instances (the spare half of the mbarrier slot of the group's first warp)
+  volatile uint32_t* grp_done = reinterpret_cast<volatile uint32_t*>(
+      smem_raw + P.tiles_bytes + (size_t)((warp / P.align_group) * P.align_group) * P.smem_per_warp + P.so.mbar + 8);
+  if (lane == 0 && warp % P.align_group == 0) *grp_done = 0u;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   uint32_t mbar_phase = 0u;
@@ -2485,9 +2493,11 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
     step_instance(P, smem_raw, P.inst_first + (int)t, warp, lane, mbar_phase);
   }
   if (P.tick_barrier) {
-    // keep meeting the warps that still tick; leave together once every warp of the CTA has run out of instances
-    if (lane == 0) atomicAdd(const_cast<uint32_t*>(cta_done), 1u);
-    do { __syncthreads_or(0); } while (*cta_done < (blockDim.x >> 5));  // (the same barrier operation as the ticking warps use)
+    // keep meeting the warps of the group that still tick; leave together once all of them have run out of instances
+    const int nw = blockDim.x >> 5, g = warp / P.align_group;
+    const uint32_t members = (uint32_t)min(P.align_group, nw - g * P.align_group);
+    if (lane == 0) atomicAdd(const_cast<uint32_t*>(grp_done), 1u);
+    do { align_barrier(P.align_group); } while (*grp_done < members);
   }
   if (lane == 0) {
     const uint32_t left = atomicAdd(P.tickets + 1, 1u);
