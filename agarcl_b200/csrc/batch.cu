@@ -21,6 +21,7 @@
 
 namespace ag {
 cudaError_t launch_step(const SimParams& P, cudaStream_t stream);
+cudaError_t launch_order(const uint32_t* cost, uint32_t* perm, int N, cudaStream_t stream);
 cudaError_t launch_obs(const ObsParams& P, cudaStream_t stream);
 cudaError_t launch_reset(const ResetParams& P, cudaStream_t stream);
 cudaError_t launch_ram(const RamParams& P, cudaStream_t stream);
@@ -45,6 +46,9 @@ struct agarcl_batch {
   uint64_t* d_seeds = nullptr;
   uint8_t* d_mask = nullptr;
   uint32_t* d_tickets = nullptr;  // k_step's ticket counter pair (self-rewinding)
+  uint32_t *d_cost = nullptr, *d_perm = nullptr;  // per-instance cost of the last step and the cost-sorted schedule made from it (k_order)
+  bool perm_valid = false;
+  int sort_schedule = 1;  // AGARCL_SORT_SCHEDULE=0 turns the cost-sorted schedule off (A/B timing)
   float *d_lut_radius = nullptr, *d_lut_speed = nullptr, *d_lut_split = nullptr;
   std::vector<uint64_t> seeds;
   ag::Luts T;
@@ -105,6 +109,8 @@ static void fill_sim_params(const agarcl_batch* b, ag::SimParams& P) {
   P.before = b->d_before;
   P.replay = b->d_replay;
   P.tickets = b->d_tickets;
+  P.cost = nullptr;
+  P.perm = nullptr;
   P.N = b->N;
   P.instance_base = b->cfg.instance_base;
   P.mode = b->cfg.mode_number;
@@ -180,7 +186,7 @@ extern "C" int agarcl_batch_destroy(agarcl_batch* b) {
   ag::mirror_destroy(b->mirror);
   cudaFree(b->d_ram);
   cudaFree(b->d_state); cudaFree(b->d_obs); cudaFree(b->d_rewards); cudaFree(b->d_dones); cudaFree(b->d_before);
-  cudaFree(b->d_dxdy); cudaFree(b->d_act); cudaFree(b->d_replay); cudaFree(b->d_seeds); cudaFree(b->d_mask); cudaFree(b->d_tickets);
+  cudaFree(b->d_dxdy); cudaFree(b->d_act); cudaFree(b->d_replay); cudaFree(b->d_seeds); cudaFree(b->d_mask); cudaFree(b->d_tickets); cudaFree(b->d_cost); cudaFree(b->d_perm);
   cudaFree(b->d_lut_radius); cudaFree(b->d_lut_speed); cudaFree(b->d_lut_split);
   for (cudaEvent_t e : b->ev) cudaEventDestroy(e);
   delete b;
@@ -210,6 +216,7 @@ extern "C" int agarcl_batch_create(const agarcl_cfg* cfg, agarcl_batch** out) {
   b->C = L.obs_channels;
   b->frames = cfg->num_frames;
   if (const char* e = std::getenv("AGARCL_FUSE_CLEAR")) b->fuse_clear = std::atoi(e);
+  if (const char* e = std::getenv("AGARCL_SORT_SCHEDULE")) b->sort_schedule = std::atoi(e);
   b->obs_elems = (size_t)b->N * b->A * b->frames * b->C * b->G * b->G;
   b->obs_bytes = b->obs_elems * (cfg->obs_dtype == AGARCL_OBS_I16 ? 2 : 4);
   // spatial hash resolution: about 3 pellets per hash cell, 4..64 cells per side
@@ -239,6 +246,8 @@ extern "C" int agarcl_batch_create(const agarcl_cfg* cfg, agarcl_batch** out) {
   ALLOC(b->d_seeds, (size_t)b->N * sizeof(uint64_t));
   ALLOC(b->d_mask, (size_t)b->N);
   ALLOC(b->d_tickets, 2 * sizeof(uint32_t));
+  ALLOC(b->d_cost, (size_t)b->N * sizeof(uint32_t));
+  ALLOC(b->d_perm, (size_t)b->N * sizeof(uint32_t));
   cudaMemset(b->d_tickets, 0, 2 * sizeof(uint32_t));
   if (L.cap_replay > 0) ALLOC(b->d_replay, (size_t)b->N * L.cap_replay * sizeof(float));
   if (cfg->ram_obs) {
@@ -451,13 +460,16 @@ static int step_impl(agarcl_batch* b, cudaStream_t s, bool want_lists, bool* lis
   } else if (b->frames == 1) {
     P.n_ticks = tps; P.do_begin = 1; P.do_end = 1;
     const int fused = fuse_obs_clear(b, P, 0) ? 1 : 0;
-    if (want_lists && P.obs_finish && b->mirror && 5 + 2 * ((b->G + 31) / 32) <= 32) {  // (the image's record is one warp store)
+    if (want_lists && P.obs_finish && b->mirror && 6 + 2 * ((b->G + 31) / 32) <= 32) {  // (the image's record is one warp store)
       P.pk = ag::mirror_pack_out(b->mirror);
       *lists_made = true;
     }
+    const bool sorted = P.tick_barrier && b->sort_schedule;
+    if (sorted) { P.cost = b->d_cost; P.perm = b->perm_valid ? b->d_perm : nullptr; }
     if (b->timing) { if (b->ev_used >= 3 * 2048) collect_timing(b); CK(cudaEventRecord(next_event(b), s)); }
     CK(ag::launch_step(P, s)); launches++;
     if (b->timing) CK(cudaEventRecord(next_event(b), s));
+    if (sorted) { CK(ag::launch_order(b->d_cost, b->d_perm, b->N, s)); b->perm_valid = true; launches++; }
     if (!P.obs_finish) { int rc = render_frame(b, 0, s, 1, fused); if (rc) return rc; launches++; }
     if (b->timing) CK(cudaEventRecord(next_event(b), s));
   } else {

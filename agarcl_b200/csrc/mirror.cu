@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const PackParams P) {
       }
     }
     if (bad) s_bad = 1;
-    uint32_t* mk = blk + pk_off_rec(P.pk) + (size_t)li * P.pk.rec_words + 2 + (size_t)f * 2 * MW;
+    uint32_t* mk = blk + pk_off_rec(P.pk) + (size_t)li * P.pk.rec_words + 3 + (size_t)f * 2 * MW;
     for (uint32_t w = tid; w < 2u * MW; w += kPackThreads) {
       const uint8_t* any = w < MW ? row_any : col_any;
       const uint32_t w0 = (w % MW) * 32;
@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const PackParams P) {
     uint32_t* rec = blk + pk_off_rec(P.pk) + (size_t)li * P.pk.rec_words;
     rec[0] = cnt;
     rec[1] = b0;
+    rec[2] = img;  // slot = image on this path
     s_cnt = cnt;
     s_base = b0;
   }
@@ -285,6 +286,7 @@ struct HostMirror {
   uint32_t* d_flags = nullptr;                 // its device address
   uint32_t seq = 0;
   int cur = 0;
+  std::vector<uint32_t> slot_of[2];  // per staging buffer: the slot that describes image i
   std::vector<size_t> guess;      // per chunk: entries fetched together with the meta words (the remainder, if any, in a second copy)
   Pool* pool = nullptr;
   MirrorStats stats{};
@@ -319,39 +321,52 @@ static void apply_mask_delta(T* p, const uint32_t* om, const uint32_t* nm, int G
 }
 
 // The elements an image's two lists touch are scattered over its 512 KB: ask for their cache lines (for writing)
-// one image ahead, so that the misses of image i+1 overlap the read-modify-writes of image i.
+// one slot ahead, so that the misses of the next image overlap the read-modify-writes of this one.
 template <typename T>
-static void prefetch_image(const HostMirror* m, int img) {
+static void prefetch_slot(const HostMirror* m, int slot) {
   const int cur = m->cur, prev = cur ^ 1;
   const PackOut& k = m->pk;
-  const int chunk = img / (int)k.ipc, li = img - chunk * (int)k.ipc;
+  const uint32_t* cb = m->blk(cur, slot / (int)k.ipc);
+  const uint32_t* crec = cb + pk_off_rec(k) + (size_t)(slot % (int)k.ipc) * k.rec_words;
+  const uint32_t img = crec[2];
+  if (img >= (uint32_t)m->n_img) return;
   const T* p = reinterpret_cast<const T*>(m->h_obs) + (size_t)img * m->img_elems;
-  for (int w = 0; w < 2; w++) {
-    const uint32_t* b = m->blk(w ? prev : cur, chunk);
-    const uint32_t* rec = b + pk_off_rec(k) + (size_t)li * k.rec_words;
-    if (rec[0] == kPackDense) continue;
-    const uint2* e = reinterpret_cast<const uint2*>(b + pk_off_entries(k)) + rec[1];
-    for (uint32_t i = 0; i < rec[0]; i++) __builtin_prefetch(p + (e[i].x & kPkOffMask), 1, 1);
+  if (crec[0] != kPackDense) {
+    const uint2* e = reinterpret_cast<const uint2*>(cb + pk_off_entries(k)) + crec[1];
+    for (uint32_t i = 0; i < crec[0]; i++) __builtin_prefetch(p + (e[i].x & kPkOffMask), 1, 1);
+  }
+  const uint32_t ps = m->slot_of[prev][img];
+  const uint32_t* pb = m->blk(prev, (int)(ps / k.ipc));
+  const uint32_t* prec = pb + pk_off_rec(k) + (size_t)(ps % k.ipc) * k.rec_words;
+  if (prec[0] != kPackDense) {
+    const uint2* e = reinterpret_cast<const uint2*>(pb + pk_off_entries(k)) + prec[1];
+    for (uint32_t i = 0; i < prec[0]; i++) __builtin_prefetch(p + (e[i].x & kPkOffMask), 1, 1);
   }
 }
 
+// Slots [lo, hi) of the current lists: every slot names its image; the image's previous lists are found through slot_of.
 template <typename T>
 static void expand_range(HostMirror* m, int lo, int hi, const uint32_t* zero_masks) {
   const int cur = m->cur, prev = cur ^ 1;
   const PackOut& k = m->pk;
   const size_t mw2 = 2 * (size_t)m->MW, plane = (size_t)m->G * m->G;
-  prefetch_image<T>(m, lo);
-  for (int img = lo; img < hi; img++) {
-    if (img + 1 < hi) prefetch_image<T>(m, img + 1);
-    const int chunk = img / (int)k.ipc, li = img - chunk * (int)k.ipc;
-    const uint32_t *cb = m->blk(cur, chunk), *pb = m->blk(prev, chunk);
-    const uint32_t *crec = cb + pk_off_rec(k) + (size_t)li * k.rec_words, *prec = pb + pk_off_rec(k) + (size_t)li * k.rec_words;
+  prefetch_slot<T>(m, lo);
+  for (int slot = lo; slot < hi; slot++) {
+    if (slot + 1 < hi) prefetch_slot<T>(m, slot + 1);
+    const uint32_t* cb = m->blk(cur, slot / (int)k.ipc);
+    const uint32_t* crec = cb + pk_off_rec(k) + (size_t)(slot % (int)k.ipc) * k.rec_words;
+    const uint32_t img = crec[2];
+    if (img >= (uint32_t)m->n_img) continue;  // (cannot happen with lists the kernels wrote)
+    const uint32_t ps = m->slot_of[prev][img];
+    m->slot_of[cur][img] = (uint32_t)slot;
+    const uint32_t* pb = m->blk(prev, (int)(ps / k.ipc));
+    const uint32_t* prec = pb + pk_off_rec(k) + (size_t)(ps % k.ipc) * k.rec_words;
     const uint32_t cnt = crec[0];
     if (cnt == kPackDense) continue;  // the dense copy of this image is made by the calling thread
     T* p = reinterpret_cast<T*>(m->h_obs) + (size_t)img * m->img_elems;
     const uint32_t pcnt = prec[0];
-    const uint32_t* om = prec + 2;
-    const uint32_t* nm = crec + 2;
+    const uint32_t* om = prec + 3;
+    const uint32_t* nm = crec + 3;
     if (pcnt == kPackDense) {
       std::memset(p, 0, m->img_bytes);
       om = nullptr;
@@ -424,7 +439,7 @@ HostMirror* mirror_create(int n_img, int agents, int CH, int C, int G, int dtype
   PackOut& k = m->pk;
   k.ipc = (uint32_t)ipc_inst * (uint32_t)agents;
   m->n_chunks = (n_img + (int)k.ipc - 1) / (int)k.ipc;
-  k.rec_words = (uint32_t)(2 + m->frames * 2 * m->MW + 3);
+  k.rec_words = (uint32_t)(3 + m->frames * 2 * m->MW + 3);
   k.MW = m->MW;
   k.n_img = (uint32_t)n_img;
   uint32_t per_img = (m->cap_img < 1024 ? m->cap_img : 1024) & ~1u;  // entries per image (k_step: the image's slot)
@@ -485,6 +500,10 @@ HostMirror* mirror_create(int n_img, int agents, int CH, int C, int G, int dtype
   m->pool = new Pool(nt - 1);
   m->stats.host_threads = (uint64_t)nt;
   m->guess.assign((size_t)m->n_chunks, (size_t)k.ipc * 64);
+  for (int w = 0; w < 2; w++) {
+    m->slot_of[w].resize((size_t)n_img);
+    for (int i = 0; i < n_img; i++) m->slot_of[w][(size_t)i] = (uint32_t)i;
+  }
   // first touch of the mirror by the threads that will write it
   {
     std::atomic<int> next{0};
@@ -600,13 +619,16 @@ static int collect(HostMirror* m, const void* d_obs, cudaStream_t s, bool flagge
     }
     for (int i = lo; i < hi; i++) {
       const uint32_t* rec = hb + pk_off_rec(k) + (size_t)(i - lo) * k.rec_words;
-      if (rec[0] == kPackDense) dense_imgs.push_back(i);
+      const uint32_t img = rec[2];
+      if (img >= (uint32_t)m->n_img) { rc = agarcl_set_error(AGARCL_ERR_STATE, "mirror slot %d names image %u of %d", i, img, m->n_img); break; }
+      if (rec[0] == kPackDense) dense_imgs.push_back((int)img);
       else entries += rec[0];
       if (flagged) {  // reward and done flag of the step came with the record
-        if (rewards_out) std::memcpy(rewards_out + i, rec + k.rec_words - 3, sizeof(double));
-        if (dones_out) dones_out[i] = (uint8_t)rec[k.rec_words - 1];
+        if (rewards_out) std::memcpy(rewards_out + img, rec + k.rec_words - 3, sizeof(double));
+        if (dones_out) dones_out[img] = (uint8_t)rec[k.rec_words - 1];
       }
     }
+    if (rc != AGARCL_OK) break;
     if (flagged) d2h += (size_t)(hi - lo) * k.rec_words * 4 + 4;  // what the kernel wrote over PCIe: records + flag (entries below)
     wait_s += std::chrono::duration<double>(clk::now() - w0).count();
     avail.store(hi, std::memory_order_release);

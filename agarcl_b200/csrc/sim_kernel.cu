@@ -106,7 +106,9 @@ struct Ctx {
   bool vc_valid;        // the virus cache in shared memory matches the virus array
   bool lanes_dirty;     // players_collision changed players: lanes must reload their registers
   uint32_t pre_lo, pre_hi;  // players whose move + self-collisions of this tick are already done (premove_players)
+  long long work, t_mark;   // cycles this instance has worked (waiting at the alignment barriers excluded) / start of the current stretch
   int inst_local;
+  int pos;              // position of the instance in this launch's schedule (the host mirror's lists are laid out by position)
   float W;
   static constexpr float dt = (float)(1.0 / 30.0);
   __device__ Ctx(const SimParams& p) : P(p) {}
@@ -1974,15 +1976,16 @@ __device__ void obs_finish_warp(Ctx& c) {
     bool emit = P.pk.chunks != nullptr;
     uint32_t* pk_rec = nullptr;
     uint4* pk_ent = nullptr;     // the image's slot, two entries per 16-byte store
-    uint32_t pk_mine = 0u;       // lane l holds word l of the record: count, base, row masks, column masks
+    uint32_t pk_mine = 0u;       // lane l holds word l of the record: count, base, image, row masks, column masks
     uint32_t wq = 0u;            // entries listed so far (warp-uniform, even)
     if (emit) {
-      const uint32_t img = (uint32_t)c.inst_local * (uint32_t)A + (uint32_t)a;
-      const uint32_t chunk = img / P.pk.ipc, li = img - chunk * P.pk.ipc;
+      const uint32_t slot = (uint32_t)c.pos * (uint32_t)A + (uint32_t)a;  // the image's place in this launch's schedule
+      const uint32_t chunk = slot / P.pk.ipc, li = slot - chunk * P.pk.ipc;
       uint32_t* blk = P.pk.chunks + (size_t)chunk * P.pk.chunk_words;
       pk_rec = blk + pk_off_rec(P.pk) + (size_t)li * P.pk.rec_words;
       pk_ent = reinterpret_cast<uint4*>(blk + pk_off_entries(P.pk)) + (size_t)li * (P.pk.slot / 2u);
       if (lane == 1) pk_mine = li * P.pk.slot;
+      if (lane == 2) pk_mine = (uint32_t)c.inst_local * (uint32_t)A + (uint32_t)a;  // which image this is
       const int MW = P.pk.MW;
       for (int i0 = 0, w = 0; i0 < G; i0 += 32, w++) {  // the row / column bit masks of channel 0 from the predicates above
         const int i = i0 + lane;
@@ -1990,8 +1993,8 @@ __device__ void obs_finish_warp(Ctx& c) {
         const float wy = py + ((float)i - centering) * view / (float)G;
         const unsigned rb = __ballot_sync(AG_FULL, i < G && !(0 <= wx && wx < W));
         const unsigned cb = __ballot_sync(AG_FULL, i < G && !(0 <= wy && wy < W));
-        if (lane == 2 + w) pk_mine = rb;
-        if (lane == 2 + MW + w) pk_mine = cb;
+        if (lane == 3 + w) pk_mine = rb;
+        if (lane == 3 + MW + w) pk_mine = cb;
       }
     }
     auto grid_of = [&](float x, float y, int& gx, int& gy) -> bool {
@@ -2153,7 +2156,9 @@ __device__ void engine_tick(Ctx& c, LaneState& ls) {
   const int P = c.P.L.P;
   if (c.lanes_dirty) { ls.fresh = false; c.lanes_dirty = false; }
   premove_players(c);
-  if (c.P.tick_barrier >= 2) align_barrier(c.P.align_group);  // ... and enter the player loop together (see step_instance)
+  if (c.P.tick_barrier >= 2) {  // ... and enter the player loop together (see step_instance)
+    c.work += clock64() - c.t_mark; align_barrier(c.P.align_group); c.t_mark = clock64();
+  }
   tick_players_block(c, 0, ls);
   for (int base = 32; base < P; base += 32) {  // more than 32 players: the further blocks reload every tick
     LaneState tmp;
@@ -2203,10 +2208,12 @@ __device__ void respawn_player(Ctx& c, int p, uint32_t k) {
 // ------------------------------------------------------------------------------------------------
 // kernel: BaseEnvironment::step for one instance per warp
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_raw, const int inst, const int warp, const int lane,
-                                              uint32_t& mbar_phase) {
+__device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_raw, const int inst, const int pos, const int warp,
+                                              const int lane, uint32_t& mbar_phase) {
   Ctx c(P);
   c.lane = lane;
+  c.pos = pos;
+  c.work = 0; c.t_mark = clock64();
   c.inst_local = inst;
   c.blob = P.state + (size_t)inst * P.L.stride;
   c.sm.base = smem_raw + P.tiles_bytes + (size_t)warp * P.smem_per_warp;
@@ -2360,7 +2367,7 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
     // warp waits for the slowest one is far less than what the shared fetch saves (2.22 -> 1.69 ms per steady-state
     // step).  Finer alignment (per phase, per solver batch) loses more to waiting than it gains (measured).
     // Warps that have run out of instances keep arriving (k_step) until every warp of the CTA is done.
-    if (P.tick_barrier) align_barrier(P.align_group);
+    if (P.tick_barrier) { c.work += clock64() - c.t_mark; align_barrier(P.align_group); c.t_mark = clock64(); }
     engine_tick(c, ls);
   }
   zero_chunk(c, 0xffffffffu);  // whatever is left (n_ticks == 0, rounding)
@@ -2412,7 +2419,7 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
       const uint8_t dn = (a == 0) ? (uint8_t)(c.done_sticky != 0u) : (uint8_t)0;
       P.dones[gi] = dn;
       if (P.pk.chunks != nullptr && P.obs_finish) {  // host mirror: reward and done travel in the image's record
-        const uint32_t img = (uint32_t)gi, chunk = img / P.pk.ipc, li = img - chunk * P.pk.ipc;
+        const uint32_t slot = (uint32_t)c.pos * (uint32_t)A + (uint32_t)a, chunk = slot / P.pk.ipc, li = slot - chunk * P.pk.ipc;
         uint32_t* tail = P.pk.chunks + (size_t)chunk * P.pk.chunk_words + pk_off_rec(P.pk) + (size_t)li * P.pk.rec_words + (P.pk.rec_words - 3u);
         const unsigned long long rb = (unsigned long long)__double_as_longlong(r);
         tail[0] = (uint32_t)rb; tail[1] = (uint32_t)(rb >> 32); tail[2] = (uint32_t)dn;
@@ -2440,6 +2447,10 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
     hdr->n_pellets = c.n_pellets; hdr->n_viruses = c.n_viruses; hdr->n_foods = c.n_foods;
     hdr->rng_cursor = c.cursor; hdr->flags = c.flags; hdr->done_sticky = c.done_sticky;
   }
+  if (P.cost && lane == 0) {  // what the instance cost this step: next step's schedule puts equals together (k_order)
+    const long long w = c.work + (clock64() - c.t_mark);
+    P.cost[inst] = (uint32_t)(w < 0xffffffffll ? w : 0xffffffffll);
+  }
   if (P.pk.chunks != nullptr && P.do_end && P.obs_finish) {
     // host mirror: the warp that finishes the last instance of a chunk rewinds the chunk's counter for the next
     // launch and raises the flag the host polls; the system-scope fences order every warp's list stores (pinned
@@ -2447,7 +2458,7 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
     __threadfence_system();
     __syncwarp();
     if (lane == 0) {
-      const uint32_t chunk = ((uint32_t)inst * (uint32_t)A) / P.pk.ipc;
+      const uint32_t chunk = ((uint32_t)pos * (uint32_t)A) / P.pk.ipc;
       const uint32_t in_chunk = min(P.pk.ipc, P.pk.n_img - chunk * P.pk.ipc);
       if (atomicAdd(P.pk.done + chunk, (uint32_t)A) + (uint32_t)A == in_chunk) {
         P.pk.done[chunk] = 0u;
@@ -2485,12 +2496,30 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   uint32_t mbar_phase = 0u;
-  while (true) {
-    uint32_t t = 0;
-    if (lane == 0) t = atomicAdd(P.tickets, 1u);
-    t = __shfl_sync(AG_FULL, t, 0);
-    if (t >= (uint32_t)P.N) break;
-    step_instance(P, smem_raw, P.inst_first + (int)t, warp, lane, mbar_phase);
+  if (P.tick_barrier) {
+    // Aligned warps move through their instances in rounds anyway (every instance runs the same number of barriers),
+    // so the schedule is static: in round r this CTA takes the r-th stripe of blockDim/32 consecutive positions of the
+    // cost-sorted order `perm` (k_order: most expensive first, so the instances of one round of one CTA cost about the
+    // same and nobody waits long at the barriers), odd rounds in reverse CTA order (the CTAs with the expensive stripes
+    // of round r get the cheap ones of round r+1).
+    const uint32_t nw = blockDim.x >> 5, stripes = ((uint32_t)P.N + nw - 1u) / nw;
+    for (uint32_t r = 0;; r++) {
+      const uint32_t k = (r & 1u) ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
+      const uint32_t stripe = r * gridDim.x + k;
+      if (r * gridDim.x >= stripes) break;
+      const uint32_t t = stripe * nw + (uint32_t)warp;
+      if (stripe >= stripes || t >= (uint32_t)P.N) break;  // nothing left for this warp (positions only grow): it keeps arriving at the barriers below
+      const uint32_t inst = P.perm ? P.perm[t] : t;
+      step_instance(P, smem_raw, P.inst_first + (int)inst, (int)t, warp, lane, mbar_phase);
+    }
+  } else {
+    while (true) {
+      uint32_t t = 0;
+      if (lane == 0) t = atomicAdd(P.tickets, 1u);
+      t = __shfl_sync(AG_FULL, t, 0);
+      if (t >= (uint32_t)P.N) break;
+      step_instance(P, smem_raw, P.inst_first + (int)t, (int)t, warp, lane, mbar_phase);
+    }
   }
   if (P.tick_barrier) {
     // keep meeting the warps of the group that still tick; leave together once all of them have run out of instances
@@ -2499,10 +2528,50 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
     if (lane == 0) atomicAdd(const_cast<uint32_t*>(grp_done), 1u);
     do { align_barrier(P.align_group); } while (*grp_done < members);
   }
-  if (lane == 0) {
+  if (!P.tick_barrier && lane == 0) {
     const uint32_t left = atomicAdd(P.tickets + 1, 1u);
     if (left == gridDim.x * (blockDim.x >> 5) - 1u) { P.tickets[0] = 0u; P.tickets[1] = 0u; }
   }
+}
+
+// Cost-sorted schedule for the next step (one CTA): perm = instance indices ordered by the cycles they worked in this
+// step, most expensive first -- a 256-bucket counting sort on the cost relative to the maximum is all the precision
+// the schedule needs (the order inside a bucket is arbitrary; it only moves instances between warps, never results).
+__global__ void __launch_bounds__(1024) k_order(const uint32_t* __restrict__ cost, uint32_t* __restrict__ perm, int N) {
+  __shared__ uint32_t s_max, cnt[256];
+  const int tid = threadIdx.x;
+  if (tid == 0) s_max = 1u;
+  if (tid < 256) cnt[tid] = 0u;
+  __syncthreads();
+  uint32_t mx = 0u;
+  for (int i = tid; i < N; i += 1024) mx = max(mx, cost[i]);
+  mx = __reduce_max_sync(AG_FULL, mx);
+  if ((tid & 31) == 0) atomicMax(&s_max, mx);
+  __syncthreads();
+  const float scale = 255.0f / (float)s_max;
+  auto bucket = [&](uint32_t c) { return 255 - min(255, (int)((float)c * scale)); };
+  for (int i = tid; i < N; i += 1024) atomicAdd(&cnt[bucket(cost[i])], 1u);
+  __syncthreads();
+  if (tid < 32) {  // exclusive scan of the 256 counters by one warp
+    uint32_t carry = 0u;
+    for (int b0 = 0; b0 < 256; b0 += 32) {
+      const uint32_t v = cnt[b0 + tid];
+      uint32_t incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(AG_FULL, incl, o);
+        if (tid >= o) incl += t;
+      }
+      cnt[b0 + tid] = carry + incl - v;
+      carry += __shfl_sync(AG_FULL, incl, 31);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += 1024) perm[atomicAdd(&cnt[bucket(cost[i])], 1u)] = (uint32_t)i;
+}
+cudaError_t launch_order(const uint32_t* cost, uint32_t* perm, int N, cudaStream_t stream) {
+  k_order<<<1, 1024, 0, stream>>>(cost, perm, N);
+  return cudaGetLastError();
 }
 
 // One CTA per SM, as many warps (= concurrent instances) as the shared memory holds, at most kMaxWarpsPerCta.

@@ -29,8 +29,10 @@ struct SmemOff {
 // observation finish of k_step (no second pass over the dense tensor) or by k_pack.  The agent images are grouped
 // into CHUNKS of `ipc` consecutive images; one chunk = one contiguous block of 32-bit words
 //   [0] entries used in the chunk (k_pack only)   [1..3] pad
-//   rec[ipc][rec_words]   per image: count (entries of the image, or 0xFFFFFFFF: does not fit the scheme, copy the
-//                         image densely), base (its first entry in the chunk's entry array), then per frame the row
+//   rec[ipc][rec_words]   per slot: count (entries of the image, or 0xFFFFFFFF: does not fit the scheme, copy the
+//                         image densely), base (its first entry in the chunk's entry array), the index of the image
+//                         the slot describes (k_step fills the slots in the order of its schedule, so that the chunks
+//                         complete one after the other while it runs; k_pack: slot = image), then per frame the row
 //                         bit mask and the column bit mask of the out-of-bounds channel (bit i: row i out of bounds),
 //                         then the agent's reward (f64, two words) and done flag of the step (k_step only)
 //   entries[cap_chunk]    uint2 (op << 29 | element offset inside the image, operand): the integer operation the
@@ -48,8 +50,8 @@ struct PackOut {
   uint32_t* done;            // [n_chunks] images finished (self-rewinding)
   volatile uint32_t* flags;  // [n_chunks] host-mapped: last step sequence number whose chunk is complete; may be nullptr
   uint32_t chunk_words;      // words between consecutive chunk blocks
-  uint32_t ipc;              // images per chunk (a multiple of the agents per instance)
-  uint32_t rec_words;        // 2 + frames * 2 * MW + 3
+  uint32_t ipc;              // slots (images) per chunk (a multiple of the agents per instance)
+  uint32_t rec_words;        // 3 + frames * 2 * MW + 3
   uint32_t cap_chunk;        // entry capacity of a chunk
   uint32_t slot;             // k_step: entries per image slot (even; ipc * slot <= cap_chunk)
   uint32_t n_img;
@@ -74,7 +76,9 @@ struct SimParams {
   uint8_t* dones;          // [N*A]
   float* before;           // [N*A] masses<float>() at step begin (BaseEnvironment.hpp:92)
   const float* replay;     // [N*cap_replay] or nullptr
-  uint32_t* tickets;       // [2] persistent-grid work counter: next instance, warps that have left (k_step)
+  uint32_t* tickets;       // [2] persistent-grid work counter: next instance, warps that have left (k_step without alignment)
+  uint32_t* cost;          // [N] cycles every instance worked in this step (nullptr: not wanted)
+  const uint32_t* perm;    // [N] cost-sorted instance order of the previous step (nullptr: identity)
   int32_t N;
   int32_t instance_base;
   int32_t n_ticks;         // ticks to run in this launch

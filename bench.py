@@ -435,7 +435,9 @@ def run_ours(args):
         sim_avg, obs_avg = sim_ms / max(tsteps, 1), obs_ms / max(tsteps, 1)
         fuse = int(os.environ.get("AGARCL_FUSE_CLEAR", "2"))
         obs_b = A * 8 * 128 * 128 * 4
-        if launches == K:      # one kernel per step: ticks + the whole observation
+        n_order = 1 if (int(os.environ.get("AGARCL_SORT_SCHEDULE", "1")) and int(os.environ.get("AGARCL_TICK_BARRIER", "2"))) else 0
+        single = (launches == K * (1 + n_order))  # k_step (ticks + the whole observation) [+ k_order, the tiny schedule sort]
+        if single:
             kern = {"k_step": (sim_avg, ab["step"] * N)}
         elif fuse == 1:        # k_step also streams channels 1..7, k_obs writes channel 0 + scatter
             kern = {"k_step": (sim_avg, (ab["sim_kernel"] + obs_b * 7 // 8) * N),
@@ -443,7 +445,7 @@ def run_ours(args):
         else:
             kern = {"k_step": (sim_avg, ab["sim_kernel"] * N), "k_obs": (obs_avg, ab["obs_kernel"] * N)}
         dom = max(kern, key=lambda k: kern[k][0])
-        traffic = measured_traffic(dom if launches == K else None)
+        traffic = measured_traffic(dom if single else None)
         def rf(k):
             t_ms, byt = kern[k]
             ach = byt / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
