@@ -2156,7 +2156,7 @@ __device__ void engine_tick(Ctx& c, LaneState& ls) {
   const int P = c.P.L.P;
   if (c.lanes_dirty) { ls.fresh = false; c.lanes_dirty = false; }
   premove_players(c);
-  if (c.P.tick_barrier >= 2) {  // ... and enter the player loop together (see step_instance)
+  if (c.P.tick_barrier & 2) {  // ... and enter the player loop together (see step_instance)
     c.work += clock64() - c.t_mark; align_barrier(c.P.align_group); c.t_mark = clock64();
   }
   tick_players_block(c, 0, ls);
@@ -2169,10 +2169,13 @@ __device__ void engine_tick(Ctx& c, LaneState& ls) {
     tick_players_block(c, base, tmp);
   }
   zero_chunk(c, c.zchunk);
+  if (c.P.tick_barrier & 16) { c.work += clock64() - c.t_mark; align_barrier(c.P.align_group); c.t_mark = clock64(); }
   apply_removals(c);
   zero_chunk(c, c.zchunk);
+  if (c.P.tick_barrier & 4) { c.work += clock64() - c.t_mark; align_barrier(c.P.align_group); c.t_mark = clock64(); }  // ... and the cross-player sweep
   players_collision(c);
   zero_chunk(c, c.zchunk);
+  if (c.P.tick_barrier & 8) { c.work += clock64() - c.t_mark; align_barrier(c.P.align_group); c.t_mark = clock64(); }
   move_foods(c);
   if (c.P.L.regen && c.tick % 120u == 0u) regen(c);
   c.tick++;
@@ -2367,7 +2370,7 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
     // warp waits for the slowest one is far less than what the shared fetch saves (2.22 -> 1.69 ms per steady-state
     // step).  Finer alignment (per phase, per solver batch) loses more to waiting than it gains (measured).
     // Warps that have run out of instances keep arriving (k_step) until every warp of the CTA is done.
-    if (P.tick_barrier) { c.work += clock64() - c.t_mark; align_barrier(P.align_group); c.t_mark = clock64(); }
+    if (P.tick_barrier & 1) { c.work += clock64() - c.t_mark; align_barrier(P.align_group); c.t_mark = clock64(); }
     engine_tick(c, ls);
   }
   zero_chunk(c, 0xffffffffu);  // whatever is left (n_ticks == 0, rounding)
@@ -2488,47 +2491,42 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // CTA-wide count of warps that have run out of instances (the spare half of warp 0's mbarrier slot)
-  // per alignment group: count of warps that have run out of instances (the spare half of the mbarrier slot of the group's first warp)
-  volatile uint32_t* grp_done = reinterpret_cast<volatile uint32_t*>(
-      smem_raw + P.tiles_bytes + (size_t)((warp / P.align_group) * P.align_group) * P.smem_per_warp + P.so.mbar + 8);
-  if (lane == 0 && warp % P.align_group == 0) *grp_done = 0u;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   uint32_t mbar_phase = 0u;
   if (P.tick_barrier) {
-    // Aligned warps move through their instances in rounds anyway (every instance runs the same number of barriers),
-    // so the schedule is static: in round r this CTA takes the r-th stripe of blockDim/32 consecutive positions of the
-    // cost-sorted order `perm` (k_order: most expensive first, so the instances of one round of one CTA cost about the
-    // same and nobody waits long at the barriers), odd rounds in reverse CTA order (the CTAs with the expensive stripes
-    // of round r get the cheap ones of round r+1).
-    const uint32_t nw = blockDim.x >> 5, stripes = ((uint32_t)P.N + nw - 1u) / nw;
-    for (uint32_t r = 0;; r++) {
+    // Aligned warps move through their instances in rounds (every instance runs the same number of barriers), so the
+    // schedule is static: in round r this CTA takes the r-th stripe of consecutive positions of the cost-sorted order
+    // `perm` (k_order: most expensive first, so the instances of one round of one CTA cost about the same and nobody
+    // waits long at the barriers), odd rounds in reverse CTA order (the CTAs with the expensive stripes of round r get
+    // the cheap ones of round r+1).  The last, partial round is cut into narrower stripes so that it still uses every
+    // SM (12 instances on each of 148 SMs run faster than 16 on each of 108).  A warp without an instance in a round
+    // arrives at the round's barriers all the same.
+    const uint32_t nw = blockDim.x >> 5, per_round = gridDim.x * nw;
+    const uint32_t full = (uint32_t)P.N / per_round, rem = (uint32_t)P.N - full * per_round;
+    const uint32_t wl = (rem + gridDim.x - 1u) / gridDim.x;  // stripe width of the last round
+    const int bars = P.n_ticks * __popc((unsigned)P.tick_barrier & 31u);  // alignment barriers of one instance
+    for (uint32_t r = 0; r <= full; r++) {
       const uint32_t k = (r & 1u) ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
-      const uint32_t stripe = r * gridDim.x + k;
-      if (r * gridDim.x >= stripes) break;
-      const uint32_t t = stripe * nw + (uint32_t)warp;
-      if (stripe >= stripes || t >= (uint32_t)P.N) break;  // nothing left for this warp (positions only grow): it keeps arriving at the barriers below
-      const uint32_t inst = P.perm ? P.perm[t] : t;
-      step_instance(P, smem_raw, P.inst_first + (int)inst, (int)t, warp, lane, mbar_phase);
+      const uint32_t width = r < full ? nw : wl;
+      const uint32_t t = r * per_round + k * width + (uint32_t)warp;
+      if ((uint32_t)warp < width && t < (uint32_t)P.N) {
+        const uint32_t inst = P.perm ? P.perm[t] : t;
+        step_instance(P, smem_raw, P.inst_first + (int)inst, (int)t, warp, lane, mbar_phase);
+      } else {
+        for (int b = 0; b < bars; b++) align_barrier(P.align_group);
+      }
     }
-  } else {
-    while (true) {
-      uint32_t t = 0;
-      if (lane == 0) t = atomicAdd(P.tickets, 1u);
-      t = __shfl_sync(AG_FULL, t, 0);
-      if (t >= (uint32_t)P.N) break;
-      step_instance(P, smem_raw, P.inst_first + (int)t, (int)t, warp, lane, mbar_phase);
-    }
+    return;
   }
-  if (P.tick_barrier) {
-    // keep meeting the warps of the group that still tick; leave together once all of them have run out of instances
-    const int nw = blockDim.x >> 5, g = warp / P.align_group;
-    const uint32_t members = (uint32_t)min(P.align_group, nw - g * P.align_group);
-    if (lane == 0) atomicAdd(const_cast<uint32_t*>(grp_done), 1u);
-    do { align_barrier(P.align_group); } while (*grp_done < members);
+  while (true) {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(P.tickets, 1u);
+    t = __shfl_sync(AG_FULL, t, 0);
+    if (t >= (uint32_t)P.N) break;
+    step_instance(P, smem_raw, P.inst_first + (int)t, (int)t, warp, lane, mbar_phase);
   }
-  if (!P.tick_barrier && lane == 0) {
+  if (lane == 0) {
     const uint32_t left = atomicAdd(P.tickets + 1, 1u);
     if (left == gridDim.x * (blockDim.x >> 5) - 1u) { P.tickets[0] = 0u; P.tickets[1] = 0u; }
   }
