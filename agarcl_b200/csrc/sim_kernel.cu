@@ -521,17 +521,17 @@ __device__ void build_virus_cache(Ctx& c) {
 // Engine::tick_player
 // ------------------------------------------------------------------------------------------------
 // Engine::move_player for one cell (Engine.hpp:609-630)
-__device__ __forceinline__ void move_cell(Ctx& c, Cell& me, float tx, float ty) {
+__device__ __forceinline__ void move_cell(const SimParams& P, uint32_t& flags, Cell& me, float tx, float ty) {
   me.vx = 3.0f * (tx - me.x);
   me.vy = 3.0f * (ty - me.y);
-  float limit = max_speed_of(c.P.T, me.mass, c.flags);
+  float limit = max_speed_of(P.T, me.mass, flags);
   if (vmag(me.vx, me.vy) > limit) {  // Velocity::clamp_speed + set_speed (quirk Q8)
     me.vx *= limit / vmag(me.vx, me.vy);
     me.vy *= limit / vmag(me.vx, me.vy);
   }
-  cell_move(me, c.dt);
-  decelerate(me.svx, me.svy, 80.0f, c.dt);
-  bound_cell(c, me);
+  cell_move(me, Ctx::dt);
+  decelerate(me.svx, me.svy, 80.0f, Ctx::dt);
+  bound_cell_r(P.W, me, radius_of(P.T, me.mass));
 }
 
 // Engine::move_player + check_player_self_collisions of the multi-cell players, BEFORE the ordered player loop.
@@ -541,48 +541,140 @@ __device__ __forceinline__ void move_cell(Ctx& c, Cell& me, float tx, float ty) 
 // of up to 16) are moved and resolved side by side in lane groups -- in mature games the pair sequences of split
 // and popped players are most of the work of a tick.  Not on bot-decision ticks (every 10th): there a target may
 // come out of the ordered loop itself.  The results go back to the cell arrays; tick_player skips what is done.
-__device__ void premove_players(Ctx& c) {
-  c.pre_lo = 0u; c.pre_hi = 0u;
-  if (c.tick % 10u == 0u) return;
-  const int Pn = c.P.L.P, lane = c.lane;
-  for (int base = 0; base < Pn; base += 32) {
-    const int k = base + lane;
-    const int p = k < Pn ? c.P.L.order[k] : 0;
-    const int np = k < Pn ? __float_as_int(c.sm.psum()[p].w) : 0;
+// One batch of the pair solver: up to 32 >> gshift players of one instance (state blob `blob`), one lane group each.
+// desc: w0 = gshift | players << 8, w1 / w2 = (player | cells << 8) of the groups, 16 bits each.  Returns the
+// players done as a bit mask (lo, hi) and ORs state flags into `flags`; everything else goes back to the cell arrays.
+__device__ void premove_batch(const SimParams& P, uint8_t* blob, uint32_t w0, uint32_t w1, uint32_t w2, int lane,
+                              uint32_t& done_lo, uint32_t& done_hi, uint32_t& flags) {
+  const int gshift = (int)(w0 & 0xffu), count = (int)(w0 >> 8), gw = 1 << gshift;
+  const int g = lane >> gshift, gl = lane & (gw - 1), gbase = g << gshift;
+  const bool have = g < count;
+  const uint32_t pn = ((g < 2 ? w1 : w2) >> ((g & 1) * 16)) & 0xffffu;
+  const int gp = (int)(pn & 0xffu), gn = have ? (int)(pn >> 8) : 0;
+  agarcl_cell* cells = reinterpret_cast<agarcl_cell*>(blob + P.L.off_cells) + (size_t)gp * AGARCL_MAX_CELLS;
+  Cell me;
+  me.x = me.y = me.vx = me.vy = me.svx = me.svy = 0.0f;
+  me.mass = 0; me.id = 0; me.rec = 0;
+  float tx = 0.0f, ty = 0.0f;
+  const bool valid = have && gl < gn;
+  if (have) {
+    const agarcl_player* pl = reinterpret_cast<const agarcl_player*>(blob + P.L.off_players) + gp;
+    tx = pl->target_x; ty = pl->target_y;
+  }
+  if (valid) {
+    me = cell_load(cells + gl);
+    move_cell(P, flags, me, tx, ty);
+  }
+  me = self_collisions_fn(me, radius_of(P.T, me.mass), gn, tx, ty, gbase, gl, gw, P.W);
+  if (valid) cell_store(cells + gl, me);
+  const bool mark = have && gl == 0;
+  done_lo |= __reduce_or_sync(AG_FULL, (mark && gp < 32) ? 1u << gp : 0u);
+  done_hi |= __reduce_or_sync(AG_FULL, (mark && gp >= 32) ? 1u << (gp - 32) : 0u);
+}
+
+// The warp's mailbox for the pooled pair solver (scratch that is dead before the player loop):
+// [0] batches  [1] [2] players done (lo, hi)  [3] state flags  [4] instance  [5] cycles spent on its batches  [8 + 4k ..] batch k
+constexpr int kMailHdr = 8, kMailBatches = 64;
+static_assert((kMailHdr + 4 * kMailBatches) * 4 <= kCandCap * 8 + (kPremCap * 2 + 15) / 16 * 16 + (kVremCap * 2 + 15) / 16 * 16 + 32 * kLaneCand * 2,
+              "the mailbox must fit into the player-loop scratch");
+__device__ __forceinline__ volatile uint32_t* mailbox(const SimParams& P, uint8_t* smem_raw, int warp) {
+  return reinterpret_cast<volatile uint32_t*>(smem_raw + P.tiles_bytes + (size_t)warp * P.smem_per_warp + P.so.cand);
+}
+
+// Engine::move_player + check_player_self_collisions of the multi-cell players, BEFORE the ordered player loop.
+// Both depend only on the player's own cells and its target, i.e. on nothing another player does in the same
+// tick (pellets, viruses and foods are touched by the later phases of tick_player; cells of other players only by
+// players_collision after the loop), so they can leave the serial order: four players of up to 8 cells (or two
+// of up to 16) are moved and resolved side by side in lane groups -- in mature games the pair sequences of split
+// and popped players are most of the work of a tick.  Not on bot-decision ticks (every 10th): there a target may
+// come out of the ordered loop itself.  The results go back to the cell arrays; tick_player skips what is done.
+//
+// POOLED over the CTA (c == nullptr: a warp without an instance in this round only helps): every warp lists the
+// batches of its instance in its mailbox, the warps meet, and then ANY warp takes the next batch of ANY instance
+// of the CTA from a shared counter -- the solver needs nothing but the state blob -- so the instance with three
+// popped players no longer keeps fifteen warps waiting at the barrier behind the solver.
+__device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, int warp, int lane) {
+  const int nw = blockDim.x >> 5;
+  volatile uint32_t* mine = mailbox(P, smem_raw, warp);
+  volatile uint32_t* cta_next = reinterpret_cast<volatile uint32_t*>(smem_raw + P.tiles_bytes + P.so.mbar + 12);
+  uint32_t nb = 0;
+  if (c && c->tick % 10u != 0u) {
+    const int Pn = P.L.P;
+    for (int base = 0; base < Pn; base += 32) {
+      const int k = base + lane;
+      const int p = k < Pn ? P.L.order[k] : 0;
+      const int np = k < Pn ? __float_as_int(c->sm.psum()[p].w) : 0;
 #pragma unroll 1
-    for (int wide = 0; wide < 2; wide++) {
-      const int gshift = wide ? 4 : 3, gw = 1 << gshift;
-      const int g = lane >> gshift, gl = lane & (gw - 1), gbase = g << gshift;
-      unsigned todo = __ballot_sync(AG_FULL, wide ? (np > 8 && np <= 16) : (np >= 2 && np <= 8));
-      while (todo) {
-        const unsigned src = __fns(todo, 0, g + 1);  // this group's player: the (g+1)-th one still to do
-        const bool have = src != 0xffffffffu;
-        const int gp = __shfl_sync(AG_FULL, p, (int)(src & 31u));
-        const int gn_src = __shfl_sync(AG_FULL, np, (int)(src & 31u));
-        const int gn = have ? gn_src : 0;
-        for (int i = 0; i < (32 >> gshift); i++) todo &= todo - 1u;
-        Cell me;
-        me.x = me.y = me.vx = me.vy = me.svx = me.svy = 0.0f;
-        me.mass = 0; me.id = 0; me.rec = 0;
-        float tx = 0.0f, ty = 0.0f;
-        const bool valid = have && gl < gn;
-        if (have) {
-          const agarcl_player* pl = c.players_() + gp;
-          tx = pl->target_x; ty = pl->target_y;
+      for (int wide = 0; wide < 2; wide++) {
+        const int gshift = wide ? 4 : 3, per = 32 >> gshift;
+        unsigned todo = __ballot_sync(AG_FULL, wide ? (np > 8 && np <= 16) : (np >= 2 && np <= 8));
+        while (todo) {
+          uint32_t w12[2] = {0u, 0u};
+          int count = 0;
+          for (int g = 0; g < per && todo; g++) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const uint32_t pn = (uint32_t)__shfl_sync(AG_FULL, p, src) | ((uint32_t)__shfl_sync(AG_FULL, np, src) << 8);
+            w12[g >> 1] |= pn << ((g & 1) * 16);
+            count++;
+          }
+          if (nb < (uint32_t)kMailBatches) {
+            if (lane == 0) {
+              mine[kMailHdr + 4 * nb] = (uint32_t)gshift | ((uint32_t)count << 8);
+              mine[kMailHdr + 4 * nb + 1] = w12[0];
+              mine[kMailHdr + 4 * nb + 2] = w12[1];
+            }
+            nb++;
+          }  // (more batches than the mailbox holds: tick_player does those players itself)
         }
-        if (valid) {
-          me = cell_load(c.pcells(gp) + gl);
-          move_cell(c, me, tx, ty);
-        }
-        self_collisions(c, me, gn, tx, ty, gbase, gl, gw);
-        if (valid) cell_store(c.pcells(gp) + gl, me);
-        const bool mark = have && gl == 0;
-        c.pre_lo |= __reduce_or_sync(AG_FULL, (mark && gp < 32) ? 1u << gp : 0u);
-        c.pre_hi |= __reduce_or_sync(AG_FULL, (mark && gp >= 32) ? 1u << (gp - 32) : 0u);
       }
     }
   }
-  c.flags = __reduce_or_sync(AG_FULL, c.flags);
+  if (lane == 0) {
+    mine[0] = nb; mine[1] = 0u; mine[2] = 0u; mine[3] = 0u; mine[5] = 0u;
+    mine[4] = c ? (uint32_t)c->inst_local : 0u;
+  }
+  if (c) c->work += clock64() - c->t_mark;
+  align_barrier(nw);  // every mailbox is filled
+  {
+    const uint32_t cnt = lane < nw ? mailbox(P, smem_raw, lane)[0] : 0u;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(AG_FULL, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(AG_FULL, incl, 31), first = incl - cnt;
+    for (;;) {
+      uint32_t k = 0;
+      if (lane == 0) k = atomicAdd(const_cast<uint32_t*>(cta_next), 1u);
+      k = __shfl_sync(AG_FULL, k, 0);
+      if (k >= total) break;
+      const int owner = __ffs(__ballot_sync(AG_FULL, k >= first && k < first + cnt)) - 1;
+      const uint32_t idx = k - __shfl_sync(AG_FULL, first, owner);
+      volatile uint32_t* mb = mailbox(P, smem_raw, owner);
+      const long long t0 = clock64();
+      uint32_t lo = 0u, hi = 0u, fl = 0u;
+      premove_batch(P, P.state + (size_t)mb[4] * P.L.stride, mb[kMailHdr + 4 * idx], mb[kMailHdr + 4 * idx + 1], mb[kMailHdr + 4 * idx + 2],
+                    lane, lo, hi, fl);
+      fl = __reduce_or_sync(AG_FULL, fl);
+      if (lane == 0) {
+        atomicOr(const_cast<uint32_t*>(mb + 1), lo);
+        atomicOr(const_cast<uint32_t*>(mb + 2), hi);
+        if (fl) atomicOr(const_cast<uint32_t*>(mb + 3), fl);
+        atomicAdd(const_cast<uint32_t*>(mb + 5), (uint32_t)(clock64() - t0));
+      }
+    }
+  }
+  __threadfence_block();
+  align_barrier(nw);  // every batch is done: the cells are back in the cell arrays, the mailboxes say which players
+  if (warp == 0 && lane == 0) *cta_next = 0u;  // (nobody touches it again before the next tick's first barrier)
+  if (c) {
+    c->pre_lo = mine[1]; c->pre_hi = mine[2];
+    c->flags |= mine[3];
+    c->work += (long long)mine[5];
+    c->t_mark = clock64();
+  }
   __syncwarp();
 }
 
@@ -624,7 +716,7 @@ __device__ void tick_player(Ctx& c, int p) {
   uint32_t smallest = 0xffffffffu;
   if (lane < n) {
     smallest = me.mass;
-    if (!premoved) move_cell(c, me, tx, ty);
+    if (!premoved) move_cell(c.P, c.flags, me, tx, ty);
   }
   smallest = warp_min_u32(smallest);
   c.flags = __reduce_or_sync(AG_FULL, c.flags);
@@ -2155,9 +2247,11 @@ __device__ void engine_tick(Ctx& c, LaneState& ls) {
   c.nvrem = 0;
   const int P = c.P.L.P;
   if (c.lanes_dirty) { ls.fresh = false; c.lanes_dirty = false; }
-  premove_players(c);
-  if (c.P.tick_barrier & 2) {  // ... and enter the player loop together (see step_instance)
-    c.work += clock64() - c.t_mark; align_barrier(c.P.align_group); c.t_mark = clock64();
+  if (c.P.tick_barrier & 2) {  // the pair solver, pooled over the CTA; the warps enter the player loop together behind it
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    premove_players(c.P, smem_raw, &c, (int)(threadIdx.x >> 5), c.lane);
+  } else {
+    c.pre_lo = 0u; c.pre_hi = 0u;  // (no alignment barriers: tick_player moves and resolves every player itself)
   }
   tick_players_block(c, 0, ls);
   for (int base = 32; base < P; base += 32) {  // more than 32 players: the further blocks reload every tick
@@ -2491,6 +2585,8 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // the CTA's batch counter of the pooled pair solver (spare word of warp 0's mbarrier slot)
+  if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(smem_raw + P.tiles_bytes + P.so.mbar + 12) = 0u;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   uint32_t mbar_phase = 0u;
@@ -2505,7 +2601,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
     const uint32_t nw = blockDim.x >> 5, per_round = gridDim.x * nw;
     const uint32_t full = (uint32_t)P.N / per_round, rem = (uint32_t)P.N - full * per_round;
     const uint32_t wl = (rem + gridDim.x - 1u) / gridDim.x;  // stripe width of the last round
-    const int bars = P.n_ticks * __popc((unsigned)P.tick_barrier & 31u);  // alignment barriers of one instance
+    const int bars_rest = __popc((unsigned)P.tick_barrier & 28u);  // barriers of a tick behind the pair solver
     for (uint32_t r = 0; r <= full; r++) {
       const uint32_t k = (r & 1u) ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
       const uint32_t width = r < full ? nw : wl;
@@ -2513,8 +2609,12 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
       if ((uint32_t)warp < width && t < (uint32_t)P.N) {
         const uint32_t inst = P.perm ? P.perm[t] : t;
         step_instance(P, smem_raw, P.inst_first + (int)inst, (int)t, warp, lane, mbar_phase);
-      } else {
-        for (int b = 0; b < bars; b++) align_barrier(P.align_group);
+      } else {  // no instance in this round: arrive at its barriers, and help with the pooled pair solver
+        for (int tk = 0; tk < P.n_ticks; tk++) {
+          if (P.tick_barrier & 1) align_barrier(P.align_group);
+          if (P.tick_barrier & 2) premove_players(P, smem_raw, nullptr, warp, lane);
+          for (int b = 0; b < bars_rest; b++) align_barrier(P.align_group);
+        }
       }
     }
     return;
