@@ -132,7 +132,7 @@ static void fill_sim_params(const agarcl_batch* b, ag::SimParams& P) {
   P.obs_finish = 0; P.obs_G = b->G; P.obs_C = b->C;
   P.zero_chunks = 0;
   if (const char* e = std::getenv("AGARCL_ZERO_CHUNKS")) P.zero_chunks = std::atoi(e);
-  P.tick_barrier = 7;
+  P.tick_barrier = 6;  // bit mask of the alignment barriers of a tick (sim_kernel.cu, step_instance)
   if (const char* e = std::getenv("AGARCL_TICK_BARRIER")) P.tick_barrier = std::atoi(e);  // (A/B timing)
   P.align_group = ag::kMaxWarpsPerCta;
   if (const char* e = std::getenv("AGARCL_ALIGN_GROUP")) P.align_group = std::atoi(e);

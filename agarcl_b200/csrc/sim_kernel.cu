@@ -605,7 +605,7 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
       const int p = k < Pn ? P.L.order[k] : 0;
       const int np = k < Pn ? __float_as_int(c->sm.psum()[p].w) : 0;
 #pragma unroll 1
-      for (int wide = 0; wide < 2; wide++) {
+      for (int wide = 1; wide >= 0; wide--) {  // the long pair sequences (players of 9..16 cells) first
         const int gshift = wide ? 4 : 3, per = 32 >> gshift;
         unsigned todo = __ballot_sync(AG_FULL, wide ? (np > 8 && np <= 16) : (np >= 2 && np <= 8));
         while (todo) {
@@ -637,21 +637,18 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
   if (c) c->work += clock64() - c->t_mark;
   align_barrier(nw);  // every mailbox is filled
   {
+    // batch k of every warp before batch k + 1 of any: the mailboxes list their long batches first, so the longest
+    // sequences of the CTA start first (longest-processing-time order) and the short ones fill in behind them
     const uint32_t cnt = lane < nw ? mailbox(P, smem_raw, lane)[0] : 0u;
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(AG_FULL, incl, o);
-      if (lane >= o) incl += t;
-    }
-    const uint32_t total = __shfl_sync(AG_FULL, incl, 31), first = incl - cnt;
+    const uint32_t most = warp_max_u32(cnt);
     for (;;) {
       uint32_t k = 0;
       if (lane == 0) k = atomicAdd(const_cast<uint32_t*>(cta_next), 1u);
       k = __shfl_sync(AG_FULL, k, 0);
-      if (k >= total) break;
-      const int owner = __ffs(__ballot_sync(AG_FULL, k >= first && k < first + cnt)) - 1;
-      const uint32_t idx = k - __shfl_sync(AG_FULL, first, owner);
+      const uint32_t idx = k / (uint32_t)nw;
+      const int owner = (int)(k % (uint32_t)nw);
+      if (idx >= most) break;
+      if (idx >= __shfl_sync(AG_FULL, cnt, owner)) continue;
       volatile uint32_t* mb = mailbox(P, smem_raw, owner);
       const long long t0 = clock64();
       uint32_t lo = 0u, hi = 0u, fl = 0u;
@@ -2457,13 +2454,14 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
   }
   for (int t = 0; t < P.n_ticks; t++) {
     // INSTRUCTION-FETCH ALIGNMENT.  k_step is ~440 KB of code against a 32 KB instruction cache per SM, and 16 warps
-    // at unrelated places of it make the kernel instruction-fetch bound (65 % of the stall cycles of steady-state games
-    // were no_instruction).  The warps of the CTA therefore meet at the start of every tick (and again behind the pair
-    // solver, engine_tick): they then run the same code at about the same time and one fetch serves all of them.
-    // Every instance runs the same number of barriers, so the warps also take their next instances together; what a
-    // warp waits for the slowest one is far less than what the shared fetch saves (2.22 -> 1.69 ms per steady-state
-    // step).  Finer alignment (per phase, per solver batch) loses more to waiting than it gains (measured).
-    // Warps that have run out of instances keep arriving (k_step) until every warp of the CTA is done.
+    // at unrelated places of it made the kernel instruction-fetch bound (65 % of the stall cycles of steady-state games
+    // were no_instruction, profiles/r01l_*).  The warps of the CTA therefore meet inside every tick -- around the pooled
+    // pair solver (premove_players, tick_barrier bit 2) and in front of players_collision (bit 4); bits 1 / 8 / 16 are
+    // further places kept for A/B timing -- so that they run the same code at about the same time and one fetch serves
+    // all of them: no_instruction fell from 10 to 0.5 stall cycles per issued instruction.  Every instance runs the same
+    // number of barriers, so the warps move through their instances in rounds (k_step: cost-sorted stripes); what a
+    // warp waits for the slowest one is far less than what the shared fetch saves (2.22 -> 1.41 ms per steady-state
+    // step with the sorted schedule).  Finer alignment (per solver batch, more phases) loses more than it gains.
     if (P.tick_barrier & 1) { c.work += clock64() - c.t_mark; align_barrier(P.align_group); c.t_mark = clock64(); }
     engine_tick(c, ls);
   }

@@ -106,7 +106,8 @@ struct SimParams {
   int32_t obs_finish, obs_G, obs_C;
   int32_t zero_chunks;          // > 0: the clear is queued in this many pieces (4 per tick); 0: spread over the ticks
   int32_t observe_cells, observe_others, observe_viruses, observe_pellets;
-  int32_t tick_barrier;         // instruction-fetch alignment (step_instance): 0 off, 1 CTA barrier at every tick start, 2 also behind the pair solver
+  int32_t tick_barrier;         // instruction-fetch alignment (step_instance), bit mask of the CTA barriers of a tick: 1 tick start, 2 around the
+                                // pooled pair solver, 4 before players_collision, 8 before move_foods, 16 before apply_removals; 0: free-running warps
   int32_t align_group;          // warps per alignment group (a divisor-free choice: the last group of a CTA may be smaller)
   PackOut pk;                   // with obs_finish only
   int32_t inst_first;           // this launch steps instances [inst_first, inst_first + N) of the batch

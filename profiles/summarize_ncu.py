@@ -22,6 +22,9 @@ def main(rep):
         for k in KEYS:
             if k in hdr:
                 print(f'  {k:75s} {r[hdr.index(k)]:>18s} {units[hdr.index(k)]}')
+        stalls = sorted(((float(r[i]), h.split('issue_stalled_')[1].split('_per_')[0]) for i, h in enumerate(hdr)
+                         if 'smsp__average_warps_issue_stalled' in h and h.endswith('_per_issue_active.ratio') and r[i]), reverse=True)
+        print('  warp stall cycles per issued instruction: ' + ', '.join(f'{n} {v:.2f}' for v, n in stalls[:8]))
         print()
 
 
