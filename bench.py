@@ -300,8 +300,19 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: agarcl_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line, nothing else
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        # stdout carries the one JSON line and nothing else: NCCL's version banner (printed when the communicator is
+        # created) goes to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     if world > 1:  # the mirror's host threads: share the box's cores between the ranks
         os.environ.setdefault("AGARCL_HOST_THREADS", str(max(2, (os.cpu_count() or 2) // world)))
     N = args.instances
