@@ -107,6 +107,42 @@ def test_results_independent_of_sharding():
     assert np.array_equal(a.batch.obs_tensor()[5].cpu().numpy(), b.batch.obs_tensor()[1].cpu().numpy())
 
 
+def test_results_independent_of_schedule(monkeypatch):
+    """More instances than one round of the persistent grid holds (148 SMs x 16 warps): the aligned, cost-sorted, pooled
+    schedule (default) and free-running warps on a ticket counter produce identical states, observations, rewards and
+    dones for every instance -- scheduling only moves instances between warps and rounds."""
+    import torch
+    from agarcl_b200.env import BatchedGridEnvironment
+    from agarcl_b200._abi import compare_states
+    N = 2600
+    kw = dict(num_bots=12, arena_size=400, num_pellets=300, num_viruses=12)
+    outs = []
+    for env in ({}, {"AGARCL_TICK_BARRIER": "0"}):
+        for k in ("AGARCL_TICK_BARRIER",):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        e = BatchedGridEnvironment(N, **kw)
+        e.configure_observation({"grid_size": 32})
+        e.seed(123)
+        e.reset()
+        rng = np.random.default_rng(5)
+        rew_sum = np.zeros(N, np.float64)
+        for st in range(60):
+            dxdy = rng.uniform(-1, 1, size=(N, 2)).astype(np.float32)
+            act = rng.integers(0, 3, size=N).astype(np.int32)
+            obs, rew, done = e.step(dxdy, act)
+            rew_sum += rew.cpu().numpy()
+        torch.cuda.synchronize()
+        outs.append((obs.cpu().numpy().copy(), rew_sum, done.cpu().numpy().copy(), [e.batch.download_state(i) for i in (0, 777, 1500, 2368, 2599)]))
+        e.close()
+    a, b = outs
+    assert np.array_equal(a[0], b[0]), "observations differ between schedules"
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    for sa, sb in zip(a[3], b[3]):
+        assert not compare_states(sa, sb)
+
+
 def test_int16_observation_matches_int32():
     import torch
     from agarcl_b200 import OBS_I16

@@ -69,3 +69,15 @@ def test_cuda_matches_oracle(name):
     cfg_kwargs, run_kwargs = CASES[name]
     stats = run_parity(cfg_kwargs, seeds=[11, 12, 13], **run_kwargs)
     print(name, stats)
+
+
+@pytest.mark.parametrize("env", [{"AGARCL_TICK_BARRIER": "0"}, {"AGARCL_SORT_SCHEDULE": "0"}, {"AGARCL_TICK_BARRIER": "31"}])
+def test_schedule_variants_match_oracle(env, monkeypatch):
+    """Scheduling never changes results: free-running warps (no alignment barriers, ticket counter), the aligned
+    schedule without cost sorting, and the schedule with every alignment barrier all reproduce the oracle bit for bit
+    (more instances than one CTA holds, so that rounds, stripes and idle warps all occur)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    stats = run_parity(dict(num_agents=2, num_bots=10, arena_size=300, num_pellets=300, num_viruses=12, cap_foods=2048),
+                       seeds=list(range(41, 41 + 20)), steps=60, obs_every=10, boost=400, p_feed=0.2, p_split=0.3)
+    print(env, stats)
