@@ -29,6 +29,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -350,9 +351,10 @@ static void expand_range(HostMirror* m, int lo, int hi, const uint32_t* zero_mas
   const int cur = m->cur, prev = cur ^ 1;
   const PackOut& k = m->pk;
   const size_t mw2 = 2 * (size_t)m->MW, plane = (size_t)m->G * m->G;
-  prefetch_slot<T>(m, lo);
+  static const int ahead = [] { const char* e = std::getenv("AGARCL_MIRROR_PREFETCH"); return e ? std::atoi(e) : 2; }();
+  for (int a = 0; a < ahead && lo + a < hi; a++) prefetch_slot<T>(m, lo + a);
   for (int slot = lo; slot < hi; slot++) {
-    if (slot + 1 < hi) prefetch_slot<T>(m, slot + 1);
+    if (slot + ahead < hi) prefetch_slot<T>(m, slot + ahead);
     const uint32_t* cb = m->blk(cur, slot / (int)k.ipc);
     const uint32_t* crec = cb + pk_off_rec(k) + (size_t)(slot % (int)k.ipc) * k.rec_words;
     const uint32_t img = crec[2];
@@ -427,9 +429,9 @@ HostMirror* mirror_create(int n_img, int agents, int CH, int C, int G, int dtype
   m->img_bytes = m->img_elems * esz;
   m->cap_img = 2048;
   if (const char* e = std::getenv("AGARCL_MIRROR_CAP_IMG")) m->cap_img = (uint32_t)std::atoi(e);
-  // chunks: whole instances, about 8 per batch but not smaller than 64 images
+  // chunks: whole instances, about 32 per batch but not smaller than 64 images
   if (agents < 1) agents = 1;
-  int want = 8;
+  int want = 32;
   if (const char* e = std::getenv("AGARCL_MIRROR_CHUNKS")) want = std::atoi(e);
   if (want < 1) want = 1;
   const int inst = n_img / agents;
@@ -557,22 +559,30 @@ static int collect(HostMirror* m, const void* d_obs, cudaStream_t s, bool flagge
   const int cur = m->cur, K = m->n_chunks;
   const PackOut& k = m->pk;
   std::vector<uint32_t> zero_masks(2 * (size_t)m->MW, 0u);
-  std::atomic<int> next{0}, avail{0};
+  // Chunks become ready in ANY order (under the cost-sorted schedule the first positions are the most expensive
+  // instances and finish late): the calling thread appends them to `ready`, the workers take tasks (a chunk's slots in
+  // pieces of `grab`) in that order.
+  const int grab = 8, tpc = ((int)k.ipc + grab - 1) / grab;  // tasks per chunk
+  std::vector<int> ready((size_t)K, 0);
+  std::atomic<int> next{0}, n_ready{0};
   std::atomic<bool> abort{false};
-  const int grab = 8;
   const std::function<void()> job = [&] {
     for (;;) {
       int i = next.load(std::memory_order_relaxed);
-      if (i >= m->n_img || abort.load(std::memory_order_relaxed)) break;
-      const int av = avail.load(std::memory_order_acquire);
-      if (i >= av) { cpu_relax(); continue; }
-      const int hi = i + grab < av ? i + grab : av;
-      if (!next.compare_exchange_weak(i, hi, std::memory_order_relaxed)) continue;
-      if (m->dtype == AGARCL_OBS_I16) expand_range<int16_t>(m, i, hi, zero_masks.data());
-      else expand_range<int32_t>(m, i, hi, zero_masks.data());
+      if (i >= K * tpc || abort.load(std::memory_order_relaxed)) break;
+      if (i >= n_ready.load(std::memory_order_acquire) * tpc) { cpu_relax(); continue; }
+      if (!next.compare_exchange_weak(i, i + 1, std::memory_order_relaxed)) continue;
+      const int c = ready[(size_t)(i / tpc)];
+      const int base = c * (int)k.ipc, end = base + (int)k.ipc < m->n_img ? base + (int)k.ipc : m->n_img;
+      const int lo = base + (i % tpc) * grab, hi = lo + grab < end ? lo + grab : end;
+      if (lo >= hi) continue;
+      if (m->dtype == AGARCL_OBS_I16) expand_range<int16_t>(m, lo, hi, zero_masks.data());
+      else expand_range<int32_t>(m, lo, hi, zero_masks.data());
     }
   };
   m->pool->start(job);
+  static const bool trace_env = std::getenv("AGARCL_MIRROR_TRACE") != nullptr;
+  const bool trace = trace_env && flagged && (m->seq % 16u == 0u);
   uint64_t d2h = 0, entries = 0;
   std::vector<int> dense_imgs;
   double wait_s = 0.0;
@@ -580,27 +590,59 @@ static int collect(HostMirror* m, const void* d_obs, cudaStream_t s, bool flagge
   auto fail = [&](cudaError_t e, const char* what) {
     rc = agarcl_set_error(AGARCL_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
   };
-  for (int c = 0; c < K && rc == AGARCL_OK; c++) {
+  // one chunk has arrived in host memory: its records (dense fallbacks, rewards, dones), then hand it to the workers
+  auto publish = [&](int c) {
+    const uint32_t* hb = m->blk(cur, c);
+    const int lo = c * (int)k.ipc, hi = lo + (int)k.ipc < m->n_img ? lo + (int)k.ipc : m->n_img;
+    for (int i = lo; i < hi; i++) {
+      const uint32_t* rec = hb + pk_off_rec(k) + (size_t)(i - lo) * k.rec_words;
+      const uint32_t img = rec[2];
+      if (img >= (uint32_t)m->n_img) { rc = agarcl_set_error(AGARCL_ERR_STATE, "mirror slot %d names image %u of %d", i, img, m->n_img); return; }
+      if (rec[0] == kPackDense) dense_imgs.push_back((int)img);
+      else entries += rec[0];
+      if (flagged) {  // reward and done flag of the step came with the record
+        if (rewards_out) std::memcpy(rewards_out + img, rec + k.rec_words - 3, sizeof(double));
+        if (dones_out) dones_out[img] = (uint8_t)rec[k.rec_words - 1];
+      }
+    }
+    if (flagged) d2h += (size_t)(hi - lo) * k.rec_words * 4 + 4;  // what the kernel wrote over PCIe: records + flag (entries below)
+    const int r = n_ready.load(std::memory_order_relaxed);
+    ready[(size_t)r] = c;
+    n_ready.store(r + 1, std::memory_order_release);
+    if (trace) std::fprintf(stderr, "chunk %d ready at %.0f us, workers at task %d of %d\n", c,
+                            std::chrono::duration<double>(clk::now() - t0).count() * 1e6, next.load(), K * tpc);
+  };
+  if (flagged) {
+    // the kernel flags finished chunks in host-mapped memory; keep an eye on the stream so that a failed launch cannot hang us
+    std::vector<uint8_t> seen((size_t)K, 0);
+    int left = K;
+    uint32_t spins = 0;
     const auto w0 = clk::now();
-    if (flagged) {
-      // the kernel flags chunk c in host-mapped memory; keep an eye on the stream so that a failed launch cannot hang us
-      uint32_t spins = 0;
-      while (m->h_flags[c] != m->seq) {
-        cpu_relax();
-        if ((++spins & 0xFFFu) == 0u) {
-          const cudaError_t q = cudaStreamQuery(s);
-          if (q == cudaSuccess) {
-            if (m->h_flags[c] != m->seq) rc = agarcl_set_error(AGARCL_ERR_STATE, "step kernel finished without completing mirror chunk %d", c);
-            break;
-          }
-          if (q != cudaErrorNotReady) { fail(q, "cudaStreamQuery"); break; }
+    while (left > 0 && rc == AGARCL_OK) {
+      bool any = false;
+      for (int c = 0; c < K && rc == AGARCL_OK; c++)
+        if (!seen[(size_t)c] && m->h_flags[c] == m->seq) {
+          seen[(size_t)c] = 1; left--; any = true;
+          publish(c);
+        }
+      if (any || left == 0) continue;
+      cpu_relax();
+      if ((++spins & 0x3FFu) == 0u) {
+        const cudaError_t q = cudaStreamQuery(s);
+        if (q == cudaSuccess) {
+          bool all = true;
+          for (int c = 0; c < K; c++) all = all && (seen[(size_t)c] || m->h_flags[c] == m->seq);
+          if (!all) rc = agarcl_set_error(AGARCL_ERR_STATE, "step kernel finished without completing every mirror chunk");
+        } else if (q != cudaErrorNotReady) {
+          fail(q, "cudaStreamQuery");
         }
       }
-      if (rc != AGARCL_OK) break;
     }
-    uint32_t* hb = m->blk(cur, c);
-    const int lo = c * (int)k.ipc, hi = lo + (int)k.ipc < m->n_img ? lo + (int)k.ipc : m->n_img;
-    if (!flagged) {  // k_pack left a compact block in device memory: one copy (a second one if the guess was short)
+    wait_s = std::chrono::duration<double>(clk::now() - w0).count();
+  } else {
+    for (int c = 0; c < K && rc == AGARCL_OK; c++) {  // k_pack left compact blocks in device memory: one copy each (a second one if the guess was short)
+      const auto w0 = clk::now();
+      uint32_t* hb = m->blk(cur, c);
       const uint32_t* db = m->d_chunks + (size_t)c * k.chunk_words;
       size_t got = m->guess[c] < k.cap_chunk ? m->guess[c] : k.cap_chunk;
       cudaError_t e = cudaMemcpyAsync(hb, db, (m->meta_words + 2 * got) * 4, cudaMemcpyDeviceToHost, s);
@@ -616,22 +658,9 @@ static int collect(HostMirror* m, const void* d_obs, cudaStream_t s, bool flagge
         d2h += (total - got) * 8;
       }
       m->guess[c] = total + total / 8 + 1024;
+      wait_s += std::chrono::duration<double>(clk::now() - w0).count();
+      publish(c);
     }
-    for (int i = lo; i < hi; i++) {
-      const uint32_t* rec = hb + pk_off_rec(k) + (size_t)(i - lo) * k.rec_words;
-      const uint32_t img = rec[2];
-      if (img >= (uint32_t)m->n_img) { rc = agarcl_set_error(AGARCL_ERR_STATE, "mirror slot %d names image %u of %d", i, img, m->n_img); break; }
-      if (rec[0] == kPackDense) dense_imgs.push_back((int)img);
-      else entries += rec[0];
-      if (flagged) {  // reward and done flag of the step came with the record
-        if (rewards_out) std::memcpy(rewards_out + img, rec + k.rec_words - 3, sizeof(double));
-        if (dones_out) dones_out[img] = (uint8_t)rec[k.rec_words - 1];
-      }
-    }
-    if (rc != AGARCL_OK) break;
-    if (flagged) d2h += (size_t)(hi - lo) * k.rec_words * 4 + 4;  // what the kernel wrote over PCIe: records + flag (entries below)
-    wait_s += std::chrono::duration<double>(clk::now() - w0).count();
-    avail.store(hi, std::memory_order_release);
   }
   if (flagged) d2h += entries * 8;
   // images that do not fit the scheme: dense copies into the pinned mirror (the workers skip them); in the fused
@@ -648,6 +677,7 @@ static int collect(HostMirror* m, const void* d_obs, cudaStream_t s, bool flagge
   const uint64_t dense = dense_imgs.size();
   if (rc != AGARCL_OK) abort.store(true);
   m->pool->join();
+  if (trace) std::fprintf(stderr, "join done at %.0f us\n", std::chrono::duration<double>(clk::now() - t0).count() * 1e6);
   // Every chunk flag is up: all instances have been stepped and everything the caller reads is in host memory.  The
   // kernel's last warps may still be leaving; whatever is enqueued on `s` next is ordered behind them, so only the
   // dense copies (if any) need the stream.
