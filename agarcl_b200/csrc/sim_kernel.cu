@@ -590,13 +590,13 @@ __device__ __forceinline__ volatile uint32_t* mailbox(const SimParams& P, uint8_
 // come out of the ordered loop itself.  The results go back to the cell arrays; tick_player skips what is done.
 //
 // POOLED over the CTA (c == nullptr: a warp without an instance in this round only helps): every warp lists the
-// batches of its instance in its mailbox, the warps meet, and then ANY warp takes the next batch of ANY instance
-// of the CTA from a shared counter -- the solver needs nothing but the state blob -- so the instance with three
-// popped players no longer keeps fifteen warps waiting at the barrier behind the solver.
+// batches of its instance in its mailbox and publishes it, and ANY warp takes the next batch of ANY published
+// instance of the CTA -- the solver needs nothing but the state blob -- so the instance with three popped players
+// no longer keeps fifteen warps waiting at the barrier behind the solver, and a warp that arrives late finds its
+// own batches already being worked on.
 __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, int warp, int lane) {
   const int nw = blockDim.x >> 5;
   volatile uint32_t* mine = mailbox(P, smem_raw, warp);
-  volatile uint32_t* cta_next = reinterpret_cast<volatile uint32_t*>(smem_raw + P.tiles_bytes + P.so.mbar + 12);
   uint32_t nb = 0;
   if (c && c->tick % 10u != 0u) {
     const int Pn = P.L.P;
@@ -630,42 +630,56 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
       }
     }
   }
+  // publish: header, then (fenced) this warp's publication counter -- it lives in the spare half of the warp's mbarrier
+  // slot, because the mailbox itself is scratch that the rest of the tick overwrites
+  volatile uint32_t* pub = reinterpret_cast<volatile uint32_t*>(smem_raw + P.tiles_bytes + (size_t)warp * P.smem_per_warp + P.so.mbar + 8);
+  uint32_t epoch = 0u;  // the same in every warp: all of them come here once per tick of a round
+  if (lane == 0) epoch = *pub + 1u;
+  epoch = __shfl_sync(AG_FULL, epoch, 0);
   if (lane == 0) {
-    mine[0] = nb; mine[1] = 0u; mine[2] = 0u; mine[3] = 0u; mine[5] = 0u;
+    mine[0] = nb; mine[1] = 0u; mine[2] = 0u; mine[3] = 0u; mine[5] = 0u; mine[7] = 0u;
     mine[4] = c ? (uint32_t)c->inst_local : 0u;
+    __threadfence_block();
+    *pub = epoch;
   }
+  __syncwarp();
   if (c) c->work += clock64() - c->t_mark;
-  align_barrier(nw);  // every mailbox is filled
-  {
-    // batch k of every warp before batch k + 1 of any: the mailboxes list their long batches first, so the longest
-    // sequences of the CTA start first (longest-processing-time order) and the short ones fill in behind them
-    const uint32_t cnt = lane < nw ? mailbox(P, smem_raw, lane)[0] : 0u;
-    const uint32_t most = warp_max_u32(cnt);
-    for (;;) {
-      uint32_t k = 0;
-      if (lane == 0) k = atomicAdd(const_cast<uint32_t*>(cta_next), 1u);
-      k = __shfl_sync(AG_FULL, k, 0);
-      const uint32_t idx = k / (uint32_t)nw;
-      const int owner = (int)(k % (uint32_t)nw);
-      if (idx >= most) break;
-      if (idx >= __shfl_sync(AG_FULL, cnt, owner)) continue;
-      volatile uint32_t* mb = mailbox(P, smem_raw, owner);
-      const long long t0 = clock64();
-      uint32_t lo = 0u, hi = 0u, fl = 0u;
-      premove_batch(P, P.state + (size_t)mb[4] * P.L.stride, mb[kMailHdr + 4 * idx], mb[kMailHdr + 4 * idx + 1], mb[kMailHdr + 4 * idx + 2],
-                    lane, lo, hi, fl);
-      fl = __reduce_or_sync(AG_FULL, fl);
-      if (lane == 0) {
-        atomicOr(const_cast<uint32_t*>(mb + 1), lo);
-        atomicOr(const_cast<uint32_t*>(mb + 2), hi);
-        if (fl) atomicOr(const_cast<uint32_t*>(mb + 3), fl);
-        atomicAdd(const_cast<uint32_t*>(mb + 5), (uint32_t)(clock64() - t0));
-      }
+  // No barrier in front of the pool: a warp that gets here early starts on whatever has been published (its own
+  // batches included) instead of waiting for the slowest instance of the CTA to arrive.  It takes the next batch of
+  // the mailbox that has handed out the fewest so far (the mailboxes list their long batches first: roughly
+  // longest-processing-time order) and leaves when every warp has published and nothing is left to take.
+  for (;;) {
+    const bool pubd = lane < nw &&
+        *reinterpret_cast<volatile uint32_t*>(smem_raw + P.tiles_bytes + (size_t)lane * P.smem_per_warp + P.so.mbar + 8) == epoch;
+    volatile uint32_t* ml = mailbox(P, smem_raw, lane < nw ? lane : 0);
+    const uint32_t cnt = pubd ? ml[0] : 0u, tk = pubd ? ml[7] : 0u;
+    const bool open = pubd && tk < cnt;
+    const unsigned om = __ballot_sync(AG_FULL, open), pm = __ballot_sync(AG_FULL, pubd);
+    if (om == 0u) {
+      if (__popc(pm) == nw) break;
+      __nanosleep(100);
+      continue;
+    }
+    const int owner = (int)(warp_min_u32(open ? (tk << 8 | (uint32_t)lane) : 0xffffffffu) & 0xffu);
+    volatile uint32_t* mb = mailbox(P, smem_raw, owner);
+    uint32_t idx = 0;
+    if (lane == 0) idx = atomicAdd(const_cast<uint32_t*>(mb + 7), 1u);
+    idx = __shfl_sync(AG_FULL, idx, 0);
+    if (idx >= __shfl_sync(AG_FULL, cnt, owner)) continue;  // (another warp was quicker)
+    const long long t0 = clock64();
+    uint32_t lo = 0u, hi = 0u, fl = 0u;
+    premove_batch(P, P.state + (size_t)mb[4] * P.L.stride, mb[kMailHdr + 4 * idx], mb[kMailHdr + 4 * idx + 1], mb[kMailHdr + 4 * idx + 2],
+                  lane, lo, hi, fl);
+    fl = __reduce_or_sync(AG_FULL, fl);
+    if (lane == 0) {
+      atomicOr(const_cast<uint32_t*>(mb + 1), lo);
+      atomicOr(const_cast<uint32_t*>(mb + 2), hi);
+      if (fl) atomicOr(const_cast<uint32_t*>(mb + 3), fl);
+      atomicAdd(const_cast<uint32_t*>(mb + 5), (uint32_t)(clock64() - t0));
     }
   }
   __threadfence_block();
   align_barrier(nw);  // every batch is done: the cells are back in the cell arrays, the mailboxes say which players
-  if (warp == 0 && lane == 0) *cta_next = 0u;  // (nobody touches it again before the next tick's first barrier)
   if (c) {
     c->pre_lo = mine[1]; c->pre_hi = mine[2];
     c->flags |= mine[3];
@@ -2583,8 +2597,8 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // the CTA's batch counter of the pooled pair solver (spare word of warp 0's mbarrier slot)
-  if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(smem_raw + P.tiles_bytes + P.so.mbar + 12) = 0u;
+  // this warp's publication counter of the pooled pair solver (spare half of its mbarrier slot)
+  if (lane == 0) *reinterpret_cast<volatile uint32_t*>(smem_raw + P.tiles_bytes + (size_t)warp * P.smem_per_warp + P.so.mbar + 8) = 0u;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   uint32_t mbar_phase = 0u;
