@@ -38,6 +38,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+
+def host_cores():
+    """cores this process may run on (affinity / cgroup aware, unlike os.cpu_count())"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
 WORKLOAD = dict(num_agents=1, ticks_per_step=4, arena_size=1000, pellet_regen=True, num_pellets=1000, num_viruses=25,
                 num_bots=25, reward_type=1, c_death=0, mode_number=0, num_frames=1, grid_size=128,
                 observe_cells=True, observe_others=True, observe_viruses=True, observe_pellets=True)
@@ -199,7 +207,7 @@ def _cpu_reference_rate_inproc(seconds_target=12.0, threads=None, settle=2000):
     lib, cfg = _ref_pool()
     if lib is None:
         return None
-    threads = threads or (os.cpu_count() or 1)
+    threads = threads or host_cores()
     inst = 2 * threads
     pool = C.c_void_p(lib.ref_pool_create(C.byref(cfg), inst, 1234))
     if settle > 0:
@@ -218,7 +226,7 @@ def _reference_arm_inproc(steps, warmup, gpus, threads=None, settle=2000):
     lib, cfg = _ref_pool()
     if lib is None:
         return {"impl": "reference", "unavailable": "oracle/_ref/libagarcl_ref.so missing and /root/reference absent"}
-    threads = threads or (os.cpu_count() or 1)
+    threads = threads or host_cores()
     inst = 2 * threads
     pool = C.c_void_p(lib.ref_pool_create(C.byref(cfg), inst, 1234))
     if settle > 0:
@@ -266,7 +274,7 @@ def _ref_child(what, steps, warmup, gpus, threads, budget_s, settle=2000):
 
 
 def cpu_reference_rate(settle):
-    r = _ref_child("cpu_baseline", 0, 0, 1, os.cpu_count() or 1, 180, settle)
+    r = _ref_child("cpu_baseline", 0, 0, 1, host_cores(), 180, settle)
     if r is None or "failed" in r:
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {r and r['failed']}"}
     return r
@@ -277,7 +285,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     budget = 240 + 2 * (args.steps + args.warmup + 3)  # settling + steps of at most about 0.5 s
-    line = _ref_child("arm", args.steps, args.warmup, args.gpus, os.cpu_count() or 1, budget, args.settle)
+    line = _ref_child("arm", args.steps, args.warmup, args.gpus, host_cores(), budget, args.settle)
     if "failed" in line:
         line = {"impl": "reference", "unavailable": line["failed"]}
     print(json.dumps(line))
@@ -314,7 +322,7 @@ def run_ours(args):
             os.dup2(saved, 1)
             os.close(saved)
     if world > 1:  # the mirror's host threads: share the box's cores between the ranks
-        os.environ.setdefault("AGARCL_HOST_THREADS", str(max(2, (os.cpu_count() or 2) // world)))
+        os.environ.setdefault("AGARCL_HOST_THREADS", str(max(2, host_cores() // world)))
     N = args.instances
     cfg = make_cfg(n_instances=N, device=local_rank, instance_base=rank * N, **WORKLOAD)
     b = Batch(cfg)
