@@ -1621,10 +1621,15 @@ __device__ void umap_place(uint16_t* list, int& n, int nb, int key) {
 
 struct PairRec { uint16_t q, g; uint32_t eaten_mass, eater_id, eaten_id; };  // 16 B
 
-// exact PrecisionCollisionDetection::solve + application, run by ONE lane (rare path: only for the
-// query cells the all-pairs pre-test flagged; everything the strip sweep can return is in that set).
+// exact PrecisionCollisionDetection::solve + application (rare path: only for the query cells the all-pairs
+// pre-test flagged; everything the strip sweep can return is in that set).  The strip search is run by the whole
+// warp -- the members of a strip are gathered with ballots, ranked by (y, snapshot index) (what the reference's
+// std::sort == insertion sort does for <= 16 elements), and the scan from the lower bound to the first own cell is
+// one ballot -- because every other warp of the CTA waits at the next barrier while this one is busy here.  Strips
+// of more than 32 cells, the results map and the application of the results stay with one lane.
 __device__ void players_collision_exact(Ctx& c, int total, int nhit, bool staged) {
   const Luts& T = c.P.T;
+  const int lane = c.lane;
   const uint16_t* ref = c.sm.cellref();  // (player << 8 | cell) in snapshot order
   const int16_t* rows = c.sm.rows();     // strip id of every snapshot cell (filled by the caller)
   uint16_t* strip = c.sm.strip();        // one strip, sorted by y (stable)
@@ -1636,7 +1641,7 @@ __device__ void players_collision_exact(Ctx& c, int total, int nhit, bool staged
   auto gy_of = [&](int g) -> float { return staged ? c.sm.snap()[g].y : cellp(g)->y; };
   auto gx_of = [&](int g) -> float { return staged ? c.sm.snap()[g].x : cellp(g)->x; };
   auto gm_of = [&](int g) -> uint32_t { return staged ? __float_as_uint(c.sm.snap()[g].z) : cellp(g)->mass; };
-  int npairs = 0, nres = 0;
+  int npairs = 0, nres = 0;  // warp-uniform
   for (int hq = 0; hq < nhit; hq++) {
     int q = c.sm.hitq()[hq];
     int qp = ref[q] >> 8;
@@ -1648,40 +1653,102 @@ __device__ void players_collision_exact(Ctx& c, int total, int nhit, bool staged
     int top = get_row(left, c.W), bottom = get_row(right, c.W);
     bool opened = false;
     for (int row = top; row <= bottom; row++) {
+      // members of the strip, in snapshot order
       int l = 0;
-      for (int g = 0; g < total; g++) {
-        if (rows[g] != row) continue;
-        float gy = gy_of(g);  // insertion sort by y == libstdc++ std::sort for <= 16 elements
-        int b = l - 1;
-        while (b >= 0 && gy < gy_of(strip[b])) { strip[b + 1] = strip[b]; b--; }
-        strip[b + 1] = (uint16_t)g;
-        l++;
+      for (int g0 = 0; g0 < total; g0 += 32) {
+        const int g = g0 + lane;
+        const bool mem = g < total && rows[g] == row;
+        const unsigned bm = __ballot_sync(AG_FULL, mem);
+        if (mem) strip[l + __popc(bm & lanemask_lt(lane))] = (uint16_t)g;
+        l += __popc(bm);
       }
       if (l == 0) continue;
-      if (l > 16)
-        for (int a = 1; a < l; a++)
-          if (gy_of(strip[a]) == gy_of(strip[a - 1])) c.flags |= AGARCL_FLAG_PCD_TIE;
-      int start_pos = 0;
-      for (int j = 10; j >= 0; j--)
-        if (start_pos + (1 << j) < l && gy_of(strip[start_pos + (1 << j)]) < left) start_pos += (1 << j);
-      for (int j = start_pos; j < l; j++) {
-        int g = strip[j];
-        int gp = ref[g] >> 8;
-        if (gp == qp) break;  // quirk Q7: the scan stops at the first own cell
-        uint32_t gm = gm_of(g);
-        if (collides(qx, qy, qr, gx_of(g), gy_of(g), radius_of(T, gm)) && cell_can_eat_cell(qm, gm)) {
-          const agarcl_cell* gc = cellp(g);
-          if (npairs < kPairCap) {
-            if (!opened) { rkeys[nres++] = (uint16_t)q; opened = true; }
-            pairs[npairs].q = (uint16_t)q; pairs[npairs].g = (uint16_t)g;
-            pairs[npairs].eaten_mass = gm; pairs[npairs].eater_id = qc->id; pairs[npairs].eaten_id = gc->id;
-            npairs++;
-          } else c.flags |= AGARCL_FLAG_EATER_OVERFLOW;
+      __syncwarp();
+      if (l > 32) {  // long strip: one lane, literally (insertion sort == libstdc++ std::sort only up to 16: flagged beyond)
+        if (lane == 0) {
+          for (int a = 1; a < l; a++) {
+            const uint16_t g = strip[a];
+            const float gy = gy_of(g);
+            int b = a - 1;
+            while (b >= 0 && gy < gy_of(strip[b])) { strip[b + 1] = strip[b]; b--; }
+            strip[b + 1] = g;
+          }
+          for (int a = 1; a < l; a++)
+            if (gy_of(strip[a]) == gy_of(strip[a - 1])) c.flags |= AGARCL_FLAG_PCD_TIE;
+          int start_pos = 0;
+          for (int j = 10; j >= 0; j--)
+            if (start_pos + (1 << j) < l && gy_of(strip[start_pos + (1 << j)]) < left) start_pos += (1 << j);
+          for (int j = start_pos; j < l; j++) {
+            int g = strip[j];
+            int gp = ref[g] >> 8;
+            if (gp == qp) break;  // quirk Q7: the scan stops at the first own cell
+            uint32_t gm = gm_of(g);
+            if (collides(qx, qy, qr, gx_of(g), gy_of(g), radius_of(T, gm)) && cell_can_eat_cell(qm, gm)) {
+              const agarcl_cell* gc = cellp(g);
+              if (npairs < kPairCap) {
+                if (!opened) { rkeys[nres++] = (uint16_t)q; opened = true; }
+                pairs[npairs].q = (uint16_t)q; pairs[npairs].g = (uint16_t)g;
+                pairs[npairs].eaten_mass = gm; pairs[npairs].eater_id = qc->id; pairs[npairs].eaten_id = gc->id;
+                npairs++;
+              } else c.flags |= AGARCL_FLAG_EATER_OVERFLOW;
+            }
+          }
         }
+        npairs = __shfl_sync(AG_FULL, npairs, 0);
+        nres = __shfl_sync(AG_FULL, nres, 0);
+        opened = __shfl_sync(AG_FULL, (int)opened, 0) != 0;
+        __syncwarp();
+        continue;
       }
+      // stable rank by y: lane i holds member i
+      const int myg = lane < l ? (int)strip[lane] : 0;
+      const float myy = lane < l ? gy_of(myg) : 0.0f;
+      int rank = 0;
+      for (int j = 0; j < l; j++) {
+        const float yj = __shfl_sync(AG_FULL, myy, j);
+        rank += (yj < myy || (yj == myy && j < lane)) ? 1 : 0;
+      }
+      __syncwarp();
+      if (lane < l) strip[rank] = (uint16_t)myg;
+      __syncwarp();
+      const int sg = lane < l ? (int)strip[lane] : 0;  // lane j holds position j of the sorted strip
+      const float sy = lane < l ? gy_of(sg) : 0.0f;
+      {
+        const float prev = __shfl_up_sync(AG_FULL, sy, 1);
+        if (l > 16 && __ballot_sync(AG_FULL, lane >= 1 && lane < l && sy == prev)) c.flags |= AGARCL_FLAG_PCD_TIE;
+      }
+      // the reference's lower-bound stepping on a sorted strip: the last position >= 1 whose y is left of the query, else 0
+      const unsigned lt = __ballot_sync(AG_FULL, lane >= 1 && lane < l && sy < left);
+      const int start_pos = lt ? 31 - __clz(lt) : 0;
+      const int gp = lane < l ? (int)(ref[sg] >> 8) : -1;
+      const unsigned own = __ballot_sync(AG_FULL, lane >= start_pos && lane < l && gp == qp);
+      const int stop = own ? __ffs(own) - 1 : l;  // quirk Q7: the scan stops at the first own cell
+      const bool inr = lane >= start_pos && lane < stop;
+      const uint32_t gm = inr ? gm_of(sg) : 0u;
+      const bool hit = inr && collides(qx, qy, qr, gx_of(sg), sy, radius_of(T, gm)) && cell_can_eat_cell(qm, gm);
+      const unsigned hm = __ballot_sync(AG_FULL, hit);
+      if (hm) {
+        const int pos = npairs + __popc(hm & lanemask_lt(lane));
+        const bool fits = hit && pos < kPairCap;
+        const unsigned fm = __ballot_sync(AG_FULL, fits);
+        if (fm && !opened) {
+          if (lane == 0) rkeys[nres] = (uint16_t)q;
+          nres++;
+          opened = true;
+        }
+        if (fits) {
+          pairs[pos].q = (uint16_t)q; pairs[pos].g = (uint16_t)sg;
+          pairs[pos].eaten_mass = gm; pairs[pos].eater_id = qc->id; pairs[pos].eaten_id = cellp(sg)->id;
+        }
+        if (fm != hm) c.flags |= AGARCL_FLAG_EATER_OVERFLOW;
+        npairs += __popc(fm);
+      }
+      __syncwarp();
     }
   }
-  if (npairs == 0) return;
+  c.flags = __reduce_or_sync(AG_FULL, c.flags);
+  __syncwarp();
+  if (npairs == 0 || lane != 0) return;
   // iteration order of std::unordered_map<int, vector<...>> results (Engine.hpp:168)
   int cnt = 0, nb = 1, next_resize = 0;
   for (int k = 0; k < nres; k++) {
@@ -1836,7 +1903,7 @@ __device__ void players_collision(Ctx& c) {
   }
   __syncwarp();
   if (c.P.so.sweep_in_hash) c.hash_valid = false;  // the sweep's scratch (rows above included) lies over the hash's index array
-  if (lane == 0) players_collision_exact(c, total, nhit, staged);
+  players_collision_exact(c, total, nhit, staged);
   __syncwarp();
   c.flags = __shfl_sync(AG_FULL, c.flags, 0);
   c.lanes_dirty = true;  // masses / cell lists changed under the lanes' registers
