@@ -1,16 +1,20 @@
 // sim_kernel.cu — the engine tick for N lockstep instances, hand-written for sm_100a.
 //
-// Mapping: ONE WARP OWNS ONE GAME INSTANCE for a whole env-step (ticks_per_step ticks); a CTA is
-// up to kMaxWarpsPerCta independent warps (no block barriers — only __syncwarp / shuffles / ballots).
+// Mapping: ONE WARP OWNS ONE GAME INSTANCE for a whole env-step (ticks_per_step ticks); a CTA is up to
+// kMaxWarpsPerCta such warps.  Inside an instance only __syncwarp / shuffles / ballots; the warps of a CTA meet at
+// alignment barriers inside every tick (instruction-fetch sharing, step_instance) and share the pair solver's
+// batches through shared-memory mailboxes (premove_players).
 //   * a player's cells live in REGISTERS, one cell per lane (<= 32 cells), for the whole of its
 //     Engine::tick_player; order-dependent reference semantics (Gauss-Seidel self-collision,
 //     swap-pop recombine, eat order) are replayed with ballots + shuffles instead of loops over memory;
-//   * per-tick uniform-grid spatial hash of the pellets built by a warp-level counting sort in
-//     shared memory (count -> warp scan -> scatter), used to FIND pellet candidates; hits are then
+//   * uniform-grid spatial hash of the pellets built by a warp-level counting sort in shared memory
+//     (count -> warp scan -> scatter) and patched on removals, used to FIND pellet candidates; hits are then
 //     re-ordered and applied in the reference's order (510-unit buckets, ascending index,
 //     Engine.hpp:976-1000) so that events are bit-exact;
 //   * everything of an instance is one contiguous blob in HBM (include/agarcl_b200.h), read with
-//     16-byte vector loads; the instance stays L1/L2 resident for the 4 ticks of a step.
+//     16-byte vector loads / one TMA bulk load (pellets); it stays shared-memory / L2 resident for the step;
+//   * the grid observation is written by the same kernel: TMA bulk stores of zeros during the ticks,
+//     channel 0 rows and the entity scatter after the last tick (obs_finish_warp).
 // Control flow is warp-uniform everywhere a shuffle/ballot is issued.
 //
 // Reference functions restated here (agario/engine/Engine.hpp unless noted): tick 208-240,
@@ -2646,12 +2650,13 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
   __syncwarp();
 }
 
-// PERSISTENT grid: as many CTAs as fit on the GPU at once (launch_step), every warp draws the next
-// instance from a global ticket counter until the batch is exhausted.  Instances differ a lot in cost
-// (bot-decision ticks, split players, eat events); with a ticket a warp that finishes early just takes
-// another instance instead of idling until the slowest warp of its CTA is done, and there is no tail wave.
-// tickets[0] = next instance, tickets[1] = warps that have left; the last warp to leave rewinds both,
-// so the next launch on the stream (stream order) starts from zero again without a memset.
+// PERSISTENT grid: one CTA per SM (launch_step) of as many warps as the shared memory holds; every warp owns one
+// instance at a time and the CTA walks through the batch.  Two schedules:
+//   * aligned (tick_barrier != 0, the default): the warps of a CTA meet at barriers inside every tick (step_instance)
+//     and therefore move through their instances in rounds; a CTA takes stripes of the cost-sorted order `perm`.
+//   * free-running (tick_barrier == 0): every warp draws the next instance from a global ticket counter
+//     (tickets[0] = next instance, tickets[1] = warps that have left; the last warp to leave rewinds both, so the next
+//     launch on the stream starts from zero again without a memset).
 __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_constant__ SimParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
