@@ -566,18 +566,29 @@ static int collect(HostMirror* m, const void* d_obs, cudaStream_t s, bool flagge
   std::vector<int> ready((size_t)K, 0);
   std::atomic<int> next{0}, n_ready{0};
   std::atomic<bool> abort{false};
-  const std::function<void()> job = [&] {
-    for (;;) {
-      int i = next.load(std::memory_order_relaxed);
-      if (i >= K * tpc || abort.load(std::memory_order_relaxed)) break;
-      if (i >= n_ready.load(std::memory_order_acquire) * tpc) { cpu_relax(); continue; }
-      if (!next.compare_exchange_weak(i, i + 1, std::memory_order_relaxed)) continue;
-      const int c = ready[(size_t)(i / tpc)];
-      const int base = c * (int)k.ipc, end = base + (int)k.ipc < m->n_img ? base + (int)k.ipc : m->n_img;
-      const int lo = base + (i % tpc) * grab, hi = lo + grab < end ? lo + grab : end;
-      if (lo >= hi) continue;
+  // one task, if there is one: 1 done, 0 nothing ready yet, -1 all tasks taken (or aborted)
+  auto try_one = [&]() -> int {
+    int i = next.load(std::memory_order_relaxed);
+    if (i >= K * tpc || abort.load(std::memory_order_relaxed)) return -1;
+    if (i >= n_ready.load(std::memory_order_acquire) * tpc) return 0;
+    if (!next.compare_exchange_weak(i, i + 1, std::memory_order_relaxed)) return 1;
+    const int c = ready[(size_t)(i / tpc)];
+    const int base = c * (int)k.ipc, end = base + (int)k.ipc < m->n_img ? base + (int)k.ipc : m->n_img;
+    const int lo = base + (i % tpc) * grab, hi = lo + grab < end ? lo + grab : end;
+    if (lo < hi) {
       if (m->dtype == AGARCL_OBS_I16) expand_range<int16_t>(m, lo, hi, zero_masks.data());
       else expand_range<int32_t>(m, lo, hi, zero_masks.data());
+    }
+    return 1;
+  };
+  const std::function<void()> job = [&] {
+    uint32_t idle = 0;
+    for (;;) {
+      const int r = try_one();
+      if (r < 0) break;
+      if (r == 1) { idle = 0; continue; }
+      cpu_relax();
+      if (++idle >= 4096u) { idle = 0; std::this_thread::yield(); }  // (a fully subscribed box: let the threads that have work run)
     }
   };
   m->pool->start(job);
@@ -626,8 +637,10 @@ static int collect(HostMirror* m, const void* d_obs, cudaStream_t s, bool flagge
           publish(c);
         }
       if (any || left == 0) continue;
-      cpu_relax();
-      if ((++spins & 0x3FFu) == 0u) {
+      if (try_one() == 1) spins += 64u;  // the calling thread patches too while it waits for the next flag
+      else { cpu_relax(); spins += 1u; }
+      if (spins >= 1024u) {
+        spins = 0u;
         const cudaError_t q = cudaStreamQuery(s);
         if (q == cudaSuccess) {
           bool all = true;
