@@ -322,8 +322,7 @@ def run_ours(args):
             os.dup2(saved, 1)
             os.close(saved)
     if world > 1:  # the mirror's host threads: share the box's cores between the ranks
-        # (one core per rank is left to the driver / NCCL / Python threads: the mirror's workers spin while they wait)
-        os.environ.setdefault("AGARCL_HOST_THREADS", str(max(2, host_cores() // world - 1)))
+        os.environ.setdefault("AGARCL_HOST_THREADS", str(max(2, host_cores() // world)))
     N = args.instances
     cfg = make_cfg(n_instances=N, device=local_rank, instance_base=rank * N, **WORKLOAD)
     b = Batch(cfg)
