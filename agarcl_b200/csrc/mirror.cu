@@ -351,7 +351,7 @@ static void expand_range(HostMirror* m, int lo, int hi, const uint32_t* zero_mas
   const int cur = m->cur, prev = cur ^ 1;
   const PackOut& k = m->pk;
   const size_t mw2 = 2 * (size_t)m->MW, plane = (size_t)m->G * m->G;
-  static const int ahead = [] { const char* e = std::getenv("AGARCL_MIRROR_PREFETCH"); return e ? std::atoi(e) : 2; }();
+  static const int ahead = [] { const char* e = std::getenv("AGARCL_MIRROR_PREFETCH"); return e ? std::atoi(e) : 1; }();
   for (int a = 0; a < ahead && lo + a < hi; a++) prefetch_slot<T>(m, lo + a);
   for (int slot = lo; slot < hi; slot++) {
     if (slot + ahead < hi) prefetch_slot<T>(m, slot + ahead);
