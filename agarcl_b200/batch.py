@@ -94,9 +94,29 @@ class Batch:
         _lib.check(_lib.lib().agarcl_batch_ram(self._h, C.byref(p), C.byref(shape)))
         return torch.as_tensor(_CudaView(p.value, tuple(shape), "<f4", self), device=f"cuda:{self.cfg.device}")
 
+    def _host_actions(self, dxdy, act):
+        """the C ABI reads raw float32 / int32 buffers: coerce (and check the sizes of) whatever the caller hands in"""
+        dxdy = np.ascontiguousarray(dxdy, dtype=np.float32)
+        act = np.ascontiguousarray(act, dtype=np.int32)
+        if dxdy.size != self.N * self.A * 2 or act.size != self.N * self.A:
+            raise _lib.AgarclError("Number of actions does not match number of agents")
+        return dxdy, act
+
+    @staticmethod
+    def _host_out(a, dtype, size, what):
+        if a is None:
+            return None
+        if not (isinstance(a, np.ndarray) and a.dtype == dtype and a.flags.c_contiguous and a.size == size):
+            raise _lib.AgarclError(f"{what} must be a C-contiguous {np.dtype(dtype).name} array of {size} elements")
+        return a.ctypes.data_as(_vp)
+
     def step_host(self, dxdy, act, obs_out=None, rewards_out=None, dones_out=None):
-        f = lambda a: a.ctypes.data_as(_vp) if a is not None else None
-        _lib.check(_lib.lib().agarcl_batch_step_host(self._h, f(dxdy), f(act), f(obs_out), f(rewards_out), f(dones_out)))
+        dxdy, act = self._host_actions(dxdy, act)
+        NA = self.N * self.A
+        _lib.check(_lib.lib().agarcl_batch_step_host(
+            self._h, dxdy.ctypes.data_as(_vp), act.ctypes.data_as(_vp),
+            self._host_out(obs_out, self.obs_dtype, int(np.prod(self.obs_shape)), "obs_out"),
+            self._host_out(rewards_out, np.float64, NA, "rewards_out"), self._host_out(dones_out, np.uint8, NA, "dones_out")))
 
     # ---- host-resident observation mirror (include/agarcl_b200.h, mirror.cu)
     def mirror(self):
@@ -118,9 +138,12 @@ class Batch:
 
     def step_mirror(self, dxdy, act, rewards_out=None, dones_out=None):
         """take_actions (host arrays) + step + mirror sync; returns the mirror view"""
-        f = lambda a: a.ctypes.data_as(_vp) if a is not None else None
+        dxdy, act = self._host_actions(dxdy, act)
+        NA = self.N * self.A
         self.mirror()
-        _lib.check(_lib.lib().agarcl_batch_step_mirror(self._h, f(dxdy), f(act), f(rewards_out), f(dones_out)))
+        _lib.check(_lib.lib().agarcl_batch_step_mirror(
+            self._h, dxdy.ctypes.data_as(_vp), act.ctypes.data_as(_vp),
+            self._host_out(rewards_out, np.float64, NA, "rewards_out"), self._host_out(dones_out, np.uint8, NA, "dones_out")))
         return self._mirror
 
     def mirror_stats(self):
@@ -142,6 +165,13 @@ class Batch:
 
     def launches_per_step(self):
         return _lib.lib().agarcl_batch_launches_per_step(self._h)
+
+    def flags(self, stream=0):
+        """(OR of hdr.flags over all instances, {flag name: instances with it set}); reduced on the device"""
+        from ._abi import FLAG_NAMES
+        o, counts = C.c_uint32(), (C.c_uint32 * 32)()
+        _lib.check(_lib.lib().agarcl_batch_flags(self._h, _vp(stream), C.byref(o), C.byref(counts)))
+        return int(o.value), {FLAG_NAMES.get(1 << i, f"bit{i}"): int(counts[i]) for i in range(32) if counts[i]}
 
     # ---- parity / snapshot transport
     def download_state(self, i):

@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cstring>
 #include <new>
+#include <random>
 #include <vector>
 
 #include "host_util.h"
@@ -25,6 +26,7 @@ cudaError_t launch_order(const uint32_t* cost, uint32_t* perm, int N, cudaStream
 cudaError_t launch_obs(const ObsParams& P, cudaStream_t stream);
 cudaError_t launch_reset(const ResetParams& P, cudaStream_t stream);
 cudaError_t launch_ram(const RamParams& P, cudaStream_t stream);
+cudaError_t launch_flags(const uint8_t* state, const agarcl_layout& L, int N, uint32_t* out33, cudaStream_t stream);
 }  // namespace ag
 
 struct agarcl_batch {
@@ -51,6 +53,15 @@ struct agarcl_batch {
   int sort_schedule = 1;  // AGARCL_SORT_SCHEDULE=0 turns the cost-sorted schedule off (A/B timing)
   float *d_lut_radius = nullptr, *d_lut_speed = nullptr, *d_lut_split = nullptr;
   std::vector<uint64_t> seeds;
+  // AGARCL_RNG_MT19937: the reference's generator per instance (GameState::rng, GameState.hpp:51), kept on the host; its
+  // uniform_real_distribution<float> draws are fed to the device through d_replay used as a RING that refill_replay keeps
+  // filled ahead of every instance's draw cursor (filled[i] = draws generated so far; the ring holds [filled - cap, filled))
+  std::vector<std::mt19937_64> gens;
+  std::vector<uint64_t> filled;
+  int64_t draw_budget = 0;      // draws every instance is known to have ahead of its cursor
+  int64_t max_draws_per_step = 0;
+  uint8_t* d_fresh = nullptr;   // [N] instance (re)seeded since its last reset (ResetParams::fresh)
+  uint32_t* d_flagbuf = nullptr;  // [33] agarcl_batch_flags scratch
   ag::Luts T;
   int HG;
   uint32_t smem_per_warp;
@@ -179,12 +190,75 @@ static void fill_obs_params(const agarcl_batch* b, ag::ObsParams& P, int frame, 
   P.W = (float)b->cfg.arena_size;
 }
 
+// ---- AGARCL_RNG_MT19937 stream plumbing
+static inline float mt_next(std::mt19937_64& g) {  // exactly what agarcl_mt19937_draws / Engine::random<float> draw (random.hpp:6-20)
+  std::uniform_real_distribution<float> d(0.0f, 1.0f);
+  return d(g);
+}
+// Generates draws [filled, upto) of instance i and stores them at their ring positions on the device.
+static int mt_extend(agarcl_batch* b, int i, uint64_t upto) {
+  const uint64_t cap = (uint64_t)b->L.cap_replay;
+  if (upto <= b->filled[i]) return AGARCL_OK;
+  uint64_t from = b->filled[i];
+  if (upto - from > cap) {  // (only the last `cap` draws can live in the ring)
+    for (uint64_t k = from; k < upto - cap; k++) (void)mt_next(b->gens[i]);
+    from = upto - cap;
+  }
+  std::vector<float> buf((size_t)(upto - from));
+  for (auto& v : buf) v = mt_next(b->gens[i]);
+  float* row = b->d_replay + (size_t)i * cap;
+  uint64_t k = from;
+  while (k < upto) {
+    const uint64_t pos = k % cap, n = std::min<uint64_t>(upto - k, cap - pos);
+    if (cudaMemcpy(row + pos, buf.data() + (k - from), (size_t)n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+      return agarcl_set_error(AGARCL_ERR_CUDA, "replay ring upload failed");
+    k += n;
+  }
+  b->filled[i] = upto;
+  return AGARCL_OK;
+}
+// (Re)starts instance i's stream at draw index `at` from `seed` (Engine::seed, Engine.hpp:242-245) and fills the ring ahead of it.
+static int mt_restart(agarcl_batch* b, int i, uint64_t seed, uint64_t at) {
+  b->gens[i].seed((unsigned)seed);  // BaseEnvironment::seed(int) -> Engine::seed(unsigned)
+  b->filled[i] = 0;
+  for (uint64_t k = 0; k < at; k++) (void)mt_next(b->gens[i]);
+  b->filled[i] = at;
+  return mt_extend(b, i, at + (uint64_t)b->L.cap_replay);
+}
+// Called behind every launch that may draw (step, reset): when the instances may have come within one step's worth of
+// draws of the end of what the ring holds, read the cursors back and fill the ring ahead of them again.
+static int refill_replay(agarcl_batch* b, cudaStream_t s) {
+  if (b->cfg.rng_mode != AGARCL_RNG_MT19937) return AGARCL_OK;
+  b->draw_budget -= b->max_draws_per_step;
+  if (b->draw_budget >= b->max_draws_per_step) return AGARCL_OK;
+  std::vector<uint32_t> cur((size_t)b->N);
+  if (cudaMemcpy2DAsync(cur.data(), sizeof(uint32_t), b->d_state + b->L.off_hdr + offsetof(agarcl_inst_hdr, rng_cursor), b->L.stride,
+                        sizeof(uint32_t), (size_t)b->N, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      cudaStreamSynchronize(s) != cudaSuccess)
+    return agarcl_set_error(AGARCL_ERR_CUDA, "draw cursor read-back failed: %s", cudaGetErrorString(cudaGetLastError()));
+  int64_t budget = b->L.cap_replay;
+  for (int i = 0; i < b->N; i++) {
+    // the 32-bit device cursor counts modulo 2^32; the stream position is the one nearest below `filled`
+    uint64_t c = (b->filled[i] & ~0xffffffffull) | cur[i];
+    if (c > b->filled[i]) c -= 0x100000000ull;
+    const uint64_t ahead = b->filled[i] - c;
+    if ((int64_t)ahead < (int64_t)b->L.cap_replay / 2 || (int64_t)ahead < 2 * b->max_draws_per_step) {
+      int rc = mt_extend(b, i, c + (uint64_t)b->L.cap_replay);
+      if (rc) return rc;
+    }
+    budget = std::min<int64_t>(budget, (int64_t)(b->filled[i] - c));
+  }
+  b->draw_budget = budget;
+  return AGARCL_OK;
+}
+
 extern "C" int agarcl_batch_destroy(agarcl_batch* b) {
   if (!b) return AGARCL_OK;
   ag::mirror_destroy(b->mirror);
   cudaFree(b->d_ram);
   cudaFree(b->d_state); cudaFree(b->d_obs); cudaFree(b->d_rewards); cudaFree(b->d_dones); cudaFree(b->d_before);
   cudaFree(b->d_dxdy); cudaFree(b->d_act); cudaFree(b->d_replay); cudaFree(b->d_seeds); cudaFree(b->d_mask); cudaFree(b->d_tickets); cudaFree(b->d_cost); cudaFree(b->d_perm);
+  cudaFree(b->d_fresh); cudaFree(b->d_flagbuf);
   cudaFree(b->d_lut_radius); cudaFree(b->d_lut_speed); cudaFree(b->d_lut_split);
   for (cudaEvent_t e : b->ev) cudaEventDestroy(e);
   delete b;
@@ -247,6 +321,9 @@ extern "C" int agarcl_batch_create(const agarcl_cfg* cfg, agarcl_batch** out) {
   ALLOC(b->d_cost, (size_t)b->N * sizeof(uint32_t));
   ALLOC(b->d_perm, (size_t)b->N * sizeof(uint32_t));
   cudaMemset(b->d_tickets, 0, 2 * sizeof(uint32_t));
+  ALLOC(b->d_fresh, (size_t)b->N);
+  cudaMemset(b->d_fresh, 1, (size_t)b->N);
+  ALLOC(b->d_flagbuf, 33 * sizeof(uint32_t));
   if (L.cap_replay > 0) ALLOC(b->d_replay, (size_t)b->N * L.cap_replay * sizeof(float));
   if (cfg->ram_obs) {
     ALLOC(b->d_ram, (size_t)b->N * L.P * AGARCL_RAM_RECORD * sizeof(float));
@@ -287,6 +364,26 @@ extern "C" int agarcl_batch_create(const agarcl_cfg* cfg, agarcl_batch** out) {
   }
   b->seeds.resize(b->N);
   for (int i = 0; i < b->N; i++) b->seeds[i] = (uint64_t)(cfg->instance_base + i);
+  b->max_draws_per_step = 2 * ((int64_t)L.cap_pellets + L.cap_viruses + L.P);  // regen deficits + respawns of one step; a whole reset
+  if (cfg->rng_mode == AGARCL_RNG_MT19937) {
+    // an UNSEEDED reference environment draws from std::random_device (GameState.hpp:59): so does an unseeded batch
+    if ((int64_t)L.cap_replay <= b->max_draws_per_step) {
+      agarcl_batch_destroy(b);
+      return agarcl_set_error(AGARCL_ERR_INVALID, "cap_replay %d cannot hold the draws of one step (%lld): raise cfg.cap_replay", L.cap_replay,
+                              (long long)b->max_draws_per_step);
+    }
+    b->gens.resize(b->N);
+    b->filled.assign(b->N, 0);
+    std::random_device rd;
+    for (int i = 0; i < b->N; i++) {
+      uint64_t s0;
+      try { s0 = rd(); } catch (...) { s0 = (uint64_t)(cfg->instance_base + i) * 0x9E3779B97F4A7C15ull + 1u; }
+      b->seeds[i] = s0 & 0xffffffffull;
+      int rc2 = mt_restart(b, i, b->seeds[i], 0);
+      if (rc2) { agarcl_batch_destroy(b); return rc2; }
+    }
+    b->draw_budget = L.cap_replay;
+  }
   cudaMemcpy(b->d_seeds, b->seeds.data(), b->N * sizeof(uint64_t), cudaMemcpyHostToDevice);
   CK(cudaDeviceSynchronize());
   *out = b;
@@ -305,12 +402,14 @@ extern "C" int agarcl_batch_seed(agarcl_batch* b, const uint64_t* seeds) {
   for (int i = 0; i < b->N; i++) b->seeds[i] = seeds[i];
   CK(cudaMemcpy(b->d_seeds, b->seeds.data(), b->N * sizeof(uint64_t), cudaMemcpyHostToDevice));
   if (b->cfg.rng_mode == AGARCL_RNG_MT19937) {
-    std::vector<float> draws(b->L.cap_replay);
+    CK(cudaDeviceSynchronize());
     for (int i = 0; i < b->N; i++) {
-      agarcl_mt19937_draws(seeds[i], draws.data(), b->L.cap_replay);
-      CK(cudaMemcpy(b->d_replay + (size_t)i * b->L.cap_replay, draws.data(), draws.size() * sizeof(float), cudaMemcpyHostToDevice));
+      int rc = mt_restart(b, i, seeds[i], 0);
+      if (rc) return rc;
     }
+    b->draw_budget = b->L.cap_replay;
   }
+  CK(cudaMemset(b->d_fresh, 1, (size_t)b->N));  // seed() restarts the stream: the next reset draws from index 0
   return AGARCL_OK;
 }
 
@@ -321,6 +420,7 @@ extern "C" int agarcl_batch_set_replay(agarcl_batch* b, int32_t instance, const 
   if (n > b->L.cap_replay) n = b->L.cap_replay;
   CK(cudaSetDevice(b->cfg.device));
   CK(cudaMemcpy(b->d_replay + (size_t)instance * b->L.cap_replay, draws, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemset(b->d_fresh + instance, 1, 1));  // a new stream starts at its first draw
   return AGARCL_OK;
 }
 
@@ -382,6 +482,7 @@ extern "C" int agarcl_batch_reset(agarcl_batch* b, const uint8_t* mask, void* st
   }
   P.seeds = b->d_seeds;
   P.replay = b->d_replay;
+  P.fresh = b->d_fresh;
   P.dones = b->d_dones;
   P.N = b->N;
   P.instance_base = b->cfg.instance_base;
@@ -391,6 +492,7 @@ extern "C" int agarcl_batch_reset(agarcl_batch* b, const uint8_t* mask, void* st
   P.W = (float)b->cfg.arena_size;
   CK(ag::launch_reset(P, s));
   b->was_reset = true;
+  { int rc = refill_replay(b, s); if (rc) return rc; }
   if (b->d_ram) {  // GoBiggerEnvironment::reset ends with observation.clear() (GoBiggerEnvironment.hpp:698-702)
     const size_t per = (size_t)b->L.P * AGARCL_RAM_RECORD * sizeof(float);
     if (!mask) CK(cudaMemsetAsync(b->d_ram, 0, per * b->N, s));
@@ -485,7 +587,7 @@ static int step_impl(agarcl_batch* b, cudaStream_t s, bool want_lists, bool* lis
   }
   if (b->d_ram) { int rc = render_ram(b, s, 1); if (rc) return rc; launches++; }
   b->launches_last_step = launches;
-  return AGARCL_OK;
+  return refill_replay(b, s);
 }
 
 extern "C" int agarcl_batch_step(agarcl_batch* b, void* stream) {
@@ -513,6 +615,19 @@ extern "C" int agarcl_batch_get_timing(agarcl_batch* b, double* sim_ms, double* 
 }
 
 extern "C" int agarcl_batch_launches_per_step(const agarcl_batch* b) { return b ? b->launches_last_step : 0; }
+
+extern "C" int agarcl_batch_flags(agarcl_batch* b, void* stream, uint32_t* or_all, uint32_t counts[32]) {
+  if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");
+  CK(cudaSetDevice(b->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(ag::launch_flags(b->d_state, b->L, b->N, b->d_flagbuf, s));
+  uint32_t h[33];
+  CK(cudaMemcpyAsync(h, b->d_flagbuf, sizeof(h), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (or_all) *or_all = h[32];
+  if (counts) std::memcpy(counts, h, 32 * sizeof(uint32_t));
+  return AGARCL_OK;
+}
 
 extern "C" int agarcl_batch_obs(agarcl_batch* b, void** dev_ptr, int64_t shape[4], int32_t* dtype) {
   if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");
@@ -644,12 +759,11 @@ extern "C" int agarcl_batch_load_env_state(agarcl_batch* b, int32_t instance, co
   int rc = agarcl_snapshot_read(&b->cfg, &b->L, blob.data(), path, lossless);
   if (rc) return rc;
   const agarcl_inst_hdr* hdr = reinterpret_cast<const agarcl_inst_hdr*>(blob.data() + b->L.off_hdr);
-  b->seeds[instance] = hdr->seed_lo;
+  b->seeds[instance] = (uint64_t)hdr->seed_lo | ((uint64_t)hdr->seed_hi << 32);
   CK(cudaMemcpy(b->d_seeds + instance, &b->seeds[instance], sizeof(uint64_t), cudaMemcpyHostToDevice));
-  if (b->cfg.rng_mode == AGARCL_RNG_MT19937) {  // Engine::seed(agarcl_data["seed"]): the mt19937_64 stream restarts
-    std::vector<float> draws(b->L.cap_replay);
-    agarcl_mt19937_draws(hdr->seed_lo, draws.data(), b->L.cap_replay);
-    CK(cudaMemcpy(b->d_replay + (size_t)instance * b->L.cap_replay, draws.data(), draws.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (b->cfg.rng_mode == AGARCL_RNG_MT19937) {  // Engine::seed(agarcl_data["seed"]): the mt19937_64 stream restarts (at the saved cursor when lossless)
+    rc = mt_restart(b, instance, hdr->seed_lo, hdr->rng_cursor);
+    if (rc) return rc;
   }
   CK(cudaMemcpy(b->d_state + (size_t)instance * b->L.stride, blob.data(), b->L.stride, cudaMemcpyHostToDevice));
   return AGARCL_OK;

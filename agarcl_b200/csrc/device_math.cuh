@@ -137,56 +137,91 @@ __device__ __forceinline__ void decelerate(float& dx, float& dy, float decel, fl
 }
 
 // ---------------------------------------------------------------------------------------------
-// Portable trigonometry for Engine::disrupt (Engine.hpp:1279-1283; Velocity::direction and
-// Velocity(angle, speed), core/types.hpp:158-174).  The reference calls glibc atanf/cosf/sinf, which
-// are not correctly rounded (measured: ~1 % of results differ from the correctly rounded value by
-// one ulp), so they cannot be matched bit-for-bit on a GPU.  This is the "stated fp32 tolerance"
-// site of the path.  Both the device and oracle.c (trig_mode 1) use the SAME fixed algorithm in IEEE
-// double arithmetic without contraction, so GPU == oracle bit-for-bit, and both are within 1 ulp
-// (fp32) of the reference.
+// Trigonometry of Engine::disrupt (Engine.hpp:1279-1283; Velocity::direction and Velocity(angle, speed),
+// core/types.hpp:158-174).  The reference calls libm's atanf / cosf / sinf.  They are not correctly rounded, so
+// "any accurate implementation" does not reproduce them; but they are deterministic algorithms, restated here
+// operation for operation:
+//   atanf  -- the fdlibm single-precision routine (glibc sysdeps/ieee754/flt-32/s_atanf.c): argument reduction to
+//             one of four intervals, an 11-term odd/even polynomial, all in fp32
+//   sinf / cosf -- the "optimized routines" implementation glibc has shipped since 2.28 (sysdeps/ieee754/flt-32/
+//             s_sinf.c, s_cosf.c, sincosf.h): reduction by pi/2 and a degree-7/8 polynomial, all in fp64, one rounding
+// atanf is plain fp32 arithmetic (-fmad=false: every a*b+c is two IEEE operations).  For sinf / cosf glibc selects its
+// FMA build at run time on every x86-64 CPU that has the instruction (sysdeps/x86_64/fpu/multiarch): the polynomial
+// and the reduction below fuse exactly where that build does (explicit fma()); the non-FMA build differs from it for
+// 34 of the 2^32 fp32 arguments.  oracle/trig_check.c compares the restatement with the libm of the build box over
+// ALL 2^32 arguments: no difference.
+// The oracle's trig_mode 1 is the same restatement in C; its trig_mode 0 calls libm itself.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double p_atan(double q) {
-  if (q != q) return q;
-  bool neg = q < 0.0;
-  double t = neg ? -q : q;
-  bool inv = t > 1.0;
-  if (inv) t = 1.0 / t;  // 1/inf = 0
-  bool shift = t > 0.4142135623730950488;
-  if (shift) t = (t - 1.0) / (t + 1.0);
-  double z = t * t, s = 0.0;
-  for (int k = 24; k >= 0; --k) s = s * z + ((k & 1) ? -1.0 : 1.0) / (double)(2 * k + 1);
-  double r = t * s;
-  if (shift) r = 0.78539816339744830962 + r;
-  if (inv) r = 1.57079632679489661923 - r;
-  return neg ? -r : r;
-}
-__device__ __forceinline__ void p_sincos(double x, double* sn, double* cs) {
-  if (!(x > -1.0e6 && x < 1.0e6)) { *sn = __longlong_as_double(0x7ff8000000000000LL); *cs = *sn; return; }
-  double k = rint(x * 0.63661977236758134308);
-  double r = (x - k * 1.57079632673412561417e+00) - k * 6.07710050650619224932e-11;  // Cody-Waite, hi has 33 bits
-  double z = r * r;
-  double ps = 0.0, pc = 0.0;
-  // Taylor: sin r = r * sum (-z)^j / (2j+1)!,  cos r = sum (-z)^j / (2j)!
-  const double fs[10] = {1.0, 6.0, 120.0, 5040.0, 362880.0, 39916800.0, 6227020800.0, 1307674368000.0,
-                         355687428096000.0, 121645100408832000.0};
-  const double fc[10] = {1.0, 2.0, 24.0, 720.0, 40320.0, 3628800.0, 479001600.0, 87178291200.0,
-                         20922789888000.0, 6402373705728000.0};
-  for (int j = 9; j >= 0; --j) {
-    double sg = (j & 1) ? -1.0 : 1.0;
-    ps = ps * z + sg / fs[j];
-    pc = pc * z + sg / fc[j];
+// (cold code: out of line, scalar constants only -- nothing of it may cost the hot paths registers or stack)
+static __device__ __noinline__ float g_atanf(float x) {
+  const float hi3 = 1.5707962513e+00f, lo3 = 7.5497894159e-08f;
+  const int32_t hx = __float_as_int(x), ix = hx & 0x7fffffff;
+  if (ix >= 0x4c000000) {  // |x| >= 2^25
+    if (ix > 0x7f800000) return x + x;  // NaN
+    return hx > 0 ? hi3 + lo3 : -hi3 - lo3;
   }
-  double s0 = r * ps, c0 = pc;
-  long long q = (long long)k;
-  int m = (int)(((q % 4) + 4) % 4);
-  double s1 = (m == 0) ? s0 : (m == 1) ? c0 : (m == 2) ? -s0 : -c0;
-  double c1 = (m == 0) ? c0 : (m == 1) ? -s0 : (m == 2) ? -c0 : s0;
-  *sn = s1;
-  *cs = c1;
+  float hi = 0.0f, lo = 0.0f;  // atanhi[id], atanlo[id]
+  bool reduced = true;
+  if (ix < 0x3ee00000) {  // |x| < 0.4375
+    if (ix < 0x31000000) return x;  // |x| < 2^-29
+    reduced = false;
+  } else {
+    x = fabsf(x);
+    if (ix < 0x3f980000) {  // |x| < 1.1875
+      if (ix < 0x3f300000) { hi = 4.6364760399e-01f; lo = 5.0121582440e-09f; x = (2.0f * x - 1.0f) / (2.0f + x); }  // 7/16 <= |x| < 11/16
+      else { hi = 7.8539812565e-01f; lo = 3.7748947079e-08f; x = (x - 1.0f) / (x + 1.0f); }                        // 11/16 <= |x| < 19/16
+    } else {
+      if (ix < 0x401c0000) { hi = 9.8279368877e-01f; lo = 3.4473217170e-08f; x = (x - 1.5f) / (1.0f + 1.5f * x); }  // |x| < 2.4375
+      else { hi = hi3; lo = lo3; x = -1.0f / x; }
+    }
+  }
+  const float z = x * x, w = z * z;
+  const float s1 = z * (3.3333334327e-01f + w * (1.4285714924e-01f + w * (9.0908870101e-02f + w * (6.6610731184e-02f + w * (4.9768779427e-02f + w * 1.6285819933e-02f)))));
+  const float s2 = w * (-2.0000000298e-01f + w * (-1.1111110449e-01f + w * (-7.6918758452e-02f + w * (-5.8335702866e-02f + w * -3.6531571299e-02f))));
+  if (!reduced) return x - x * (s1 + s2);
+  const float r = hi - ((x * (s1 + s2) - lo) - x);
+  return hx < 0 ? -r : r;
+}
+// sincosf.h: sinf_poly with the table row `neg` (row 1 = negated cosine coefficients) and quadrant parity n
+static __device__ __forceinline__ float g_sincos_poly(double x, double x2, bool neg, int n) {
+  if ((n & 1) == 0) {
+    const double s1c = -0x1.555545995a603p-3, s2c = 0x1.1107605230bc4p-7, s3c = -0x1.994eb3774cf24p-13;
+    const double x3 = x * x2;
+    const double s1 = fma(x2, s3c, s2c);
+    const double x7 = x3 * x2;
+    const double s = fma(x3, s1c, x);
+    return (float)fma(x7, s1, s);
+  }
+  const double sg = neg ? -1.0 : 1.0;
+  const double c0 = sg * 0x1p0, c1c = sg * -0x1.ffffffd0c621cp-2, c2c = sg * 0x1.55553e1068f19p-5, c3c = sg * -0x1.6c087e89a359dp-10,
+               c4c = sg * 0x1.99343027bf8c3p-16;
+  const double x4 = x2 * x2;
+  const double c2 = fma(x2, c4c, c3c);
+  const double c1 = fma(x2, c1c, c0);
+  const double x6 = x4 * x2;
+  const double c = fma(x4, c2c, c1);
+  return (float)fma(x6, c2, c);
+}
+// s_sinf.c / s_cosf.c; |y| >= 120 (reduce_large there) cannot come out of Engine::disrupt, whose angles stay below 5 pi: NaN
+static __device__ __noinline__ float g_sincosf(float y, int is_cos) {
+  const uint32_t top = (__float_as_uint(y) >> 20) & 0x7ffu;  // abstop12
+  double x = (double)y;
+  if (top < ((__float_as_uint(0x1.921fb6p-1f) >> 20) & 0x7ffu)) {  // |y| < pi/4
+    if (top < ((__float_as_uint(0x1p-12f) >> 20) & 0x7ffu)) return is_cos ? 1.0f : y;
+    return g_sincos_poly(x, x * x, false, is_cos);
+  }
+  if (top < ((__float_as_uint(120.0f) >> 20) & 0x7ffu)) {
+    const double r = x * 0x1.45F306DC9C883p+23;  // 2/pi * 2^24: the quadrant ends up in bits 24..31
+    const int n = (__double2int_rz(r) + 0x800000) >> 24;
+    x = fma(-(double)n, 0x1.921FB54442D18p0, x);
+    const double sgn = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;  // sign[] = {1, -1, -1, 1}
+    return g_sincos_poly(x * sgn, x * x, (n & 2) != 0, n ^ is_cos);
+  }
+  return __int_as_float(0x7fc00000);
 }
 // Velocity::direction, core/types.hpp:167-174 (quirk Q9: atan(dx/dy), then +-pi in double)
 __device__ __forceinline__ float vel_direction(float dx, float dy) {
-  float angle = (float)p_atan((double)(dx / dy));
+  float angle = g_atanf(dx / dy);
   if (dx < 0) {
     if (dy > 0) angle = (float)((double)angle + AG_PI);
     else angle = (float)((double)angle - AG_PI);

@@ -21,6 +21,8 @@ struct ResetCtx {
 
 __device__ __forceinline__ float rdraw(ResetCtx& c, uint32_t k) {
   if (c.P.rng_mode == AGARCL_RNG_PHILOX) return philox_uniform(c.seed_lo, c.seed_hi, c.inst_global, k);
+  // the host keeps the mt19937_64 stream filled ahead of the cursor in a ring (batch.cu, refill_replay)
+  if (c.P.rng_mode == AGARCL_RNG_MT19937 && c.P.replay) return c.P.replay[(size_t)c.inst_local * c.P.L.cap_replay + k % (uint32_t)c.P.L.cap_replay];
   if ((int)k < c.P.L.cap_replay && c.P.replay) return c.P.replay[(size_t)c.inst_local * c.P.L.cap_replay + k];
   c.flags |= AGARCL_FLAG_REPLAY_EXHAUSTED;
   return 0.5f;
@@ -49,7 +51,9 @@ __global__ void __launch_bounds__(128) k_reset(const __grid_constant__ ResetPara
   agarcl_virus* vir = reinterpret_cast<agarcl_virus*>(blob + P.L.off_viruses);
   float2* pel = reinterpret_cast<float2*>(blob + P.L.off_pellets);
   const float W = P.W;
-  uint32_t cursor = 0;
+  // Engine::reset does not touch the RNG (Engine.hpp:98-117): a second episode goes on in the stream; only seed() restarts it
+  uint32_t cursor = (P.fresh && !P.fresh[inst]) ? hdr->rng_cursor : 0u;
+  __syncwarp();
   int n_pellets = 0;
 
   if (P.L.squared_pellets) {
@@ -79,10 +83,10 @@ __global__ void __launch_bounds__(128) k_reset(const __grid_constant__ ResetPara
     float r = radius_of(P.T, AGARCL_PELLET_MASS);
     for (int k = lane; k < P.num_pellets; k += 32) {
       float x, y;
-      rloc(c, 2u * (uint32_t)k, r, x, y);
+      rloc(c, cursor + 2u * (uint32_t)k, r, x, y);
       if (k < P.L.cap_pellets) pel[k] = make_float2(x, y);
     }
-    cursor = 2u * (uint32_t)P.num_pellets;
+    cursor += 2u * (uint32_t)P.num_pellets;
     n_pellets = min(P.num_pellets, P.L.cap_pellets);
   }
   {
@@ -128,6 +132,7 @@ __global__ void __launch_bounds__(128) k_reset(const __grid_constant__ ResetPara
   c.flags = __reduce_or_sync(AG_FULL, c.flags);
   for (int a = lane; a < P.L.A; a += 32) P.dones[(size_t)inst * P.L.A + a] = 0;
   if (lane == 0) {
+    if (P.fresh) P.fresh[inst] = 0;
     hdr->tick = 0;
     hdr->next_cell_id = 1u + (uint32_t)P.L.P;
     hdr->n_pellets = n_pellets;
@@ -140,6 +145,29 @@ __global__ void __launch_bounds__(128) k_reset(const __grid_constant__ ResetPara
     hdr->respawned_lo = 0; hdr->respawned_hi = 0;
     for (int q = 0; q < 4; q++) hdr->pad[q] = 0;
   }
+}
+
+// agarcl_batch_flags: OR and per-bit instance counts of hdr.flags over the whole batch (out[0..31] counts, out[32] OR)
+__global__ void __launch_bounds__(256) k_flags(const uint8_t* __restrict__ state, uint32_t off_hdr, uint32_t stride, int N, uint32_t* __restrict__ out) {
+  __shared__ uint32_t cnt[33];
+  if (threadIdx.x < 33) cnt[threadIdx.x] = 0u;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    uint32_t f = reinterpret_cast<const agarcl_inst_hdr*>(state + (size_t)i * stride + off_hdr)->flags;
+    if (f) atomicOr(&cnt[32], f);
+    while (f) { const int bit = __ffs(f) - 1; f &= f - 1u; atomicAdd(&cnt[bit], 1u); }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32 && cnt[threadIdx.x]) atomicAdd(&out[threadIdx.x], cnt[threadIdx.x]);
+  if (threadIdx.x == 32 && cnt[32]) atomicOr(&out[32], cnt[32]);
+}
+cudaError_t launch_flags(const uint8_t* state, const agarcl_layout& L, int N, uint32_t* out33, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(out33, 0, 33 * sizeof(uint32_t), stream);
+  if (e != cudaSuccess) return e;
+  int ctas = (N + 255) / 256;
+  if (ctas > 148) ctas = 148;
+  k_flags<<<ctas, 256, 0, stream>>>(state, L.off_hdr, L.stride, N, out33);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_reset(const ResetParams& P, cudaStream_t stream) {

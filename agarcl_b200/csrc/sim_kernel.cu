@@ -125,6 +125,8 @@ __device__ __forceinline__ float draw_at(Ctx& c, uint32_t k) {
     const agarcl_inst_hdr* hdr = reinterpret_cast<const agarcl_inst_hdr*>(c.blob + c.P.L.off_hdr);
     return philox_uniform(hdr->seed_lo, hdr->seed_hi, (uint32_t)(c.P.instance_base + c.inst_local), k);
   }
+  // the host keeps the mt19937_64 stream filled ahead of the cursor in a ring (batch.cu, refill_replay)
+  if (c.P.rng_mode == AGARCL_RNG_MT19937 && c.P.replay) return c.P.replay[(size_t)c.inst_local * c.P.L.cap_replay + k % (uint32_t)c.P.L.cap_replay];
   if ((int)k < c.P.L.cap_replay && c.P.replay) return c.P.replay[(size_t)c.inst_local * c.P.L.cap_replay + k];
   c.flags |= AGARCL_FLAG_REPLAY_EXHAUSTED;
   return 0.5f;
@@ -794,11 +796,9 @@ __device__ void tick_player(Ctx& c, int p) {
           if (ci >= 0 && ci < num) {
             float dvel = theta + (float)(2 * AG_PI * ci / num);
             float ang = theta + dvel;
-            double sn, cs;
-            p_sincos((double)ang, &sn, &cs);
             me.x = vc.x; me.y = vc.y;
             me.vx = par.vx; me.vy = par.vy;
-            me.svx = sp * (float)cs; me.svy = sp * (float)sn;
+            me.svx = sp * g_sincosf(ang, 1); me.svy = sp * g_sincosf(ang, 0);  // Velocity(angle, speed), core/types.hpp:158-159
             me.mass = 25u;
             me.id = c.next_id + (uint32_t)ci;
             me.rec = c.tick + AGARCL_RECOMBINE_TICKS;

@@ -120,6 +120,9 @@ struct ResetParams {
   const uint8_t* mask;     // [N] or nullptr (all)
   const uint64_t* seeds;   // [N]
   const float* replay;
+  uint8_t* fresh;          // [N] != 0: the instance was (re)seeded since its last reset -> its draw stream starts at 0; otherwise the
+                           // stream goes on where the last episode left it, like the reference's engine RNG across reset()
+                           // (BaseEnvironment.hpp:179-204 does not reseed); cleared by the kernel
   uint8_t* dones;
   int32_t N, instance_base, rng_mode, num_pellets, num_viruses;
   float W;

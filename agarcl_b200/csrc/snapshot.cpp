@@ -140,8 +140,9 @@ extern "C" int agarcl_snapshot_write(const agarcl_cfg* c, const agarcl_layout* L
           c->arena_size, c->c_death, c->mode_number, c->num_agents, c->num_bots);
   fprintf(f, "    \"pellet_count\": %d,\n    \"pellet_regen\": %s,\n    \"reward_type\": %d,\n    \"ticks_per_step\": %d,\n",
           hdr->n_pellets, c->pellet_regen ? "true" : "false", c->reward_type, c->ticks_per_step);
-  fprintf(f, "    \"seed\": %u,\n    \"ticks\": %u,\n    \"rng_cursor\": %u,\n    \"next_cell_id\": %u,\n", hdr->seed_lo, hdr->tick,
-          hdr->rng_cursor, hdr->next_cell_id);
+  // "seed" is what the reference reads back (Engine.hpp:346, 32 bits); the upper half of a 64-bit Philox key travels as an extra key
+  fprintf(f, "    \"seed\": %u,\n    \"seed_hi\": %u,\n    \"ticks\": %u,\n    \"rng_cursor\": %u,\n    \"next_cell_id\": %u,\n", hdr->seed_lo,
+          hdr->seed_hi, hdr->tick, hdr->rng_cursor, hdr->next_cell_id);
   fprintf(f, "    \"players\": [");
   for (int k = 0; k < L->P; k++) {
     const int p = k;
@@ -291,8 +292,10 @@ extern "C" int agarcl_snapshot_read(const agarcl_cfg* c, const agarcl_layout* L,
   hdr->tick = tick;
   hdr->next_cell_id = lossless && root.get("next_cell_id") ? (uint32_t)root.n("next_cell_id") : max_id + 1u;
   hdr->rng_cursor = lossless ? (uint32_t)root.n("rng_cursor", 0) : 0u;  // seed(agarcl_data["seed"]) restarts the stream (Engine.hpp:346)
-  hdr->seed_lo = (uint32_t)root.n("seed", hdr->seed_lo);
-  hdr->seed_hi = 0;
+  if (root.get("seed")) {  // (a file without a seed leaves the instance's key alone)
+    hdr->seed_lo = (uint32_t)root.n("seed", hdr->seed_lo);
+    hdr->seed_hi = (uint32_t)root.n("seed_hi", 0);  // absent in files written by the reference: its seeds are 32 bits
+  }
   hdr->flags = 0;
   hdr->done_sticky = 0;
   hdr->respawned_lo = hdr->respawned_hi = 0;

@@ -39,9 +39,9 @@ class _Base:
     def _ensure(self):
         if self._batch is None:
             self._batch = Batch(make_cfg(**self._ctor, **self._obs_cfg))
+            self._batch.reset()  # the reference constructor ends with reset() (BaseEnvironment.hpp:66), before any seed() can reach it
             if self._seeds is not None:
-                self._batch.seed(self._seeds)
-            self._batch.reset()  # the reference constructor ends with reset() (BaseEnvironment.hpp:66)
+                self._batch.seed(self._seeds)  # restarts the draw stream: the next reset() is the seed's first episode
         return self._batch
 
     def configure_observation(self, config):
@@ -61,6 +61,20 @@ class _Base:
         if self._batch is not None:
             self._batch.close()
             self._batch = None
+
+    _FATAL_FLAGS = 0x020  # AGARCL_FLAG_REPLAY_EXHAUSTED: the recorded draw stream ran out, spawn points are no longer the reference's
+
+    def _check_flags(self, b):
+        """the reference's containers grow without bound; this library's are fixed: tell the user instead of diverging silently"""
+        f, names = b.flags()
+        if f & self._FATAL_FLAGS:
+            raise RuntimeError(f"agarcl_b200: simulator state flags {sorted(names)}: the replayed RNG stream is exhausted "
+                               "(raise cfg.cap_replay or use rng_mode=RNG_MT19937 / RNG_PHILOX)")
+        if f and f != getattr(self, "_flags_warned", 0):
+            import warnings
+            self._flags_warned = f
+            warnings.warn(f"agarcl_b200: simulator state flags {sorted(names)} (a fixed capacity was reached or a libc rand() "
+                          "site of the reference was taken; results may differ from the reference from here on)")
 
     def render(self):
         raise RuntimeError("OpenGL rendering is out of scope of agarcl_b200 (SURVEY.md section 2, rows 11-13)")
@@ -101,6 +115,7 @@ class GridEnvironment(_Base):
         b.step()
         import torch
         rew = b.rewards_tensor().cpu().numpy()
+        self._check_flags(b)
         if self._order_agents is None:
             L = b.layout
             self._order_agents = [p for p in list(L.order)[:L.P] if p < L.A]
@@ -325,8 +340,18 @@ class BatchedGridEnvironment(_Base):
         """dxdy: [N*A, 2] float32, act: [N*A] int32 — numpy (copied) or CUDA torch tensors (zero-copy)"""
         b = self._ensure()
         if hasattr(dxdy, "data_ptr"):
-            assert dxdy.is_cuda and act.is_cuda and dxdy.is_contiguous() and act.is_contiguous()
-            assert dxdy.numel() == self.n_instances * self.num_agents * 2, "Number of actions does not match number of agents"
+            import torch
+            # the C ABI reads the raw device buffers as float32 / int32: anything else would be silently reinterpreted
+            na = self.n_instances * self.num_agents
+            dev = torch.device("cuda", self._ctor["device"])
+            if not (dxdy.is_cuda and act.is_cuda and dxdy.device == dev and act.device == dev):
+                raise RuntimeError(f"actions must live on {dev}")
+            if dxdy.dtype != torch.float32 or act.dtype != torch.int32:
+                raise RuntimeError(f"actions must be float32 (dx, dy) and int32 (action), got {dxdy.dtype} / {act.dtype}")
+            if not (dxdy.is_contiguous() and act.is_contiguous()):
+                raise RuntimeError("action tensors must be contiguous")
+            if dxdy.numel() != na * 2 or act.numel() != na:
+                raise RuntimeError(f"Number of actions does not match number of agents ({na})")
             b.set_actions_device(dxdy.data_ptr(), act.data_ptr(), stream)
         else:
             b.set_actions(dxdy, act, stream)
@@ -335,6 +360,10 @@ class BatchedGridEnvironment(_Base):
 
     def ram(self):
         return self._ensure().ram_tensor()
+
+    def flags(self):
+        """(OR over all instances, {AGARCL_FLAG name: instances}): a fixed capacity was hit / a non-replayable reference path taken"""
+        return self._ensure().flags()
 
     @property
     def batch(self):

@@ -237,6 +237,10 @@ class BatchedAgarioEnv:
                 self._steps[mask] = 0
         return self._obs(), rewards, done.view(-1), trunc.view(-1), {"steps": self._steps}
 
+    def flags(self):
+        """(OR over all instances, {AGARCL_FLAG name: instances}) -- fixed capacities hit since the instances' last reset"""
+        return self._env.flags()
+
     def close(self):
         self._env.close()
 

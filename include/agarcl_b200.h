@@ -68,8 +68,11 @@ typedef enum agarcl_status {
 typedef enum agarcl_rng_mode {
   AGARCL_RNG_PHILOX = 0,  /* counter-based per-instance Philox4x32-10 on device */
   AGARCL_RNG_REPLAY = 1,  /* draws come from a per-instance stream uploaded with agarcl_batch_set_replay */
-  AGARCL_RNG_MT19937 = 2  /* host fills the replay stream from std::mt19937_64(seed) exactly as
-                             Engine::seed + random_location do (Engine.hpp:143-148,242-245) */
+  AGARCL_RNG_MT19937 = 2  /* the host keeps one std::mt19937_64 per instance -- seeded by agarcl_batch_seed exactly as
+                             Engine::seed does (Engine.hpp:242-245), from std::random_device when never seeded
+                             (GameState.hpp:59) -- and feeds its uniform_real_distribution<float> draws
+                             (random_location, Engine.hpp:143-148) to the device through a ring that it refills
+                             ahead of every instance's cursor: the stream never runs out */
 } agarcl_rng_mode;
 
 typedef enum agarcl_obs_dtype { AGARCL_OBS_I32 = 0, AGARCL_OBS_I16 = 1 } agarcl_obs_dtype;
@@ -170,7 +173,9 @@ int agarcl_batch_get_layout(const agarcl_batch* b, agarcl_layout* out);
 
 /* BaseEnvironment::seed (BaseEnvironment.hpp:211): seeds[i] for instance i (host pointer, N entries). */
 int agarcl_batch_seed(agarcl_batch* b, const uint64_t* seeds);
-/* BaseEnvironment::reset (BaseEnvironment.hpp:179-204) for instances with mask[i]!=0 (NULL = all). */
+/* BaseEnvironment::reset (BaseEnvironment.hpp:179-204) for instances with mask[i]!=0 (NULL = all).  Like the reference's,
+ * a reset does not reseed: the instance's draw stream goes on where the last episode left it (successive episodes
+ * differ); only agarcl_batch_seed / agarcl_batch_set_replay / a snapshot load restart it at its first draw. */
 int agarcl_batch_reset(agarcl_batch* b, const uint8_t* mask, void* stream);
 /* BaseEnvironment::take_actions (BaseEnvironment.hpp:141-176): dxdy[N*A*2], act[N*A].
  * on_device!=0: device pointers, read by the next step without a copy. */
@@ -267,6 +272,10 @@ int agarcl_batch_set_timing(agarcl_batch* b, int enable);
 int agarcl_batch_get_timing(agarcl_batch* b, double* sim_ms, double* obs_ms, int32_t* steps);
 /* Number of kernel launches issued by the last agarcl_batch_step. */
 int agarcl_batch_launches_per_step(const agarcl_batch* b);
+/* hdr.flags of the whole batch, reduced on the device: *or_all = OR over all instances, counts[bit] = instances with
+ * AGARCL_FLAG bit `bit` set (either pointer may be NULL).  Synchronises `stream`.  The reference has no counterpart: its
+ * containers grow without bound where this library has fixed capacities (BaseEnvironment.hpp / Engine.hpp vectors). */
+int agarcl_batch_flags(agarcl_batch* b, void* stream, uint32_t* or_all, uint32_t counts[32]);
 /* Host helper: first n canonical floats of std::mt19937_64(seed) as uniform_real_distribution<float>
  * draws them (random.hpp:6-20). */
 int agarcl_mt19937_draws(uint64_t seed, float* out, int32_t n);

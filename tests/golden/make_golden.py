@@ -25,6 +25,9 @@ CASES = {
                           dict(seed=104, steps=160, boost=3000)),
     "dense_no_virus": (dict(num_agents=2, num_bots=20, arena_size=250, num_pellets=250, num_viruses=0, cap_foods=1024),
                        dict(seed=107, steps=160, boost=2000)),
+    # many virus pops (Engine::disrupt with its libm trigonometry), fed viruses, 14-cell players
+    "virus_heavy": (dict(num_agents=3, num_bots=10, arena_size=250, num_pellets=200, num_viruses=40, cap_foods=2048, cap_viruses=256),
+                    dict(seed=108, steps=200, boost=400, p_feed=0.5, p_split=0.1)),
     "mode2_squares_decay": (dict(num_bots=0, num_viruses=0, arena_size=350, num_pellets=500, mode_number=2), dict(seed=105, steps=100)),
     "mode9_one_bot": (dict(num_bots=1, num_viruses=0, arena_size=100, num_pellets=50, mode_number=9), dict(seed=106, steps=120, boost=150)),
 }
@@ -71,5 +74,7 @@ def make(name, cfg_kwargs, seed, steps, p_feed=1 / 3, p_split=1 / 3, boost=None,
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]  # fixture names; none = all
     for name, (ck, rk) in CASES.items():
-        make(name, ck, **rk)
+        if not only or name in only:
+            make(name, ck, **rk)

@@ -21,9 +21,12 @@ def load(path):
     return z, cfg
 
 
+@pytest.mark.parametrize("trig_mode", [0, 1], ids=["libm", "restated"])
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
-def test_oracle_replays_reference_trace(path):
-    oracle_lib().oracle_set_trig_mode(0)
+def test_oracle_replays_reference_trace(path, trig_mode):
+    """trig_mode 0: libm, what the reference executes; 1: the restatement of glibc's atanf / sinf / cosf that the CUDA path
+    runs (tests/test_trig_exact.py) -- both replay every trace bit-exactly, virus pops included."""
+    oracle_lib().oracle_set_trig_mode(trig_mode)
     z, cfg = load(path)
     L = oracle_layout(cfg)
     assert list(L.order)[:L.P] == z["order"].tolist()
@@ -52,12 +55,9 @@ def test_oracle_replays_reference_trace(path):
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_cuda_replays_reference_trace(path):
-    """The reference trace is reproduced bit-exactly — every discrete field, every fp32 field, rewards, dones and
-    observations — for as long as no virus has been touched.  Engine::disrupt is the one place the reference calls
-    glibc atanf/cosf/sinf (not correctly rounded, so no GPU code matches them bit-for-bit); from the first virus
-    contact on, trajectories may drift by ulps and then diverge chaotically, so that regime is covered instead by
-    the bit-exact CUDA-vs-oracle tests (tests/test_gpu_parity.py, same portable trigonometry on both sides) and by
-    the measured bound on the trigonometric difference (tests/test_trig_tolerance.py)."""
+    """The reference trace is reproduced bit-exactly -- every discrete field, every fp32 field, rewards, dones and
+    observations -- over its WHOLE length, virus contacts included: Engine::disrupt's atanf / cosf / sinf are glibc's
+    own algorithms restated on the device (device_math.cuh g_atanf / g_sincosf, pinned by tests/test_trig_exact.py)."""
     import torch
     from agarcl_b200 import RNG_REPLAY
     from agarcl_b200.batch import Batch
@@ -76,10 +76,8 @@ def test_cuda_replays_reference_trace(path):
         b.upload_state(0, sv)
     assert not compare_states(StateView(L, z["blob0"].copy()), b.download_state(0))
     hits = z["virus_hits"]
-    n_exact = int(np.argmax(hits > 0)) if (hits > 0).any() else len(hits)  # steps before the first virus contact
     bi = oi = 0
-    checked = 0
-    for st in range(n_exact):
+    for st in range(len(hits)):
         b.set_actions(z["dxdy"][st], z["act"][st])
         b.step()
         rew = b.rewards_tensor().cpu().numpy()
@@ -94,8 +92,6 @@ def test_cuda_replays_reference_trace(path):
             got = b.obs_tensor().cpu().numpy()
             assert np.array_equal(got, z["obs"][oi].astype(np.int32)), f"obs at step {st}"
             oi += 1
-        checked += 1
-    if n_exact:  # state right before the first virus contact
-        pass
-    print(os.path.basename(path), "exact prefix:", n_exact, "of", len(hits), "steps;", bi, "state checkpoints,", oi, "observations")
+    assert bi == len(z["blob_steps"]) and oi == len(z["obs_steps"])
+    print(os.path.basename(path), len(hits), "steps,", int(hits[-1]), "virus contacts,", bi, "state checkpoints,", oi, "observations")
     b.close()

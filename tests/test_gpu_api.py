@@ -301,3 +301,123 @@ def test_snapshot_save_load_through_the_device(tmp_path):
     with pytest.raises(RuntimeError):
         b.load_env_state(0, tmp_path / "missing.json")
     e.close()
+
+
+def test_unseeded_default_env_spreads_its_pellets():
+    """An unseeded reference environment draws from std::random_device (GameState.hpp:59): so does an unseeded drop-in
+    (AGARCL_RNG_MT19937 is the default of GridEnvironment / make()); two unseeded environments differ."""
+    from agarcl_b200.gym_env import make
+    layouts = []
+    for _ in range(2):
+        env = make("agario-grid-v0", num_bots=3, arena_size=400, num_pellets=300)
+        env.reset()
+        sv = env._env._ensure().download_state(0)
+        px, py = sv.pellets["x"][:300], sv.pellets["y"][:300]
+        assert px.std() > 60 and py.std() > 60 and len(np.unique(px)) > 290, "pellets are not spread over the arena"
+        assert len({(float(sv.cells[p][0]["x"]), float(sv.cells[p][0]["y"])) for p in range(4)}) == 4
+        layouts.append(px.copy())
+        env.close()
+    assert not np.array_equal(layouts[0], layouts[1])
+
+
+def test_mt19937_stream_never_runs_out_and_resets_continue_it():
+    """AGARCL_RNG_MT19937: the host refills the draw ring ahead of the cursor, so a long game consumes far more draws than
+    the ring holds and still equals the oracle fed the seed's whole mt19937_64 stream; a second reset() does NOT restart
+    the stream (BaseEnvironment::reset does not reseed, BaseEnvironment.hpp:179-204) but goes on at the cursor."""
+    from _helpers import Oracle, oracle_lib
+    from agarcl_b200 import make_cfg, RNG_MT19937, RNG_REPLAY
+    from agarcl_b200._abi import compare_states
+    from agarcl_b200.batch import Batch
+    oracle_lib().oracle_set_trig_mode(1)
+    kw = dict(num_agents=1, num_bots=3, arena_size=60, num_pellets=150, num_viruses=2)
+    cap = 1024  # one step can draw at most 2 * (150 + 34 + 4) = 376
+    b = Batch(make_cfg(rng_mode=RNG_MT19937, cap_replay=cap, **kw))
+    b.seed(123)
+    b.reset()
+    ocfg = make_cfg(rng_mode=RNG_REPLAY, cap_replay=1 << 16, **kw)
+    ora = Oracle(ocfg)
+    ora.seed_mt(123, 1 << 16)
+    ora.reset()
+    assert not compare_states(ora.state, b.download_state(0))
+    rng = np.random.default_rng(0)
+    for st in range(700):
+        dxdy = rng.uniform(-1, 1, size=(1, 2)).astype(np.float32)
+        act = np.zeros(1, np.int32)
+        b.set_actions(dxdy, act)
+        b.step()
+        ora.set_actions(dxdy, act)
+        ora.step()
+        if st % 50 == 49:
+            gs = b.download_state(0)
+            assert not compare_states(ora.state, gs), st
+            assert int(gs.hdr["rng_cursor"]) == int(ora.state.hdr["rng_cursor"])
+    gs = b.download_state(0)
+    cur = int(gs.hdr["rng_cursor"])
+    assert cur > 2 * cap, f"only {cur} draws consumed: the ring was never wrapped"
+    assert int(gs.hdr["flags"]) == int(ora.state.hdr["flags"]) and not (b.flags()[0] & 0x20)  # never AGARCL_FLAG_REPLAY_EXHAUSTED
+    # second episode: the stream goes on where the first one stopped
+    b.reset()
+    ora2 = Oracle(ocfg)
+    ora2.set_replay(ora.replay[cur:])
+    ora2.reset()
+    g2 = b.download_state(0)
+    assert not compare_states(ora2.state, g2)
+    assert int(g2.hdr["rng_cursor"]) == cur + int(ora2.state.hdr["rng_cursor"])
+    # seed() restarts it
+    b.seed(123)
+    b.reset()
+    ora3 = Oracle(ocfg)
+    ora3.seed_mt(123, 1 << 16)
+    ora3.reset()
+    assert not compare_states(ora3.state, b.download_state(0))
+    b.close()
+
+
+def test_philox_episodes_differ_after_auto_reset():
+    """counter-based stream: a reset goes on at the instance's cursor, so successive episodes of an instance differ"""
+    from agarcl_b200.env import BatchedGridEnvironment
+    e = BatchedGridEnvironment(3, num_bots=2, arena_size=200, num_pellets=100, num_viruses=2)
+    e.seed(9)
+    e.reset()
+    first = e.batch.download_state(1).pellets["x"][:100].copy()
+    e.reset(np.array([0, 1, 0], np.uint8))
+    second = e.batch.download_state(1)
+    assert not np.array_equal(first, second.pellets["x"][:100]) and int(second.hdr["rng_cursor"]) == 2 * (2 * (100 + 2 + 3))
+    e.seed(9)
+    e.reset()
+    assert np.array_equal(first, e.batch.download_state(1).pellets["x"][:100])
+    e.close()
+
+
+def test_action_buffers_are_type_checked():
+    import torch
+    from agarcl_b200.env import BatchedGridEnvironment
+    e = BatchedGridEnvironment(4, num_bots=1, arena_size=100, num_pellets=50, num_viruses=0)
+    e.reset()
+    dxdy = torch.zeros((4, 2), device="cuda")
+    with pytest.raises(RuntimeError, match="int32"):
+        e.step(dxdy, torch.zeros(4, dtype=torch.int64, device="cuda"))  # torch.randint's default dtype
+    with pytest.raises(RuntimeError, match="float32"):
+        e.step(dxdy.double(), torch.zeros(4, dtype=torch.int32, device="cuda"))
+    with pytest.raises(RuntimeError, match="number of agents"):
+        e.step(dxdy[:3].contiguous(), torch.zeros(4, dtype=torch.int32, device="cuda"))
+    e.step(np.zeros((4, 2), np.float64), np.zeros(4, np.int64))  # host arrays are converted
+    b = e.batch
+    with pytest.raises(RuntimeError):
+        b.step_mirror(np.zeros((4, 2), np.float32), np.zeros(4, np.int32), rewards_out=np.zeros(4, np.float32))
+    e.close()
+
+
+def test_flags_reduced_over_the_batch():
+    """agarcl_batch_flags: OR and per-flag instance counts of hdr.flags, reduced on the device"""
+    from agarcl_b200.env import BatchedGridEnvironment
+    e = BatchedGridEnvironment(300, num_bots=1, arena_size=100, num_pellets=50, num_viruses=0)
+    e.reset()
+    assert e.flags() == (0, {})
+    b = e.batch
+    for i, f in ((7, 0x001), (150, 0x041), (299, 0x040)):
+        sv = b.download_state(i)
+        sv.hdr["flags"] = f
+        b.upload_state(i, sv)
+    assert e.flags() == (0x041, {"FOOD_OVERFLOW": 2, "PCD_TIE": 2})
+    e.close()

@@ -19,6 +19,8 @@ CASES = {
     "mode1_squares": (dict(num_bots=0, num_viruses=0, arena_size=350, num_pellets=500, mode_number=1), dict(steps=100)),
     "mode3_done": (dict(num_bots=0, num_viruses=0, arena_size=350, num_pellets=500, mode_number=3), dict(steps=60, boost=22990)),
     "mode5_mass1000": (dict(num_bots=0, num_viruses=0, arena_size=350, num_pellets=500, mode_number=5), dict(steps=100)),
+    "mode6_mass1000_viruses": (dict(num_bots=0, num_viruses=3, arena_size=350, num_pellets=500, mode_number=6), dict(steps=100, p_split=0.2)),
+    "mode7_hungry_bot_done": (dict(num_bots=1, num_viruses=0, arena_size=100, num_pellets=50, mode_number=7), dict(steps=150, boost=200)),
     "mode8_one_bot_done": (dict(num_bots=1, num_viruses=0, arena_size=100, num_pellets=50, mode_number=8), dict(steps=150, boost=200)),
     "mode10": (dict(num_bots=1, num_viruses=3, arena_size=100, num_pellets=50, mode_number=10), dict(steps=100)),
     "tps1_grid64_absreward": (dict(num_bots=5, ticks_per_step=1, grid_size=64, arena_size=200, num_pellets=100, num_viruses=2, reward_type=0), dict(steps=150)),
@@ -36,6 +38,19 @@ LONG_CASES = {
     "crowded_virus_field_500_steps": (dict(num_agents=2, num_bots=20, arena_size=400, num_pellets=600, num_viruses=30, cap_foods=2048,
                                            cap_viruses=256), dict(steps=500, obs_every=25, boost=300, p_feed=0.2, p_split=0.2)),
 }
+
+
+def test_cuda_matches_oracle_philox_2000_steps_configs1():
+    """BASELINE.json configs[1] exactly as bench.py runs it -- AGARCL_RNG_PHILOX, default schedule -- over 2000 env-steps
+    (the age bench.py measures at) for 8 instances: the oracle is fed the Philox stream computed by the numpy restatement
+    (pinned to Random123's known answers in tests/test_philox_kat.py), so this pins the device's generator, every spawn
+    point, and the steady-state regime (popped 14-cell players, cells eaten, AGARCL_FLAG_PCD_TIE) bit-exactly.  Rewards and
+    dones are compared every step, the full state every 20 steps, the observation every 100."""
+    stats = run_parity(dict(), seeds=[1001 + 7 * i for i in range(8)], steps=2000, obs_every=100, state_every=20, philox=True,
+                       replay_len=1 << 17, instance_base=5)
+    assert stats["viruses_eaten"] > 0 and stats["max_cells"] >= 14 and stats["cells_eaten"] > 0, stats
+    assert set(stats["flags"]) <= {"PCD_TIE"}, stats
+    print("philox 2000 steps x 8:", stats)
 
 
 @pytest.mark.parametrize("name", list(LONG_CASES))

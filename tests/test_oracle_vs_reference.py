@@ -12,14 +12,14 @@ from agarcl_b200._abi import compare_states, make_cfg
 pytestmark = pytest.mark.skipif(ref_lib() is None, reason="compiled reference not available")
 
 
-def lockstep(cfg_kwargs, seed, steps, p_feed=1 / 3, p_split=1 / 3, boost=None, obs_every=10):
-    oracle_lib().oracle_set_trig_mode(0)  # libm trig == what the reference executes
+def lockstep(cfg_kwargs, seed, steps, p_feed=1 / 3, p_split=1 / 3, boost=None, obs_every=10, state_every=1, trig_mode=0, replay_len=1 << 16):
+    oracle_lib().oracle_set_trig_mode(trig_mode)  # 0: libm trig == what the reference executes; 1: the restatement the CUDA path runs
     cfg = make_cfg(**cfg_kwargs)
     L = oracle_layout(cfg)
     ref = Reference(cfg, L)
     ref.seed(seed)
     ora = Oracle(cfg, L)
-    ora.seed_mt(seed, 1 << 16)  # the oracle's own mt19937_64 restatement feeds the same stream
+    ora.seed_mt(seed, replay_len)  # the oracle's own mt19937_64 restatement feeds the same stream
     assert np.array_equal(ref.peek_draws(4096), ora.replay[:4096])
     ref.reset()
     ora.reset()
@@ -37,10 +37,11 @@ def lockstep(cfg_kwargs, seed, steps, p_feed=1 / 3, p_split=1 / 3, boost=None, o
         ora.set_actions(dxdy, act)
         rr, rd = ref.step()
         orr, od, _ = ora.step()
-        rs, miss = ref.dump()
-        assert miss == 0, f"reference exceeded a blob capacity at step {st}"
-        d = compare_states(rs, ora.state)
-        assert not d, f"step {st}: {d[:6]}"
+        if st % state_every == 0 or st == steps - 1:
+            rs, miss = ref.dump()
+            assert miss == 0, f"reference exceeded a blob capacity at step {st}"
+            d = compare_states(rs, ora.state)
+            assert not d, f"step {st}: {d[:6]}"
         assert np.array_equal(rr, orr) and np.array_equal(rd, od), (st, rr, orr, rd, od)
         if st % obs_every == 0:
             for a in range(L.A):
@@ -69,6 +70,19 @@ for m in range(1, 11):
 def test_oracle_matches_reference(name):
     ck, rk = CASES[name]
     lockstep(ck, seed=31 + len(name), **rk)
+
+
+@pytest.mark.parametrize("seed", [41, 42, 43, 44])
+def test_long_horizon_configs1_steady_state(seed):
+    """BASELINE.json configs[1] over 2500 env-steps (10 000 ticks): the regime bench.py measures in (game age 2000+: players
+    popped by viruses into 14 cells, dozens of cells eaten, crowded PrecisionCollisionDetection strips).  Oracle (with the
+    trigonometry the CUDA path runs) == compiled reference: rewards and dones every step, every state field every 25 steps,
+    the observation every 100.  AGARCL_FLAG_PCD_TIE (> 16 cells with equal y in one strip: the relative order libstdc++'s
+    introsort leaves them in is not specified) typically comes up around step 2000; the results stay identical."""
+    s = lockstep(dict(), seed=seed, steps=2500, obs_every=100, state_every=25, trig_mode=1, replay_len=1 << 18)
+    assert int(s.players["viruses_eaten"].sum()) > 0 and int(s.players["n_cells"].max()) >= 2
+    assert not (int(s.hdr["flags"]) & ~0x40), s.flag_names()
+    print("seed", seed, "flags", s.flag_names(), "viruses eaten", int(s.players["viruses_eaten"].sum()), "cells eaten", int(s.players["cells_eaten"].sum()))
 
 
 def test_recombine_after_300_ticks():

@@ -137,3 +137,24 @@ def test_we_load_the_reference_snapshot(tmp_path):
     sv.players["bot_type"][:] = list(L.bot_type)[:L.P]
     assert _lib.lib().agarcl_snapshot_read(C.byref(cfg), C.byref(L), sv.ptr, str(path).encode(), 0) == 0, _lib.lib().agarcl_last_error()
     assert miss == 0 and not compare_states(as_loaded_by_reference(rs), sv)
+
+
+def test_64_bit_seed_survives_the_round_trip(tmp_path):
+    """the reference's "seed" key is 32 bits (Engine.hpp:346); the upper half of a 64-bit Philox key travels as "seed_hi",
+    which the reference ignores; a file without a seed leaves the instance's key alone"""
+    cfg, L, ora = played_oracle(steps=3)
+    lib = _lib.lib()
+    ora.state.hdr["seed_lo"], ora.state.hdr["seed_hi"] = 0x89abcdef, 0x01234567
+    path = str(tmp_path / "snap.json").encode()
+    assert lib.agarcl_snapshot_write(C.byref(cfg), C.byref(L), ora.state.ptr, path) == 0
+    doc = json.load(open(path))
+    assert doc["seed"] == 0x89abcdef and doc["seed_hi"] == 0x01234567
+    back = StateView(L, ora.state.blob.copy())
+    back.hdr["seed_lo"], back.hdr["seed_hi"] = 1, 2
+    assert lib.agarcl_snapshot_read(C.byref(cfg), C.byref(L), back.ptr, path, 1) == 0
+    assert int(back.hdr["seed_lo"]) == 0x89abcdef and int(back.hdr["seed_hi"]) == 0x01234567
+    del doc["seed"], doc["seed_hi"]
+    json.dump(doc, open(path, "w"))
+    back.hdr["seed_lo"], back.hdr["seed_hi"] = 11, 22
+    assert lib.agarcl_snapshot_read(C.byref(cfg), C.byref(L), back.ptr, path, 1) == 0
+    assert int(back.hdr["seed_lo"]) == 11 and int(back.hdr["seed_hi"]) == 22
