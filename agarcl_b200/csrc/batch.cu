@@ -502,6 +502,7 @@ extern "C" int agarcl_batch_reset(agarcl_batch* b, const uint8_t* mask, void* st
   }
   // the reference ends reset() with _partial_observation (BaseEnvironment.hpp:202-203)
   // (a masked reset touches only the observations of the instances it resets)
+  if (b->cfg.ram_obs == 2) return AGARCL_OK;  // no grid observation in this mode
   const uint8_t* dm = mask ? b->d_mask : nullptr;
   auto clear_obs = [&]() -> cudaError_t {
     if (!mask) return cudaMemsetAsync(b->d_obs, 0, b->obs_bytes, s);
@@ -557,6 +558,15 @@ static int step_impl(agarcl_batch* b, cudaStream_t s, bool want_lists, bool* lis
     CK(ag::launch_step(P, s)); launches++;
     int frame = 0 - (tps - b->frames);
     if (frame >= 0) { int rc = render_frame(b, frame, s, 1); if (rc) return rc; launches++; }
+  } else if (b->cfg.ram_obs == 2) {
+    // structured observation only (agario-ram-v0): no grid frame is rendered at all
+    P.n_ticks = tps; P.do_begin = 1; P.do_end = 1;
+    const bool sorted = P.tick_barrier && b->sort_schedule;
+    if (sorted) { P.cost = b->d_cost; P.perm = b->perm_valid ? b->d_perm : nullptr; }
+    if (b->timing) { if (b->ev_used >= 3 * 2048) collect_timing(b); CK(cudaEventRecord(next_event(b), s)); }
+    CK(ag::launch_step(P, s)); launches++;
+    if (b->timing) CK(cudaEventRecord(next_event(b), s));
+    if (sorted) { CK(ag::launch_order(b->d_cost, b->d_perm, b->N, s)); b->perm_valid = true; launches++; }
   } else if (b->frames == 1) {
     P.n_ticks = tps; P.do_begin = 1; P.do_end = 1;
     const int fused = fuse_obs_clear(b, P, 0) ? 1 : 0;
@@ -585,7 +595,10 @@ static int step_impl(agarcl_batch* b, cudaStream_t s, bool want_lists, bool* lis
     P.n_ticks = 0; P.do_begin = 0; P.do_end = 1;
     CK(ag::launch_step(P, s)); launches++;
   }
-  if (b->d_ram) { int rc = render_ram(b, s, 1); if (rc) return rc; launches++; }
+  if (b->d_ram) {
+    int rc = render_ram(b, s, 1); if (rc) return rc; launches++;
+    if (b->timing && b->cfg.ram_obs == 2) CK(cudaEventRecord(next_event(b), s));  // (k_ram is this mode's observation kernel)
+  }
   b->launches_last_step = launches;
   return refill_replay(b, s);
 }

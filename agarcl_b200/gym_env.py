@@ -200,7 +200,7 @@ class BatchedAgarioEnv:
         extra = {k: kwargs[k] for k in ("device", "rng_mode", "obs_dtype", "instance_base") if k in kwargs}
         self._env = BatchedGridEnvironment(n_envs, a["num_agents"], a["ticks_per_step"], a["arena_size"], a["pellet_regen"],
                                            a["num_pellets"], a["num_viruses"], a["num_bots"], a["reward_type"], a["c_death"],
-                                           a["mode"], ram_obs=(obs_type == "ram"), **extra)
+                                           a["mode"], ram_obs=(2 if obs_type == "ram" else 0), **extra)
         self._env.configure_observation({k: kwargs[k] for k in _OBS_KEYS if k in kwargs})
         self._steps = None
 

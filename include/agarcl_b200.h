@@ -92,7 +92,8 @@ typedef struct agarcl_cfg {
   int32_t cap_viruses, cap_foods, cap_replay; /* 0 = defaults */
   int32_t device;           /* CUDA device ordinal */
   int32_t instance_base;    /* global index of local instance 0 (multi-GPU sharding; keys the RNG) */
-  int32_t ram_obs;          /* 1: every step also produces the structured observation (agarcl_batch_ram) */
+  int32_t ram_obs;          /* 1: every step also produces the structured observation (agarcl_batch_ram); 2: ONLY that one
+                               (agario-ram-v0: the grid frame is not rendered, agarcl_batch_obs stays zero) */
   int32_t reserved[2];
 } agarcl_cfg;
 

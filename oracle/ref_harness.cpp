@@ -133,6 +133,9 @@ static void fresh_reset(RefEnv* r) {
   r->env->reset();
 }
 
+static bool g_pool_silenced = false;  /* ref_pool_run has redirected cout / cerr for all its worker threads */
+struct NullBuf : std::streambuf { int overflow(int c) override { return c; } };
+
 extern "C" {
 
 void* ref_create(const agarcl_cfg* c) {
@@ -212,15 +215,18 @@ void ref_ram_clear(void* h) {
 void ref_ram_obs(void* h, int P, float* out) {
   auto* r = static_cast<RefEnv*>(h);
   r->bind_clock();
-  CoutSilencer quiet;
-  std::streambuf* olderr = std::cerr.rdbuf(quiet.sink.rdbuf());
+  /* GoBiggerObservation chats on cout / cerr ("Player id not found ..."): silenced per call, or once around a whole
+   * multi-threaded pool run (the stream buffers are process-wide: swapping them from several threads is a race) */
+  std::unique_ptr<CoutSilencer> quiet;
+  std::streambuf* olderr = nullptr;
+  if (!g_pool_silenced) { quiet.reset(new CoutSilencer()); olderr = std::cerr.rdbuf(quiet->sink.rdbuf()); }
   if (!r->ram) {
     r->ram.reset(new RefRamT(r->arena, r->arena, 0, 0, r->num_agents));
     r->ram->configure(1, r->grid, true, true, true, true);
   }
   auto& player = r->env->engine_.player(r->env->pids_[0]);
   r->ram->add_frame(player, r->env->engine_.game_state(), 0);
-  std::cerr.rdbuf(olderr);
+  if (olderr) std::cerr.rdbuf(olderr);
   for (auto& kv : r->ram->get_player_states().get_all_player_states()) {
     int pid = kv.first;
     if (pid < 0 || pid >= P) continue;
@@ -430,6 +436,7 @@ struct RefPool {
   agarcl_cfg cfg;
   std::vector<RefEnv*> envs;
   std::vector<std::mt19937> arng;
+  float p_feed = -1.0f, p_split = -1.0f;  /* < 0: a ~ U{0,1,2} (bench/go_bigger_example.py:100-103) */
 };
 
 void* ref_pool_create(const agarcl_cfg* c, int instances, unsigned base_seed) {
@@ -443,6 +450,16 @@ void* ref_pool_create(const agarcl_cfg* c, int instances, unsigned base_seed) {
     p->arng.emplace_back(base_seed * 7919u + (unsigned)i);
   }
   return p;
+}
+/* action mix of the pool's random-walk policy (feed w.p. p_feed, split w.p. p_split, else none) and, with boost > 0,
+ * every agent's first cell raised to that mass with Cell::set_mass (BASELINE configs[3]) */
+void ref_pool_profile(void* h, float p_feed, float p_split, unsigned boost) {
+  auto* p = static_cast<RefPool*>(h);
+  p->p_feed = p_feed;
+  p->p_split = p_split;
+  if (boost)
+    for (auto* r : p->envs)
+      for (int a = 0; a < p->cfg.num_agents; a++) ref_set_cell_mass(r, a, 0, boost);
 }
 void ref_pool_destroy(void* h) {
   auto* p = static_cast<RefPool*>(h);
@@ -460,19 +477,28 @@ double ref_pool_run(void* h, int threads, int steps, int with_obs) {
     RefEnv* r = p->envs[i];
     std::vector<int32_t> obs((size_t)r->forced->length());
     std::mt19937& arng = p->arng[i];
-    std::uniform_real_distribution<float> u(-1.0f, 1.0f);
+    std::uniform_real_distribution<float> u(-1.0f, 1.0f), u01(0.0f, 1.0f);
+    std::vector<float> ram;
+    const int P = c->num_agents + c->num_bots;
+    if (with_obs == 2) ram.resize((size_t)P * AGARCL_RAM_RECORD);
     for (int s = 0; s < steps; s++) {
       for (int a = 0; a < c->num_agents; a++) {
         dxdy[2 * a] = u(arng);
         dxdy[2 * a + 1] = u(arng);
-        act[a] = (int)(arng() % 3u);
+        if (p->p_feed < 0.0f) act[a] = (int)(arng() % 3u);
+        else { const float v = u01(arng); act[a] = v < p->p_feed ? 1 : (v < p->p_feed + p->p_split ? 2 : 0); }
       }
       ref_take_actions(r, dxdy.data(), act.data());
       ref_step(r, rew.data());
-      if (with_obs)
+      if (with_obs == 1)
         for (int a = 0; a < c->num_agents; a++) ref_obs(r, a, obs.data());
+      else if (with_obs == 2)  /* GoBiggerObservation::add_frame for every player + the records (the "ram" observation) */
+        ref_ram_obs(r, P, ram.data());
     }
   };
+  NullBuf nullbuf;  /* (a streambuf that drops everything is safe to share between the workers) */
+  std::streambuf *oldout = nullptr, *olderr = nullptr;
+  if (with_obs == 2) { oldout = std::cout.rdbuf(&nullbuf); olderr = std::cerr.rdbuf(&nullbuf); g_pool_silenced = true; }
   auto t0 = std::chrono::high_resolution_clock::now();
   {
     std::atomic<int> next(0);
@@ -485,6 +511,7 @@ double ref_pool_run(void* h, int threads, int steps, int with_obs) {
     for (auto& w : workers) w.join();
   }
   auto t1 = std::chrono::high_resolution_clock::now();
+  if (with_obs == 2) { std::cout.rdbuf(oldout); std::cerr.rdbuf(olderr); g_pool_silenced = false; }
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
