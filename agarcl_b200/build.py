@@ -20,12 +20,34 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
+def pybind_module_path():
+    import sysconfig
+    return os.path.join(HERE, "agarcl" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_pybind(force=False):
+    """The reference's Python module `agarcl` (environment/bindings.cpp) over the C ABI: csrc/pybind_agarcl.cpp ->
+    agarcl_b200/agarcl.<abi>.so, linked against libagarcl_b200.so next to it ($ORIGIN rpath)."""
+    import sysconfig
+    import pybind11
+    out, src = pybind_module_path(), os.path.join(CSRC, "pybind_agarcl.cpp")
+    deps = [src, LIB, os.path.join(HERE, "..", "include", "agarcl_b200.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    # the system g++ (what nvcc uses as -ccbin), NOT $CXX: the image's /opt/gcc links its own libstdc++ statically, which clashes with the
+    # interpreter's at run time
+    cmd = [os.environ.get("AGARCL_CXX", "g++"), "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-I" + pybind11.get_include(),
+           "-I" + sysconfig.get_paths()["include"], src, "-o", out, "-L" + HERE, "-lagarcl_b200", "-Wl,-rpath,$ORIGIN"]
     subprocess.check_call(cmd)
+    return out
+
+
+def build(force=False, verbose=False):
+    if force or needs_build():
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
+        subprocess.check_call(cmd)
+    build_pybind(force)
     return LIB
 
 

@@ -162,11 +162,11 @@ static bool fuse_obs_clear(const agarcl_batch* b, ag::SimParams& P, int frame) {
   P.zero_skip_vec = (uint32_t)(plane / 16);
   P.zero_vec_per_agent = (uint32_t)((size_t)(b->C - 1) * plane / 16);
   P.agent_stride_vec = (uint32_t)((size_t)b->frames * b->C * plane / 16);
-  // the whole observation in the engine-tick kernel: int32, rows of whole 16-byte vectors, masks fit the scratch
-  P.obs_finish = (b->fuse_clear >= 2 && b->cfg.obs_dtype == AGARCL_OBS_I32 && b->G % 4 == 0 &&
-                  (size_t)b->G * 4 <= (size_t)ag::kZeroTileBytes &&  // one row of channel 0 = one bulk store from the ones tile
-                  (size_t)b->G * 4 <= (size_t)(b->so.vcache - b->so.cellref)) ? 1 : 0;
-  if (P.obs_finish) P.tiles_bytes = ag::kZeroTileBytes + (((uint32_t)b->G * 4u + 127u) & ~127u);
+  // the whole observation in the engine-tick kernel: rows of whole 16-byte vectors, masks fit the scratch (1: int32, 2: int16)
+  P.obs_finish = (b->fuse_clear >= 2 && ((size_t)b->G * esz) % 16 == 0 &&
+                  (size_t)b->G * esz <= (size_t)ag::kZeroTileBytes &&  // one row of channel 0 = one bulk store from the ones tile
+                  (size_t)b->G * esz <= (size_t)(b->so.vcache - b->so.cellref)) ? (esz == 2 ? 2 : 1) : 0;
+  if (P.obs_finish) P.tiles_bytes = ag::kZeroTileBytes + (((uint32_t)b->G * (uint32_t)esz + 127u) & ~127u);
   return true;
 }
 
@@ -451,6 +451,14 @@ extern "C" int agarcl_batch_ram(agarcl_batch* b, float** dev_ptr, int64_t shape[
   if (!b->d_ram) return agarcl_set_error(AGARCL_ERR_STATE, "batch was created without cfg.ram_obs");
   *dev_ptr = b->d_ram;
   if (shape) { shape[0] = b->N; shape[1] = b->L.P; shape[2] = AGARCL_RAM_RECORD; }
+  return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_ram_host(agarcl_batch* b, float* out) {
+  if (!b || !out) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  if (!b->d_ram) return agarcl_set_error(AGARCL_ERR_STATE, "batch was created without cfg.ram_obs");
+  CK(cudaSetDevice(b->cfg.device));
+  CK(cudaMemcpy(out, b->d_ram, (size_t)b->N * b->L.P * AGARCL_RAM_RECORD * sizeof(float), cudaMemcpyDeviceToHost));
   return AGARCL_OK;
 }
 

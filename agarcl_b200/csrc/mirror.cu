@@ -381,12 +381,15 @@ static void expand_range(HostMirror* m, int lo, int hi, const uint32_t* zero_mas
       if (std::memcmp(o, nm + f * mw2, mw2 * 4) != 0) apply_mask_delta<T>(p + (size_t)f * m->C * plane, o, nm + f * mw2, m->G, m->MW);
     }
     const uint2* ne = reinterpret_cast<const uint2*>(cb + pk_off_entries(k)) + crec[1];
+    // (operands are masses / counts >= 0; the 16-bit dtype saturates exactly like the device's updates, sim_kernel.cu FinOps<int16_t>)
+    constexpr int32_t kTop = sizeof(T) == 2 ? 32767 : 2147483647;
     for (uint32_t e = 0; e < cnt; e++) {
       T& x = p[ne[e].x & kPkOffMask];
-      const T v = (T)(int32_t)ne[e].y;
+      const int32_t v32 = (int32_t)ne[e].y;
+      const T v = (T)(v32 > kTop ? kTop : v32);
       switch (ne[e].x >> 29) {
         case kPkSet: x = v; break;
-        case kPkAdd: x = (T)(x + v); break;
+        case kPkAdd: { const int64_t t = (int64_t)x + v32; x = (T)(t > kTop ? kTop : t); break; }
         case kPkMinNz: x = (x != 0 && x < v) ? x : v; break;
         default: x = x > v ? x : v; break;
       }

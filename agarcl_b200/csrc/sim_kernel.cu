@@ -2098,11 +2098,50 @@ __device__ __forceinline__ void zero_chunk(Ctx& c, uint32_t nvec) {
 // the in-view entities are scattered with L2 atomics.  Runs BEFORE repsawn_all_players, like the
 // reference (BaseEnvironment.hpp:96-101).  Same arithmetic as k_obs (obs_kernel.cu), int32 only.
 // ------------------------------------------------------------------------------------------------
+// Element updates of the scatter.  int32 (the reference's dtype): L2 reductions / atomics.  int16 (opt-in, half the bytes):
+// there are no 16-bit global atomics, so every update is a CAS on the containing 32-bit word (two grid cells share it),
+// saturating at 32767 like k_obs (obs_kernel.cu ObsOps<int16_t>); sums only grow and min / max / set are idempotent, so the
+// result does not depend on the order of the updates.
+template <typename T> struct FinOps;
+template <> struct FinOps<int32_t> {
+  static __device__ __forceinline__ void set_stream(int32_t* p, int v) { __stcs(p, v); }
+  static __device__ __forceinline__ void add_stream(int32_t* p, int v) { red_add_stream(p, v); }
+  static __device__ __forceinline__ void add(int32_t* p, int v) { atomicAdd(p, v); }
+  static __device__ __forceinline__ void set(int32_t* p, int v) { *p = v; }
+  static __device__ __forceinline__ void min_nz(int32_t* p, int v) {  // empty cell: take the mass; otherwise minimum (masses are > 0)
+    const int old = atomicCAS(p, 0, v);
+    if (old != 0) atomicMin(p, v);
+  }
+  static __device__ __forceinline__ void maxs(int32_t* p, int v) { atomicMax(p, v); }
+};
+template <> struct FinOps<int16_t> {
+  template <typename F> static __device__ __forceinline__ void rmw(int16_t* p, F f) {
+    unsigned* w = reinterpret_cast<unsigned*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+    const int sh = (reinterpret_cast<uintptr_t>(p) & 2) ? 16 : 0;
+    unsigned old = *reinterpret_cast<volatile unsigned*>(w), assumed;
+    do {
+      assumed = old;
+      const int16_t cur = (int16_t)((assumed >> sh) & 0xffffu);
+      const int16_t nv = f(cur);
+      if (nv == cur) break;
+      old = atomicCAS(w, assumed, (assumed & ~(0xffffu << sh)) | (((unsigned)(uint16_t)nv) << sh));
+    } while (old != assumed);
+  }
+  static __device__ __forceinline__ int16_t sat(int v) { return (int16_t)(v > 32767 ? 32767 : v); }
+  static __device__ __forceinline__ void set_stream(int16_t* p, int v) { set(p, v); }
+  static __device__ __forceinline__ void add_stream(int16_t* p, int v) { add(p, v); }
+  static __device__ __forceinline__ void add(int16_t* p, int v) { rmw(p, [v](int16_t c) { return sat((int)c + v); }); }
+  static __device__ __forceinline__ void set(int16_t* p, int v) { const int16_t s = sat(v); rmw(p, [s](int16_t) { return s; }); }
+  static __device__ __forceinline__ void min_nz(int16_t* p, int v) { const int16_t s = sat(v); rmw(p, [s](int16_t c) { return (c != 0 && c < s) ? c : s; }); }
+  static __device__ __forceinline__ void maxs(int16_t* p, int v) { const int16_t s = sat(v); rmw(p, [s](int16_t c) { return c > s ? c : s; }); }
+};
+
+template <typename T>
 __device__ void obs_finish_warp(Ctx& c) {
   const SimParams& P = c.P;
   const int G = P.obs_G, lane = c.lane, A = P.L.A, Pn = P.L.P;
   const size_t plane = (size_t)G * G;
-  int32_t* yrow = reinterpret_cast<int32_t*>(c.sm.cellref());  // [G]: the collision scratch is free now
+  T* yrow = reinterpret_cast<T*>(c.sm.cellref());  // [G]: the collision scratch is free now
   if (!c.vc_valid && P.observe_viruses) { build_virus_cache(c); c.vc_valid = true; }
   // the zero vectors of this instance must have landed before anything is scattered onto them
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -2115,7 +2154,7 @@ __device__ void obs_finish_warp(Ctx& c) {
   const uint32_t ones_tile = (uint32_t)__cvta_generic_to_shared(smem_raw + kZeroTileBytes);  // (present with obs_finish)
   const uint32_t yrow_s = (uint32_t)__cvta_generic_to_shared(yrow);
   for (int a = 0; a < A; a++) {
-    int32_t* out = reinterpret_cast<int32_t*>(P.obs) + ((size_t)c.inst_local * A + a) * ((size_t)P.agent_stride_vec * 4u);
+    T* out = reinterpret_cast<T*>(P.obs) + ((size_t)c.inst_local * A + a) * ((size_t)P.agent_stride_vec * (16u / sizeof(T)));
     const float4 s = c.sm.psum()[a];
     const float px = s.x, py = s.y;  // Player::x / y: NaN for a dead agent (quirk Q20)
     const uint32_t tot = __float_as_uint(s.z);
@@ -2130,14 +2169,14 @@ __device__ void obs_finish_warp(Ctx& c) {
     }
     for (int j = lane; j < G; j += 32) {
       float wy = py + ((float)j - centering) * view / (float)G;
-      yrow[j] = (0 <= wy && wy < W) ? 0 : -1;
+      yrow[j] = (0 <= wy && wy < W) ? (T)0 : (T)-1;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     {
       uint64_t zpolicy;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(zpolicy));
-      const uint32_t row_bytes = (uint32_t)G * 4u;
+      const uint32_t row_bytes = (uint32_t)G * (uint32_t)sizeof(T);
       for (int i = lane; i < G; i += 32) {
         float wx = px + ((float)i - centering) * view / (float)G;
         const uint32_t src = (0 <= wx && wx < W) ? yrow_s : ones_tile;
@@ -2195,8 +2234,8 @@ __device__ void obs_finish_warp(Ctx& c) {
           const bool hit = valid && grid_of(pq.x, pq.y, gx, gy);
           const uint32_t o = (uint32_t)gx * G + gy;
           if (hit) {
-            __stcs(out + o1 + o, 1);           // at_least_: data = mass (1)
-            red_add_stream(out + o2 + o, 1);  // total_mass_
+            FinOps<T>::set_stream(out + o1 + o, 1);  // at_least_: data = mass (1)
+            FinOps<T>::add_stream(out + o2 + o, 1);  // total_mass_
           }
           list2(hit, kPkSet, o1 + o, 1u, kPkAdd, o2 + o, 1u);
         };
@@ -2238,13 +2277,13 @@ __device__ void obs_finish_warp(Ctx& c) {
           const uint32_t vm = __float_as_uint(vk.w);
           bool last = true;
           if (hit) {
-            atomicAdd(out + o4 + o, (int)vm);
+            FinOps<T>::add(out + o4 + o, (int)vm);
             // at_least_ keeps the LAST writer in index order: write only if no later virus shares the cell
             for (int k2 = k + 1; k2 < nv; k2++) {
               int hx, hy;
               if (grid_of(vc[k2].x, vc[k2].y, hx, hy) && hx == gx && hy == gy) { last = false; break; }
             }
-            if (last) out[o3 + o] = (int)vm;
+            if (last) FinOps<T>::set(out + o3 + o, (int)vm);
           }
           list2(hit, kPkAdd, o4 + o, vm, last ? kPkSet : kPkAdd, last ? o3 + o : o4 + o, last ? vm : 0u);  // (not last: a no-op)
         }
@@ -2256,7 +2295,7 @@ __device__ void obs_finish_warp(Ctx& c) {
           int gx = 0, gy = 0;
           const bool hit = valid && grid_of(x, y, gx, gy);
           const uint32_t o = (uint32_t)gx * G + gy;
-          if (hit) atomicAdd(out + o5 + o, (int)m);
+          if (hit) FinOps<T>::add(out + o5 + o, (int)m);
           list2(hit, kPkAdd, o5 + o, m, kPkAdd, o5 + o, 0u);  // (entries come in pairs: the second is a no-op)
         };
         const float4 pcv = c.sm.pcell()[a];
@@ -2280,10 +2319,8 @@ __device__ void obs_finish_warp(Ctx& c) {
           const bool hit = valid && grid_of(x, y, gx, gy);
           const uint32_t o = (uint32_t)gx * G + gy;
           if (hit) {
-            int32_t* p6 = out + o6 + o;
-            int old = atomicCAS(p6, 0, (int)m);  // empty cell: take the mass; otherwise minimum (masses are > 0)
-            if (old != 0) atomicMin(p6, (int)m);
-            atomicMax(out + o7 + o, (int)m);
+            FinOps<T>::min_nz(out + o6 + o, (int)m);
+            FinOps<T>::maxs(out + o7 + o, (int)m);
           }
           list2(hit, kPkMinNz, o6 + o, m, kPkMax, o7 + o, m);
         };
@@ -2553,7 +2590,8 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
   zero_chunk(c, 0xffffffffu);  // whatever is left (n_ticks == 0, rounding)
 
   if (P.do_end) {
-    if (P.obs_finish) obs_finish_warp(c);
+    if (P.obs_finish == 1) obs_finish_warp<int32_t>(c);
+    else if (P.obs_finish == 2) obs_finish_warp<int16_t>(c);
     if (P.mode == 0) {
       // repsawn_all_players in map order: the r-th dead player takes draw pair r
       uint32_t rank_base = 0;

@@ -101,8 +101,8 @@ struct SimParams {
   uint32_t zero_vec_per_agent;  // 16-byte vectors to clear per agent frame
   uint32_t zero_skip_vec;       // vectors of channel 0 in front of them
   uint32_t agent_stride_vec;    // vectors between consecutive agents' frame slots
-  // fused observation finish (int32, one frame): after the last tick each warp also writes channel 0
-  // and scatters the entities of its instance, so the step is ONE kernel.  obs_finish == 0: k_obs does it.
+  // fused observation finish (one frame): after the last tick each warp also writes channel 0
+  // and scatters the entities of its instance, so the step is ONE kernel.  obs_finish == 0: k_obs does it; 1: int32; 2: int16.
   int32_t obs_finish, obs_G, obs_C;
   int32_t zero_chunks;          // > 0: the clear is queued in this many pieces (4 per tick); 0: spread over the ticks
   int32_t observe_cells, observe_others, observe_viruses, observe_pellets;

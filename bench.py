@@ -534,12 +534,50 @@ def run_ours(args):
     # std::sort tie warning AGARCL_FLAG_PCD_TIE) in that many instances since their reset
     flags_seen, flag_counts = b.flags()
 
+    # ---- the opt-in int16 observation (half the observation bytes; SURVEY 7 hard part 4): same workload, same game age, the
+    # fused single-kernel step with 16-bit cells, timed on the device like `value`
+    int16_profile = None
+    if not ram_mode and not args.no_int16:
+        from agarcl_b200 import OBS_I16
+        cfg16 = make_cfg(n_instances=N, device=local_rank, instance_base=rank * N, obs_dtype=OBS_I16, **WORKLOAD)
+        b16 = Batch(cfg16)
+        b16.seed(np.arange(N, dtype=np.uint64) + np.uint64(rank * N + 1))
+        b16.reset()
+        if cf["boost"]:
+            for i in range(N):
+                sv16 = b16.download_state(i)
+                for a in range(A):
+                    sv16.cells[a][0]["mass"] = cf["boost"]
+                b16.upload_state(i, sv16)
+
+        def step16(i):
+            b16.set_actions_device(dxdy[i % n_act].data_ptr(), act[i % n_act].data_ptr(), stream)
+            b16.step(stream)
+
+        for i in range(args.settle + W_):
+            step16(i)
+        barrier()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record()
+        for i in range(K):
+            step16(i)
+        i1.record()
+        barrier()
+        ms16 = i0.elapsed_time(i1) / K
+        l16 = b16.launches_per_step()
+        b16.close()
+        int16_profile = {"ms_per_step": ms16, "launches_per_step": l16}
+
     # max over ranks
     if world > 1:
         t = torch.tensor([ms, e2e_s, sim_ms, obs_ms, dense_s or 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s, sim_ms, obs_ms, dense_max = [float(x) for x in t.tolist()]
         dense_s = dense_max if dense_s is not None else None
+        if int16_profile is not None:
+            t16 = torch.tensor([int16_profile["ms_per_step"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t16, op=dist.ReduceOp.MAX)
+            int16_profile["ms_per_step"] = float(t16.item())
         fl = torch.tensor([flags_seen], device="cuda", dtype=torch.int64)
         gathered = [torch.zeros_like(fl) for _ in range(world)]
         dist.all_gather(gathered, fl)
@@ -579,6 +617,16 @@ def run_ours(args):
             a["value"] = world * N / (a["ms_per_step"] * 1e-3)
         age_profile.append({"age_env_steps": args.settle, "ms_per_step": ms / K, "value": value})
         whole = ab["step"] * value / 1e9 / world
+        int16_line = None
+        if int16_profile is not None:
+            ab16 = algorithmic_bytes(n_pel=int(sv.hdr["n_pellets"]), n_vir=int(sv.hdr["n_viruses"]), n_food=int(sv.hdr["n_foods"]),
+                                     n_cell=n_cell, P=b.layout.P, A=A, s_obs=2)
+            v16 = world * N / (int16_profile["ms_per_step"] * 1e-3)
+            int16_line = {"obs_dtype": "int16 (opt-in, saturating at 32767; the reference's is int32)", "age_env_steps": args.settle,
+                          "ms_per_step": int16_profile["ms_per_step"], "value": v16, "unit": UNIT,
+                          "launches_per_step": int16_profile["launches_per_step"],
+                          "algorithmic_bytes_per_env_step": ab16["step"],
+                          "roofline_frac": ab16["step"] * v16 / world / 1e9 / peak}
         if ram_mode:
             e2e_obj = {"value": world * N * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                        "note": "vector-env calls a user makes (BatchedGridEnvironment.step with ram_obs): pinned host actions copied in; every "
@@ -610,6 +658,7 @@ def run_ours(args):
                            "rng": "philox4x32-10 per instance", "state_flags_seen": flags_seen,
                            "state_flag_instances": flag_counts, "instances_checked_for_flags": N},
                 "age_profile": age_profile,
+                "int16_profile": int16_line,
                 "roofline": rf(dom),
                 "roofline_all": {"kernels": [rf(k) for k in kern],
                                  "whole_step": {"achieved": whole, "peak": peak, "unit": "GB/s", "frac": whole / peak,
@@ -638,6 +687,7 @@ def main():
     ap.add_argument("--settle", type=int, default=None, help="untimed env-steps before the timed region: game age (both arms; default: the config's)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-int16", action="store_true", help="skip the second measurement with the opt-in int16 observation")
     ap.add_argument("--tps", type=int, default=None, help="diagnostic only: ticks per env-step (the workload's is 4)")
     ap.add_argument("--_refchild", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--_threads", type=int, default=None, help=argparse.SUPPRESS)

@@ -245,6 +245,9 @@ int agarcl_batch_mirror_timing(const agarcl_batch* b, uint64_t out[4]);
 #define AGARCL_RAM_RECORD (AGARCL_RAM_OFF_CLONE + 8 * AGARCL_RAM_KC) /* 1224 floats per player */
 /* Device pointer to the records [N, P, AGARCL_RAM_RECORD] float32 (cfg.ram_obs must be 1). */
 int agarcl_batch_ram(agarcl_batch* b, float** dev_ptr, int64_t shape[3]);
+/* get_state() of agarcl.GoBiggerEnvironment (bindings.cpp:28-47) with a HOST buffer: all records [N, P, AGARCL_RAM_RECORD]
+ * copied out (synchronises the device). */
+int agarcl_batch_ram_host(agarcl_batch* b, float* out);
 /* Run only the structured-observation kernel on the current state (tests). */
 int agarcl_batch_render_ram(agarcl_batch* b, void* stream);
 

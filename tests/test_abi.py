@@ -103,3 +103,35 @@ def test_take_actions_size_check_like_reference():
     assert env.observation_shape() == (8, 128, 128)
     env.configure_observation({"grid_size": 64, "observe_others": False, "num_frames": 2})
     assert env.observation_shape() == (12, 64, 64)
+
+
+def test_compiled_agarcl_module_surface():
+    """The pybind11 module `agarcl` (agarcl_b200/csrc/pybind_agarcl.cpp) is compiled, imports by the reference's name, and
+    exposes the classes / methods environment/bindings.cpp:94-135,181-374 binds; errors come back as RuntimeError."""
+    import agarcl
+    assert agarcl.has_screen_env is False
+    for cls in ("GridEnvironment", "GoBiggerEnvironment", "FoodInfo", "VirusInfo", "SporeInfo", "CloneInfo", "GlobalState",
+                "PlayerState", "PlayerStates"):
+        assert hasattr(agarcl, cls), cls
+    for m in ("seed", "configure_observation", "observation_shape", "dones", "take_actions", "reset", "render", "step", "get_state",
+              "get_frame", "close", "save_env_state"):
+        assert hasattr(agarcl.GridEnvironment, m), m
+    for m in ("configure_observation", "get_state", "take_actions", "dones", "observation_shape", "seed", "reset", "step", "render",
+              "close", "load_env_state", "save_env_state"):
+        assert hasattr(agarcl.GoBiggerEnvironment, m), m
+    env = agarcl.GridEnvironment(2, 4, 1000, True, 1000, 25, 25, 1, 0, 0)
+    assert env.observation_shape() == (8, 128, 128)
+    env.configure_observation({"grid_size": 64, "observe_others": False, "num_frames": 2})
+    assert env.observation_shape() == (12, 64, 64)
+    with pytest.raises(RuntimeError):
+        agarcl.GridEnvironment(1, 4, 1000, True, 1000, 25, 25, 1, 0, 11)  # Engine::set_mode throws on a bad mode
+    with pytest.raises(TypeError):
+        agarcl.GridEnvironment(1, 4)  # the ten positional arguments of bindings.cpp:102
+    g = agarcl.GoBiggerEnvironment(512, 512, 1000, 1, 4, 300, True, 200, 4, 5, 1)  # defaults: c_death, mode_number, load_env_snapshot, agent_view
+    assert g.observation_shape() == (0, 512, 512)
+    gs = agarcl.GlobalState(width=3, height=4, frame_limit=5, last_frame=0, team_num=2)
+    assert str(gs) == "GlobalState(map_width=3, map_height=4, frame_limit=5, team_num=2)"
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            env.reset()

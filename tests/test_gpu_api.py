@@ -153,14 +153,16 @@ def test_int16_observation_matches_int32():
         e.seed(9)
         e.reset()
     rng = np.random.default_rng(2)
-    for st in range(30):
+    for st in range(60):
         dxdy = rng.uniform(-1, 1, size=(32, 2)).astype(np.float32)
         act = rng.integers(0, 3, size=32).astype(np.int32)
         o32, _, _ = e32.step(dxdy, act)
         o16, _, _ = e16.step(dxdy, act)
+        assert o16.dtype == torch.int16
+        assert torch.equal(o32.clamp(-32768, 32767).to(torch.int16), o16), st
     torch.cuda.synchronize()
-    assert o16.dtype == torch.int16
-    assert torch.equal(o32.clamp(-32768, 32767).to(torch.int16), o16)
+    # the int16 frame comes out of the fused step kernel like the int32 one (no separate observation kernel)
+    assert e16.batch.launches_per_step() == e32.batch.launches_per_step() == 2  # k_step + k_order
 
 
 def test_strict_reference_frame_quirk_q11():
@@ -421,3 +423,72 @@ def test_flags_reduced_over_the_batch():
         b.upload_state(i, sv)
     assert e.flags() == (0x041, {"FOOD_OVERFLOW": 2, "PCD_TIE": 2})
     e.close()
+
+
+def test_compiled_agarcl_module_drop_in_against_oracle(tmp_path):
+    """`import agarcl` (the COMPILED pybind11 module, agarcl_b200/csrc/pybind_agarcl.cpp): GridEnvironment and GoBiggerEnvironment
+    used exactly as gym_agario/AgarioEnv.py uses the reference's module, against the oracle with the seed's mt19937_64 stream."""
+    import agarcl
+    from _helpers import Oracle, oracle_lib
+    from agarcl_b200 import make_cfg, RNG_REPLAY
+    oracle_lib().oracle_set_trig_mode(1)
+    env = agarcl.GridEnvironment(2, 4, 500, True, 300, 5, 6, 1, 0, 0)
+    env.seed(77)
+    env.reset()
+    cfg = make_cfg(num_agents=2, ticks_per_step=4, arena_size=500, num_pellets=300, num_viruses=5, num_bots=6, rng_mode=RNG_REPLAY,
+                   cap_replay=16384)
+    ora = Oracle(cfg)
+    ora.seed_mt(77, 16384)
+    ora.reset()
+    L = ora.L
+    agents_in_map_order = [p for p in list(L.order)[:L.P] if p < L.A]
+    first = env.get_state()
+    assert [np.array_equal(first[a], ora.obs(a)) for a in range(2)] == [True, True] and env.dones() == [False, False]
+    rng = np.random.default_rng(0)
+    for st in range(40):
+        acts = [(float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1)), int(rng.integers(0, 3))) for _ in range(2)]
+        env.take_actions(acts)
+        rew = env.step()
+        ora.set_actions(np.array([[a[0], a[1]] for a in acts], np.float32), np.array([a[2] for a in acts], np.int32))
+        orew, odone, oobs = ora.step(with_obs=True)
+        assert rew == [float(orew[p]) for p in agents_in_map_order]  # quirk Q15 ordering
+        assert env.dones() == [bool(x) for x in odone]
+        state = env.get_state()
+        assert len(state) == 2 and state[0].shape == (8, 128, 128) and state[0].dtype == np.int32 and state[0].flags.owndata
+        for a in range(2):
+            assert np.array_equal(state[a], oobs[a])
+    with pytest.raises(RuntimeError, match="does not match number of agents"):
+        env.take_actions([(0.0, 0.0, 0)])
+    env.save_env_state(str(tmp_path / "s.json"))
+    assert (tmp_path / "s.json").stat().st_size > 1000
+    env.close()
+    # GoBiggerEnvironment.get_state(): [{"global_state", "player_states"}] with the bound info classes
+    g = agarcl.GoBiggerEnvironment(512, 512, 1000, 1, 4, 300, True, 200, 4, 5, 1)
+    g.seed(5)
+    g.reset()
+    cfg = make_cfg(num_agents=1, arena_size=300, num_pellets=200, num_viruses=4, num_bots=5, rng_mode=RNG_REPLAY, cap_replay=16384)
+    ora = Oracle(cfg)
+    ora.seed_mt(5, 16384)
+    ora.reset()
+    ora.ram_clear()
+    rng = np.random.default_rng(4)
+    for st in range(25):
+        a = (float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1)), int(rng.integers(0, 3)))
+        g.take_actions([a])
+        g.step()
+        ora.set_actions(np.array([[a[0], a[1]]], np.float32), np.array([a[2]], np.int32))
+        ora.step_with_ram()
+    st = g.get_state()
+    assert len(st) == 1 and set(st[0]) == {"global_state", "player_states"} and st[0]["global_state"].get_map_width() == 512
+    ps = st[0]["player_states"].get_all_player_states()
+    assert set(ps) == {p for p in range(6) if ora.ram[p, :4].sum() > 0}
+    for p, s in ps.items():
+        rec = ora.ram[p]
+        assert [len(s.get_food_infos()), len(s.get_virus_infos()), len(s.get_spore_infos()), len(s.get_clone_infos())] == \
+            [int(min(rec[0], 192)), int(min(rec[1], 16)), int(min(rec[2], 32)), int(min(rec[3], 32))]
+        assert s.get_score() == float(rec[4]) and s.get_player_id() == p
+        c0 = s.get_clone_infos()[0]
+        assert np.float32(c0.position.x) == rec[968] and np.float32(c0.get_position_y()) == rec[969] and np.float32(c0.radius) == rec[970]
+        assert c0.owner == p and c0.teamId == 0
+    assert g.observation_shape() == (25, 512, 512)
+    g.close()
