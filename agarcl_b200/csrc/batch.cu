@@ -22,7 +22,7 @@
 
 namespace ag {
 cudaError_t launch_step(const SimParams& P, cudaStream_t stream);
-cudaError_t launch_order(const uint32_t* cost, uint32_t* perm, int N, cudaStream_t stream);
+cudaError_t launch_order(const uint32_t* cost, uint32_t* perm, int N, uint32_t* sched, cudaStream_t stream);
 cudaError_t launch_obs(const ObsParams& P, cudaStream_t stream);
 cudaError_t launch_reset(const ResetParams& P, cudaStream_t stream);
 cudaError_t launch_ram(const RamParams& P, cudaStream_t stream);
@@ -48,6 +48,8 @@ struct agarcl_batch {
   uint64_t* d_seeds = nullptr;
   uint8_t* d_mask = nullptr;
   uint32_t* d_tickets = nullptr;  // k_step's ticket counter pair (self-rewinding)
+  uint32_t* d_sched = nullptr;   // [2] schedule selector of k_step (SimParams::sched); AGARCL_AUTO_SCHEDULE=0 turns it off
+  int auto_schedule = 1;
   uint32_t *d_cost = nullptr, *d_perm = nullptr;  // per-instance cost of the last step and the cost-sorted schedule made from it (k_order)
   bool perm_valid = false;
   int sort_schedule = 1;  // AGARCL_SORT_SCHEDULE=0 turns the cost-sorted schedule off (A/B timing)
@@ -122,6 +124,7 @@ static void fill_sim_params(const agarcl_batch* b, ag::SimParams& P) {
   P.tickets = b->d_tickets;
   P.cost = nullptr;
   P.perm = nullptr;
+  P.sched = nullptr;
   P.N = b->N;
   P.instance_base = b->cfg.instance_base;
   P.mode = b->cfg.mode_number;
@@ -258,7 +261,7 @@ extern "C" int agarcl_batch_destroy(agarcl_batch* b) {
   cudaFree(b->d_ram);
   cudaFree(b->d_state); cudaFree(b->d_obs); cudaFree(b->d_rewards); cudaFree(b->d_dones); cudaFree(b->d_before);
   cudaFree(b->d_dxdy); cudaFree(b->d_act); cudaFree(b->d_replay); cudaFree(b->d_seeds); cudaFree(b->d_mask); cudaFree(b->d_tickets); cudaFree(b->d_cost); cudaFree(b->d_perm);
-  cudaFree(b->d_fresh); cudaFree(b->d_flagbuf);
+  cudaFree(b->d_fresh); cudaFree(b->d_flagbuf); cudaFree(b->d_sched);
   cudaFree(b->d_lut_radius); cudaFree(b->d_lut_speed); cudaFree(b->d_lut_split);
   for (cudaEvent_t e : b->ev) cudaEventDestroy(e);
   delete b;
@@ -321,6 +324,9 @@ extern "C" int agarcl_batch_create(const agarcl_cfg* cfg, agarcl_batch** out) {
   ALLOC(b->d_cost, (size_t)b->N * sizeof(uint32_t));
   ALLOC(b->d_perm, (size_t)b->N * sizeof(uint32_t));
   cudaMemset(b->d_tickets, 0, 2 * sizeof(uint32_t));
+  ALLOC(b->d_sched, 2 * sizeof(uint32_t));
+  { const uint32_t init[2] = {1u, 0u}; cudaMemcpy(b->d_sched, init, sizeof(init), cudaMemcpyHostToDevice); }
+  if (const char* e = std::getenv("AGARCL_AUTO_SCHEDULE")) b->auto_schedule = std::atoi(e);
   ALLOC(b->d_fresh, (size_t)b->N);
   cudaMemset(b->d_fresh, 1, (size_t)b->N);
   ALLOC(b->d_flagbuf, 33 * sizeof(uint32_t));
@@ -570,11 +576,11 @@ static int step_impl(agarcl_batch* b, cudaStream_t s, bool want_lists, bool* lis
     // structured observation only (agario-ram-v0): no grid frame is rendered at all
     P.n_ticks = tps; P.do_begin = 1; P.do_end = 1;
     const bool sorted = P.tick_barrier && b->sort_schedule;
-    if (sorted) { P.cost = b->d_cost; P.perm = b->perm_valid ? b->d_perm : nullptr; }
+    if (sorted) { P.cost = b->d_cost; P.perm = b->perm_valid ? b->d_perm : nullptr; P.sched = b->auto_schedule ? b->d_sched : nullptr; }
     if (b->timing) { if (b->ev_used >= 3 * 2048) collect_timing(b); CK(cudaEventRecord(next_event(b), s)); }
     CK(ag::launch_step(P, s)); launches++;
     if (b->timing) CK(cudaEventRecord(next_event(b), s));
-    if (sorted) { CK(ag::launch_order(b->d_cost, b->d_perm, b->N, s)); b->perm_valid = true; launches++; }
+    if (sorted) { CK(ag::launch_order(b->d_cost, b->d_perm, b->N, P.sched, s)); b->perm_valid = true; launches++; }
   } else if (b->frames == 1) {
     P.n_ticks = tps; P.do_begin = 1; P.do_end = 1;
     const int fused = fuse_obs_clear(b, P, 0) ? 1 : 0;
@@ -583,11 +589,11 @@ static int step_impl(agarcl_batch* b, cudaStream_t s, bool want_lists, bool* lis
       *lists_made = true;
     }
     const bool sorted = P.tick_barrier && b->sort_schedule;
-    if (sorted) { P.cost = b->d_cost; P.perm = b->perm_valid ? b->d_perm : nullptr; }
+    if (sorted) { P.cost = b->d_cost; P.perm = b->perm_valid ? b->d_perm : nullptr; P.sched = b->auto_schedule ? b->d_sched : nullptr; }
     if (b->timing) { if (b->ev_used >= 3 * 2048) collect_timing(b); CK(cudaEventRecord(next_event(b), s)); }
     CK(ag::launch_step(P, s)); launches++;
     if (b->timing) CK(cudaEventRecord(next_event(b), s));
-    if (sorted) { CK(ag::launch_order(b->d_cost, b->d_perm, b->N, s)); b->perm_valid = true; launches++; }
+    if (sorted) { CK(ag::launch_order(b->d_cost, b->d_perm, b->N, P.sched, s)); b->perm_valid = true; launches++; }
     if (!P.obs_finish) { int rc = render_frame(b, 0, s, 1, fused); if (rc) return rc; launches++; }
     if (b->timing) CK(cudaEventRecord(next_event(b), s));
   } else {

@@ -111,6 +111,7 @@ struct Ctx {
   bool lanes_dirty;     // players_collision changed players: lanes must reload their registers
   uint32_t pre_lo, pre_hi;  // players whose move + self-collisions of this tick are already done (premove_players)
   long long work, t_mark;   // cycles this instance has worked (waiting at the alignment barriers excluded) / start of the current stretch
+  int tb;               // the alignment barriers of this launch (P.tick_barrier, or 0 when the launch runs the free-running schedule)
   int inst_local;
   int pos;              // position of the instance in this launch's schedule (the host mirror's lists are laid out by position)
   float W;
@@ -604,6 +605,7 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
   const int nw = blockDim.x >> 5;
   volatile uint32_t* mine = mailbox(P, smem_raw, warp);
   uint32_t nb = 0;
+  __syncwarp();  // the mailbox lies over scratch the lanes read until the end of the previous tick (collision snapshot, removal lists)
   if (c && c->tick % 10u != 0u) {
     const int Pn = P.L.P;
     for (int base = 0; base < Pn; base += 32) {
@@ -2366,7 +2368,7 @@ __device__ void engine_tick(Ctx& c, LaneState& ls) {
   c.nvrem = 0;
   const int P = c.P.L.P;
   if (c.lanes_dirty) { ls.fresh = false; c.lanes_dirty = false; }
-  if (c.P.tick_barrier & 2) {  // the pair solver, pooled over the CTA; the warps enter the player loop together behind it
+  if (c.tb & 2) {  // the pair solver, pooled over the CTA; the warps enter the player loop together behind it
     extern __shared__ __align__(128) uint8_t smem_raw[];
     premove_players(c.P, smem_raw, &c, (int)(threadIdx.x >> 5), c.lane);
   } else {
@@ -2382,13 +2384,13 @@ __device__ void engine_tick(Ctx& c, LaneState& ls) {
     tick_players_block(c, base, tmp);
   }
   zero_chunk(c, c.zchunk);
-  if (c.P.tick_barrier & 16) { c.work += clock64() - c.t_mark; align_barrier(c.P.align_group); c.t_mark = clock64(); }
+  if (c.tb & 16) { c.work += clock64() - c.t_mark; align_barrier(c.P.align_group); c.t_mark = clock64(); }
   apply_removals(c);
   zero_chunk(c, c.zchunk);
-  if (c.P.tick_barrier & 4) { c.work += clock64() - c.t_mark; align_barrier(c.P.align_group); c.t_mark = clock64(); }  // ... and the cross-player sweep
+  if (c.tb & 4) { c.work += clock64() - c.t_mark; align_barrier(c.P.align_group); c.t_mark = clock64(); }  // ... and the cross-player sweep
   players_collision(c);
   zero_chunk(c, c.zchunk);
-  if (c.P.tick_barrier & 8) { c.work += clock64() - c.t_mark; align_barrier(c.P.align_group); c.t_mark = clock64(); }
+  if (c.tb & 8) { c.work += clock64() - c.t_mark; align_barrier(c.P.align_group); c.t_mark = clock64(); }
   move_foods(c);
   if (c.P.L.regen && c.tick % 120u == 0u) regen(c);
   c.tick++;
@@ -2425,8 +2427,9 @@ __device__ void respawn_player(Ctx& c, int p, uint32_t k) {
 // kernel: BaseEnvironment::step for one instance per warp
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_raw, const int inst, const int pos, const int warp,
-                                              const int lane, uint32_t& mbar_phase) {
+                                              const int lane, uint32_t& mbar_phase, const int tb) {
   Ctx c(P);
+  c.tb = tb;
   c.lane = lane;
   c.pos = pos;
   c.work = 0; c.t_mark = clock64();
@@ -2584,7 +2587,7 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
     // number of barriers, so the warps move through their instances in rounds (k_step: cost-sorted stripes); what a
     // warp waits for the slowest one is far less than what the shared fetch saves (2.22 -> 1.41 ms per steady-state
     // step with the sorted schedule).  Finer alignment (per solver batch, more phases) loses more than it gains.
-    if (P.tick_barrier & 1) { c.work += clock64() - c.t_mark; align_barrier(P.align_group); c.t_mark = clock64(); }
+    if (c.tb & 1) { c.work += clock64() - c.t_mark; align_barrier(P.align_group); c.t_mark = clock64(); }
     engine_tick(c, ls);
   }
   zero_chunk(c, 0xffffffffu);  // whatever is left (n_ticks == 0, rounding)
@@ -2665,6 +2668,11 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
     hdr->n_pellets = c.n_pellets; hdr->n_viruses = c.n_viruses; hdr->n_foods = c.n_foods;
     hdr->rng_cursor = c.cursor; hdr->flags = c.flags; hdr->done_sticky = c.done_sticky;
   }
+  if (P.sched) {  // instances that hold a multi-cell player when the launch ends: k_order picks the next launch's schedule from the count
+    bool multi = false;
+    for (int p = lane; p < Pn; p += 32) multi |= __float_as_int(c.sm.psum()[p].w) >= 2;
+    if (__ballot_sync(AG_FULL, multi) && lane == 0) atomicAdd(P.sched + 1, 1u);
+  }
   if (P.cost && lane == 0) {  // what the instance cost this step: next step's schedule puts equals together (k_order)
     const long long w = c.work + (clock64() - c.t_mark);
     P.cost[inst] = (uint32_t)(w < 0xffffffffll ? w : 0xffffffffll);
@@ -2712,7 +2720,12 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   uint32_t mbar_phase = 0u;
-  if (P.tick_barrier) {
+  // The schedule of this launch.  Aligned warps pay for the slowest instance of their CTA at every barrier; that buys the
+  // shared instruction fetch mature games need, but young games (every player one cell: short, uniform ticks) run ~10 %
+  // faster free.  k_order decides for the NEXT launch from what this one counts: the aligned schedule as soon as 5 % of the
+  // instances hold a multi-cell player (P.sched[0]; nullptr: always what tick_barrier says).
+  const int tb = (P.sched && *reinterpret_cast<volatile const uint32_t*>(P.sched) == 0u) ? 0 : P.tick_barrier;
+  if (tb) {
     // Aligned warps move through their instances in rounds (every instance runs the same number of barriers), so the
     // schedule is static: in round r this CTA takes the r-th stripe of consecutive positions of the cost-sorted order
     // `perm` (k_order: most expensive first, so the instances of one round of one CTA cost about the same and nobody
@@ -2723,18 +2736,18 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
     const uint32_t nw = blockDim.x >> 5, per_round = gridDim.x * nw;
     const uint32_t full = (uint32_t)P.N / per_round, rem = (uint32_t)P.N - full * per_round;
     const uint32_t wl = (rem + gridDim.x - 1u) / gridDim.x;  // stripe width of the last round
-    const int bars_rest = __popc((unsigned)P.tick_barrier & 28u);  // barriers of a tick behind the pair solver
+    const int bars_rest = __popc((unsigned)tb & 28u);  // barriers of a tick behind the pair solver
     for (uint32_t r = 0; r <= full; r++) {
       const uint32_t k = (r & 1u) ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
       const uint32_t width = r < full ? nw : wl;
       const uint32_t t = r * per_round + k * width + (uint32_t)warp;
       if ((uint32_t)warp < width && t < (uint32_t)P.N) {
         const uint32_t inst = P.perm ? P.perm[t] : t;
-        step_instance(P, smem_raw, P.inst_first + (int)inst, (int)t, warp, lane, mbar_phase);
+        step_instance(P, smem_raw, P.inst_first + (int)inst, (int)t, warp, lane, mbar_phase, tb);
       } else {  // no instance in this round: arrive at its barriers, and help with the pooled pair solver
         for (int tk = 0; tk < P.n_ticks; tk++) {
-          if (P.tick_barrier & 1) align_barrier(P.align_group);
-          if (P.tick_barrier & 2) premove_players(P, smem_raw, nullptr, warp, lane);
+          if (tb & 1) align_barrier(P.align_group);
+          if (tb & 2) premove_players(P, smem_raw, nullptr, warp, lane);
           for (int b = 0; b < bars_rest; b++) align_barrier(P.align_group);
         }
       }
@@ -2746,7 +2759,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
     if (lane == 0) t = atomicAdd(P.tickets, 1u);
     t = __shfl_sync(AG_FULL, t, 0);
     if (t >= (uint32_t)P.N) break;
-    step_instance(P, smem_raw, P.inst_first + (int)t, (int)t, warp, lane, mbar_phase);
+    step_instance(P, smem_raw, P.inst_first + (int)t, (int)t, warp, lane, mbar_phase, 0);
   }
   if (lane == 0) {
     const uint32_t left = atomicAdd(P.tickets + 1, 1u);
@@ -2757,9 +2770,13 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
 // Cost-sorted schedule for the next step (one CTA): perm = instance indices ordered by the cycles they worked in this
 // step, most expensive first -- a 256-bucket counting sort on the cost relative to the maximum is all the precision
 // the schedule needs (the order inside a bucket is arbitrary; it only moves instances between warps, never results).
-__global__ void __launch_bounds__(1024) k_order(const uint32_t* __restrict__ cost, uint32_t* __restrict__ perm, int N) {
+__global__ void __launch_bounds__(1024) k_order(const uint32_t* __restrict__ cost, uint32_t* __restrict__ perm, int N, uint32_t* sched) {
   __shared__ uint32_t s_max, cnt[256];
   const int tid = threadIdx.x;
+  if (sched && tid == 0) {  // aligned schedule from 5 % multi-cell instances on (k_step), free-running below
+    sched[0] = (sched[1] * 20u >= (uint32_t)N) ? 1u : 0u;
+    sched[1] = 0u;
+  }
   if (tid == 0) s_max = 1u;
   if (tid < 256) cnt[tid] = 0u;
   __syncthreads();
@@ -2789,8 +2806,8 @@ __global__ void __launch_bounds__(1024) k_order(const uint32_t* __restrict__ cos
   __syncthreads();
   for (int i = tid; i < N; i += 1024) perm[atomicAdd(&cnt[bucket(cost[i])], 1u)] = (uint32_t)i;
 }
-cudaError_t launch_order(const uint32_t* cost, uint32_t* perm, int N, cudaStream_t stream) {
-  k_order<<<1, 1024, 0, stream>>>(cost, perm, N);
+cudaError_t launch_order(const uint32_t* cost, uint32_t* perm, int N, uint32_t* sched, cudaStream_t stream) {
+  k_order<<<1, 1024, 0, stream>>>(cost, perm, N, sched);
   return cudaGetLastError();
 }
 

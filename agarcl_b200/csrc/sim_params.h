@@ -79,6 +79,8 @@ struct SimParams {
   uint32_t* tickets;       // [2] persistent-grid work counter: next instance, warps that have left (k_step without alignment)
   uint32_t* cost;          // [N] cycles every instance worked in this step (nullptr: not wanted)
   const uint32_t* perm;    // [N] cost-sorted instance order of the previous step (nullptr: identity)
+  uint32_t* sched;         // [2] or nullptr: [0] schedule of this launch (1: aligned as tick_barrier says, 0: free-running), set by k_order
+                           // from [1], the instances that held a multi-cell player at the end of the previous launch
   int32_t N;
   int32_t instance_base;
   int32_t n_ticks;         // ticks to run in this launch

@@ -554,7 +554,21 @@ def run_ours(args):
             b16.set_actions_device(dxdy[i % n_act].data_ptr(), act[i % n_act].data_ptr(), stream)
             b16.step(stream)
 
-        for i in range(args.settle + W_):
+        young16 = None
+        done16 = 0
+        if args.settle > young_at:  # the young-game figure on the way, like the int32 arm's age_profile
+            for i in range(young_at + W_):
+                step16(i)
+            barrier()
+            j0, j1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            j0.record()
+            for i in range(K):
+                step16(i)
+            j1.record()
+            barrier()
+            young16 = j0.elapsed_time(j1) / K
+            done16 = young_at + W_ + K
+        for i in range(max(0, args.settle - done16) + W_):
             step16(i)
         barrier()
         i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -566,7 +580,7 @@ def run_ours(args):
         ms16 = i0.elapsed_time(i1) / K
         l16 = b16.launches_per_step()
         b16.close()
-        int16_profile = {"ms_per_step": ms16, "launches_per_step": l16}
+        int16_profile = {"ms_per_step": ms16, "launches_per_step": l16, "young_ms_per_step": young16}
 
     # max over ranks
     if world > 1:
@@ -627,6 +641,10 @@ def run_ours(args):
                           "launches_per_step": int16_profile["launches_per_step"],
                           "algorithmic_bytes_per_env_step": ab16["step"],
                           "roofline_frac": ab16["step"] * v16 / world / 1e9 / peak}
+            if int16_profile["young_ms_per_step"]:
+                vy = world * N / (int16_profile["young_ms_per_step"] * 1e-3)
+                int16_line["young_games"] = {"age_env_steps": young_at + W_, "ms_per_step": int16_profile["young_ms_per_step"], "value": vy,
+                                             "roofline_frac": ab16["step"] * vy / world / 1e9 / peak}
         if ram_mode:
             e2e_obj = {"value": world * N * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                        "note": "vector-env calls a user makes (BatchedGridEnvironment.step with ram_obs): pinned host actions copied in; every "
