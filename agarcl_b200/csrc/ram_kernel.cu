@@ -7,7 +7,10 @@
 //
 // One CTA per instance: the pellet array is staged once in shared memory (it is scanned by every
 // player), then each warp takes players round-robin: centroid in cell order (Player::x / y), view,
-// and four ordered compactions (ballot + prefix popcount keep the reference's index order).  A record
+// and four ordered compactions (ballot + prefix popcount keep the reference's index order).  The
+// pellets -- 1000 per player, of which a few dozen are in view -- first go through a cheap bounding-box
+// filter into a per-warp candidate list (ascending index); the exact in-view test with its two IEEE
+// divisions per pellet then runs over the candidates only (r01: every pellet twice).  A record
 // is written whole — used entries then zero padding — with coalesced 16-byte stores; a player with
 // nothing in view keeps its previous record (the reference only commits a PlayerState when an entity
 // lands inside the grid).  HBM-write bound: P * 4896 B per instance.
@@ -24,6 +27,8 @@ __global__ void __launch_bounds__(kRamWarps * 32) k_ram(const __grid_constant__ 
   float2* s_pel = reinterpret_cast<float2*>(smem_raw);  // [cap_pellets]
   const int inst = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cand_cap = (P.L.cap_pellets + 7) & ~7;
+  uint16_t* s_cand = reinterpret_cast<uint16_t*>(smem_raw + (size_t)cand_cap * sizeof(float2)) + (size_t)warp * cand_cap;  // this warp's candidates
   const uint8_t* blob = P.state + (size_t)inst * P.L.stride;
   const agarcl_inst_hdr* hdr = reinterpret_cast<const agarcl_inst_hdr*>(blob + P.L.off_hdr);
   const agarcl_player* players = reinterpret_cast<const agarcl_player*>(blob + P.L.off_players);
@@ -75,11 +80,27 @@ __global__ void __launch_bounds__(kRamWarps * 32) k_ram(const __grid_constant__ 
     float4* clone4 = reinterpret_cast<float4*>(rec + AGARCL_RAM_OFF_CLONE);
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 
+    // ---- pass 0: pellets that can be in view at all (the exact test truncates towards zero, so column 0 reaches one grid
+    //      cell beyond -view/2; one more world unit of slack on top), in index order
+    int nc = 0;
+    {
+      const float h = 0.5f * view + view / (float)G + 1.0f;
+      for (int b = 0; b < np; b += 32) {
+        const int i = b + lane;
+        bool near = false;
+        if (i < np) { const float2 q = s_pel[i]; near = fabsf(q.x - px) <= h && fabsf(q.y - py) <= h; }
+        const unsigned m = __ballot_sync(AG_FULL, near);
+        if (near) s_cand[nc + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+        nc += __popc(m);
+      }
+      __syncwarp();
+    }
     // ---- pass 1: counts only (nothing may be written when nothing is in view)
     int n_food = 0, n_virus = 0, n_spore = 0, n_clone = 0;
-    for (int b = 0; b < np; b += 32) {
-      int i = b + lane;
-      bool in = i < np && inside(s_pel[i].x, s_pel[i].y);
+    for (int b = 0; b < nc; b += 32) {
+      const int k = b + lane;
+      bool in = false;
+      if (k < nc) { const float2 q = s_pel[s_cand[k]]; in = inside(q.x, q.y); }
       n_food += __popc(__ballot_sync(AG_FULL, in));
     }
     for (int b = 0; b < nv; b += 32) {
@@ -96,14 +117,14 @@ __global__ void __launch_bounds__(kRamWarps * 32) k_ram(const __grid_constant__ 
     const bool clone_in = lane < n && inside(cx, cy);
     const unsigned clone_mask = __ballot_sync(AG_FULL, clone_in);
     n_clone = __popc(clone_mask);
-    if (n_food + n_virus + n_spore + n_clone == 0) continue;
+    if (n_food + n_virus + n_spore + n_clone == 0) { __syncwarp(); continue; }
 
     // ---- pass 2: ordered compaction + zero padding
     int w = 0;
-    for (int b = 0; b < np; b += 32) {
-      int i = b + lane;
-      float2 q = i < np ? s_pel[i] : make_float2(0.f, 0.f);
-      bool in = i < np && inside(q.x, q.y);
+    for (int b = 0; b < nc; b += 32) {
+      const int k = b + lane;
+      const float2 q = k < nc ? s_pel[s_cand[k]] : make_float2(0.f, 0.f);
+      const bool in = k < nc && inside(q.x, q.y);
       unsigned m = __ballot_sync(AG_FULL, in);
       int pos = w + __popc(m & ((1u << lane) - 1u));
       if (in && pos < AGARCL_RAM_KP) food4[pos] = make_float4(q.x - px, q.y - py, r_pellet, (float)AGARCL_PELLET_MASS);
@@ -148,11 +169,13 @@ __global__ void __launch_bounds__(kRamWarps * 32) k_ram(const __grid_constant__ 
       reinterpret_cast<float4*>(rec)[0] = make_float4((float)n_food, (float)n_virus, (float)n_spore, (float)n_clone);
       reinterpret_cast<float4*>(rec)[1] = make_float4((float)tot, px, py, (float)ovf);
     }
+    __syncwarp();  // (the candidate list is reused for the warp's next player)
   }
 }
 
 cudaError_t launch_ram(const RamParams& P, cudaStream_t stream) {
-  size_t smem = (size_t)P.L.cap_pellets * sizeof(float2);
+  const size_t cand_cap = ((size_t)P.L.cap_pellets + 7) & ~(size_t)7;
+  size_t smem = cand_cap * sizeof(float2) + (size_t)kRamWarps * cand_cap * sizeof(uint16_t);  // pellets + one candidate list per warp
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(k_ram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -369,8 +369,18 @@ def run_ours(args):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    if world > 1:  # the mirror's host threads: share the box's cores between the ranks
-        os.environ.setdefault("AGARCL_HOST_THREADS", str(max(2, host_cores() // world)))
+    if world > 1:
+        # the mirror's host threads: every rank gets its own contiguous slice of the box's cores and is BOUND to it before it
+        # allocates anything, so that its patch threads do not migrate and its pinned mirror (first touch) sits on the slice's NUMA node
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+            if os.environ.get("AGARCL_BIND_CORES", "1") != "0":
+                os.sched_setaffinity(0, mine)
+            os.environ.setdefault("AGARCL_HOST_THREADS", str(max(2, len(mine))))
+        except (AttributeError, OSError):
+            os.environ.setdefault("AGARCL_HOST_THREADS", str(max(2, host_cores() // world)))
     N = args.instances
     cf = CONFIGS[CONFIG]
     ram_mode = cf["obs"] == "ram"
