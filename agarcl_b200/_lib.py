@@ -15,7 +15,7 @@ SYMBOLS = [
     "agarcl_make_layout", "agarcl_batch_create", "agarcl_batch_destroy", "agarcl_batch_get_layout",
     "agarcl_batch_seed", "agarcl_batch_reset", "agarcl_batch_set_actions", "agarcl_batch_step",
     "agarcl_batch_obs", "agarcl_batch_rewards", "agarcl_batch_dones", "agarcl_batch_step_host",
-    "agarcl_batch_mirror", "agarcl_batch_sync_mirror", "agarcl_batch_step_mirror", "agarcl_batch_mirror_stats", "agarcl_batch_mirror_timing",
+    "agarcl_batch_mirror", "agarcl_batch_sync_mirror", "agarcl_batch_step_mirror", "agarcl_batch_mirror_stats", "agarcl_batch_mirror_timing", "agarcl_batch_step_lists", "agarcl_batch_lists_expand",
     "agarcl_batch_download_state", "agarcl_batch_upload_state", "agarcl_batch_save_env_state", "agarcl_batch_load_env_state",
     "agarcl_snapshot_write", "agarcl_snapshot_read", "agarcl_batch_set_replay",
     "agarcl_batch_render", "agarcl_batch_ram", "agarcl_batch_ram_host", "agarcl_batch_render_ram", "agarcl_batch_launches_per_step", "agarcl_batch_flags", "agarcl_batch_set_timing", "agarcl_batch_get_timing", "agarcl_mt19937_draws",
@@ -53,6 +53,8 @@ def lib():
         L.agarcl_batch_step_mirror.argtypes = [_vp, _vp, _vp, _vp, _vp]
         L.agarcl_batch_mirror_stats.argtypes = [_vp, C.POINTER(C.c_uint64 * 4)]
         L.agarcl_batch_mirror_timing.argtypes = [_vp, C.POINTER(C.c_uint64 * 4)]
+        L.agarcl_batch_step_lists.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
+        L.agarcl_batch_lists_expand.argtypes = [_vp, C.c_int32, _vp]
         L.agarcl_batch_download_state.argtypes = [_vp, C.c_int32, _vp]
         L.agarcl_batch_upload_state.argtypes = [_vp, C.c_int32, _vp]
         L.agarcl_batch_save_env_state.argtypes = [_vp, C.c_int32, C.c_char_p]

@@ -21,6 +21,81 @@ class _CudaView:
         self._owner = owner
 
 
+class _ObsListsStruct(C.Structure):
+    """struct agarcl_obs_lists"""
+    _fields_ = [(n, C.c_int32) for n in ("n_images", "n_chunks", "images_per_chunk", "frames", "channels", "grid", "obs_dtype",
+                                         "mask_words", "rec_words", "entries_per_image")] + \
+               [(n, C.c_uint32) for n in ("off_rec", "off_entries", "chunk_words")] + [("chunks", _vp), ("slot_of", _vp)]
+
+
+class ObsLists:
+    """numpy view of the lists of the last Batch.step_lists (layout: include/agarcl_b200.h, agarcl_obs_lists)"""
+
+    def __init__(self, batch, L):
+        self._b, self.L = batch, L
+        words = L.n_chunks * L.chunk_words
+        self.words = np.ctypeslib.as_array(C.cast(L.chunks, C.POINTER(C.c_uint32)), shape=(words,))
+        self.slot_of = np.ctypeslib.as_array(C.cast(L.slot_of, C.POINTER(C.c_uint32)), shape=(L.n_images,))
+
+    def record(self, image):
+        L = self.L
+        s = int(self.slot_of[image])
+        c, li = divmod(s, L.images_per_chunk)
+        base = c * L.chunk_words
+        rec = self.words[base + L.off_rec + li * L.rec_words: base + L.off_rec + (li + 1) * L.rec_words]
+        return c, rec
+
+    def entries(self, image):
+        """(op, element offset, operand) arrays of the image, in application order; None if it overflowed its slot"""
+        L = self.L
+        c, rec = self.record(image)
+        if int(rec[0]) == 0xFFFFFFFF:
+            return None
+        e0 = c * L.chunk_words + L.off_entries + 2 * int(rec[1])
+        e = self.words[e0: e0 + 2 * int(rec[0])].reshape(-1, 2)
+        return e[:, 0] >> 29, e[:, 0] & 0x1FFFFFFF, e[:, 1].astype(np.int64)
+
+    def decode(self, image):
+        """pure-numpy decoder of one image from the documented layout (what a consumer writes; the C decoder is expand())"""
+        L = self.L
+        G, CH = L.grid, L.frames * L.channels
+        dt = np.int16 if L.obs_dtype == OBS_I16 else np.int32
+        top = 32767 if dt == np.int16 else 2147483647
+        out = np.zeros((CH, G, G), np.int64)
+        _, rec = self.record(image)
+        ent = self.entries(image)
+        if ent is None:
+            return None
+        for f in range(L.frames):
+            m = rec[3 + 2 * f * L.mask_words: 3 + 2 * (f + 1) * L.mask_words]
+            bits = lambda w: np.unpackbits(w.view(np.uint8), bitorder="little")[:G].astype(bool)  # noqa: E731
+            rows, cols = bits(m[:L.mask_words].copy()), bits(m[L.mask_words:].copy())
+            out[f * L.channels][rows[:, None] | cols[None, :]] = -1
+        flat = out.reshape(-1)
+        for op, off, v in zip(*ent):
+            x = flat[off]
+            v = min(int(v), top)
+            flat[off] = v if op == 0 else min(x + v, top) if op == 1 else (x if (x != 0 and x < v) else v) if op == 2 else max(x, v)
+        return out.astype(dt)
+
+    def expand(self, image):
+        """dense [frames*C, G, G] frame of one image (C decoder, agarcl_batch_lists_expand)"""
+        L = self.L
+        out = np.empty((L.frames * L.channels, L.grid, L.grid), np.int16 if L.obs_dtype == OBS_I16 else np.int32)
+        _lib.check(_lib.lib().agarcl_batch_lists_expand(self._b._h, int(image), out.ctypes.data_as(_vp)))
+        return out
+
+    def rewards_dones(self):
+        """(rewards f64 [n_images], dones u8 [n_images]) read from the records"""
+        L = self.L
+        rew, done = np.zeros(L.n_images, np.float64), np.zeros(L.n_images, np.uint8)
+        for i in range(L.n_images):
+            _, rec = self.record(i)
+            rew[i] = rec[L.rec_words - 3: L.rec_words - 1].copy().view(np.float64)[0]
+            done[i] = rec[L.rec_words - 1]
+        return rew, done
+
+
 class Batch:
     def __init__(self, cfg):
         self.cfg = cfg
@@ -145,6 +220,18 @@ class Batch:
             self._h, dxdy.ctypes.data_as(_vp), act.ctypes.data_as(_vp),
             self._host_out(rewards_out, np.float64, NA, "rewards_out"), self._host_out(dones_out, np.uint8, NA, "dones_out")))
         return self._mirror
+
+    # ---- the observation as lists (include/agarcl_b200.h, agarcl_obs_lists): no dense host tensor, nothing to patch
+    def step_lists(self, dxdy, act, rewards_out=None, dones_out=None):
+        """take_actions (host arrays) + step; rewards / dones to host; returns an ObsLists view of the library-owned pinned
+        lists (valid until the next step call)"""
+        dxdy, act = self._host_actions(dxdy, act)
+        NA = self.N * self.A
+        L = _ObsListsStruct()
+        _lib.check(_lib.lib().agarcl_batch_step_lists(
+            self._h, dxdy.ctypes.data_as(_vp), act.ctypes.data_as(_vp),
+            self._host_out(rewards_out, np.float64, NA, "rewards_out"), self._host_out(dones_out, np.uint8, NA, "dones_out"), C.byref(L)))
+        return ObsLists(self, L)
 
     def mirror_stats(self):
         out = (C.c_uint64 * 4)()

@@ -73,6 +73,7 @@ struct agarcl_batch {
                        // 2: it also writes channel 0 and scatters the entities (one kernel per step).  AGARCL_FUSE_CLEAR overrides (A/B timing)
   int launches_last_step = 0;
   ag::HostMirror* mirror = nullptr;  // host-resident observation mirror (mirror.cu), created on first use
+  ag::HostMirror* lists = nullptr;   // the lists-only twin behind agarcl_batch_step_lists (no dense tensor, no worker threads)
   uint64_t mirror_launch_us = 0, mirror_call_us = 0;  // last agarcl_batch_step_mirror: staging + launch, whole call
   // optional per-kernel timing: (start, after sim, after obs) event triples of steps not yet collected
   bool timing = false;
@@ -258,6 +259,7 @@ static int refill_replay(agarcl_batch* b, cudaStream_t s) {
 extern "C" int agarcl_batch_destroy(agarcl_batch* b) {
   if (!b) return AGARCL_OK;
   ag::mirror_destroy(b->mirror);
+  ag::mirror_destroy(b->lists);
   cudaFree(b->d_ram);
   cudaFree(b->d_state); cudaFree(b->d_obs); cudaFree(b->d_rewards); cudaFree(b->d_dones); cudaFree(b->d_before);
   cudaFree(b->d_dxdy); cudaFree(b->d_act); cudaFree(b->d_replay); cudaFree(b->d_seeds); cudaFree(b->d_mask); cudaFree(b->d_tickets); cudaFree(b->d_cost); cudaFree(b->d_perm);
@@ -557,7 +559,8 @@ extern "C" int agarcl_batch_set_actions(agarcl_batch* b, const float* dxdy, cons
 
 // One env-step of every instance.  `want_lists`: the caller is agarcl_batch_step_mirror; when the step is the single
 // fused kernel, it also leaves the host mirror's transfer lists (*lists_made = true) and the k_pack pass is not needed.
-static int step_impl(agarcl_batch* b, cudaStream_t s, bool want_lists, bool* lists_made) {
+static int step_impl(agarcl_batch* b, cudaStream_t s, bool want_lists, bool* lists_made, ag::HostMirror* target = nullptr) {
+  if (!target) target = b->mirror;
   if (lists_made) *lists_made = false;
   if (!b->was_reset) return agarcl_set_error(AGARCL_ERR_STATE, "step() before reset()");
   CK(cudaSetDevice(b->cfg.device));
@@ -584,8 +587,8 @@ static int step_impl(agarcl_batch* b, cudaStream_t s, bool want_lists, bool* lis
   } else if (b->frames == 1) {
     P.n_ticks = tps; P.do_begin = 1; P.do_end = 1;
     const int fused = fuse_obs_clear(b, P, 0) ? 1 : 0;
-    if (want_lists && P.obs_finish && b->mirror && 6 + 2 * ((b->G + 31) / 32) <= 32) {  // (the image's record is one warp store)
-      P.pk = ag::mirror_pack_out(b->mirror);
+    if (want_lists && P.obs_finish && target && 6 + 2 * ((b->G + 31) / 32) <= 32) {  // (the image's record is one warp store)
+      P.pk = ag::mirror_pack_out(target);
       *lists_made = true;
     }
     const bool sorted = P.tick_barrier && b->sort_schedule;
@@ -745,6 +748,42 @@ extern "C" int agarcl_batch_step_mirror(agarcl_batch* b, const float* dxdy, cons
   b->launches_last_step += 1;  // k_pack
   b->mirror_call_us = (uint64_t)(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e6);
   return rc;
+}
+
+extern "C" int agarcl_batch_step_lists(agarcl_batch* b, const float* dxdy, const int32_t* act, double* rewards_out, uint8_t* dones_out,
+                                       agarcl_obs_lists* out) {
+  if (!b || !dxdy || !act || !out) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  if (b->frames != 1 || b->cfg.strict_reference || b->cfg.ram_obs == 2)
+    return agarcl_set_error(AGARCL_ERR_STATE, "observation lists need the single fused step kernel (one frame, strict_reference = 0, a grid observation)");
+  CK(cudaSetDevice(b->cfg.device));
+  if (!b->lists) {
+    b->lists = ag::mirror_create(b->N * b->A, b->A, b->frames * b->C, b->C, b->G, b->cfg.obs_dtype, true);
+    if (!b->lists) return AGARCL_ERR_NOMEM;
+  }
+  ag::mirror_stage_actions(b->lists, dxdy, act, &b->cur_dxdy, &b->cur_act);
+  bool lists_made = false;
+  int rc = step_impl(b, nullptr, true, &lists_made, b->lists);
+  if (rc) return rc;
+  if (!lists_made) {
+    CK(cudaStreamSynchronize(nullptr));
+    return agarcl_set_error(AGARCL_ERR_STATE, "this observation configuration is not finished by the step kernel: no lists");
+  }
+  rc = ag::mirror_collect_lists(b->lists, nullptr, rewards_out, dones_out);
+  if (rc) return rc;
+  ag::mirror_lists_view(b->lists, out);
+  return AGARCL_OK;
+}
+
+extern "C" int agarcl_batch_lists_expand(agarcl_batch* b, int32_t image, void* dense_out) {
+  if (!b || !dense_out) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  if (!b->lists) return agarcl_set_error(AGARCL_ERR_STATE, "no lists yet (agarcl_batch_step_lists)");
+  if (image < 0 || image >= b->N * b->A) return agarcl_set_error(AGARCL_ERR_INVALID, "image out of range");
+  if (ag::mirror_lists_expand(b->lists, image, dense_out) == 1) {  // overflowed its slot: the dense frame is on the device
+    CK(cudaSetDevice(b->cfg.device));
+    const size_t bytes = b->obs_bytes / ((size_t)b->N * b->A);
+    CK(cudaMemcpy(dense_out, (const uint8_t*)b->d_obs + bytes * (size_t)image, bytes, cudaMemcpyDeviceToHost));
+  }
+  return AGARCL_OK;
 }
 
 extern "C" int agarcl_batch_mirror_stats(const agarcl_batch* b, uint64_t out[4]) {

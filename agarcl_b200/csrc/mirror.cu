@@ -290,6 +290,7 @@ struct HostMirror {
   std::vector<uint32_t> slot_of[2];  // per staging buffer: the slot that describes image i
   std::vector<size_t> guess;      // per chunk: entries fetched together with the meta words (the remainder, if any, in a second copy)
   Pool* pool = nullptr;
+  bool lists_only = false;        // no dense mirror: the lists themselves are the product (agarcl_batch_step_lists)
   MirrorStats stats{};
   uint32_t* blk(int w, int chunk) const { return h_chunks[w] + (size_t)chunk * pk.chunk_words; }
 };
@@ -397,6 +398,96 @@ static void expand_range(HostMirror* m, int lo, int hi, const uint32_t* zero_mas
   }
 }
 
+// ---- the lists as the observation (agarcl_batch_step_lists): wait for every chunk flag of the launch that was handed
+// mirror_pack_out(); nothing is expanded.  rewards / dones come from the records.
+int mirror_collect_lists(HostMirror* m, cudaStream_t s, double* rewards_out, uint8_t* dones_out) {
+  m->cur ^= 1;
+  const int cur = m->cur, K = m->n_chunks;
+  const PackOut& k = m->pk;
+  std::vector<uint8_t> seen((size_t)K, 0);
+  int left = K;
+  uint32_t spins = 0;
+  uint64_t entries = 0, dense = 0;
+  while (left > 0) {
+    bool any = false;
+    for (int c = 0; c < K; c++)
+      if (!seen[(size_t)c] && m->h_flags[c] == m->seq) {
+        seen[(size_t)c] = 1; left--; any = true;
+        const uint32_t* hb = m->blk(cur, c);
+        const int lo = c * (int)k.ipc, hi = lo + (int)k.ipc < m->n_img ? lo + (int)k.ipc : m->n_img;
+        for (int i = lo; i < hi; i++) {
+          const uint32_t* rec = hb + pk_off_rec(k) + (size_t)(i - lo) * k.rec_words;
+          const uint32_t img = rec[2];
+          if (img >= (uint32_t)m->n_img) return agarcl_set_error(AGARCL_ERR_STATE, "list slot %d names image %u of %d", i, img, m->n_img);
+          m->slot_of[cur][img] = (uint32_t)i;
+          if (rec[0] == kPackDense) dense++; else entries += rec[0];
+          if (rewards_out) std::memcpy(rewards_out + img, rec + k.rec_words - 3, sizeof(double));
+          if (dones_out) dones_out[img] = (uint8_t)rec[k.rec_words - 1];
+        }
+      }
+    if (any || left == 0) continue;
+    cpu_relax();
+    if (++spins >= 4096u) {
+      spins = 0u;
+      const cudaError_t q = cudaStreamQuery(s);
+      if (q == cudaSuccess) {
+        bool all = true;
+        for (int c = 0; c < K; c++) all = all && (seen[(size_t)c] || m->h_flags[c] == m->seq);
+        if (!all) return agarcl_set_error(AGARCL_ERR_STATE, "step kernel finished without completing every list chunk");
+      } else if (q != cudaErrorNotReady) {
+        return agarcl_set_error(AGARCL_ERR_CUDA, "cudaStreamQuery failed: %s", cudaGetErrorString(q));
+      }
+    }
+  }
+  m->stats.entries = entries;
+  m->stats.dense_images = dense;
+  m->stats.d2h_bytes = (uint64_t)m->n_img * k.rec_words * 4 + entries * 8 + (uint64_t)K * 4;
+  return AGARCL_OK;
+}
+
+void mirror_lists_view(const HostMirror* m, agarcl_obs_lists* out) {
+  const PackOut& k = m->pk;
+  out->n_images = m->n_img; out->n_chunks = m->n_chunks; out->images_per_chunk = (int32_t)k.ipc;
+  out->frames = m->frames; out->channels = m->C; out->grid = m->G; out->obs_dtype = m->dtype;
+  out->mask_words = m->MW; out->rec_words = (int32_t)k.rec_words; out->entries_per_image = (int32_t)k.slot;
+  out->off_rec = pk_off_rec(k); out->off_entries = pk_off_entries(k); out->chunk_words = k.chunk_words;
+  out->chunks = m->h_chunks[m->cur];
+  out->slot_of = m->slot_of[m->cur].data();
+}
+
+// Decodes image `img` of the current lists into a dense [CH][G][G] frame of the mirror's dtype.  Returns 1 when the image did
+// not fit its slot (the caller takes it from the device tensor), 0 otherwise.
+template <typename T>
+static int lists_expand_t(const HostMirror* m, int img, T* p) {
+  const PackOut& k = m->pk;
+  const uint32_t slot = m->slot_of[m->cur][(size_t)img];
+  const uint32_t* cb = m->h_chunks[m->cur] + (size_t)(slot / k.ipc) * k.chunk_words;
+  const uint32_t* rec = cb + pk_off_rec(k) + (size_t)(slot % k.ipc) * k.rec_words;
+  if (rec[0] == kPackDense) return 1;
+  std::memset(p, 0, m->img_bytes);
+  std::vector<uint32_t> zero_masks(2 * (size_t)m->MW, 0u);
+  const size_t plane = (size_t)m->G * m->G, mw2 = 2 * (size_t)m->MW;
+  for (int f = 0; f < m->frames; f++) apply_mask_delta<T>(p + (size_t)f * m->C * plane, zero_masks.data(), rec + 3 + f * mw2, m->G, m->MW);
+  const uint2* ne = reinterpret_cast<const uint2*>(cb + pk_off_entries(k)) + rec[1];
+  constexpr int32_t kTop = sizeof(T) == 2 ? 32767 : 2147483647;
+  for (uint32_t e = 0; e < rec[0]; e++) {
+    T& x = p[ne[e].x & kPkOffMask];
+    const int32_t v32 = (int32_t)ne[e].y;
+    const T v = (T)(v32 > kTop ? kTop : v32);
+    switch (ne[e].x >> 29) {
+      case kPkSet: x = v; break;
+      case kPkAdd: { const int64_t t = (int64_t)x + v32; x = (T)(t > kTop ? kTop : t); break; }
+      case kPkMinNz: x = (x != 0 && x < v) ? x : v; break;
+      default: x = x > v ? x : v; break;
+    }
+  }
+  return 0;
+}
+int mirror_lists_expand(const HostMirror* m, int img, void* dense_out) {
+  return m->dtype == AGARCL_OBS_I16 ? lists_expand_t<int16_t>(m, img, static_cast<int16_t*>(dense_out))
+                                    : lists_expand_t<int32_t>(m, img, static_cast<int32_t*>(dense_out));
+}
+
 void mirror_destroy(HostMirror* m) {
   if (!m) return;
   delete m->pool;
@@ -415,7 +506,7 @@ void mirror_destroy(HostMirror* m) {
   delete m;
 }
 
-HostMirror* mirror_create(int n_img, int agents, int CH, int C, int G, int dtype) {
+HostMirror* mirror_create(int n_img, int agents, int CH, int C, int G, int dtype, bool lists_only) {
   const size_t esz = dtype == AGARCL_OBS_I16 ? 2 : 4;
   if (((size_t)G * G * esz) % 16 != 0 || G > 4096 || (uint64_t)CH * G * G > kPkOffMask) {
     agarcl_set_error(AGARCL_ERR_INVALID, "the host mirror needs grid planes that are multiples of 16 bytes (grid_size %d)", G);
@@ -457,7 +548,8 @@ HostMirror* mirror_create(int n_img, int agents, int CH, int C, int G, int dtype
   // the mirror itself: 2 MB-aligned, transparent huge pages requested (random element updates over gigabytes are
   // TLB-bound with 4 KB pages), then page-locked; plain cudaHostAlloc if that does not work
   bool ok = true;
-  {
+  m->lists_only = lists_only;
+  if (!lists_only) {
     const size_t bytes = (size_t)n_img * m->img_bytes, two_mb = (size_t)2 << 20;
     void* p = nullptr;
     if (!std::getenv("AGARCL_MIRROR_NO_THP") && posix_memalign(&p, two_mb, (bytes + two_mb - 1) / two_mb * two_mb) == 0 && p) {
@@ -502,6 +594,7 @@ HostMirror* mirror_create(int n_img, int agents, int CH, int C, int G, int dtype
   if (const char* e = std::getenv("AGARCL_HOST_THREADS")) nt = std::atoi(e);
   nt = nt < 1 ? 1 : (nt > 64 ? 64 : nt);
   if (nt > n_img) nt = n_img;
+  if (lists_only) nt = 1;  // (nobody expands anything: the caller reads the lists)
   m->pool = new Pool(nt - 1);
   m->stats.host_threads = (uint64_t)nt;
   m->guess.assign((size_t)m->n_chunks, (size_t)k.ipc * 64);
@@ -510,7 +603,7 @@ HostMirror* mirror_create(int n_img, int agents, int CH, int C, int G, int dtype
     for (int i = 0; i < n_img; i++) m->slot_of[w][(size_t)i] = (uint32_t)i;
   }
   // first touch of the mirror by the threads that will write it
-  {
+  if (!lists_only) {
     std::atomic<int> next{0};
     m->pool->run([&] {
       for (int i; (i = next.fetch_add(8)) < n_img;) {
@@ -519,7 +612,7 @@ HostMirror* mirror_create(int n_img, int agents, int CH, int C, int G, int dtype
       }
     });
   }
-  if (m->obs_malloced) {  // page-lock it (dense fallback copies land here; callers may copy it to a device)
+  if (m->obs_malloced && !lists_only) {  // page-lock it (dense fallback copies land here; callers may copy it to a device)
     if (cudaHostRegister(m->h_obs, (size_t)n_img * m->img_bytes, cudaHostRegisterDefault) == cudaSuccess) m->obs_registered = true;
     else cudaGetLastError();  // stays pageable: only the rare dense copies get slower
   }

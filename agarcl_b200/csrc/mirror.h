@@ -22,7 +22,7 @@ struct MirrorStats {
 
 // n_img = instances * agents images of CH = frames*C channels of G x G elements; dtype: agarcl_obs_dtype.
 // nullptr + agarcl_set_error on failure.
-HostMirror* mirror_create(int n_img, int agents, int CH, int C, int G, int dtype);
+HostMirror* mirror_create(int n_img, int agents, int CH, int C, int G, int dtype, bool lists_only = false);
 void mirror_destroy(HostMirror* m);
 void* mirror_ptr(HostMirror* m);
 // Makes the host mirror identical to the device observation `d_obs`: k_pack enqueued on `s`, then synchronised;
@@ -37,5 +37,12 @@ PackOut mirror_pack_out(HostMirror* m);
 int mirror_collect(HostMirror* m, const void* d_obs, cudaStream_t s, double* rewards_out, uint8_t* dones_out);
 void mirror_stage_actions(HostMirror* m, const float* dxdy, const int32_t* act, const float** d_dxdy, const int32_t** d_act);
 void mirror_stats(const HostMirror* m, MirrorStats* out);
+// The lists themselves as the observation (agarcl_batch_step_lists, include/agarcl_b200.h): a HostMirror created with
+// lists_only has no dense tensor and no worker threads; mirror_collect_lists waits for the chunk flags of the launch that
+// got mirror_pack_out() and fills rewards / dones from the records; mirror_lists_view describes the current lists;
+// mirror_lists_expand decodes one image into a dense frame (1: the image overflowed its slot, take it from the device).
+int mirror_collect_lists(HostMirror* m, cudaStream_t s, double* rewards_out, uint8_t* dones_out);
+void mirror_lists_view(const HostMirror* m, agarcl_obs_lists* out);
+int mirror_lists_expand(const HostMirror* m, int img, void* dense_out);
 
 }  // namespace ag

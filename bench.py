@@ -482,7 +482,7 @@ def run_ours(args):
         return time.perf_counter() - t0
 
     h2d = N * A * (2 * 4 + 4)
-    dense_s, d2h_dense, mirror_ok, mstats, e2e_kernel_ms, e2e_ksteps = None, None, None, None, 0.0, 0
+    dense_s, d2h_dense, mirror_ok, mstats, e2e_kernel_ms, e2e_ksteps, lists_s, lists_ok = None, None, None, None, 0.0, 0, None, None
     if ram_mode:
         # agario-ram-v0 hands every AGENT its record (gym_env.BatchedAgarioEnv._obs): pinned host actions in; the agents' records,
         # rewards and dones out, through the vector-env calls a user makes
@@ -534,6 +534,24 @@ def run_ours(args):
         b.set_timing(False)
         mstats = b.mirror_stats()
         d2h = mstats["d2h_bytes"] + N * A * (8 + 1)
+        # (c) the observation as LISTS (agarcl_batch_step_lists): the same call without the host-side replay -- what the kernel wrote
+        # into pinned host memory is handed to the caller as it is (include/agarcl_b200.h, agarcl_obs_lists)
+        from agarcl_b200.batch import _ObsListsStruct
+        from agarcl_b200 import _lib as _l
+        ol = _ObsListsStruct()
+
+        def host_step_lists():
+            _l.check(_l.lib().agarcl_batch_step_lists(b._h, vp(h_dxdy.data_ptr()), vp(h_act.data_ptr()), vp(h_rew.data_ptr()),
+                                                      vp(h_done.data_ptr()), C.byref(ol)))
+
+        lists_s = time_host(host_step_lists, Km)
+        lists_ok = True
+        obs_dev = b.obs_tensor()
+        dense_img = np.empty(b.obs_shape[1:], np.int32)
+        for i in range(0, N * A, max(1, (N * A) // 64)):  # the C decoder on a spread of images against the device tensor
+            _l.check(_l.lib().agarcl_batch_lists_expand(b._h, i, vp(dense_img.ctypes.data)))
+            lists_ok = lists_ok and bool(torch.equal(torch.from_numpy(dense_img).cuda(), obs_dev[i]))
+        host_step_mirror()  # (the dense mirror is compared below: bring it up to date with the state the lists steps left)
         # the WHOLE mirror against the device tensor, in slices (not a sample)
         obs_dev = b.obs_tensor()
         mirror_ok = True
@@ -594,10 +612,11 @@ def run_ours(args):
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms, e2e_s, sim_ms, obs_ms, dense_s or 0.0], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, sim_ms, obs_ms, dense_s or 0.0, lists_s or 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, sim_ms, obs_ms, dense_max = [float(x) for x in t.tolist()]
+        ms, e2e_s, sim_ms, obs_ms, dense_max, lists_max = [float(x) for x in t.tolist()]
         dense_s = dense_max if dense_s is not None else None
+        lists_s = lists_max if lists_s is not None else None
         if int16_profile is not None:
             t16 = torch.tensor([int16_profile["ms_per_step"]], device="cuda", dtype=torch.float64)
             dist.all_reduce(t16, op=dist.ReduceOp.MAX)
@@ -673,7 +692,12 @@ def run_ours(args):
                        "k_step_ms_in_e2e": e2e_kernel_ms / max(e2e_ksteps, 1),
                        "mirror_dense_images": mstats["dense_images"],
                        "dense_copy": {"value": world * N / dense_s, "unit": UNIT, "d2h_bytes_per_step": d2h_dense,
-                                      "note": "agarcl_batch_step_host: the whole int32 observation copied D2H every step (PCIe bound)"}}
+                                      "note": "agarcl_batch_step_host: the whole int32 observation copied D2H every step (PCIe bound)"},
+                       "lists": {"value": world * N * Ke / lists_s, "unit": UNIT, "decodes_to_device_observation": lists_ok,
+                                 "note": "agarcl_batch_step_lists: pinned host actions in; rewards + dones out; the observation handed over as the "
+                                         "lists the kernel wrote into pinned host memory (row / column masks + integer operations per image, "
+                                         "include/agarcl_b200.h agarcl_obs_lists) instead of being replayed into a dense host tensor -- no host "
+                                         "threads, so it scales with the GPU count where the dense mirror is bound by the box's cores"}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",

@@ -219,6 +219,38 @@ int agarcl_batch_mirror_stats(const agarcl_batch* b, uint64_t out[4]);
  * copies), out[1] first wait to mirror complete, out[2] action staging + kernel launch, out[3] the whole call. */
 int agarcl_batch_mirror_timing(const agarcl_batch* b, uint64_t out[4]);
 
+/* ---------------------------------------------------- the observation as LISTS (zero-copy, no dense host tensor)
+ * A grid observation is almost entirely structure: per frame the out-of-bounds channel is a row mask and a column mask
+ * (GridEnvironment.hpp:235-248) and the other channels hold a few dozen non-zero elements (:212-232).  The step kernel
+ * writes exactly that -- per image a record and a list of integer operations -- straight into pinned host memory while it
+ * runs; the dense mirror above is those lists replayed by host threads, which is what stops scaling when 8 GPUs feed one
+ * host.  agarcl_batch_step_lists hands the lists themselves to the caller: take_actions (host) + step +
+ * rewards / dones to host, observation left in library-owned pinned memory as described by agarcl_obs_lists, valid until
+ * the next step call on the batch.  A learner expands them where it trains (one scatter per image) or consumes them as
+ * they are; agarcl_batch_lists_expand is the reference decoder for one image.  Requires the configuration whose step is
+ * the single fused kernel (one frame, strict_reference = 0); AGARCL_ERR_STATE otherwise.
+ *   chunk c                = chunks + c * chunk_words                     (32-bit words)
+ *   slot s (of n_images)   : chunk s / images_per_chunk, index li = s % images_per_chunk inside it; slot_of[image] = s
+ *   record of the slot     = chunk + off_rec + li * rec_words :
+ *        [0] entries (0xFFFFFFFF: the image overflowed entries_per_image -> read it from agarcl_batch_obs)
+ *        [1] index of its first entry in the chunk's entry array   [2] the image (instance * agents + agent)
+ *        [3 ..] per frame: mask_words words of ROW bits (bit i: row i of channel 0 is -1), then mask_words of COLUMN bits
+ *        [rec_words-3, -2] the agent's reward (f64)   [rec_words-1] its done flag
+ *   entries of the chunk   = (uint32 pairs) chunk + off_entries : (op << 29 | element offset inside the image, operand), applied in
+ *        order onto a zero frame: op 0 x = v, 1 x += v, 2 x = (x != 0 && x < v) ? x : v, 3 x = max(x, v); int16 saturates at 32767 */
+typedef struct agarcl_obs_lists {
+  int32_t n_images, n_chunks, images_per_chunk, frames, channels, grid, obs_dtype;
+  int32_t mask_words, rec_words, entries_per_image;
+  uint32_t off_rec, off_entries, chunk_words;
+  const uint32_t* chunks;   /* pinned host memory */
+  const uint32_t* slot_of;  /* [n_images] */
+} agarcl_obs_lists;
+int agarcl_batch_step_lists(agarcl_batch* b, const float* dxdy, const int32_t* act, double* rewards_out, uint8_t* dones_out,
+                            agarcl_obs_lists* out);
+/* Decodes image `image` of the lists of the last agarcl_batch_step_lists into dense_out ([frames*C, G, G] of the observation
+ * dtype, host memory); an image that overflowed its slot is copied from the device tensor instead. */
+int agarcl_batch_lists_expand(agarcl_batch* b, int32_t image, void* dense_out);
+
 /* ---------------------------------------------------- structured ("ram") observation
  * GoBiggerObservation::add_frame (environment/envs/GoBiggerEnvironment.hpp:515-548, _store_entities
  * 446-513): for EVERY player of the instance, the in-view viruses, pellets ("food"), ejected foods

@@ -114,3 +114,38 @@ def test_mirror_full_size():
         assert torch.equal(torch.from_numpy(m[i:i + 512].copy()).cuda(), dev[i:i + 512]), f"images {i}..{i + 511} differ"
     assert b.mirror_stats()["dense_images"] == 0
     env.close()
+
+
+def test_observation_lists_decode_to_the_device_observation():
+    """agarcl_batch_step_lists: the lists in pinned host memory -- per image the out-of-bounds row / column masks and the list of
+    integer operations -- decode to exactly the device observation, by the C decoder (every image) and by a numpy decoder written
+    from the layout documented in include/agarcl_b200.h (a sample); rewards and dones travel in the records."""
+    from agarcl_b200 import OBS_I16, make_cfg
+    from agarcl_b200.batch import Batch
+    for kw in (dict(), dict(obs_dtype=OBS_I16, num_agents=2, arena_size=180, num_pellets=150, num_viruses=4, num_bots=6)):
+        N = 80
+        b = Batch(make_cfg(n_instances=N, **kw))
+        b.seed(33)
+        b.reset()
+        NA = N * b.A
+        rng = np.random.default_rng(5)
+        rew, done = np.zeros(NA, np.float64), np.zeros(NA, np.uint8)
+        for st in range(40):
+            dxdy = rng.uniform(-1, 1, size=(NA, 2)).astype(np.float32)
+            act = rng.integers(0, 3, size=NA).astype(np.int32)
+            ol = b.step_lists(dxdy, act, rew, done)
+            if st % 8 == 7:
+                dev = b.obs_tensor().cpu().numpy()
+                assert np.array_equal(rew, b.rewards_tensor().cpu().numpy()) and np.array_equal(done, b.dones_tensor().cpu().numpy())
+                r2, d2 = ol.rewards_dones()
+                assert np.array_equal(r2, rew) and np.array_equal(d2, done)
+                for i in range(NA):
+                    assert np.array_equal(ol.expand(i), dev[i]), f"step {st}: image {i} decodes differently"
+                for i in (0, 1, NA // 2, NA - 1):
+                    assert np.array_equal(ol.decode(i), dev[i]), f"step {st}: numpy decoder, image {i}"
+                assert sorted(ol.slot_of.tolist()) == list(range(NA))
+        b.close()
+    with pytest.raises(RuntimeError, match="single fused step kernel"):
+        b2 = Batch(make_cfg(n_instances=4, num_frames=2))
+        b2.reset()
+        b2.step_lists(np.zeros((4, 2), np.float32), np.zeros(4, np.int32))
