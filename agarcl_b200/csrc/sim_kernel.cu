@@ -56,6 +56,21 @@ __device__ __forceinline__ Cell cell_load(const agarcl_cell* g) {
   c.rec = ldg_keep(reinterpret_cast<const uint32_t*>(g) + 8);
   return c;
 }
+constexpr int kPremoveShadow = 16;  // cell slot of a premoved player's first result cell (players of up to 16 cells are premoved)
+// a premoved player's cell: position and velocities from the result slot, mass / id / recombine tick from the live cell
+__device__ __forceinline__ Cell cell_load_premoved(const agarcl_cell* g) {
+  const float4* r = reinterpret_cast<const float4*>(g + kPremoveShadow);
+  const float4* p = reinterpret_cast<const float4*>(g);
+  float4 a = ldg_keep(r);
+  float4 b = ldg_keep(r + 1);
+  float4 o = ldg_keep(p + 1);
+  Cell c;
+  c.x = a.x; c.y = a.y; c.vx = a.z; c.vy = a.w;
+  c.svx = b.x; c.svy = b.y;
+  c.mass = __float_as_uint(o.z); c.id = __float_as_uint(o.w);
+  c.rec = ldg_keep(reinterpret_cast<const uint32_t*>(g) + 8);
+  return c;
+}
 __device__ __forceinline__ void cell_store(agarcl_cell* g, const Cell& c) {
   float4* p = reinterpret_cast<float4*>(g);
   stg_keep(p, make_float4(c.x, c.y, c.vx, c.vy));
@@ -573,7 +588,13 @@ __device__ void premove_batch(const SimParams& P, uint8_t* blob, uint32_t w0, ui
     move_cell(P, flags, me, tx, ty);
   }
   me = self_collisions_fn(me, radius_of(P.T, me.mass), gn, tx, ty, gbase, gl, gw, P.W);
-  if (valid) cell_store(cells + gl, me);
+  // the results go to the UPPER half of the player's cell slots (kPremoveShadow): the live cells stay as they were until the
+  // player's own turn, which is what a looking bot earlier in the order must see on a decision tick (bot_chase reads cells)
+  if (valid) {
+    float4* r = reinterpret_cast<float4*>(cells + kPremoveShadow + gl);
+    stg_keep(r, make_float4(me.x, me.y, me.vx, me.vy));
+    stg_keep(r + 1, make_float4(me.svx, me.svy, 0.0f, 0.0f));
+  }
   const bool mark = have && gl == 0;
   done_lo |= __reduce_or_sync(AG_FULL, (mark && gp < 32) ? 1u << gp : 0u);
   done_hi |= __reduce_or_sync(AG_FULL, (mark && gp >= 32) ? 1u << (gp - 32) : 0u);
@@ -606,12 +627,30 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
   volatile uint32_t* mine = mailbox(P, smem_raw, warp);
   uint32_t nb = 0;
   __syncwarp();  // the mailbox lies over scratch the lanes read until the end of the previous tick (collision snapshot, removal lists)
-  if (c && c->tick % 10u != 0u) {
+  if (c) {
     const int Pn = P.L.P;
+    const bool deciding = c->tick % 10u == 0u;  // bots decide on this tick (Engine.hpp:498-499)
     for (int base = 0; base < Pn; base += 32) {
       const int k = base + lane;
       const int p = k < Pn ? P.L.order[k] : 0;
-      const int np = k < Pn ? __float_as_int(c->sm.psum()[p].w) : 0;
+      int np = k < Pn ? __float_as_int(c->sm.psum()[p].w) : 0;
+      if (deciding) {
+        // A target that comes out of the ordered loop cannot be premoved -- but HungryBot's does not: it is the pellet nearest
+        // to the bot's location at the START of the tick (HungryBot.hpp:19-22, Bot::nearest_pellet Bot.hpp:92-129; pellets
+        // only disappear behind the loop), so the multi-cell HungryBots decide HERE, every one on its own lane, and join the
+        // pool; agents keep the target of their action.  The bots that look at other players (types 1..3) stay in the loop.
+        const int bt = k < Pn ? P.L.bot_type[p] : 0;
+        if (np >= 2 && np <= 16 && bt == 0 && c->n_pellets > 0 && c->hash_valid) {
+          const float4 sp = c->sm.psum()[p];
+          float tx = 0.0f, ty = 0.0f;
+          lane_nearest_pellet(*c, sp.x, sp.y, tx, ty);
+          agarcl_player* pl = c->players_() + p;
+          pl->target_x = tx; pl->target_y = ty;
+          pl->action = 0;
+        } else if (bt >= 0) {
+          np = 0;  // (decides in the loop: not premoved)
+        }
+      }
 #pragma unroll 1
       for (int wide = 1; wide >= 0; wide--) {  // the long pair sequences (players of 9..16 cells) first
         const int gshift = wide ? 4 : 3, per = 32 >> gshift;
@@ -709,13 +748,15 @@ __device__ void tick_player(Ctx& c, int p) {
   const int bot_type = pl->bot_type;
   int elapsed = pl->elapsed_ticks + 1;
 
+  // Engine::move_player + check_player_self_collisions may have run ahead in the pooled pair solver (premove_players)
+  const bool premoved = ((p < 32 ? c.pre_lo >> p : c.pre_hi >> (p - 32)) & 1u) != 0u;
   Cell me;
   me.x = me.y = me.vx = me.vy = me.svx = me.svy = 0.0f;
   me.mass = 0; me.id = 0; me.rec = 0;
-  if (lane < n) me = cell_load(c.pcells(p) + lane);
+  if (lane < n) me = premoved ? cell_load_premoved(c.pcells(p) + lane) : cell_load(c.pcells(p) + lane);
 
-  // ---- bots decide every 10th tick (Engine.hpp:498-499)
-  if (c.tick % 10u == 0u && bot_type >= 0) {
+  // ---- bots decide every 10th tick (Engine.hpp:498-499); a premoved bot has decided already (premove_players)
+  if (c.tick % 10u == 0u && bot_type >= 0 && !premoved) {
     float4 s = c.sm.psum()[p];
     float lx = s.x, ly = s.y;
     bool decided = false;
@@ -731,7 +772,6 @@ __device__ void tick_player(Ctx& c, int p) {
   }
 
   // ---- Engine::move_player + check_player_self_collisions (unless premove_players has done them for this tick)
-  const bool premoved = ((p < 32 ? c.pre_lo >> p : c.pre_hi >> (p - 32)) & 1u) != 0u;
   uint32_t smallest = 0xffffffffu;
   if (lane < n) {
     smallest = me.mass;
