@@ -32,6 +32,8 @@
 // BaseEnvironment.hpp:89-122,164-176).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "sim_params.h"
 #include "sim_shared.cuh"
 
@@ -125,6 +127,7 @@ struct Ctx {
   bool vc_valid;        // the virus cache in shared memory matches the virus array
   bool lanes_dirty;     // players_collision changed players: lanes must reload their registers
   uint32_t pre_lo, pre_hi;  // players whose move + self-collisions of this tick are already done (premove_players)
+  uint32_t sorted_lo, sorted_hi;  // players whose cells are known to be in ascending id order (sort_player_cells can be skipped)
   long long work, t_mark;   // cycles this instance has worked (waiting at the alignment barriers excluded) / start of the current stretch
   int tb;               // the alignment barriers of this launch (P.tick_barrier, or 0 when the launch runs the free-running schedule)
   int inst_local;
@@ -739,7 +742,7 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
 __device__ void tick_player(Ctx& c, int p) {
   const Luts& T = c.P.T;
   agarcl_player* pl = c.players_() + p;
-  int n = pl->n_cells;
+  int n = __float_as_int(c.sm.psum()[p].w);  // == pl->n_cells, without the trip to memory in front of the cell loads
   c.emitted = 0;
   if (n == 0) return;  // dead players are not ticked (Engine.hpp:216)
   const int lane = c.lane;
@@ -1143,6 +1146,7 @@ __device__ void tick_player(Ctx& c, int p) {
   n = min(n + created, 32);
 
   // ---- recombine_cells (swap-with-back semantics)
+  bool merged = false;  // (a merge moves the last cell into the hole: the only thing that breaks the ascending id order)
   if (n >= 2) {
     for (int a = 0; a < n; a++) {
       uint32_t arec = __shfl_sync(AG_FULL, me.rec, a);
@@ -1161,6 +1165,7 @@ __device__ void tick_player(Ctx& c, int p) {
         if (lane == b) me = last;
         n--;
         b_cur = b;
+        merged = true;
       }
     }
   }
@@ -1188,6 +1193,7 @@ __device__ void tick_player(Ctx& c, int p) {
     __syncwarp();
   }
 
+  if (merged) { if (p < 32) c.sorted_lo &= ~(1u << p); else c.sorted_hi &= ~(1u << (p - 32)); }
   // ---- publish: centroid for later readers this tick, cells and player record back to the blob
   float4 s = centroid_of(me, n);
   if (lane < n) cell_store(c.pcells(p) + lane, me);
@@ -1673,6 +1679,11 @@ struct PairRec { uint16_t q, g; uint32_t eaten_mass, eater_id, eaten_id; };  // 
 // std::sort == insertion sort does for <= 16 elements), and the scan from the lower bound to the first own cell is
 // one ballot -- because every other warp of the CTA waits at the next barrier while this one is busy here.  Strips
 // of more than 32 cells, the results map and the application of the results stay with one lane.
+// the pre-test snapshot in shared memory: x[kSnapCap], y[kSnapCap], (mass | player << 24)[kSnapCap] (12 bytes per cell)
+__device__ __forceinline__ float* snap_x(const Ctx& c) { return reinterpret_cast<float*>(c.sm.snap()); }
+__device__ __forceinline__ float* snap_y(const Ctx& c) { return reinterpret_cast<float*>(c.sm.snap()) + kSnapCap; }
+__device__ __forceinline__ uint32_t* snap_mp(const Ctx& c) { return reinterpret_cast<uint32_t*>(c.sm.snap()) + 2 * kSnapCap; }
+
 __device__ void players_collision_exact(Ctx& c, int total, int nhit, bool staged) {
   const Luts& T = c.P.T;
   const int lane = c.lane;
@@ -1684,9 +1695,9 @@ __device__ void players_collision_exact(Ctx& c, int total, int nhit, bool staged
   uint16_t* rorder = c.sm.resorder();    // iteration order of the results map
   auto cellp = [&](int g) -> const agarcl_cell* { return c.pcells(ref[g] >> 8) + (ref[g] & 0xff); };
   // the sweep reads the pre-application snapshot (Engine.hpp:153-166): shared-memory copy when staged
-  auto gy_of = [&](int g) -> float { return staged ? c.sm.snap()[g].y : cellp(g)->y; };
-  auto gx_of = [&](int g) -> float { return staged ? c.sm.snap()[g].x : cellp(g)->x; };
-  auto gm_of = [&](int g) -> uint32_t { return staged ? __float_as_uint(c.sm.snap()[g].z) : cellp(g)->mass; };
+  auto gy_of = [&](int g) -> float { return staged ? snap_y(c)[g] : cellp(g)->y; };
+  auto gx_of = [&](int g) -> float { return staged ? snap_x(c)[g] : cellp(g)->x; };
+  auto gm_of = [&](int g) -> uint32_t { return staged ? (snap_mp(c)[g] & 0xffffffu) : cellp(g)->mass; };
   int npairs = 0, nres = 0;  // warp-uniform
   for (int hq = 0; hq < nhit; hq++) {
     int q = c.sm.hitq()[hq];
@@ -1858,7 +1869,12 @@ __device__ void players_collision(Ctx& c) {
     while (multi) {
       int src = __ffs(multi) - 1;
       multi &= multi - 1;
-      sort_player_cells(c, __shfl_sync(AG_FULL, p, src), __shfl_sync(AG_FULL, n, src));
+      const int sp = __shfl_sync(AG_FULL, p, src);
+      // new cells get ascending ids and are appended, erased cells close the gap: a player that was in order stays in order
+      // until a merge (tick_player) -- no need to load its cells just to find that out
+      if ((sp < 32 ? c.sorted_lo >> sp : c.sorted_hi >> (sp - 32)) & 1u) continue;
+      sort_player_cells(c, sp, __shfl_sync(AG_FULL, n, src));
+      if (sp < 32) c.sorted_lo |= 1u << sp; else c.sorted_hi |= 1u << (sp - 32);
     }
     int incl = n;
 #pragma unroll
@@ -1875,18 +1891,22 @@ __device__ void players_collision(Ctx& c) {
   __syncwarp();
   // 2. all-pairs pre-test (superset of what the strip sweep can return); hit queries in ascending order.
   //    q can only eat g if mass_q > mass_g, so max(r_q, r_g) = r_q in Ball::collides_with.
-  const bool staged = total <= kSnapCap;
+  bool staged = total <= kSnapCap;
   if (staged) {
     for (int g = lane; g < total; g += 32) {
       int r = c.sm.cellref()[g];
       float4 pc = c.sm.pcell()[r >> 8];
+      float sx, sy;
+      uint32_t smass;
       if (pc.w >= 0.0f) {  // lane-ticked single-cell player: its cell is already in shared memory
-        c.sm.snap()[g] = make_float4(pc.x, pc.y, pc.z, __int_as_float(r >> 8));
+        sx = pc.x; sy = pc.y; smass = __float_as_uint(pc.z);
       } else {
         const agarcl_cell* gc = c.pcells(r >> 8) + (r & 0xff);
         float4 a = reinterpret_cast<const float4*>(gc)[0];
-        c.sm.snap()[g] = make_float4(a.x, a.y, __uint_as_float(gc->mass), __int_as_float(r >> 8));
+        sx = a.x; sy = a.y; smass = gc->mass;
       }
+      snap_x(c)[g] = sx; snap_y(c)[g] = sy;
+      snap_mp(c)[g] = (smass & 0xffffffu) | ((uint32_t)(r >> 8) << 24);
     }
     __syncwarp();
   }
@@ -1898,8 +1918,8 @@ __device__ void players_collision(Ctx& c) {
     int qp = -1;
     if (q < total) {
       if (staged) {
-        float4 sg = c.sm.snap()[q];
-        qx = sg.x; qy = sg.y; qm = __float_as_uint(sg.z); qp = __float_as_int(sg.w);
+        const uint32_t mp = snap_mp(c)[q];
+        qx = snap_x(c)[q]; qy = snap_y(c)[q]; qm = mp & 0xffffffu; qp = (int)(mp >> 24);
       } else {
         int r = c.sm.cellref()[q];
         qp = r >> 8;
@@ -1915,9 +1935,8 @@ __device__ void players_collision(Ctx& c) {
     bool hit = false;
     if (staged) {
       for (int g = 0; g < total; g++) {
-        float4 sg = c.sm.snap()[g];
-        if (qr2 >= sqr_dist(qx, qy, sg.x, sg.y) && hungry && __float_as_int(sg.w) != qp &&
-            can_eat_mass(qm, __float_as_uint(sg.z)))
+        const uint32_t mp = snap_mp(c)[g];
+        if (qr2 >= sqr_dist(qx, qy, snap_x(c)[g], snap_y(c)[g]) && hungry && (int)(mp >> 24) != qp && can_eat_mass(qm, mp & 0xffffffu))
           hit = true;
       }
     } else {
@@ -1943,7 +1962,7 @@ __device__ void players_collision(Ctx& c) {
   // 3. exact path: strip ids of the snapshot cells by all lanes, then the serial sweep by one
   for (int g = lane; g < total; g += 32) {
     float x;
-    if (staged) x = c.sm.snap()[g].x;
+    if (staged) x = snap_x(c)[g];
     else { int r = c.sm.cellref()[g]; x = (c.pcells(r >> 8) + (r & 0xff))->x; }
     c.sm.rows()[g] = (int16_t)get_row(x, c.W);
   }
@@ -2532,6 +2551,7 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
   c.nprem = 0; c.nvrem = 0;
   c.emitted = 0; c.hash_valid = false; c.vc_valid = false; c.lanes_dirty = false; c.min_vmass = 0xffffffffu;
   c.pel_dirty = false;
+  c.sorted_lo = 0u; c.sorted_hi = 0u;
   c.W = P.W;
 
   // player summaries (centroid, mass, count): from the registers for a one-cell player
@@ -2864,6 +2884,8 @@ cudaError_t launch_step(const SimParams& P, cudaStream_t stream) {
   }
   int warps = (int)(((size_t)smem_max - P.tiles_bytes) / P.smem_per_warp);
   if (warps > kMaxWarpsPerCta) warps = kMaxWarpsPerCta;
+  static const int cap = [] { const char* e = std::getenv("AGARCL_WARPS"); return e ? std::atoi(e) : 0; }();  // (A/B timing)
+  if (cap > 0 && warps > cap) warps = cap;
   if (warps < 1) return cudaErrorInvalidConfiguration;
   const size_t smem = (size_t)P.tiles_bytes + (size_t)P.smem_per_warp * warps;
   int ctas = (P.N + warps - 1) / warps;

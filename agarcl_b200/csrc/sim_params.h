@@ -15,7 +15,7 @@ constexpr int kVremCap = 32;          // viruses_to_remove entries per tick (Eng
 constexpr int kCandCap = 32;          // pellet candidates resolved in registers per cell
 constexpr int kLaneCand = 8;          // pellet candidates a single lane resolves in the lane-per-player phase
 constexpr int kZeroTileBytes = 4096;  // CTA-shared all-zero tile, source of the TMA bulk stores that clear the observation
-constexpr int kSnapCap = 64;          // cells staged in shared memory by the players_collision pre-test
+constexpr int kSnapCap = 96;          // cells staged in shared memory by the players_collision pre-test (12 bytes each: x, y, mass | player << 24)
 constexpr int kPairCap = 48;          // (eater, eaten) pairs per tick in players_collision
 constexpr int kCellRefCap = 256;      // total live cells per instance handled by players_collision
 

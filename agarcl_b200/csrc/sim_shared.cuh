@@ -50,8 +50,8 @@ inline uint32_t make_smem_offsets(const agarcl_layout& L, int HG, SmemOff& o) {
   o.prem = p;    p += ag_align16(kPremCap * 2u);                   // u16 [kPremCap] pellets_to_remove
   o.vrem = p;    p += ag_align16(kVremCap * 2u);                   // u16 [kVremCap] viruses_to_remove
   o.lprem = p;   p += ag_align16(32u * kLaneCand * 2u);            // u16 [32][kLaneCand] pellets eaten by each lane's player
-  o.snap = u0;                                                     // float4 [kSnapCap] snapshot: x, y, mass bits, player
-  if (p - u0 < kSnapCap * 16u) p = u0 + kSnapCap * 16u;
+  o.snap = u0;                                                     // f32 x[kSnapCap], f32 y[kSnapCap], u32 (mass | player << 24)[kSnapCap]
+  if (p - u0 < kSnapCap * 12u) p = u0 + kSnapCap * 12u;
   o.hitq = p;    p += ag_align16(kPairCap * 2u);                   // u16 [kPairCap] queries flagged by the pre-test
   o.htmp = tmp0;                                                   // u32 [HG*HG] counters of the hash build
   if (p - tmp0 < (uint32_t)(HG * HG) * 4u) p = tmp0 + ag_align16((uint32_t)(HG * HG) * 4u);
