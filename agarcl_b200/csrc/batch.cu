@@ -136,6 +136,7 @@ static void fill_sim_params(const agarcl_batch* b, ag::SimParams& P) {
   P.HG = b->HG;
   P.W = (float)b->cfg.arena_size;
   P.hash_scale = (float)b->HG / (float)b->cfg.arena_size;
+  P.r_pellet = (float)std::sqrt((double)AGARCL_PELLET_MASS / 1.0 / M_PI);
   // initialize_pellet_grid / initialize_virus_grid: int((W + size - 1) / size) in fp32 (Engine.hpp:962-965,1207-1211)
   P.gw_pellet = (int)(((float)b->cfg.arena_size + 510.0f - 1.0f) / 510.0f);
   P.gw_virus = (int)(((float)b->cfg.arena_size + 25.0f - 1.0f) / 25.0f);

@@ -746,10 +746,19 @@ __device__ void tick_player(Ctx& c, int p) {
   c.emitted = 0;
   if (n == 0) return;  // dead players are not ticked (Engine.hpp:216)
   const int lane = c.lane;
-  float tx = pl->target_x, ty = pl->target_y;
-  int action = pl->action;
-  const int bot_type = pl->bot_type;
-  int elapsed = pl->elapsed_ticks + 1;
+  // the first 64 bytes of the player record in ONE round trip, next to the cell loads below (every later field access would
+  // otherwise be its own dependent trip to L1 / L2 behind the stores in between): w0 n_cells, target x / y, action |
+  // w1 split_cd, feed_cd, anti_team_decay, elapsed_ticks | w2 last_decay_tick, bot_type, min_mass_cell, food_eaten |
+  // w3 highest_mass, cells_eaten, viruses_eaten, vet_count
+  int4 w0, w1, w2, w3;
+  {
+    const int4* rec = reinterpret_cast<const int4*>(pl);
+    w0 = ldg_keep(rec); w1 = ldg_keep(rec + 1); w2 = ldg_keep(rec + 2); w3 = ldg_keep(rec + 3);
+  }
+  float tx = __int_as_float(w0.y), ty = __int_as_float(w0.z);
+  int action = w0.w;
+  const int bot_type = w2.y;
+  int elapsed = w1.w + 1;
 
   // Engine::move_player + check_player_self_collisions may have run ahead in the pooled pair solver (premove_players)
   const bool premoved = ((p < 32 ? c.pre_lo >> p : c.pre_hi >> (p - 32)) & 1u) != 0u;
@@ -789,7 +798,7 @@ __device__ void tick_player(Ctx& c, int p) {
   int create_limit = AGARCL_PLAYER_CELL_LIMIT - n;
   const bool can_eat_virus = n >= AGARCL_PLAYER_CELL_LIMIT;
   int viruses_eaten_inc = 0;
-  int vet_count = pl->vet_count;
+  int vet_count = w3.w;
 
   // ---- optimized_check_virus_collisions: first hit in (cell, dx, dy, virus index) order
   if (c.n_viruses > 0) {
@@ -993,9 +1002,9 @@ __device__ void tick_player(Ctx& c, int p) {
       __syncwarp();
     }
   }
-  int food_eaten = pl->food_eaten + pellets_eaten;
+  int food_eaten = w2.w + pellets_eaten;
   uint32_t total_mass = warp_sum_u32(lane < n ? me.mass : 0u);
-  uint32_t highest = max(pl->highest_mass, total_mass);
+  uint32_t highest = max((uint32_t)w3.x, total_mass);
 
   // ---- may_be_auto_split for every cell (children keep cell order), then eat_food cell by cell
   {
@@ -1074,7 +1083,7 @@ __device__ void tick_player(Ctx& c, int p) {
   create_limit -= created;
 
   // ---- maybe_emit_food / emit_foods
-  int feed_cd = pl->feed_cd, split_cd = pl->split_cd;
+  int feed_cd = w1.y, split_cd = w1.x;
   if (feed_cd > 0) feed_cd -= 1;
   if (action == 1 && feed_cd == 0) {
     bool emit = lane < n && me.mass >= AGARCL_CELL_MIN_SIZE + AGARCL_FOOD_MASS;
@@ -1171,8 +1180,8 @@ __device__ void tick_player(Ctx& c, int p) {
   }
 
   // ---- once per 60 player-ticks: anti-team + decay
-  float atd = pl->anti_team_decay;
-  int last_decay = pl->last_decay_tick;
+  float atd = __int_as_float(w1.z);
+  int last_decay = w2.x;
   if (c.P.L.mass_decay && elapsed % 60 == 0) {
     int fall_off = elapsed - 60 * 60;
     __syncwarp();
@@ -1200,17 +1209,11 @@ __device__ void tick_player(Ctx& c, int p) {
   if (lane == 0) {
     c.sm.psum()[p] = s;
     c.sm.pcell()[p].w = -1.0f;  // not lane-ticked: the collision snapshot reads this player from memory
-    pl->n_cells = n;
-    pl->target_x = tx; pl->target_y = ty;
-    pl->action = action;
-    pl->split_cd = split_cd; pl->feed_cd = feed_cd;
-    pl->anti_team_decay = atd;
-    pl->elapsed_ticks = elapsed; pl->last_decay_tick = last_decay;
-    pl->min_mass_cell = smallest;
-    pl->food_eaten = food_eaten;
-    pl->highest_mass = highest;
-    pl->viruses_eaten += viruses_eaten_inc;
-    pl->vet_count = vet_count;
+    int4* rec = reinterpret_cast<int4*>(pl);  // (cells_eaten, w3.y, is players_collision's: carried over)
+    stg_keep(rec, make_int4(n, __float_as_int(tx), __float_as_int(ty), action));
+    stg_keep(rec + 1, make_int4(split_cd, feed_cd, __float_as_int(atd), elapsed));
+    stg_keep(rec + 2, make_int4(last_decay, bot_type, (int)smallest, food_eaten));
+    stg_keep(rec + 3, make_int4((int)highest, w3.y, w3.z + viruses_eaten_inc, vet_count));
   }
   __syncwarp();
 }
@@ -1295,9 +1298,12 @@ __device__ bool lane_eat_pellets(const Ctx& c, float cx, float cy, uint32_t& mas
   const Luts& T = c.P.T;
   const int HG = c.P.HG;
   const float2* pel = c.sm.spel();
-  const float rp = radius_of(T, 1u);
+  const float rp = c.P.r_pellet;  // radius_of(T, 1)
   const int gx = (int)cx / 510, gy = (int)cy / 510;
-  const float Rc = fmax_std(radius_of(T, mass + (uint32_t)kCandCap), rp);
+  // candidate radius: any upper bound of the radius the cell can reach in this scan, radius(mass + kCandCap), will do (every
+  // candidate is tested with its exact radius below) -- computed, not looked up: most scans find nothing and then never
+  // touch the table at all
+  const float Rc = fmax_std(__fsqrt_ru(__fmul_ru((float)(mass + (uint32_t)kCandCap), 0.31830990f)) * 1.00001f, rp);
   const float Rc2 = Rc * Rc;
   const int hx0 = hash_coord(c, cx - Rc), hx1 = hash_coord(c, cx + Rc);
   const int hy0 = hash_coord(c, cy - Rc), hy1 = hash_coord(c, cy + Rc);

@@ -91,6 +91,7 @@ struct SimParams {
   int32_t HG;              // spatial hash is HG x HG over the arena
   float W;                 // arena width == height
   float hash_scale;        // HG / W
+  float r_pellet;          // radius_conversion(PELLET_MASS = 1), the table's entry (core/utils.hpp:8-11)
   int32_t gw_pellet;       // reference pellet bucket grid width (bucket 510, Engine.hpp:962-965)
   int32_t gw_virus;        // reference virus bucket grid width (bucket 25, Engine.hpp:1207-1211)
   uint32_t smem_per_warp;  // bytes
