@@ -1413,18 +1413,21 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
   agarcl_player* pl = c.players_() + p;
   Cell& me = ls.me;
   int4 &w0 = ls.w0, &w1 = ls.w1, &w2 = ls.w2, &w3 = ls.w3;
-  if (valid && !ls.fresh) {  // record and first cell in ONE round trip (the cell slot exists even for a dead player)
+  // the cell count comes from the summary table (== the record's n_cells); only a lane that ticks its player itself (one cell)
+  // needs the record and the cell in registers -- the lanes of multi-cell and dead players no longer send the whole warp to
+  // memory at the start of every tick
+  const int n = valid ? __float_as_int(c.sm.psum()[p].w) : 0;
+  if (n == 1 && !ls.fresh) {  // record and cell in ONE round trip
     const int4* rec = reinterpret_cast<const int4*>(pl);
     w0 = ldg_keep(rec); w1 = ldg_keep(rec + 1); w2 = ldg_keep(rec + 2); w3 = ldg_keep(rec + 3);
     me = cell_load(c.pcells(p));
     ls.fresh = true;
   }
-  const int n = valid ? w0.x : 0;
   // lane states: a looking bot that decides this tick must see the players before it in the order as already
   // committed, so it is speculated LATE, alone, when the ordered commit reaches it
   enum { kIdle = 0, kPending = 1, kLate = 2, kReady = 3, kSerial = 4 };
   int st = n >= 2 ? kSerial : (n == 1 ? kPending : kIdle);  // dead players are not ticked (Engine.hpp:216)
-  if (st == kPending && c.tick % 10u == 0u && w2.y > 0) st = kLate;
+  if (st == kPending && c.tick % 10u == 0u && c.P.L.bot_type[p] > 0) st = kLate;
   float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t food_mass = 0;  // mass at the time of eat_food (after pellets, before decay)
   int ne = 0;
