@@ -105,6 +105,24 @@ constexpr int kHashDead = 0xffff;  // hash entry of a pellet removed since the h
 // ------------------------------------------------------------------------------------------------
 // per-warp context: uniform registers + pointers
 // ------------------------------------------------------------------------------------------------
+// The warp-uniform state of the instance that is touched a few times per tick at most.  It lives in the warp's shared memory:
+// as members of Ctx these values were spilled to local memory around every solver loop (32 copies of each, one per lane, in
+// an L1 of ~24 KB next to 227 KB of shared memory: 69 % of the spill reloads missed, profiles/r02_experiments), here they are
+// one 4-byte broadcast load away.  Every lane stores the same value (warp-uniform code only), so no lane election is needed.
+struct ColdCtx {
+  long long work, t_mark;   // cycles this instance has worked (waiting at the alignment barriers excluded) / start of the current stretch
+  uint32_t zagent, zoff, zchunk;  // fused observation clear: cursor (agent, vector) and vectors per chunk
+  uint32_t next_id, cursor, done_sticky;  // header fields
+  uint32_t min_vmass;   // smallest virus mass this tick (0xffffffff without viruses)
+  uint32_t pre_lo, pre_hi;  // players whose move + self-collisions of this tick are already done (premove_players)
+  uint32_t sorted_lo, sorted_hi;  // players whose cells are known to be in ascending id order (sort_player_cells can be skipped)
+  int emitted;          // foods appended by the last tick_player (Engine::emit_foods)
+  int inst_local;
+  int pos;              // position of the instance in this launch's schedule (the host mirror's lists are laid out by position)
+  int tb;               // the alignment barriers of this launch (P.tick_barrier, or 0 when the launch runs the free-running schedule)
+};
+static_assert(sizeof(ColdCtx) <= kColdCtxBytes, "ColdCtx outgrew its shared-memory slot");
+
 struct Ctx {
   const SimParams& P;
   int lane;
@@ -115,23 +133,15 @@ struct Ctx {
   __device__ __forceinline__ agarcl_virus* vir_() const { return reinterpret_cast<agarcl_virus*>(blob + P.L.off_viruses); }
   __device__ __forceinline__ agarcl_food* food_() const { return reinterpret_cast<agarcl_food*>(blob + P.L.off_foods); }
   __device__ __forceinline__ agarcl_pellet* pel_() const { return reinterpret_cast<agarcl_pellet*>(blob + P.L.off_pellets); }
+  __device__ __forceinline__ ColdCtx& cold() const { return *reinterpret_cast<ColdCtx*>(sm.base + P.so.cold); }
   // header, kept in registers for the whole launch
-  uint32_t tick, next_id, cursor, flags, done_sticky;
+  uint32_t tick, flags;
   int n_pellets, n_viruses, n_foods;
   int nprem, nvrem;
-  int emitted;          // foods appended by the last tick_player (Engine::emit_foods)
   bool hash_valid;      // the pellet hash in shared memory matches the pellet array
   bool pel_dirty;       // the pellet array in shared memory differs from the blob's (written back when the warp leaves the instance)
-  uint32_t min_vmass;   // smallest virus mass this tick (0xffffffff without viruses)
-  uint32_t zagent, zoff, zchunk;  // fused observation clear: cursor (agent, vector) and vectors per chunk
   bool vc_valid;        // the virus cache in shared memory matches the virus array
   bool lanes_dirty;     // players_collision changed players: lanes must reload their registers
-  uint32_t pre_lo, pre_hi;  // players whose move + self-collisions of this tick are already done (premove_players)
-  uint32_t sorted_lo, sorted_hi;  // players whose cells are known to be in ascending id order (sort_player_cells can be skipped)
-  long long work, t_mark;   // cycles this instance has worked (waiting at the alignment barriers excluded) / start of the current stretch
-  int tb;               // the alignment barriers of this launch (P.tick_barrier, or 0 when the launch runs the free-running schedule)
-  int inst_local;
-  int pos;              // position of the instance in this launch's schedule (the host mirror's lists are laid out by position)
   float W;
   static constexpr float dt = (float)(1.0 / 30.0);
   __device__ Ctx(const SimParams& p) : P(p) {}
@@ -142,11 +152,11 @@ struct Ctx {
 __device__ __forceinline__ float draw_at(Ctx& c, uint32_t k) {
   if (c.P.rng_mode == AGARCL_RNG_PHILOX) {  // seed lives in the header: draws are rare (regen, respawn)
     const agarcl_inst_hdr* hdr = reinterpret_cast<const agarcl_inst_hdr*>(c.blob + c.P.L.off_hdr);
-    return philox_uniform(hdr->seed_lo, hdr->seed_hi, (uint32_t)(c.P.instance_base + c.inst_local), k);
+    return philox_uniform(hdr->seed_lo, hdr->seed_hi, (uint32_t)(c.P.instance_base + c.cold().inst_local), k);
   }
   // the host keeps the mt19937_64 stream filled ahead of the cursor in a ring (batch.cu, refill_replay)
-  if (c.P.rng_mode == AGARCL_RNG_MT19937 && c.P.replay) return c.P.replay[(size_t)c.inst_local * c.P.L.cap_replay + k % (uint32_t)c.P.L.cap_replay];
-  if ((int)k < c.P.L.cap_replay && c.P.replay) return c.P.replay[(size_t)c.inst_local * c.P.L.cap_replay + k];
+  if (c.P.rng_mode == AGARCL_RNG_MT19937 && c.P.replay) return c.P.replay[(size_t)c.cold().inst_local * c.P.L.cap_replay + k % (uint32_t)c.P.L.cap_replay];
+  if ((int)k < c.P.L.cap_replay && c.P.replay) return c.P.replay[(size_t)c.cold().inst_local * c.P.L.cap_replay + k];
   c.flags |= AGARCL_FLAG_REPLAY_EXHAUSTED;
   return 0.5f;
 }
@@ -538,7 +548,7 @@ __device__ void build_virus_cache(Ctx& c) {
     mn = min(mn, vm);
     c.sm.vcache()[v] = make_float4(a.x, a.y, radius_of(c.P.T, vm), a.z);
   }
-  c.min_vmass = warp_min_u32(mn);
+  c.cold().min_vmass = warp_min_u32(mn);
   __syncwarp();
 }
 
@@ -688,12 +698,12 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
   epoch = __shfl_sync(AG_FULL, epoch, 0);
   if (lane == 0) {
     mine[0] = nb; mine[1] = 0u; mine[2] = 0u; mine[3] = 0u; mine[5] = 0u; mine[7] = 0u;
-    mine[4] = c ? (uint32_t)c->inst_local : 0u;
+    mine[4] = c ? (uint32_t)c->cold().inst_local : 0u;
     __threadfence_block();
     *pub = epoch;
   }
   __syncwarp();
-  if (c) c->work += clock64() - c->t_mark;
+  if (c) c->cold().work += clock64() - c->cold().t_mark;
   // No barrier in front of the pool: a warp that gets here early starts on whatever has been published (its own
   // batches included) instead of waiting for the slowest instance of the CTA to arrive.  It takes the next batch of
   // the mailbox that has handed out the fewest so far (the mailboxes list their long batches first: roughly
@@ -731,10 +741,10 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
   __threadfence_block();
   align_barrier(nw);  // every batch is done: the cells are back in the cell arrays, the mailboxes say which players
   if (c) {
-    c->pre_lo = mine[1]; c->pre_hi = mine[2];
+    c->cold().pre_lo = mine[1]; c->cold().pre_hi = mine[2];
     c->flags |= mine[3];
-    c->work += (long long)mine[5];
-    c->t_mark = clock64();
+    c->cold().work += (long long)mine[5];
+    c->cold().t_mark = clock64();
   }
   __syncwarp();
 }
@@ -743,7 +753,7 @@ __device__ void tick_player(Ctx& c, int p) {
   const Luts& T = c.P.T;
   agarcl_player* pl = c.players_() + p;
   int n = __float_as_int(c.sm.psum()[p].w);  // == pl->n_cells, without the trip to memory in front of the cell loads
-  c.emitted = 0;
+  c.cold().emitted = 0;
   if (n == 0) return;  // dead players are not ticked (Engine.hpp:216)
   const int lane = c.lane;
   // the first 64 bytes of the player record in ONE round trip, next to the cell loads below (every later field access would
@@ -761,7 +771,7 @@ __device__ void tick_player(Ctx& c, int p) {
   int elapsed = w1.w + 1;
 
   // Engine::move_player + check_player_self_collisions may have run ahead in the pooled pair solver (premove_players)
-  const bool premoved = ((p < 32 ? c.pre_lo >> p : c.pre_hi >> (p - 32)) & 1u) != 0u;
+  const bool premoved = ((p < 32 ? c.cold().pre_lo >> p : c.cold().pre_hi >> (p - 32)) & 1u) != 0u;
   Cell me;
   me.x = me.y = me.vx = me.vy = me.svx = me.svy = 0.0f;
   me.mass = 0; me.id = 0; me.rec = 0;
@@ -804,7 +814,7 @@ __device__ void tick_player(Ctx& c, int p) {
   if (c.n_viruses > 0) {
     // only cells that could eat the smallest virus can touch one at all (mass > 1.1 * virus mass): the 25-mass
     // fragments of a popped player are skipped wholesale
-    unsigned vcells = __ballot_sync(AG_FULL, lane < n && can_eat_mass(me.mass, c.min_vmass));
+    unsigned vcells = __ballot_sync(AG_FULL, lane < n && can_eat_mass(me.mass, c.cold().min_vmass));
     while (vcells) {
       const int i = __ffs(vcells) - 1;
       vcells &= vcells - 1u;
@@ -847,6 +857,7 @@ __device__ void tick_player(Ctx& c, int p) {
           float theta = vel_direction(par.vx, par.vy);
           float sp = max_speed_of(T, 25u, c.flags);
           int ci = lane - n;
+          const uint32_t nid = c.cold().next_id;
           if (ci >= 0 && ci < num) {
             float dvel = theta + (float)(2 * AG_PI * ci / num);
             float ang = theta + dvel;
@@ -854,12 +865,13 @@ __device__ void tick_player(Ctx& c, int p) {
             me.vx = par.vx; me.vy = par.vy;
             me.svx = sp * g_sincosf(ang, 1); me.svy = sp * g_sincosf(ang, 0);  // Velocity(angle, speed), core/types.hpp:158-159
             me.mass = 25u;
-            me.id = c.next_id + (uint32_t)ci;
+            me.id = nid + (uint32_t)ci;
             me.rec = c.tick + AGARCL_RECOMBINE_TICKS;
           }
           if (lane == i) { me.mass = m2; me.rec = c.tick + AGARCL_RECOMBINE_TICKS; }
           created += num;
-          c.next_id += (uint32_t)num;
+          __syncwarp();
+          c.cold().next_id = nid + (uint32_t)num;
         }
         if (c.nvrem < kVremCap) { if (lane == 0) c.sm.vrem()[c.nvrem] = (uint16_t)v; c.nvrem++; }
         else c.flags |= AGARCL_FLAG_REMOVE_OVERFLOW;
@@ -1036,14 +1048,16 @@ __device__ void tick_player(Ctx& c, int p) {
         float gx_ = __shfl_sync(AG_FULL, chx, src), gy_ = __shfl_sync(AG_FULL, chy, src);
         float gvx = __shfl_sync(AG_FULL, chvx, src), gvy = __shfl_sync(AG_FULL, chvy, src);
         uint32_t gm = __shfl_sync(AG_FULL, chm, src);
+        const uint32_t nid = c.cold().next_id;
         if (r >= 0 && r < cnt) {
           me.x = gx_; me.y = gy_; me.vx = gvx; me.vy = gvy; me.svx = gvx; me.svy = gvy;
           me.mass = floor_mass(gm);
-          me.id = c.next_id + (uint32_t)r;
+          me.id = nid + (uint32_t)r;
           me.rec = c.tick + AGARCL_RECOMBINE_TICKS;
         }
         created += cnt;
-        c.next_id += (uint32_t)cnt;
+        __syncwarp();
+        c.cold().next_id = nid + (uint32_t)cnt;
       } else if (big) {
         me.mass = AGARCL_NEW_MASS_IF_NO_SPLIT;
       }
@@ -1101,7 +1115,7 @@ __device__ void tick_player(Ctx& c, int p) {
     int add = __popc(em);
     if (c.n_foods + add > c.P.L.cap_foods) { c.flags |= AGARCL_FLAG_FOOD_OVERFLOW; add = c.P.L.cap_foods - c.n_foods; }
     c.n_foods += add;
-    c.emitted = add;
+    c.cold().emitted = add;
     feed_cd = 10;
     __syncwarp();
   }
@@ -1138,14 +1152,16 @@ __device__ void tick_player(Ctx& c, int p) {
       float gx_ = __shfl_sync(AG_FULL, chx, src), gy_ = __shfl_sync(AG_FULL, chy, src);
       float gvx = __shfl_sync(AG_FULL, chvx, src), gvy = __shfl_sync(AG_FULL, chvy, src);
       uint32_t gm = __shfl_sync(AG_FULL, chm, src);
+      const uint32_t nid = c.cold().next_id;
       if (r >= 0 && r < cnt) {
         me.x = gx_; me.y = gy_; me.vx = gvx; me.vy = gvy; me.svx = gvx; me.svy = gvy;
         me.mass = floor_mass(gm);
-        me.id = c.next_id + (uint32_t)r;
+        me.id = nid + (uint32_t)r;
         me.rec = c.tick + AGARCL_RECOMBINE_TICKS;
       }
       created += cnt;
-      c.next_id += (uint32_t)cnt;
+      __syncwarp();
+      c.cold().next_id = nid + (uint32_t)cnt;
     }
     split_cd = 30;
   }
@@ -1202,7 +1218,7 @@ __device__ void tick_player(Ctx& c, int p) {
     __syncwarp();
   }
 
-  if (merged) { if (p < 32) c.sorted_lo &= ~(1u << p); else c.sorted_hi &= ~(1u << (p - 32)); }
+  if (merged) { if (p < 32) c.cold().sorted_lo &= ~(1u << p); else c.cold().sorted_hi &= ~(1u << (p - 32)); }
   // ---- publish: centroid for later readers this tick, cells and player record back to the blob
   float4 s = centroid_of(me, n);
   if (lane < n) cell_store(c.pcells(p) + lane, me);
@@ -1404,7 +1420,7 @@ struct LaneState {
   bool fresh;           // registers == global memory (the lane committed this player itself)
 };
 
-__device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
+__device__ __forceinline__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
   const Luts& T = c.P.T;
   const int lane = c.lane;
   const int k = base + lane;
@@ -1479,7 +1495,7 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
     bound_cell(c, me);
 
     // ---- optimized_check_virus_collisions: any contact (eat or disrupt) is structural -> serial
-    if (c.n_viruses > 0 && can_eat_mass(me.mass, c.min_vmass)) {
+    if (c.n_viruses > 0 && can_eat_mass(me.mass, c.cold().min_vmass)) {
       const float cr = radius_of(T, me.mass);
       const int gx = (int)me.x / 25, gy = (int)me.y / 25;
       bool hit = false;
@@ -1579,12 +1595,12 @@ __device__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
     if (!((serm >> nxt) & 1u)) { pos = nxt; continue; }  // a late lane: it speculates now, on what has been committed
     tick_player(c, c.P.L.order[base + nxt]);
     if (lane == nxt) st = kIdle;
-    if (c.emitted > 0) {
+    if (c.cold().emitted > 0) {
       // foods emitted by this player can be eaten by later players in the same tick (Engine.hpp:1011-1025)
       bool hit = false;
       if (st == kReady && lane > nxt && can_eat_mass(food_mass, AGARCL_FOOD_MASS)) {
         const float cr = radius_of(T, food_mass), rf = radius_of(T, AGARCL_FOOD_MASS);
-        for (int j = c.n_foods - c.emitted; j < c.n_foods; j++) {
+        for (int j = c.n_foods - c.cold().emitted; j < c.n_foods; j++) {
           float4 f = reinterpret_cast<const float4*>(c.food_())[j];
           if (collides(me.x, me.y, cr, f.x, f.y, rf)) hit = true;
         }
@@ -1881,9 +1897,9 @@ __device__ void players_collision(Ctx& c) {
       const int sp = __shfl_sync(AG_FULL, p, src);
       // new cells get ascending ids and are appended, erased cells close the gap: a player that was in order stays in order
       // until a merge (tick_player) -- no need to load its cells just to find that out
-      if ((sp < 32 ? c.sorted_lo >> sp : c.sorted_hi >> (sp - 32)) & 1u) continue;
+      if ((sp < 32 ? c.cold().sorted_lo >> sp : c.cold().sorted_hi >> (sp - 32)) & 1u) continue;
       sort_player_cells(c, sp, __shfl_sync(AG_FULL, n, src));
-      if (sp < 32) c.sorted_lo |= 1u << sp; else c.sorted_hi |= 1u << (sp - 32);
+      if (sp < 32) c.cold().sorted_lo |= 1u << sp; else c.cold().sorted_hi |= 1u << (sp - 32);
     }
     int incl = n;
 #pragma unroll
@@ -2095,12 +2111,14 @@ __device__ void regen(Ctx& c) {
   int dp = c.P.target_pellets - c.n_pellets;
   if (dp > 0) {
     float r = radius_of(c.P.T, AGARCL_PELLET_MASS);
+    const uint32_t cur = c.cold().cursor;
     for (int k = c.lane; k < dp; k += 32) {
       float x, y;
-      random_location_at(c, c.cursor + 2u * (uint32_t)k, r, x, y);
+      random_location_at(c, cur + 2u * (uint32_t)k, r, x, y);
       if (c.n_pellets + k < c.P.L.cap_pellets) c.sm.spel()[c.n_pellets + k] = make_float2(x, y);
     }
-    c.cursor += 2u * (uint32_t)dp;
+    __syncwarp();
+    c.cold().cursor = cur + 2u * (uint32_t)dp;
     c.n_pellets = min(c.n_pellets + dp, c.P.L.cap_pellets);
     c.hash_valid = false;
     c.pel_dirty = true;
@@ -2109,16 +2127,18 @@ __device__ void regen(Ctx& c) {
   if (dv > 0) {
     float r = radius_of(c.P.T, AGARCL_VIRUS_INITIAL_MASS);
     int room = c.P.L.cap_viruses - c.n_viruses;
+    const uint32_t cur = c.cold().cursor;
     for (int k = c.lane; k < dv; k += 32) {
       float x, y;
-      random_location_at(c, c.cursor + 2u * (uint32_t)k, r, x, y);
+      random_location_at(c, cur + 2u * (uint32_t)k, r, x, y);
       if (k < room) {
         float4* v = reinterpret_cast<float4*>(c.vir_() + c.n_viruses + k);
         v[0] = make_float4(x, y, __uint_as_float(AGARCL_VIRUS_INITIAL_MASS), __int_as_float(0));
         v[1] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    c.cursor += 2u * (uint32_t)dv;
+    __syncwarp();
+    c.cold().cursor = cur + 2u * (uint32_t)dv;
     if (dv > room) { c.flags |= AGARCL_FLAG_VIRUS_OVERFLOW; dv = room; }
     c.n_viruses += dv;
     c.vc_valid = false;
@@ -2135,15 +2155,20 @@ __device__ void regen(Ctx& c) {
 __device__ __forceinline__ void zero_chunk(Ctx& c, uint32_t nvec) {
   const uint32_t per = c.P.zero_vec_per_agent;
   if (per == 0u) return;
-  while (nvec > 0u && c.zagent < (uint32_t)c.P.L.A) {
-    const uint32_t n = min(nvec, per - c.zoff);
+  ColdCtx& cc = c.cold();
+  uint32_t zagent = cc.zagent, zoff = cc.zoff;
+  if (zagent >= (uint32_t)c.P.L.A) return;
+  const uint32_t inst_local = (uint32_t)cc.inst_local;
+  __syncwarp();  // (every lane has read the cursor before any lane moves it)
+  while (nvec > 0u && zagent < (uint32_t)c.P.L.A) {
+    const uint32_t n = min(nvec, per - zoff);
     if (c.lane == 0) {
       extern __shared__ __align__(128) uint8_t smem_raw[];
       const uint32_t zero_tile = (uint32_t)__cvta_generic_to_shared(smem_raw);
       uint64_t zpolicy;  // L2 evict-first: the observation stream must not push the game state out of L2
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(zpolicy));
       uint8_t* dst = reinterpret_cast<uint8_t*>(c.P.obs) +
-                     16ull * (((size_t)c.inst_local * c.P.L.A + c.zagent) * c.P.agent_stride_vec + c.P.zero_skip_vec + c.zoff);
+                     16ull * (((size_t)inst_local * c.P.L.A + zagent) * c.P.agent_stride_vec + c.P.zero_skip_vec + zoff);
       uint32_t bytes = n * 16u;
       while (bytes > 0u) {
         const uint32_t b = min(bytes, (uint32_t)kZeroTileBytes);
@@ -2155,9 +2180,10 @@ __device__ __forceinline__ void zero_chunk(Ctx& c, uint32_t nvec) {
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     nvec -= n;
-    c.zoff += n;
-    if (c.zoff == per) { c.zoff = 0u; c.zagent++; }
+    zoff += n;
+    if (zoff == per) { zoff = 0u; zagent++; }
   }
+  cc.zagent = zagent; cc.zoff = zoff;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2224,7 +2250,7 @@ __device__ void obs_finish_warp(Ctx& c) {
   const uint32_t ones_tile = (uint32_t)__cvta_generic_to_shared(smem_raw + kZeroTileBytes);  // (present with obs_finish)
   const uint32_t yrow_s = (uint32_t)__cvta_generic_to_shared(yrow);
   for (int a = 0; a < A; a++) {
-    T* out = reinterpret_cast<T*>(P.obs) + ((size_t)c.inst_local * A + a) * ((size_t)P.agent_stride_vec * (16u / sizeof(T)));
+    T* out = reinterpret_cast<T*>(P.obs) + ((size_t)c.cold().inst_local * A + a) * ((size_t)P.agent_stride_vec * (16u / sizeof(T)));
     const float4 s = c.sm.psum()[a];
     const float px = s.x, py = s.y;  // Player::x / y: NaN for a dead agent (quirk Q20)
     const uint32_t tot = __float_as_uint(s.z);
@@ -2262,13 +2288,13 @@ __device__ void obs_finish_warp(Ctx& c) {
     uint32_t pk_mine = 0u;       // lane l holds word l of the record: count, base, image, row masks, column masks
     uint32_t wq = 0u;            // entries listed so far (warp-uniform, even)
     if (emit) {
-      const uint32_t slot = (uint32_t)c.pos * (uint32_t)A + (uint32_t)a;  // the image's place in this launch's schedule
+      const uint32_t slot = (uint32_t)c.cold().pos * (uint32_t)A + (uint32_t)a;  // the image's place in this launch's schedule
       const uint32_t chunk = slot / P.pk.ipc, li = slot - chunk * P.pk.ipc;
       uint32_t* blk = P.pk.chunks + (size_t)chunk * P.pk.chunk_words;
       pk_rec = blk + pk_off_rec(P.pk) + (size_t)li * P.pk.rec_words;
       pk_ent = reinterpret_cast<uint4*>(blk + pk_off_entries(P.pk)) + (size_t)li * (P.pk.slot / 2u);
       if (lane == 1) pk_mine = li * P.pk.slot;
-      if (lane == 2) pk_mine = (uint32_t)c.inst_local * (uint32_t)A + (uint32_t)a;  // which image this is
+      if (lane == 2) pk_mine = (uint32_t)c.cold().inst_local * (uint32_t)A + (uint32_t)a;  // which image this is
       const int MW = P.pk.MW;
       for (int i0 = 0, w = 0; i0 < G; i0 += 32, w++) {  // the row / column bit masks of channel 0 from the predicates above
         const int i = i0 + lane;
@@ -2428,37 +2454,36 @@ __device__ void obs_finish_warp(Ctx& c) {
 }
 
 // Engine::tick
-__device__ void engine_tick(Ctx& c, LaneState& ls) {
+__device__ __forceinline__ void engine_tick(Ctx& c, LaneState& ls) {
   if (!c.hash_valid) { build_pellet_hash(c); c.hash_valid = true; }
   if (!c.vc_valid) { build_virus_cache(c); c.vc_valid = true; }
-  zero_chunk(c, c.zchunk);
+  zero_chunk(c, c.cold().zchunk);
   c.nprem = 0;
   c.nvrem = 0;
   const int P = c.P.L.P;
   if (c.lanes_dirty) { ls.fresh = false; c.lanes_dirty = false; }
-  if (c.tb & 2) {  // the pair solver, pooled over the CTA; the warps enter the player loop together behind it
+  if (c.cold().tb & 2) {  // the pair solver, pooled over the CTA; the warps enter the player loop together behind it
     extern __shared__ __align__(128) uint8_t smem_raw[];
     premove_players(c.P, smem_raw, &c, (int)(threadIdx.x >> 5), c.lane);
   } else {
-    c.pre_lo = 0u; c.pre_hi = 0u;  // (no alignment barriers: tick_player moves and resolves every player itself)
+    c.cold().pre_lo = 0u; c.cold().pre_hi = 0u;  // (no alignment barriers: tick_player moves and resolves every player itself)
   }
-  tick_players_block(c, 0, ls);
-  for (int base = 32; base < P; base += 32) {  // more than 32 players: the further blocks reload every tick
-    LaneState tmp;
-    tmp.fresh = false;
-    tmp.w0 = tmp.w1 = tmp.w2 = tmp.w3 = make_int4(0, 0, 0, 0);
-    tmp.me.x = tmp.me.y = tmp.me.vx = tmp.me.vy = tmp.me.svx = tmp.me.svy = 0.0f;
-    tmp.me.mass = 0; tmp.me.id = 0; tmp.me.rec = 0;
-    tick_players_block(c, base, tmp);
+  // ONE call site, so that the body is inlined once (two sites made the compiler duplicate ~30 % of the kernel, or -- when it
+  // declined -- call it with Ctx in local memory): with more than 32 players every block starts from global memory, which is
+  // current because a lane commits its player before it leaves tick_players_block
+  for (int base = 0; base < P; base += 32) {
+    if (P > 32) ls.fresh = false;
+    tick_players_block(c, base, ls);
   }
-  zero_chunk(c, c.zchunk);
-  if (c.tb & 16) { c.work += clock64() - c.t_mark; align_barrier(c.P.align_group); c.t_mark = clock64(); }
+  if (P > 32) ls.fresh = false;
+  zero_chunk(c, c.cold().zchunk);
+  if (c.cold().tb & 16) { c.cold().work += clock64() - c.cold().t_mark; align_barrier(c.P.align_group); c.cold().t_mark = clock64(); }
   apply_removals(c);
-  zero_chunk(c, c.zchunk);
-  if (c.tb & 4) { c.work += clock64() - c.t_mark; align_barrier(c.P.align_group); c.t_mark = clock64(); }  // ... and the cross-player sweep
+  zero_chunk(c, c.cold().zchunk);
+  if (c.cold().tb & 4) { c.cold().work += clock64() - c.cold().t_mark; align_barrier(c.P.align_group); c.cold().t_mark = clock64(); }  // ... and the cross-player sweep
   players_collision(c);
-  zero_chunk(c, c.zchunk);
-  if (c.tb & 8) { c.work += clock64() - c.t_mark; align_barrier(c.P.align_group); c.t_mark = clock64(); }
+  zero_chunk(c, c.cold().zchunk);
+  if (c.cold().tb & 8) { c.cold().work += clock64() - c.cold().t_mark; align_barrier(c.P.align_group); c.cold().t_mark = clock64(); }
   move_foods(c);
   if (c.P.L.regen && c.tick % 120u == 0u) regen(c);
   c.tick++;
@@ -2497,14 +2522,15 @@ __device__ void respawn_player(Ctx& c, int p, uint32_t k) {
 __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_raw, const int inst, const int pos, const int warp,
                                               const int lane, uint32_t& mbar_phase, const int tb) {
   Ctx c(P);
-  c.tb = tb;
   c.lane = lane;
-  c.pos = pos;
-  c.work = 0; c.t_mark = clock64();
-  c.inst_local = inst;
   c.blob = P.state + (size_t)inst * P.L.stride;
   c.sm.base = smem_raw + P.tiles_bytes + (size_t)warp * P.smem_per_warp;
   c.sm.o = &P.so;
+  __syncwarp();  // (the previous instance of this warp is done with the slot)
+  c.cold().tb = tb;
+  c.cold().pos = pos;
+  c.cold().work = 0; c.cold().t_mark = clock64();
+  c.cold().inst_local = inst;
   // the pellet array comes in by one TMA bulk load (whole capacity: the count is not known yet); everything
   // below that does not touch pellets overlaps with it, build_pellet_hash is its first consumer
   const uint32_t pel_bytes = ((uint32_t)P.L.cap_pellets * 8u + 15u) & ~15u;  // pellets are the blob's last array: the pad is inside its stride
@@ -2522,6 +2548,7 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
   // header, this lane's player record + first cell (block 0 of the player order), two virus records per
   // lane and the agents' actions are all requested before the first of them is used.
   LaneState ls;
+  uint32_t done_sticky;  // lives in ColdCtx across the ticks
   const int k0 = lane;
   const bool valid0 = k0 < Pn;
   const int p0 = valid0 ? P.L.order[k0] : 0;
@@ -2554,13 +2581,13 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
     const int4 h0 = ldg_keep(reinterpret_cast<const int4*>(hdr));
     const int4 h1 = ldg_keep(reinterpret_cast<const int4*>(hdr) + 1);
     const int4 h2 = ldg_keep(reinterpret_cast<const int4*>(hdr) + 2);
-    c.tick = (uint32_t)h0.x; c.next_id = (uint32_t)h0.y; c.n_pellets = h0.z; c.n_viruses = h0.w;
-    c.n_foods = h1.x; c.cursor = (uint32_t)h1.y; c.flags = (uint32_t)h1.z; c.done_sticky = (uint32_t)h2.y;
+    c.tick = (uint32_t)h0.x; c.cold().next_id = (uint32_t)h0.y; c.n_pellets = h0.z; c.n_viruses = h0.w;
+    c.n_foods = h1.x; c.cold().cursor = (uint32_t)h1.y; c.flags = (uint32_t)h1.z; done_sticky = (uint32_t)h2.y;
   }
   c.nprem = 0; c.nvrem = 0;
-  c.emitted = 0; c.hash_valid = false; c.vc_valid = false; c.lanes_dirty = false; c.min_vmass = 0xffffffffu;
+  c.cold().emitted = 0; c.hash_valid = false; c.vc_valid = false; c.lanes_dirty = false; c.cold().min_vmass = 0xffffffffu;
   c.pel_dirty = false;
-  c.sorted_lo = 0u; c.sorted_hi = 0u;
+  c.cold().sorted_lo = 0u; c.cold().sorted_hi = 0u;
   c.W = P.W;
 
   // player summaries (centroid, mass, count): from the registers for a one-cell player
@@ -2596,7 +2623,7 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
         c.sm.vcache()[v] = make_float4(vpre[j].x, vpre[j].y, radius_of(P.T, vm), vpre[j].z);
       }
     }
-    c.min_vmass = warp_min_u32(mn);
+    c.cold().min_vmass = warp_min_u32(mn);
     c.vc_valid = true;
   }
   __syncwarp();
@@ -2616,7 +2643,7 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
         pl->target_y = s.y + ady * 10.0f;
         pl->action = aact;
       }
-      if (P.mode == 3 && m >= 23000u) c.done_sticky = 1u;
+      if (P.mode == 3 && m >= 23000u) done_sticky = 1u;
     }
     // the lane that holds an agent's record in registers applies the same action to its copy
     if (valid0 && p0 < A && ls.w0.x > 0) {
@@ -2625,17 +2652,18 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
       ls.w0.z = __float_as_int(s.y + hdy * 10.0f);
       ls.w0.w = hact;
     }
-    c.done_sticky = __reduce_or_sync(AG_FULL, c.done_sticky);
+    done_sticky = __reduce_or_sync(AG_FULL, done_sticky);
     __syncwarp();
   }
+  c.cold().done_sticky = done_sticky;
 
-  c.zagent = 0u; c.zoff = 0u;
+  c.cold().zagent = 0u; c.cold().zoff = 0u;
   {
     const uint32_t total = P.zero_vec_per_agent * (uint32_t)A;
     // spread evenly over all ticks: bursts of stores slow the ticks' own loads down more than the
     // last pieces cost the finish in waiting (measured, tools/exp_chunks.sh)
     const uint32_t chunks = P.zero_chunks > 0 ? (uint32_t)P.zero_chunks : (uint32_t)(4 * (P.n_ticks > 0 ? P.n_ticks : 1));
-    c.zchunk = (total + chunks - 1u) / chunks;
+    c.cold().zchunk = (total + chunks - 1u) / chunks;
   }
   {  // the pellets have arrived (all lanes observe the phase flip: their later reads are ordered behind it)
     const uint32_t mb = (uint32_t)__cvta_generic_to_shared(c.sm.mbar());
@@ -2656,11 +2684,12 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
     // number of barriers, so the warps move through their instances in rounds (k_step: cost-sorted stripes); what a
     // warp waits for the slowest one is far less than what the shared fetch saves (2.22 -> 1.41 ms per steady-state
     // step with the sorted schedule).  Finer alignment (per solver batch, more phases) loses more than it gains.
-    if (c.tb & 1) { c.work += clock64() - c.t_mark; align_barrier(P.align_group); c.t_mark = clock64(); }
+    if (c.cold().tb & 1) { c.cold().work += clock64() - c.cold().t_mark; align_barrier(P.align_group); c.cold().t_mark = clock64(); }
     engine_tick(c, ls);
   }
   zero_chunk(c, 0xffffffffu);  // whatever is left (n_ticks == 0, rounding)
 
+  done_sticky = c.cold().done_sticky;
   if (P.do_end) {
     if (P.obs_finish == 1) obs_finish_warp<int32_t>(c);
     else if (P.obs_finish == 2) obs_finish_warp<int16_t>(c);
@@ -2675,8 +2704,8 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
         unsigned dm = __ballot_sync(AG_FULL, dead);
         if (dead) {
           uint32_t r = rank_base + (uint32_t)__popc(dm & lanemask_lt(lane));
-          respawn_player(c, p, c.cursor + 2u * r);
-          c.pcells(p)->id = c.next_id + r;
+          respawn_player(c, p, c.cold().cursor + 2u * r);
+          c.pcells(p)->id = c.cold().next_id + r;
           c.sm.psum()[p] = centroid_from_global(c.pcells(p), 1);
         }
         rank_base += (uint32_t)__popc(dm);
@@ -2686,30 +2715,30 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
         resp_hi |= __reduce_or_sync(AG_FULL, (uint32_t)(bit >> 32));
       }
       if (lane == 0) { hdr->respawned_lo = resp_lo; hdr->respawned_hi = resp_hi; }
-      c.next_id += rank_base;
-      if (!(P.L.squared_pellets && c.n_pellets > 0)) c.cursor += 2u * rank_base;
+      c.cold().next_id += rank_base;
+      if (!(P.L.squared_pellets && c.n_pellets > 0)) c.cold().cursor += 2u * rank_base;
       c.flags = __reduce_or_sync(AG_FULL, c.flags);
       __syncwarp();
     } else if (P.mode > 6) {
       bool dead = false;
       for (int p = lane; p < Pn; p += 32) dead |= __float_as_int(c.sm.psum()[p].w) == 0;
-      c.done_sticky = __ballot_sync(AG_FULL, dead) ? 1u : 0u;  // dones_[0] rewritten every step (BaseEnvironment.hpp:103-114)
+      done_sticky = __ballot_sync(AG_FULL, dead) ? 1u : 0u;  // dones_[0] rewritten every step (BaseEnvironment.hpp:103-114)
     }
     for (int a = lane; a < A; a += 32) {
       uint32_t m = __float_as_uint(c.sm.psum()[a].z);
-      if (P.mode == 3 && m >= 23000u) c.done_sticky = 1u;
+      if (P.mode == 3 && m >= 23000u) done_sticky = 1u;
     }
-    c.done_sticky = __reduce_or_sync(AG_FULL, c.done_sticky);
+    done_sticky = __reduce_or_sync(AG_FULL, done_sticky);
     for (int a = lane; a < A; a += 32) {
       size_t gi = (size_t)inst * A + a;
       uint32_t m = __float_as_uint(c.sm.psum()[a].z);
       double r = (double)m;
       if (P.reward_type) r -= (double)(P.before[gi] - 0.0f);
       P.rewards[gi] = r;
-      const uint8_t dn = (a == 0) ? (uint8_t)(c.done_sticky != 0u) : (uint8_t)0;
+      const uint8_t dn = (a == 0) ? (uint8_t)(done_sticky != 0u) : (uint8_t)0;
       P.dones[gi] = dn;
       if (P.pk.chunks != nullptr && P.obs_finish) {  // host mirror: reward and done travel in the image's record
-        const uint32_t slot = (uint32_t)c.pos * (uint32_t)A + (uint32_t)a, chunk = slot / P.pk.ipc, li = slot - chunk * P.pk.ipc;
+        const uint32_t slot = (uint32_t)c.cold().pos * (uint32_t)A + (uint32_t)a, chunk = slot / P.pk.ipc, li = slot - chunk * P.pk.ipc;
         uint32_t* tail = P.pk.chunks + (size_t)chunk * P.pk.chunk_words + pk_off_rec(P.pk) + (size_t)li * P.pk.rec_words + (P.pk.rec_words - 3u);
         const unsigned long long rb = (unsigned long long)__double_as_longlong(r);
         tail[0] = (uint32_t)rb; tail[1] = (uint32_t)(rb >> 32); tail[2] = (uint32_t)dn;
@@ -2733,9 +2762,9 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
   }
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the source tiles / rows / pellets outlive their readers
   if (lane == 0) {
-    hdr->tick = c.tick; hdr->next_cell_id = c.next_id;
+    hdr->tick = c.tick; hdr->next_cell_id = c.cold().next_id;
     hdr->n_pellets = c.n_pellets; hdr->n_viruses = c.n_viruses; hdr->n_foods = c.n_foods;
-    hdr->rng_cursor = c.cursor; hdr->flags = c.flags; hdr->done_sticky = c.done_sticky;
+    hdr->rng_cursor = c.cold().cursor; hdr->flags = c.flags; hdr->done_sticky = done_sticky;
   }
   if (P.sched) {  // instances that hold a multi-cell player when the launch ends: k_order picks the next launch's schedule from the count
     bool multi = false;
@@ -2743,7 +2772,7 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
     if (__ballot_sync(AG_FULL, multi) && lane == 0) atomicAdd(P.sched + 1, 1u);
   }
   if (P.cost && lane == 0) {  // what the instance cost this step: next step's schedule puts equals together (k_order)
-    const long long w = c.work + (clock64() - c.t_mark);
+    const long long w = c.cold().work + (clock64() - c.cold().t_mark);
     P.cost[inst] = (uint32_t)(w < 0xffffffffll ? w : 0xffffffffll);
   }
   if (P.pk.chunks != nullptr && P.do_end && P.obs_finish) {

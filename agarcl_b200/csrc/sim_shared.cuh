@@ -41,6 +41,7 @@ inline uint32_t make_smem_offsets(const agarcl_layout& L, int HG, SmemOff& o) {
   // ticks and of the observation scatter is a shared-memory access, not a trip to L2 / HBM behind the obs stores
   o.spel = p;    p += ag_align16((uint32_t)L.cap_pellets * 8u);    // float2 [cap_pellets]
   o.mbar = p;    p += 16u;                                         // u64 mbarrier of the bulk load
+  o.cold = p;    p += kColdCtxBytes;                               // ColdCtx (sim_kernel.cu): the instance's warp-uniform, rarely used state
   // players_collision snapshot enumeration (also the y-mask row of the fused observation finish)
   const uint32_t tmp0 = p;
   o.cellref = p; p += ag_align16(kCellRefCap * 2u);                // u16 [kCellRefCap] (player << 8 | cell) in snapshot order
