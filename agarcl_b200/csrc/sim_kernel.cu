@@ -669,20 +669,20 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
         const int gshift = wide ? 4 : 3, per = 32 >> gshift;
         unsigned todo = __ballot_sync(AG_FULL, wide ? (np > 8 && np <= 16) : (np >= 2 && np <= 8));
         while (todo) {
-          uint32_t w12[2] = {0u, 0u};
+          uint32_t w1 = 0u, w2 = 0u;  // (two scalars: an array indexed by g lives in local memory)
           int count = 0;
           for (int g = 0; g < per && todo; g++) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1u;
-            const uint32_t pn = (uint32_t)__shfl_sync(AG_FULL, p, src) | ((uint32_t)__shfl_sync(AG_FULL, np, src) << 8);
-            w12[g >> 1] |= pn << ((g & 1) * 16);
+            const uint32_t pn = ((uint32_t)__shfl_sync(AG_FULL, p, src) | ((uint32_t)__shfl_sync(AG_FULL, np, src) << 8)) << ((g & 1) * 16);
+            if (g < 2) w1 |= pn; else w2 |= pn;
             count++;
           }
           if (nb < (uint32_t)kMailBatches) {
             if (lane == 0) {
               mine[kMailHdr + 4 * nb] = (uint32_t)gshift | ((uint32_t)count << 8);
-              mine[kMailHdr + 4 * nb + 1] = w12[0];
-              mine[kMailHdr + 4 * nb + 2] = w12[1];
+              mine[kMailHdr + 4 * nb + 1] = w1;
+              mine[kMailHdr + 4 * nb + 2] = w2;
             }
             nb++;
           }  // (more batches than the mailbox holds: tick_player does those players itself)
