@@ -121,7 +121,7 @@ struct ColdCtx {
   int pos;              // position of the instance in this launch's schedule (the host mirror's lists are laid out by position)
   int tb;               // the alignment barriers of this launch (P.tick_barrier, or 0 when the launch runs the free-running schedule)
 };
-static_assert(sizeof(ColdCtx) <= kColdCtxBytes, "ColdCtx outgrew its shared-memory slot");
+static_assert(sizeof(ColdCtx) <= kColdCtxBytes - 16, "ColdCtx outgrew its shared-memory slot");
 
 struct Ctx {
   const SimParams& P;
@@ -618,6 +618,10 @@ __device__ void premove_batch(const SimParams& P, uint8_t* blob, uint32_t w0, ui
 constexpr int kMailHdr = 8, kMailBatches = 64;
 static_assert((kMailHdr + 4 * kMailBatches) * 4 <= kCandCap * 8 + (kPremCap * 2 + 15) / 16 * 16 + (kVremCap * 2 + 15) / 16 * 16 + 32 * kLaneCand * 2,
               "the mailbox must fit into the player-loop scratch");
+// What must outlive the mailbox (scratch that the owner's player loop overwrites): [0] batches listed  [1] handed out  [2] completed.
+__device__ __forceinline__ volatile uint32_t* pool_slot(const SimParams& P, uint8_t* smem_raw, int warp) {
+  return reinterpret_cast<volatile uint32_t*>(smem_raw + P.tiles_bytes + (size_t)warp * P.smem_per_warp + P.so.cold + kColdCtxBytes - 16);
+}
 __device__ __forceinline__ volatile uint32_t* mailbox(const SimParams& P, uint8_t* smem_raw, int warp) {
   return reinterpret_cast<volatile uint32_t*>(smem_raw + P.tiles_bytes + (size_t)warp * P.smem_per_warp + P.so.cand);
 }
@@ -635,7 +639,7 @@ __device__ __forceinline__ volatile uint32_t* mailbox(const SimParams& P, uint8_
 // instance of the CTA -- the solver needs nothing but the state blob -- so the instance with three popped players
 // no longer keeps fifteen warps waiting at the barrier behind the solver, and a warp that arrives late finds its
 // own batches already being worked on.
-__device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, int warp, int lane) {
+__device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, int warp, int lane, int tb) {
   const int nw = blockDim.x >> 5;
   volatile uint32_t* mine = mailbox(P, smem_raw, warp);
   uint32_t nb = 0;
@@ -698,6 +702,8 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
   epoch = __shfl_sync(AG_FULL, epoch, 0);
   if (lane == 0) {
     mine[0] = nb; mine[1] = 0u; mine[2] = 0u; mine[3] = 0u; mine[5] = 0u; mine[7] = 0u;
+    volatile uint32_t* ps = pool_slot(P, smem_raw, warp);
+    ps[0] = nb; ps[1] = 0u; ps[2] = 0u;
     mine[4] = c ? (uint32_t)c->cold().inst_local : 0u;
     __threadfence_block();
     *pub = epoch;
@@ -711,8 +717,8 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
   for (;;) {
     const bool pubd = lane < nw &&
         *reinterpret_cast<volatile uint32_t*>(smem_raw + P.tiles_bytes + (size_t)lane * P.smem_per_warp + P.so.mbar + 8) == epoch;
-    volatile uint32_t* ml = mailbox(P, smem_raw, lane < nw ? lane : 0);
-    const uint32_t cnt = pubd ? ml[0] : 0u, tk = pubd ? ml[7] : 0u;
+    volatile uint32_t* ml = pool_slot(P, smem_raw, lane < nw ? lane : 0);
+    const uint32_t cnt = pubd ? ml[0] : 0u, tk = pubd ? ml[1] : 0u;
     const bool open = pubd && tk < cnt;
     const unsigned om = __ballot_sync(AG_FULL, open), pm = __ballot_sync(AG_FULL, pubd);
     if (om == 0u) {
@@ -723,7 +729,8 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
     const int owner = (int)(warp_min_u32(open ? (tk << 8 | (uint32_t)lane) : 0xffffffffu) & 0xffu);
     volatile uint32_t* mb = mailbox(P, smem_raw, owner);
     uint32_t idx = 0;
-    if (lane == 0) idx = atomicAdd(const_cast<uint32_t*>(mb + 7), 1u);
+    volatile uint32_t* os = pool_slot(P, smem_raw, owner);
+    if (lane == 0) idx = atomicAdd(const_cast<uint32_t*>(os + 1), 1u);
     idx = __shfl_sync(AG_FULL, idx, 0);
     if (idx >= __shfl_sync(AG_FULL, cnt, owner)) continue;  // (another warp was quicker)
     const long long t0 = clock64();
@@ -736,10 +743,25 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
       atomicOr(const_cast<uint32_t*>(mb + 2), hi);
       if (fl) atomicOr(const_cast<uint32_t*>(mb + 3), fl);
       atomicAdd(const_cast<uint32_t*>(mb + 5), (uint32_t)(clock64() - t0));
+      __threadfence_block();  // the batch's cells and the words above, then the completion count
+      atomicAdd(const_cast<uint32_t*>(os + 2), 1u);
     }
   }
-  __threadfence_block();
-  align_barrier(nw);  // every batch is done: the cells are back in the cell arrays, the mailboxes say which players
+  if (tb & 32) {
+    // no CTA barrier behind the pool: a warp goes on as soon as ITS batches are done (other warps may still be solving theirs;
+    // the barrier in front of players_collision takes up the skew).  Nothing touches a mailbox once its last batch is completed:
+    // the hand-out and completion counters live outside the scratch, and a warp cannot list the next tick's batches before every
+    // warp of the CTA has left this pool (they all meet at the barrier in front of players_collision first).
+    if (lane == 0) {
+      volatile uint32_t* ps = pool_slot(P, smem_raw, warp);
+      while (ps[2] < nb) __nanosleep(40);
+      __threadfence_block();
+    }
+    __syncwarp();
+  } else {
+    __threadfence_block();
+    align_barrier(nw);  // every batch is done: the cells are back in the cell arrays, the mailboxes say which players
+  }
   if (c) {
     c->cold().pre_lo = mine[1]; c->cold().pre_hi = mine[2];
     c->flags |= mine[3];
@@ -2464,7 +2486,7 @@ __device__ __forceinline__ void engine_tick(Ctx& c, LaneState& ls) {
   if (c.lanes_dirty) { ls.fresh = false; c.lanes_dirty = false; }
   if (c.cold().tb & 2) {  // the pair solver, pooled over the CTA; the warps enter the player loop together behind it
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    premove_players(c.P, smem_raw, &c, (int)(threadIdx.x >> 5), c.lane);
+    premove_players(c.P, smem_raw, &c, (int)(threadIdx.x >> 5), c.lane, c.cold().tb);
   } else {
     c.cold().pre_lo = 0u; c.cold().pre_hi = 0u;  // (no alignment barriers: tick_player moves and resolves every player itself)
   }
@@ -2845,7 +2867,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
       } else {  // no instance in this round: arrive at its barriers, and help with the pooled pair solver
         for (int tk = 0; tk < P.n_ticks; tk++) {
           if (tb & 1) align_barrier(P.align_group);
-          if (tb & 2) premove_players(P, smem_raw, nullptr, warp, lane);
+          if (tb & 2) premove_players(P, smem_raw, nullptr, warp, lane, tb);
           for (int b = 0; b < bars_rest; b++) align_barrier(P.align_group);
         }
       }

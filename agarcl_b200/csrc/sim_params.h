@@ -14,8 +14,8 @@ constexpr int kPremCap = 192;         // pellets_to_remove entries per tick (Eng
 constexpr int kVremCap = 32;          // viruses_to_remove entries per tick (Engine.hpp:213)
 constexpr int kCandCap = 32;          // pellet candidates resolved in registers per cell
 constexpr int kLaneCand = 8;          // pellet candidates a single lane resolves in the lane-per-player phase
-constexpr int kZeroTileBytes = 2816;  // CTA-shared all-zero tile, source of the TMA bulk stores that clear the observation
-constexpr int kColdCtxBytes = 80;    // per-warp slot of ColdCtx (sim_kernel.cu)
+constexpr int kZeroTileBytes = 2560;  // CTA-shared all-zero tile, source of the TMA bulk stores that clear the observation
+constexpr int kColdCtxBytes = 96;    // per-warp slot of ColdCtx (sim_kernel.cu) + 16 B of the solver pool's counters
 constexpr int kSnapCap = 96;          // cells staged in shared memory by the players_collision pre-test (12 bytes each: x, y, mass | player << 24)
 constexpr int kPairCap = 48;          // (eater, eaten) pairs per tick in players_collision
 constexpr int kCellRefCap = 256;      // total live cells per instance handled by players_collision
