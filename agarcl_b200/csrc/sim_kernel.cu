@@ -30,6 +30,9 @@
 // (agario/bots/Bot.hpp:31-129, HungryBot.hpp:19-22, HungryShyBot.hpp:23-44, AggressiveBot.hpp:28-52,
 // AggressiveShyBot.hpp:28-68); BaseEnvironment::step / take_action (environment/envs/
 // BaseEnvironment.hpp:89-122,164-176).
+#ifdef AGARCL_PHASE_TIMING
+#include <cstdio>
+#endif
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -123,9 +126,21 @@ struct ColdCtx {
 };
 static_assert(sizeof(ColdCtx) <= kColdCtxBytes - 16, "ColdCtx outgrew its shared-memory slot");
 
+#ifdef AGARCL_PHASE_TIMING
+// experiment builds only (tools/build_variant.sh with EXTRA=-DAGARCL_PHASE_TIMING): cycles per phase summed over all instance warps,
+// printed (running totals) by the first thread of every launch
+__device__ unsigned long long g_phase[32];
+#define AG_PH(c, i) do { const long long t_ = clock64(); if ((c).lane == 0) atomicAdd(&g_phase[i], (unsigned long long)(t_ - (c).ph_t)); (c).ph_t = t_; } while (0)
+#else
+#define AG_PH(c, i) do { } while (0)
+#endif
+
 struct Ctx {
   const SimParams& P;
   int lane;
+#ifdef AGARCL_PHASE_TIMING
+  long long ph_t;
+#endif
   uint8_t* blob;  // this instance's state; the arrays are blob + constant-bank offsets, formed where used
   WarpSmem sm;
   __device__ __forceinline__ agarcl_player* players_() const { return reinterpret_cast<agarcl_player*>(blob + P.L.off_players); }
@@ -615,9 +630,9 @@ __device__ void premove_batch(const SimParams& P, uint8_t* blob, uint32_t w0, ui
 
 // The warp's mailbox for the pooled pair solver (scratch that is dead before the player loop):
 // [0] batches  [1] [2] players done (lo, hi)  [3] state flags  [4] instance  [5] cycles spent on its batches  [8 + 4k ..] batch k
-constexpr int kMailHdr = 8, kMailBatches = 64;
-static_assert((kMailHdr + 4 * kMailBatches) * 4 <= kCandCap * 8 + (kPremCap * 2 + 15) / 16 * 16 + (kVremCap * 2 + 15) / 16 * 16 + 32 * kLaneCand * 2,
-              "the mailbox must fit into the player-loop scratch");
+constexpr int kMailHdr = 8, kMailBatches = 40;
+static_assert((kMailHdr + 4 * kMailBatches) * 4 <= kCandCap * 8 + (kPremCap * 2 + 15) / 16 * 16 + (kVremCap * 2 + 15) / 16 * 16,
+              "the mailbox must fit into cand + prem + vrem: the lanes' speculation (lprem) may run before the pool's barrier");
 // What must outlive the mailbox (scratch that the owner's player loop overwrites): [0] batches listed  [1] handed out  [2] completed.
 __device__ __forceinline__ volatile uint32_t* pool_slot(const SimParams& P, uint8_t* smem_raw, int warp) {
   return reinterpret_cast<volatile uint32_t*>(smem_raw + P.tiles_bytes + (size_t)warp * P.smem_per_warp + P.so.cold + kColdCtxBytes - 16);
@@ -747,6 +762,10 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
       atomicAdd(const_cast<uint32_t*>(os + 2), 1u);
     }
   }
+  if (tb & 64) {  // the caller finishes the pool (premove_finish) behind the work that does not need its results
+    if (c) c->cold().t_mark = clock64();
+    return;
+  }
   if (tb & 32) {
     // no CTA barrier behind the pool: a warp goes on as soon as ITS batches are done (other warps may still be solving theirs;
     // the barrier in front of players_collision takes up the skew).  Nothing touches a mailbox once its last batch is completed:
@@ -760,9 +779,25 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
     __syncwarp();
   } else {
     __threadfence_block();
+    if (c) AG_PH(*c, 2);
     align_barrier(nw);  // every batch is done: the cells are back in the cell arrays, the mailboxes say which players
   }
   if (c) {
+    c->cold().pre_lo = mine[1]; c->cold().pre_hi = mine[2];
+    c->flags |= mine[3];
+    c->cold().work += (long long)mine[5];
+    c->cold().t_mark = clock64();
+  }
+  __syncwarp();
+}
+
+// The end of the pool when premove_players left it open (tick_barrier bit 64): the CTA barrier, then the results.
+__device__ __forceinline__ void premove_finish(const SimParams& P, uint8_t* smem_raw, Ctx* c, int warp) {
+  if (c) c->cold().work += clock64() - c->cold().t_mark;
+  __threadfence_block();
+  align_barrier(blockDim.x >> 5);
+  if (c) {
+    volatile uint32_t* mine = mailbox(P, smem_raw, warp);
     c->cold().pre_lo = mine[1]; c->cold().pre_hi = mine[2];
     c->flags |= mine[3];
     c->cold().work += (long long)mine[5];
@@ -778,6 +813,7 @@ __device__ void tick_player(Ctx& c, int p) {
   c.cold().emitted = 0;
   if (n == 0) return;  // dead players are not ticked (Engine.hpp:216)
   const int lane = c.lane;
+  AG_PH(c, 22);  // (lane-path time since the last mark)
   // the first 64 bytes of the player record in ONE round trip, next to the cell loads below (every later field access would
   // otherwise be its own dependent trip to L1 / L2 behind the stores in between): w0 n_cells, target x / y, action |
   // w1 split_cd, feed_cd, anti_team_decay, elapsed_ticks | w2 last_decay_tick, bot_type, min_mass_cell, food_eaten |
@@ -799,6 +835,7 @@ __device__ void tick_player(Ctx& c, int p) {
   me.mass = 0; me.id = 0; me.rec = 0;
   if (lane < n) me = premoved ? cell_load_premoved(c.pcells(p) + lane) : cell_load(c.pcells(p) + lane);
 
+  AG_PH(c, 12);
   // ---- bots decide every 10th tick (Engine.hpp:498-499); a premoved bot has decided already (premove_players)
   if (c.tick % 10u == 0u && bot_type >= 0 && !premoved) {
     float4 s = c.sm.psum()[p];
@@ -815,6 +852,7 @@ __device__ void tick_player(Ctx& c, int p) {
     }
   }
 
+  AG_PH(c, 13);
   // ---- Engine::move_player + check_player_self_collisions (unless premove_players has done them for this tick)
   uint32_t smallest = 0xffffffffu;
   if (lane < n) {
@@ -832,6 +870,7 @@ __device__ void tick_player(Ctx& c, int p) {
   int viruses_eaten_inc = 0;
   int vet_count = w3.w;
 
+  AG_PH(c, 14);
   // ---- optimized_check_virus_collisions: first hit in (cell, dx, dy, virus index) order
   if (c.n_viruses > 0) {
     // only cells that could eat the smallest virus can touch one at all (mass > 1.1 * virus mass): the 25-mass
@@ -905,6 +944,7 @@ __device__ void tick_player(Ctx& c, int p) {
     }
   }
 
+  AG_PH(c, 15);
   // ---- get_pellets_to_remove_and_increment_cells
   int pellets_eaten = 0;
   bool pellets_done = c.n_pellets == 0;
@@ -1040,6 +1080,7 @@ __device__ void tick_player(Ctx& c, int p) {
   uint32_t total_mass = warp_sum_u32(lane < n ? me.mass : 0u);
   uint32_t highest = max((uint32_t)w3.x, total_mass);
 
+  AG_PH(c, 16);
   // ---- may_be_auto_split for every cell (children keep cell order), then eat_food cell by cell
   {
     bool big = lane < n && me.mass >= AGARCL_MAX_MASS_IN_THE_GAME;
@@ -1118,6 +1159,7 @@ __device__ void tick_player(Ctx& c, int p) {
   }
   create_limit -= created;
 
+  AG_PH(c, 17);
   // ---- maybe_emit_food / emit_foods
   int feed_cd = w1.y, split_cd = w1.x;
   if (feed_cd > 0) feed_cd -= 1;
@@ -1192,6 +1234,7 @@ __device__ void tick_player(Ctx& c, int p) {
   // ---- Player::add_cells
   n = min(n + created, 32);
 
+  AG_PH(c, 18);
   // ---- recombine_cells (swap-with-back semantics)
   bool merged = false;  // (a merge moves the last cell into the hole: the only thing that breaks the ascending id order)
   if (n >= 2) {
@@ -1217,6 +1260,7 @@ __device__ void tick_player(Ctx& c, int p) {
     }
   }
 
+  AG_PH(c, 19);
   // ---- once per 60 player-ticks: anti-team + decay
   float atd = __int_as_float(w1.z);
   int last_decay = w2.x;
@@ -1241,6 +1285,7 @@ __device__ void tick_player(Ctx& c, int p) {
   }
 
   if (merged) { if (p < 32) c.cold().sorted_lo &= ~(1u << p); else c.cold().sorted_hi &= ~(1u << (p - 32)); }
+  AG_PH(c, 20);
   // ---- publish: centroid for later readers this tick, cells and player record back to the blob
   float4 s = centroid_of(me, n);
   if (lane < n) cell_store(c.pcells(p) + lane, me);
@@ -1254,6 +1299,7 @@ __device__ void tick_player(Ctx& c, int p) {
     stg_keep(rec + 3, make_int4((int)highest, w3.y, w3.z + viruses_eaten_inc, vet_count));
   }
   __syncwarp();
+  AG_PH(c, 21);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1442,7 +1488,7 @@ struct LaneState {
   bool fresh;           // registers == global memory (the lane committed this player itself)
 };
 
-__device__ __forceinline__ void tick_players_block(Ctx& c, int base, LaneState& ls) {
+__device__ __forceinline__ void tick_players_block(Ctx& c, int base, LaneState& ls, bool pool_open) {
   const Luts& T = c.P.T;
   const int lane = c.lane;
   const int k = base + lane;
@@ -1582,7 +1628,15 @@ __device__ __forceinline__ void tick_players_block(Ctx& c, int base, LaneState& 
     st = kReady;
   } while (0);
 
+  AG_PH(c, 23);
   if (st == kSerial) ls.fresh = false;  // ticked by the whole warp below: registers are stale afterwards
+  if (pool_open) {
+    // the one-cell players have been speculated on the state of the tick's start; everything from here on (tick_player of the
+    // premoved players) needs the pool's results.  A warp that ran out of batches early has done its speculation meanwhile.
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    premove_finish(c.P, smem_raw, &c, (int)(threadIdx.x >> 5));
+    pool_open = false;
+  }
   // ---- ordered commit: the run of speculated players up to the next barrier (a whole-warp player or a late lane)
   {
     const unsigned serm = __ballot_sync(AG_FULL, st == kSerial);
@@ -1613,6 +1667,7 @@ __device__ __forceinline__ void tick_players_block(Ctx& c, int base, LaneState& 
       st = kIdle;
     }
     __syncwarp();
+    AG_PH(c, 24);
     if (nxt >= 32) break;
     if (!((serm >> nxt) & 1u)) { pos = nxt; continue; }  // a late lane: it speculates now, on what has been committed
     tick_player(c, c.P.L.order[base + nxt]);
@@ -2477,9 +2532,11 @@ __device__ void obs_finish_warp(Ctx& c) {
 
 // Engine::tick
 __device__ __forceinline__ void engine_tick(Ctx& c, LaneState& ls) {
+  AG_PH(c, 9);
   if (!c.hash_valid) { build_pellet_hash(c); c.hash_valid = true; }
   if (!c.vc_valid) { build_virus_cache(c); c.vc_valid = true; }
   zero_chunk(c, c.cold().zchunk);
+  AG_PH(c, 1);
   c.nprem = 0;
   c.nvrem = 0;
   const int P = c.P.L.P;
@@ -2490,25 +2547,31 @@ __device__ __forceinline__ void engine_tick(Ctx& c, LaneState& ls) {
   } else {
     c.cold().pre_lo = 0u; c.cold().pre_hi = 0u;  // (no alignment barriers: tick_player moves and resolves every player itself)
   }
+  AG_PH(c, 3);
   // ONE call site, so that the body is inlined once (two sites made the compiler duplicate ~30 % of the kernel, or -- when it
   // declined -- call it with Ctx in local memory): with more than 32 players every block starts from global memory, which is
   // current because a lane commits its player before it leaves tick_players_block
   for (int base = 0; base < P; base += 32) {
     if (P > 32) ls.fresh = false;
-    tick_players_block(c, base, ls);
+    tick_players_block(c, base, ls, base == 0 && (c.cold().tb & 66) == 66);
   }
   if (P > 32) ls.fresh = false;
+  AG_PH(c, 4);
   zero_chunk(c, c.cold().zchunk);
   if (c.cold().tb & 16) { c.cold().work += clock64() - c.cold().t_mark; align_barrier(c.P.align_group); c.cold().t_mark = clock64(); }
   apply_removals(c);
   zero_chunk(c, c.cold().zchunk);
+  AG_PH(c, 5);
   if (c.cold().tb & 4) { c.cold().work += clock64() - c.cold().t_mark; align_barrier(c.P.align_group); c.cold().t_mark = clock64(); }  // ... and the cross-player sweep
+  AG_PH(c, 6);
   players_collision(c);
   zero_chunk(c, c.cold().zchunk);
+  AG_PH(c, 7);
   if (c.cold().tb & 8) { c.cold().work += clock64() - c.cold().t_mark; align_barrier(c.P.align_group); c.cold().t_mark = clock64(); }
   move_foods(c);
   if (c.P.L.regen && c.tick % 120u == 0u) regen(c);
   c.tick++;
+  AG_PH(c, 8);
 }
 
 // Player::kill + Engine::respawn for a dead player, spawn point from draw pair `k` (Engine.hpp:119-137)
@@ -2545,6 +2608,9 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
                                               const int lane, uint32_t& mbar_phase, const int tb) {
   Ctx c(P);
   c.lane = lane;
+#ifdef AGARCL_PHASE_TIMING
+  c.ph_t = clock64();
+#endif
   c.blob = P.state + (size_t)inst * P.L.stride;
   c.sm.base = smem_raw + P.tiles_bytes + (size_t)warp * P.smem_per_warp;
   c.sm.o = &P.so;
@@ -2788,6 +2854,7 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
     hdr->n_pellets = c.n_pellets; hdr->n_viruses = c.n_viruses; hdr->n_foods = c.n_foods;
     hdr->rng_cursor = c.cold().cursor; hdr->flags = c.flags; hdr->done_sticky = done_sticky;
   }
+  AG_PH(c, 10);
   if (P.sched) {  // instances that hold a multi-cell player when the launch ends: k_order picks the next launch's schedule from the count
     bool multi = false;
     for (int p = lane; p < Pn; p += 32) multi |= __float_as_int(c.sm.psum()[p].w) >= 2;
@@ -2826,6 +2893,14 @@ __device__ __forceinline__ void step_instance(const SimParams& P, uint8_t* smem_
 __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_constant__ SimParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef AGARCL_PHASE_TIMING
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    printf("PHASES");
+    for (int i = 0; i < 28; i++) printf(" %llu", g_phase[i]);
+    printf("\n");
+  }
+  const long long t_kernel0 = clock64();
+#endif
   // the CTA's all-zero tile (first kZeroTileBytes of shared memory), made visible to the async proxy
   // ... and its all-ones (-1) tile right behind it, source of the out-of-bounds rows of channel 0
   for (int i = threadIdx.x; i < (int)P.tiles_bytes / 16; i += blockDim.x)
@@ -2865,13 +2940,22 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
         const uint32_t inst = P.perm ? P.perm[t] : t;
         step_instance(P, smem_raw, P.inst_first + (int)inst, (int)t, warp, lane, mbar_phase, tb);
       } else {  // no instance in this round: arrive at its barriers, and help with the pooled pair solver
+#ifdef AGARCL_PHASE_TIMING
+        const long long t_idle0 = clock64();
+#endif
         for (int tk = 0; tk < P.n_ticks; tk++) {
           if (tb & 1) align_barrier(P.align_group);
-          if (tb & 2) premove_players(P, smem_raw, nullptr, warp, lane, tb);
+          if (tb & 2) { premove_players(P, smem_raw, nullptr, warp, lane, tb); if (tb & 64) premove_finish(P, smem_raw, nullptr, warp); }
           for (int b = 0; b < bars_rest; b++) align_barrier(P.align_group);
         }
+#ifdef AGARCL_PHASE_TIMING
+        if (lane == 0) atomicAdd(&g_phase[11], (unsigned long long)(clock64() - t_idle0));
+#endif
       }
     }
+#ifdef AGARCL_PHASE_TIMING
+    if (lane == 0) atomicAdd(&g_phase[0], (unsigned long long)(clock64() - t_kernel0));  // whole kernel, per warp
+#endif
     return;
   }
   while (true) {

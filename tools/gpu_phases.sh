@@ -1,0 +1,12 @@
+# cycles per phase of k_step (variants/phases.so = a build with -DAGARCL_PHASE_TIMING); $1 = settle steps
+cp variants/phases.so agarcl_b200/libagarcl_b200.so
+timeout 600 python tools/exp_perstep.py ${1:-2000} 20 2>&1 | grep PHASES | tail -22 > gpurun_out/phases.txt
+python - <<'PY'
+rows=[list(map(int,l.split()[1:])) for l in open('gpurun_out/phases.txt')]
+names=['kernel(per warp)','hash/virus cache+zero','pool: publish+batches','pool: barrier wait','player loop: lanes after the last tick_player','apply_removals(+b16)','barrier-4 wait','players_collision','move_foods/regen','prologue','epilogue','idle warps','tp: record+cell loads','tp: bot decision','tp: move+self collisions (not premoved)','tp: virus collisions','tp: pellets','tp: auto split+eat food','tp: emit/split/add','tp: recombine','tp: decay','tp: publish','player loop: rest before a tick_player','lanes: speculation (+ food re-check)','lanes: ordered commit']+['-']*6
+d=[[b-a for a,b in zip(r0,r1)] for r0,r1 in zip(rows[:-1],rows[1:])]
+n=len(d); tot=[sum(x[i] for x in d)/n for i in range(28)]
+inst_total=sum(tot[1:11])
+print('launches averaged',n,'  mean cycles per launch summed over warps')
+for i in range(25): print(f'{names[i]:46s} {tot[i]/1e6:10.2f} Mcycles  {100*tot[i]/tot[0]:5.1f}% of warp-time')
+PY
