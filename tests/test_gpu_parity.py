@@ -26,6 +26,8 @@ CASES = {
     "tps1_grid64_absreward": (dict(num_bots=5, ticks_per_step=1, grid_size=64, arena_size=200, num_pellets=100, num_viruses=2, reward_type=0), dict(steps=150)),
     "obs_flags_off": (dict(num_bots=3, observe_pellets=False, observe_others=False, arena_size=200, num_pellets=100, num_viruses=2), dict(steps=60)),
     "players_30": (dict(num_agents=2, num_bots=30, arena_size=500, num_pellets=500, num_viruses=10, cap_foods=2048), dict(steps=150, boost=500)),
+    # more than 32 players: the lane-per-player phase runs in two blocks of the player order
+    "players_45": (dict(num_agents=3, num_bots=42, arena_size=600, num_pellets=600, num_viruses=10, cap_foods=2048), dict(steps=120, boost=400)),
     "frames2": (dict(num_bots=4, num_frames=2, arena_size=200, num_pellets=100, num_viruses=2), dict(steps=40)),
     # configs[4]: large arena, maximum pellets / viruses: 4000 pellets = 45 KB of shared memory per instance, 5 per SM
     "c5_large_arena": (dict(arena_size=2000, num_pellets=4000, num_viruses=50, cap_viruses=128), dict(steps=60, obs_every=10)),

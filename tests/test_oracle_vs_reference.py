@@ -57,6 +57,7 @@ CASES = {
     "giant_autosplit": (dict(num_agents=2, num_bots=6, arena_size=400, num_pellets=400, num_viruses=6, cap_foods=2048), dict(steps=200, boost=22400, p_feed=0.05, p_split=0.1)),
     "virus_heavy": (dict(num_agents=3, num_bots=10, arena_size=250, num_pellets=200, num_viruses=40, cap_foods=2048, cap_viruses=256), dict(steps=200, boost=400, p_feed=0.5, p_split=0.1)),
     "players_30": (dict(num_agents=2, num_bots=30, arena_size=500, num_pellets=500, num_viruses=10, cap_foods=2048), dict(steps=100, boost=500)),
+    "players_45": (dict(num_agents=3, num_bots=42, arena_size=600, num_pellets=600, num_viruses=10, cap_foods=2048), dict(steps=100, boost=400)),
     "tps1_grid64_absreward": (dict(num_bots=5, ticks_per_step=1, grid_size=64, arena_size=200, num_pellets=100, num_viruses=2, reward_type=0), dict(steps=150)),
     "obs_flags_off": (dict(num_bots=3, observe_pellets=False, observe_others=False, arena_size=200, num_pellets=100, num_viruses=2), dict(steps=60)),
 }
