@@ -415,6 +415,14 @@ int ref_dump_state(void* h, const agarcl_layout* L, void* blob_) {
 }
 
 /* iteration order of a real std::unordered_map<int, ...> after inserting keys in order (pins oracle_umap_order) */
+/* the real std::sort on the strips' element type with the comparator of collision_detection.hpp:29-31 (pins oracle.c's restatement) */
+void ref_std_sort_pairs(int* ids, float* ys, int n) {
+  std::vector<std::pair<int, float>> v;
+  for (int i = 0; i < n; i++) v.emplace_back(std::make_pair(ids[i], ys[i]));
+  std::sort(v.begin(), v.end(), [](const auto& a, const auto& b) { return a.second < b.second; });
+  for (int i = 0; i < n; i++) { ids[i] = v[i].first; ys[i] = v[i].second; }
+}
+
 void ref_umap_order(const int* keys, int n, int* out) {
   std::unordered_map<int, std::vector<int>> m;
   for (int i = 0; i < n; i++) m[keys[i]].push_back(i);
