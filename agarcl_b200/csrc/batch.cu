@@ -22,6 +22,7 @@
 
 namespace ag {
 cudaError_t launch_step(const SimParams& P, cudaStream_t stream);
+cudaError_t selftest_std_sort(const float* ys, int n, uint16_t* order_out);
 cudaError_t launch_order(const uint32_t* cost, uint32_t* perm, int N, uint32_t* sched, cudaStream_t stream);
 cudaError_t launch_obs(const ObsParams& P, cudaStream_t stream);
 cudaError_t launch_reset(const ResetParams& P, cudaStream_t stream);
@@ -646,6 +647,12 @@ extern "C" int agarcl_batch_get_timing(agarcl_batch* b, double* sim_ms, double* 
 }
 
 extern "C" int agarcl_batch_launches_per_step(const agarcl_batch* b) { return b ? b->launches_last_step : 0; }
+
+extern "C" int agarcl_selftest_std_sort(const float* ys, int32_t n, uint16_t* order_out) {
+  if (n < 0 || n > 65535 || (n > 0 && (!ys || !order_out))) return agarcl_set_error(AGARCL_ERR_INVALID, "bad keys / count");
+  CK(ag::selftest_std_sort(ys, n, order_out));
+  return AGARCL_OK;
+}
 
 extern "C" int agarcl_batch_flags(agarcl_batch* b, void* stream, uint32_t* or_all, uint32_t counts[32]) {
   if (!b) return agarcl_set_error(AGARCL_ERR_INVALID, "null batch");

@@ -36,6 +36,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <vector>
 
 #include "sim_params.h"
 #include "sim_shared.cuh"
@@ -1786,6 +1787,123 @@ __device__ __forceinline__ float* snap_x(const Ctx& c) { return reinterpret_cast
 __device__ __forceinline__ float* snap_y(const Ctx& c) { return reinterpret_cast<float*>(c.sm.snap()) + kSnapCap; }
 __device__ __forceinline__ uint32_t* snap_mp(const Ctx& c) { return reinterpret_cast<uint32_t*>(c.sm.snap()) + 2 * kSnapCap; }
 
+// The y key of a strip member for strip_std_sort: from the staged snapshot (shared memory) or from the cell itself.  Raw pointers
+// only, passed by value: nothing of Ctx may have its address taken (it would move to local memory for the whole kernel).
+struct StripKey {
+  const float* sy;
+  const uint16_t* ref;
+  const agarcl_cell* cells;
+  __device__ __forceinline__ float operator()(int g) const {
+    return sy ? sy[g] : (cells + (size_t)(ref[g] >> 8) * AGARCL_MAX_CELLS + (ref[g] & 0xff))->y;
+  }
+};
+
+// std::sort as the reference's toolchain implements it (GCC 13 libstdc++, bits/stl_algo.h: __introsort_loop with the median of
+// (first + 1, mid, last - 1) moved to first, __unguarded_partition, depth limit 2 * lg(n) with the heap-sort fallback of
+// bits/stl_heap.h, then __final_insertion_sort with threshold 16), on the members of one PrecisionCollisionDetection strip
+// (collision_detection.hpp:29-31: comparator a.second < b.second), run by ONE lane.  std::sort is not stable: for more than 16
+// elements the place of two cells with the SAME y depends on this very sequence of swaps, and that place decides where the scan
+// of the strip stops (quirk Q7) -- so it is restated operation for operation, like oracle.c's se_std_sort, which
+// tests/test_std_sort.py pins against the real std::sort.  The two halves of a partition are independent, so the recursion is
+// an explicit stack (the order in which they are finished does not matter).
+__device__ __noinline__ void strip_std_sort(uint16_t* a, int n, StripKey key) {
+  if (n <= 0) return;
+  auto swp = [&](int i, int j) { const uint16_t t = a[i]; a[i] = a[j]; a[j] = t; };
+  auto unguarded_linear_insert = [&](int last) {
+    const uint16_t val = a[last];
+    const float vy = key(val);
+    int next = last - 1;
+    while (vy < key(a[next])) { a[last] = a[next]; last = next; --next; }
+    a[last] = val;
+  };
+  auto insertion_sort = [&](int first, int last) {
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+      if (key(a[i]) < key(a[first])) {
+        const uint16_t val = a[i];
+        for (int j = i; j > first; --j) a[j] = a[j - 1];  // move_backward(first, i, i + 1)
+        a[first] = val;
+      } else {
+        unguarded_linear_insert(i);
+      }
+    }
+  };
+  // heap routines on a[base .. base + len)
+  auto adjust_heap = [&](int base, int hole, int len, uint16_t value) {
+    const int top = hole;
+    const float vy = key(value);
+    int child = hole;
+    while (child < (len - 1) / 2) {
+      child = 2 * (child + 1);
+      if (key(a[base + child]) < key(a[base + child - 1])) child--;
+      a[base + hole] = a[base + child];
+      hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+      child = 2 * (child + 1);
+      a[base + hole] = a[base + child - 1];
+      hole = child - 1;
+    }
+    int parent = (hole - 1) / 2;  // __push_heap
+    while (hole > top && key(a[base + parent]) < vy) { a[base + hole] = a[base + parent]; hole = parent; parent = (hole - 1) / 2; }
+    a[base + hole] = value;
+  };
+  auto heap_sort = [&](int first, int last) {  // __partial_sort(first, last, last)
+    const int len = last - first;
+    if (len >= 2) {
+      int parent = (len - 2) / 2;
+      for (;;) {
+        adjust_heap(first, parent, len, a[first + parent]);
+        if (parent == 0) break;
+        parent--;
+      }
+    }
+    while (last - first > 1) {
+      --last;
+      const uint16_t value = a[last];
+      a[last] = a[first];
+      adjust_heap(first, 0, last - first, value);
+    }
+  };
+  constexpr int kStack = 40;  // one entry per partitioning level: at most 2 * lg(n) + 1 <= 33
+  int sf[kStack], sl[kStack], sd[kStack], sp = 0;
+  sf[0] = 0; sl[0] = n; sd[0] = 2 * (31 - __clz(n)); sp = 1;
+  while (sp > 0) {
+    --sp;
+    int first = sf[sp], last = sl[sp], depth = sd[sp];
+    while (last - first > 16) {
+      if (depth == 0) { heap_sort(first, last); break; }
+      --depth;
+      {  // __move_median_to_first(first, first + 1, mid, last - 1)
+        const int A = first + 1, B = first + (last - first) / 2, C = last - 1;
+        const float ya = key(a[A]), yb = key(a[B]), yc = key(a[C]);
+        int m;
+        if (ya < yb) m = (yb < yc) ? B : ((ya < yc) ? C : A);
+        else m = (ya < yc) ? A : ((yb < yc) ? C : B);
+        swp(first, m);
+      }
+      const float yp = key(a[first]);
+      int lo = first + 1, hi = last;  // __unguarded_partition(first + 1, last, pivot = first)
+      for (;;) {
+        while (key(a[lo]) < yp) ++lo;
+        --hi;
+        while (yp < key(a[hi])) --hi;
+        if (!(lo < hi)) break;
+        swp(lo, hi);
+        ++lo;
+      }
+      if (sp < kStack) { sf[sp] = lo; sl[sp] = last; sd[sp] = depth; sp++; }  // __introsort_loop(cut, last, depth_limit)
+      last = lo;
+    }
+  }
+  if (n > 16) {  // __final_insertion_sort
+    insertion_sort(0, 16);
+    for (int i = 16; i != n; ++i) unguarded_linear_insert(i);
+  } else {
+    insertion_sort(0, n);
+  }
+}
+
 __device__ void players_collision_exact(Ctx& c, int total, int nhit, bool staged) {
   const Luts& T = c.P.T;
   const int lane = c.lane;
@@ -1823,17 +1941,10 @@ __device__ void players_collision_exact(Ctx& c, int total, int nhit, bool staged
       }
       if (l == 0) continue;
       __syncwarp();
-      if (l > 32) {  // long strip: one lane, literally (insertion sort == libstdc++ std::sort only up to 16: flagged beyond)
+      const StripKey skey{staged ? snap_y(c) : nullptr, ref, c.cells_()};
+      if (l > 32) {  // long strip: one lane, literally
         if (lane == 0) {
-          for (int a = 1; a < l; a++) {
-            const uint16_t g = strip[a];
-            const float gy = gy_of(g);
-            int b = a - 1;
-            while (b >= 0 && gy < gy_of(strip[b])) { strip[b + 1] = strip[b]; b--; }
-            strip[b + 1] = g;
-          }
-          for (int a = 1; a < l; a++)
-            if (gy_of(strip[a]) == gy_of(strip[a - 1])) c.flags |= AGARCL_FLAG_PCD_TIE;
+          strip_std_sort(strip, l, skey);
           int start_pos = 0;
           for (int j = 10; j >= 0; j--)
             if (start_pos + (1 << j) < l && gy_of(strip[start_pos + (1 << j)]) < left) start_pos += (1 << j);
@@ -1870,11 +1981,21 @@ __device__ void players_collision_exact(Ctx& c, int total, int nhit, bool staged
       __syncwarp();
       if (lane < l) strip[rank] = (uint16_t)myg;
       __syncwarp();
-      const int sg = lane < l ? (int)strip[lane] : 0;  // lane j holds position j of the sorted strip
-      const float sy = lane < l ? gy_of(sg) : 0.0f;
+      int sg = lane < l ? (int)strip[lane] : 0;  // lane j holds position j of the sorted strip
+      float sy = lane < l ? gy_of(sg) : 0.0f;
       {
+        // more than 16 members AND equal keys: where std::sort leaves the equal ones is up to its unstable part -- one lane redoes
+        // the strip from the snapshot order with the reference's own algorithm (rare: cells pressed against a wall)
         const float prev = __shfl_up_sync(AG_FULL, sy, 1);
-        if (l > 16 && __ballot_sync(AG_FULL, lane >= 1 && lane < l && sy == prev)) c.flags |= AGARCL_FLAG_PCD_TIE;
+        if (l > 16 && __ballot_sync(AG_FULL, lane >= 1 && lane < l && sy == prev)) {
+          __syncwarp();
+          if (lane < l) strip[lane] = (uint16_t)myg;
+          __syncwarp();
+          if (lane == 0) strip_std_sort(strip, l, skey);
+          __syncwarp();
+          sg = lane < l ? (int)strip[lane] : 0;
+          sy = lane < l ? gy_of(sg) : 0.0f;
+        }
       }
       // the reference's lower-bound stepping on a sorted strip: the last position >= 1 whose y is left of the query, else 0
       const unsigned lt = __ballot_sync(AG_FULL, lane >= 1 && lane < l && sy < left);
@@ -3013,6 +3134,27 @@ __global__ void __launch_bounds__(1024) k_order(const uint32_t* __restrict__ cos
 cudaError_t launch_order(const uint32_t* cost, uint32_t* perm, int N, uint32_t* sched, cudaStream_t stream) {
   k_order<<<1, 1024, 0, stream>>>(cost, perm, N, sched);
   return cudaGetLastError();
+}
+
+// agarcl_selftest_std_sort (include/agarcl_b200.h): strip_std_sort on keys in global memory, one thread
+__global__ void k_selftest_sort(const float* ys, uint16_t* idx, int n) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) strip_std_sort(idx, n, StripKey{ys, nullptr, nullptr});
+}
+cudaError_t selftest_std_sort(const float* ys, int n, uint16_t* order_out) {
+  float* d_y = nullptr;
+  uint16_t* d_i = nullptr;
+  std::vector<uint16_t> init((size_t)n);
+  for (int i = 0; i < n; i++) init[(size_t)i] = (uint16_t)i;
+  cudaError_t e = cudaMalloc(&d_y, sizeof(float) * (size_t)(n > 0 ? n : 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_i, sizeof(uint16_t) * (size_t)(n > 0 ? n : 1));
+  if (e == cudaSuccess && n > 0) e = cudaMemcpy(d_y, ys, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && n > 0) e = cudaMemcpy(d_i, init.data(), sizeof(uint16_t) * (size_t)n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) { k_selftest_sort<<<1, 32>>>(d_y, d_i, n); e = cudaGetLastError(); }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess && n > 0) e = cudaMemcpy(order_out, d_i, sizeof(uint16_t) * (size_t)n, cudaMemcpyDeviceToHost);
+  cudaFree(d_y);
+  cudaFree(d_i);
+  return e;
 }
 
 // One CTA per SM, as many warps (= concurrent instances) as the shared memory holds, at most kMaxWarpsPerCta.

@@ -558,8 +558,8 @@ def run_ours(args):
         for i0 in range(0, N * A, 512):
             mirror_ok = mirror_ok and bool(torch.equal(torch.from_numpy(np.array(mirror[i0:i0 + 512])).cuda(), obs_dev[i0:i0 + 512]))
         Ke = Km
-    # hdr.flags of ALL instances, reduced on the device (agarcl_batch_flags): a set bit = a fixed capacity was hit (or the
-    # std::sort tie warning AGARCL_FLAG_PCD_TIE) in that many instances since their reset
+    # hdr.flags of ALL instances, reduced on the device (agarcl_batch_flags): a set bit = a fixed capacity was hit in that many
+    # instances since their reset
     flags_seen, flag_counts = b.flags()
 
     # ---- the opt-in int16 observation (half the observation bytes; SURVEY 7 hard part 4): same workload, same game age, the

@@ -52,7 +52,7 @@ extern "C" {
 #define AGARCL_FLAG_VET_OVERFLOW 0x008u
 #define AGARCL_FLAG_EATER_OVERFLOW 0x010u
 #define AGARCL_FLAG_REPLAY_EXHAUSTED 0x020u
-#define AGARCL_FLAG_PCD_TIE 0x040u     /* >16 cells in one PCD strip with equal y: std::sort order unspecified */
+#define AGARCL_FLAG_PCD_TIE 0x040u     /* (round 1: >16 cells in one PCD strip with equal y.  No longer raised: libstdc++'s std::sort is restated exactly, ties included) */
 #define AGARCL_FLAG_RAND_SITE 0x080u   /* a libc rand() site was reached (Bot.hpp:93-96,121-126) */
 #define AGARCL_FLAG_MASS_LUT 0x100u    /* a cell mass exceeded AGARCL_LUT_SIZE */
 #define AGARCL_FLAG_REMOVE_OVERFLOW 0x200u
@@ -312,6 +312,11 @@ int agarcl_batch_launches_per_step(const agarcl_batch* b);
  * AGARCL_FLAG bit `bit` set (either pointer may be NULL).  Synchronises `stream`.  The reference has no counterpart: its
  * containers grow without bound where this library has fixed capacities (BaseEnvironment.hpp / Engine.hpp vectors). */
 int agarcl_batch_flags(agarcl_batch* b, void* stream, uint32_t* or_all, uint32_t counts[32]);
+/* Self-test of the device's restatement of libstdc++'s std::sort (k_step's strip_std_sort; the reference sorts the strips of
+ * PrecisionCollisionDetection::solve with it, agario/utils/collision_detection.hpp:29-31): sorts the indices 0..n-1 by the HOST keys
+ * ys[n] on the current device and writes the resulting order to order_out[n].  n <= 65535.  tests/test_gpu_std_sort.py compares it
+ * with the oracle's restatement, which is pinned against the real std::sort. */
+int agarcl_selftest_std_sort(const float* ys, int32_t n, uint16_t* order_out);
 /* Host helper: first n canonical floats of std::mt19937_64(seed) as uniform_real_distribution<float>
  * draws them (random.hpp:6-20). */
 int agarcl_mt19937_draws(uint64_t seed, float* out, int32_t n);

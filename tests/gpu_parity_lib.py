@@ -115,11 +115,7 @@ def run_parity(cfg_kwargs, seeds, steps, p_feed=1 / 3, p_split=1 / 3, boost=None
                 gs = b.download_state(i)
                 d = compare_states(o.state, gs)
                 assert not d, f"step {st} inst {i} (seed {seeds[i]}): {d[:6]} flags gpu={gs.flag_names()} oracle={o.state.flag_names()}"
-                # AGARCL_FLAG_PCD_TIE (0x40) is a warning about std::sort's unspecified order of equal keys in a strip of more than
-                # 16 cells: the oracle, which sorts every strip like the reference, raises it for any such strip; the device only
-                # sorts the strips of queries that can eat something, so it may stay silent where the order cannot matter
-                gf, of = int(gs.hdr["flags"]), int(o.state.hdr["flags"])
-                assert (gf & ~0x40) == (of & ~0x40) and not (gf & 0x40 & ~of), (st, i, gs.flag_names(), o.state.flag_names())
+                assert int(gs.hdr["flags"]) == int(o.state.hdr["flags"]), (st, i, gs.flag_names(), o.state.flag_names())
                 assert int(gs.hdr["rng_cursor"]) == int(o.state.hdr["rng_cursor"]), (st, i)
             assert np.array_equal(g_rew[i], o_rew), f"step {st} inst {i}: rewards {g_rew[i]} vs {o_rew}"
             assert np.array_equal(g_done[i], o_done), f"step {st} inst {i}: dones {g_done[i]} vs {o_done}"
