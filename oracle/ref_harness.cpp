@@ -115,6 +115,12 @@ struct RefEnv {
   std::unique_ptr<RefRamT> ram;    /* GoBiggerObservation fed with this engine's state */
   int arena;
   int num_agents, grid, channels;
+  /* pid of player index 0 in the current episode: 0 behind ref_reset (deviation 3), e * P behind ref_reset_native (Q3) */
+  int pid_base() const {
+    int lo = 1 << 30;
+    for (auto& pr : env->engine_.state.players) lo = std::min(lo, (int)pr.first);
+    return lo == (1 << 30) ? 0 : lo;
+  }
   void bind_clock() { SimClock::tick_ptr = &env->engine_.state.ticks; }
 };
 
@@ -170,6 +176,16 @@ void ref_reset(void* h) {
   r->bind_clock();
   fresh_reset(r);
 }
+
+/* BaseEnvironment::reset exactly as the reference runs it: the player map is cleared, not replaced, and next_pid keeps counting
+ * (quirk Q3) -- the episode's pids are e * P .. e * P + P - 1 and the map's iteration order is that of the reused bucket array */
+void ref_reset_native(void* h) {
+  auto* r = static_cast<RefEnv*>(h);
+  r->bind_clock();
+  CoutSilencer quiet;
+  r->env->reset();
+}
+int ref_pid_base(void* h) { return static_cast<RefEnv*>(h)->pid_base(); }
 
 void ref_take_actions(void* h, const float* dxdy, const int32_t* act) {
   auto* r = static_cast<RefEnv*>(h);
@@ -227,8 +243,9 @@ void ref_ram_obs(void* h, int P, float* out) {
   auto& player = r->env->engine_.player(r->env->pids_[0]);
   r->ram->add_frame(player, r->env->engine_.game_state(), 0);
   if (olderr) std::cerr.rdbuf(olderr);
+  const int pid_base = r->pid_base();
   for (auto& kv : r->ram->get_player_states().get_all_player_states()) {
-    int pid = kv.first;
+    int pid = (int)kv.first - pid_base;
     if (pid < 0 || pid >= P) continue;
     const auto& ps = kv.second;
     float* rec = out + (size_t)pid * AGARCL_RAM_RECORD;
@@ -297,7 +314,8 @@ int ref_obs_native_len(void* h) { return static_cast<RefEnv*>(h)->env->get_obser
 int ref_player_order(void* h, int32_t* out) {
   auto* r = static_cast<RefEnv*>(h);
   int k = 0;
-  for (auto& pr : r->env->engine_.state.players) out[k++] = pr.first;
+  const int base = r->pid_base();
+  for (auto& pr : r->env->engine_.state.players) out[k++] = (int)pr.first - base;
   return k;
 }
 
@@ -314,11 +332,11 @@ void ref_rng_peek(void* h, float* out, int n) {
 
 void ref_set_cell_mass(void* h, int pid, int cell, unsigned mass) {
   auto* r = static_cast<RefEnv*>(h);
-  r->env->engine_.player((agario::pid)pid).cells.at(cell).set_mass(mass);
+  r->env->engine_.player((agario::pid)(pid + r->pid_base())).cells.at(cell).set_mass(mass);  /* pid = player index */
 }
 void ref_set_cell_pos(void* h, int pid, int cell, float x, float y) {
   auto* r = static_cast<RefEnv*>(h);
-  auto& c = r->env->engine_.player((agario::pid)pid).cells.at(cell);
+  auto& c = r->env->engine_.player((agario::pid)(pid + r->pid_base())).cells.at(cell);
   c.x = x;
   c.y = y;
 }
@@ -370,8 +388,9 @@ int ref_dump_state(void* h, const agarcl_layout* L, void* blob_) {
   auto* pls = reinterpret_cast<agarcl_player*>(blob + L->off_players);
   auto* cells = reinterpret_cast<agarcl_cell*>(blob + L->off_cells);
   uint32_t max_id = 0;
+  const int pid_base = r->pid_base();
   for (auto& pr : st.players) {
-    int p = pr.first;
+    int p = (int)pr.first - pid_base;
     if (p >= L->P) { miss--; continue; }
     auto& pl = *pr.second;
     agarcl_player& o = pls[p];

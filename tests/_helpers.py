@@ -81,6 +81,10 @@ class Oracle:
     def reset(self):
         self.lib.oracle_reset(C.byref(self.cfg), C.byref(self.L), self.state.ptr, fptr(self.replay), self.replay.size)
 
+    def reset_keep_stream(self):
+        """a later episode: the draw stream goes on (Engine::reset does not reseed)"""
+        self.lib.oracle_reset_keep_stream(C.byref(self.cfg), C.byref(self.L), self.state.ptr, fptr(self.replay), self.replay.size)
+
     def set_actions(self, dxdy, act):
         dxdy = np.ascontiguousarray(dxdy, np.float32)
         act = np.ascontiguousarray(act, np.int32)
@@ -113,13 +117,13 @@ class Oracle:
         self.lib.oracle_ram_obs(C.byref(self.cfg), C.byref(self.L), self.state.ptr, fptr(self.ram))
         return self.ram
 
-    def step_with_ram(self):
+    def step_with_ram(self, with_obs=False):
         """oracle_step with the records taken where the reference takes them (after the ticks, before respawn)"""
         if not hasattr(self, "ram"):
             self.ram_clear()
         self.lib.oracle_set_ram_out(fptr(self.ram))
         try:
-            return self.step()
+            return self.step(with_obs=with_obs)
         finally:
             self.lib.oracle_set_ram_out(None)
 
@@ -144,6 +148,13 @@ class Reference:
 
     def reset(self):
         self.lib.ref_reset(self.h)
+
+    def reset_native(self):
+        """BaseEnvironment::reset as the reference runs it (pids keep counting, quirk Q3)"""
+        self.lib.ref_reset_native(self.h)
+
+    def pid_base(self):
+        return int(self.lib.ref_pid_base(self.h))
 
     def order(self):
         o = (C.c_int32 * 64)()

@@ -143,3 +143,57 @@ def test_umap_iteration_order_emulation():
             lib.oracle_umap_order(fptr(keys), n, fptr(a))
             ref.ref_umap_order(fptr(keys), n, fptr(b))
             assert np.array_equal(a, b), (n, keys.tolist())
+
+
+@pytest.mark.parametrize("ck", [dict(), dict(num_agents=2, num_bots=30, arena_size=500, num_pellets=500, num_viruses=10, cap_foods=2048),
+                                dict(num_agents=4, num_bots=8, cap_foods=2048), dict(num_agents=3, num_bots=42, arena_size=600, num_pellets=600)],
+                         ids=["P26", "P32", "P12", "P45"])
+def test_later_episodes_follow_the_reference_pid_growth(ck):
+    """Quirk Q3: BaseEnvironment::reset clears the player map but neither replaces it nor rewinds next_pid (Engine.hpp:72,98-101), so
+    episode e holds the pids e*P .. e*P + P - 1 in a reused bucket array and iterates its players in another order than a fresh engine
+    (for 26 players already from episode 1 on).  oracle_player_order_episode restates that; with the order of the episode the oracle stays
+    identical to the reference -- which is reset here exactly as a user resets it (ref_reset_native) -- over four episodes, the draw
+    stream carried across the resets."""
+    import ctypes
+    oracle_lib().oracle_set_trig_mode(0)
+    cfg = make_cfg(**ck)
+    L = oracle_layout(cfg)
+    ref = Reference(cfg, L)
+    ref.seed(77)
+    ora = Oracle(cfg, L)
+    ora.seed_mt(77, 1 << 16)
+    rng = np.random.default_rng(5)
+    changed = 0
+    for episode in range(4):
+        if episode == 0:
+            ref.reset()  # (the harness' fresh engine == the reset the reference's constructor makes)
+        else:
+            ref.reset_native()
+        order = (ctypes.c_int * 64)()
+        oracle_lib().oracle_player_order_episode(L.P, episode, order)
+        changed += int(list(order)[:L.P] != list(L.order)[:L.P])
+        for k in range(L.P):
+            L.order[k] = order[k]
+        assert ref.pid_base() == episode * L.P
+        assert ref.order() == list(L.order)[:L.P], (episode, ref.order())
+        if episode == 0:
+            ora.reset()
+        else:
+            ora.reset_keep_stream()
+        rs, miss = ref.dump()
+        assert miss == 0 and not compare_states(rs, ora.state), (episode, compare_states(rs, ora.state)[:4])
+        for st in range(40):
+            dxdy, act = random_actions(rng, L.A, 1 / 3, 1 / 3)
+            ref.set_actions(dxdy, act)
+            ora.set_actions(dxdy, act)
+            rr, rd = ref.step()
+            orr, od, _ = ora.step()
+            rs, miss = ref.dump()
+            d = compare_states(rs, ora.state)
+            assert miss == 0 and not d, f"episode {episode} step {st}: {d[:6]}"
+            assert np.array_equal(rr, orr) and np.array_equal(rd, od), (episode, st)
+            if st % 10 == 0:
+                for a in range(L.A):
+                    assert np.array_equal(ref.obs(a), ora.obs(a)), f"episode {episode} step {st} agent {a}: observation differs"
+    if L.P == 26:
+        assert changed >= 1  # (the case the default roster is in: the order of episode 1 is not that of a fresh engine)
