@@ -143,6 +143,8 @@ class Batch:
             m = np.ascontiguousarray(mask, dtype=np.uint8)
             assert m.size == self.N
         _lib.check(_lib.lib().agarcl_batch_reset(self._h, m.ctypes.data_as(_vp) if m is not None else None, _vp(stream)))
+        if m is None:  # strict_reference: the player order of the new episode (quirk Q3)
+            _lib.check(_lib.lib().agarcl_batch_get_layout(self._h, C.byref(self.layout)))
 
     def set_actions(self, dxdy, act, stream=0):
         dxdy = np.ascontiguousarray(dxdy, dtype=np.float32)

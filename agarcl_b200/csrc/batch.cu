@@ -13,6 +13,7 @@
 #include <cstring>
 #include <new>
 #include <random>
+#include <unordered_map>
 #include <vector>
 
 #include "host_util.h"
@@ -33,6 +34,12 @@ cudaError_t launch_flags(const uint8_t* state, const agarcl_layout& L, int N, ui
 struct agarcl_batch {
   agarcl_cfg cfg;
   agarcl_layout L;
+  // strict_reference, quirk Q3: the reference's player map and pid counter outlive a reset (GameState::clear keeps the bucket
+  // array, Engine::reset does not rewind next_pid), so the iteration order of the players depends on how many times the
+  // environment has been reset.  The same container, fed the same insert sequence, reset after reset.
+  std::unordered_map<unsigned short, int> pmap;
+  unsigned short next_pid = 0;
+  int32_t pid_base = 0;  // pid of player index 0 in the current episode
   int N, A, G, C, frames;
   size_t obs_elems, obs_bytes;
   uint8_t* d_state = nullptr;
@@ -452,6 +459,7 @@ static int render_ram(agarcl_batch* b, cudaStream_t s, int pre_respawn) {
   P.N = b->N;
   P.G = b->G;
   P.pre_respawn = pre_respawn;
+  P.pid_base = b->pid_base;
   CK(ag::launch_ram(P, s));
   return AGARCL_OK;
 }
@@ -508,6 +516,16 @@ extern "C" int agarcl_batch_reset(agarcl_batch* b, const uint8_t* mask, void* st
   P.num_pellets = b->cfg.num_pellets;
   P.num_viruses = b->cfg.num_viruses;
   P.W = (float)b->cfg.arena_size;
+  if (b->cfg.strict_reference && !mask) {
+    // BaseEnvironment::reset of every instance (BaseEnvironment.hpp:179-197): players.clear(), then add_player for the agents and
+    // the bots with the pids that follow the last episode's; a masked reset (one instance of a vector env) keeps the batch's order
+    b->pmap.clear();
+    b->pid_base = (int32_t)b->next_pid;
+    for (int p = 0; p < b->L.P; p++) b->pmap.insert(std::make_pair(b->next_pid++, p));
+    int k = 0;
+    for (auto& kv : b->pmap) b->L.order[k++] = kv.second;
+    P.L = b->L;
+  }
   CK(ag::launch_reset(P, s));
   b->was_reset = true;
   { int rc = refill_replay(b, s); if (rc) return rc; }

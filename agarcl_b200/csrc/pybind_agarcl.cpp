@@ -84,6 +84,7 @@ struct EnvBase {
   void reset() {
     ensure();
     ck(agarcl_batch_reset(b, nullptr, nullptr));
+    ck(agarcl_batch_get_layout(b, &L));  // (strict_reference: the player order of the new episode, quirk Q3)
     std::fill(done.begin(), done.end(), 0);
   }
   void take_actions(const py::list& actions) {  // to_action_vector + take_actions (bindings.cpp:50-64,117-119; BaseEnvironment.hpp:141-176)

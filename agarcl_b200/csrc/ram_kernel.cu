@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kRamWarps * 32) k_ram(const __grid_constant__ 
       int pos = __popc(clone_mask & ((1u << lane) - 1u));
       if (clone_in && pos < AGARCL_RAM_KC) {
         clone4[2 * pos] = make_float4(cx - px, cy - py, radius_of(P.T, cm), (float)cm);
-        clone4[2 * pos + 1] = make_float4(cvx, cvy, vel_direction(cvx, cvy), (float)p);
+        clone4[2 * pos + 1] = make_float4(cvx, cvy, vel_direction(cvx, cvy), (float)(p + P.pid_base));
       }
       for (int k = 2 * min(n_clone, AGARCL_RAM_KC) + lane; k < 2 * AGARCL_RAM_KC; k += 32) clone4[k] = zero;
     }

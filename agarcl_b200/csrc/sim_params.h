@@ -152,6 +152,7 @@ struct RamParams {
   float* ram;              // [N][P][AGARCL_RAM_RECORD]
   int32_t N, G;
   int32_t pre_respawn;     // 1: players respawned at the end of the step are still dead (BaseEnvironment.hpp:96-101)
+  int32_t pid_base;        // CloneInfo::owner is the player's pid: index + pid of player 0 (non-zero only in later episodes of strict_reference, Q3)
 };
 
 }  // namespace ag

@@ -100,6 +100,7 @@ class GridEnvironment(_Base):
 
     def reset(self):
         self._ensure().reset()
+        self._order_agents = None  # (strict_reference: the player-map order changes from episode to episode, quirk Q3)
 
     def take_actions(self, actions):
         """list of (dx, dy, action) per agent; wrong length raises like EnvironmentException (BaseEnvironment.hpp:142-144)"""

@@ -87,7 +87,10 @@ typedef struct agarcl_cfg {
   int32_t reward_type, c_death, mode_number;
   int32_t num_frames, grid_size, observe_cells, observe_others, observe_viruses, observe_pellets;
   int32_t obs_dtype;        /* agarcl_obs_dtype; int32 is the reference's */
-  int32_t strict_reference; /* 1: keep quirk Q11 (frame index) exactly; 0: always render the last frame(s) */
+  int32_t strict_reference; /* 1: keep quirk Q11 (frame index) exactly, and quirk Q3: the player order of the episode that follows the
+                               k-th unmasked agarcl_batch_reset is the one the reference has after its k-th reset (its player map and pid
+                               counter outlive a reset, Engine.hpp:72,98-101); 0: always render the last frame(s), every episode in the
+                               player order of a fresh engine */
   int32_t rng_mode;         /* agarcl_rng_mode */
   int32_t cap_viruses, cap_foods, cap_replay; /* 0 = defaults */
   int32_t device;           /* CUDA device ordinal */
@@ -178,6 +181,7 @@ int agarcl_batch_seed(agarcl_batch* b, const uint64_t* seeds);
  * a reset does not reseed: the instance's draw stream goes on where the last episode left it (successive episodes
  * differ); only agarcl_batch_seed / agarcl_batch_set_replay / a snapshot load restart it at its first draw. */
 int agarcl_batch_reset(agarcl_batch* b, const uint8_t* mask, void* stream);
+/* (strict_reference: an unmasked reset changes layout.order -- fetch it again with agarcl_batch_get_layout) */
 /* BaseEnvironment::take_actions (BaseEnvironment.hpp:141-176): dxdy[N*A*2], act[N*A].
  * on_device!=0: device pointers, read by the next step without a copy. */
 int agarcl_batch_set_actions(agarcl_batch* b, const float* dxdy, const int32_t* act, int on_device, void* stream);

@@ -492,3 +492,76 @@ def test_compiled_agarcl_module_drop_in_against_oracle(tmp_path):
         assert c0.owner == p and c0.teamId == 0
     assert g.observation_shape() == (25, 512, 512)
     g.close()
+
+
+def test_strict_reference_later_episodes_follow_pid_growth():
+    """Quirk Q3 under strict_reference: the reference's player map and pid counter outlive a reset, so the k-th reset leaves the
+    players in another iteration order than a fresh engine (26 players: from the first reset on) and CloneInfo::owner counts on.
+    The batch replays that (agarcl_batch_reset, unmasked); the oracle is given the order of the episode
+    (oracle_player_order_episode, pinned to the reference over four episodes in tests/test_oracle_vs_reference.py) and both are
+    compared field by field over three episodes, the draw stream carried across the resets."""
+    import ctypes
+    import torch
+    from _helpers import Oracle, oracle_lib, oracle_layout, random_actions
+    from agarcl_b200 import make_cfg, RNG_REPLAY
+    from agarcl_b200._abi import compare_states
+    from agarcl_b200.batch import Batch
+    oracle_lib().oracle_set_trig_mode(1)
+    n, rl = 2, 1 << 15
+    cfg = make_cfg(n_instances=n, strict_reference=True, ticks_per_step=1, rng_mode=RNG_REPLAY, cap_replay=rl, ram_obs=True,
+                   arena_size=400, num_pellets=300, num_viruses=6)
+    b = Batch(cfg)
+    oras = []
+    for i in range(n):
+        o = Oracle(cfg, oracle_layout(cfg))
+        o.seed_mt(900 + i, rl)
+        b.set_replay(i, o.replay)
+        oras.append(o)
+    P, A = b.layout.P, b.layout.A
+    assert P == 26
+    rngs = [np.random.default_rng(40 + i) for i in range(n)]
+    fresh_order = list(b.layout.order)[:P]
+    orders = []
+    try:
+        for episode in range(3):
+            b.reset()
+            want = (ctypes.c_int * 64)()
+            oracle_lib().oracle_player_order_episode(P, episode, want)
+            assert list(b.layout.order)[:P] == list(want)[:P], episode
+            orders.append(list(want)[:P])
+            oracle_lib().oracle_set_pid_base(episode * P)
+            for o in oras:
+                for k in range(P):
+                    o.L.order[k] = want[k]
+                o.reset() if episode == 0 else o.reset_keep_stream()
+                o.ram_clear()
+            for i, o in enumerate(oras):
+                d = compare_states(o.state, b.download_state(i))
+                assert not d, f"episode {episode} reset, instance {i}: {d[:4]}"
+            obs_t, rew_t, ram_t = b.obs_tensor(), b.rewards_tensor(), b.ram_tensor()
+            for st in range(30):
+                dxdy = np.zeros((n, A, 2), np.float32)
+                act = np.zeros((n, A), np.int32)
+                for i in range(n):
+                    dxdy[i], act[i] = random_actions(rngs[i], A, 1 / 3, 1 / 3)
+                b.set_actions(dxdy, act)
+                b.step()
+                torch.cuda.synchronize()
+                g_rew = rew_t.cpu().numpy().reshape(n, A)
+                g_obs = obs_t.cpu().numpy().reshape(n, A, *b.obs_shape[1:])
+                g_ram = ram_t.cpu().numpy()
+                for i, o in enumerate(oras):
+                    o.set_actions(dxdy[i], act[i])
+                    o_rew, o_done, o_obs = o.step_with_ram(with_obs=True)
+                    d = compare_states(o.state, b.download_state(i))
+                    assert not d, f"episode {episode} step {st} instance {i}: {d[:4]}"
+                    assert np.array_equal(g_rew[i], o_rew)
+                    assert np.array_equal(g_obs[i], o_obs)
+                    same = (g_ram[i].view(np.uint32) == o.ram.view(np.uint32)) | (np.isnan(g_ram[i]) & np.isnan(o.ram))
+                    assert same.all(), (episode, st, i, np.argwhere(~same)[:4].tolist())
+            if episode > 0:  # CloneInfo::owner (record word 975 = 968 + 7) of the agent's own first clone counts on with the pids
+                assert float(g_ram[0][0, 975]) >= episode * P
+        assert orders[0] == fresh_order and orders[1] != fresh_order
+    finally:
+        oracle_lib().oracle_set_pid_base(0)
+        b.close()
