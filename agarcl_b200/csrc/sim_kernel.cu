@@ -1238,7 +1238,8 @@ __device__ void tick_player(Ctx& c, int p) {
   AG_PH(c, 18);
   // ---- recombine_cells (swap-with-back semantics)
   bool merged = false;  // (a merge moves the last cell into the hole: the only thing that breaks the ascending id order)
-  if (n >= 2) {
+  // (a pair merges only if BOTH cells' timers have expired: with fewer than two such cells the pair loop cannot do anything)
+  if (n >= 2 && __popc(__ballot_sync(AG_FULL, lane < n && c.tick >= me.rec)) >= 2) {
     for (int a = 0; a < n; a++) {
       uint32_t arec = __shfl_sync(AG_FULL, me.rec, a);
       if (!(c.tick >= arec)) continue;
@@ -1377,8 +1378,9 @@ __device__ void lane_nearest_pellet(const Ctx& c, float lx, float ly, float& tx,
 }
 
 // get_pellets_to_remove_and_increment_cells (Engine.hpp:976-1000) for one cell by one lane: the
-// candidates (same superset as the warp-wide path) are taken in the reference's order by repeated
-// selection of the next key.  false: too many candidates for a lane.
+// candidates (same superset as the warp-wide path) are collected by ONE scan of the hash, put into the
+// reference's order (bucket offset, then index) and then tested one after the other against the growing
+// cell.  false: too many candidates for a lane.
 __device__ bool lane_eat_pellets(const Ctx& c, float cx, float cy, uint32_t& mass, int& ne, uint16_t* out) {
   const Luts& T = c.P.T;
   const int HG = c.P.HG;
@@ -1392,44 +1394,52 @@ __device__ bool lane_eat_pellets(const Ctx& c, float cx, float cy, uint32_t& mas
   const float Rc2 = Rc * Rc;
   const int hx0 = hash_coord(c, cx - Rc), hx1 = hash_coord(c, cx + Rc);
   const int hy0 = hash_coord(c, cy - Rc), hy1 = hash_coord(c, cy + Rc);
-  uint32_t prev = 0u, newmass = mass;  // keys are kept +1 so that 0 means "none yet"
-  int remaining = -1;
+  // the reference's order key of a pellet: 510-unit bucket offset (dx major, dy minor), then the index
+  auto key_of = [&](uint32_t idx) -> uint32_t {
+    const float2 q = pel[idx];
+    const int bx = (int)q.x / 510 - gx, by = (int)q.y / 510 - gy;
+    return ((uint32_t)((bx + 1) * 3 + (by + 1)) << 16) | idx;
+  };
+  // ONE scan of the hash: the candidates' indices go to `out` (which the eaten ones overwrite from the front afterwards)
+  int cnt = 0;
   ne = 0;
-  while (true) {
-    uint32_t best = 0xffffffffu;
-    float bestd2 = 0.0f;
-    int cnt = 0;
 #pragma unroll 1
-    for (int hy = hy0; hy <= hy1; hy++) {
-      int s, e;
-      hash_range(c, hy * HG + hx0, hy * HG + hx1, s, e);
+  for (int hy = hy0; hy <= hy1; hy++) {
+    int s, e;
+    hash_range(c, hy * HG + hx0, hy * HG + hx1, s, e);
 #pragma unroll 1
-      for (int j = s; j < e; j++) {
-        uint32_t idx = c.sm.hsorted()[j];
-        if (idx == (uint32_t)kHashDead) continue;
-        float2 q = pel[idx];
-        float d2 = sqr_dist(cx, cy, q.x, q.y);
-        if (!(d2 <= Rc2)) continue;
-        int bx = (int)q.x / 510 - gx, by = (int)q.y / 510 - gy;
-        if (bx >= -1 && bx <= 1 && by >= -1 && by <= 1) {
-          cnt++;
-          uint32_t key = (((uint32_t)((bx + 1) * 3 + (by + 1)) << 16) | idx) + 1u;
-          if (key > prev && key < best) { best = key; bestd2 = d2; }
-        }
+    for (int j = s; j < e; j++) {
+      const uint32_t idx = c.sm.hsorted()[j];
+      if (idx == (uint32_t)kHashDead) continue;
+      const float2 q = pel[idx];
+      if (!(sqr_dist(cx, cy, q.x, q.y) <= Rc2)) continue;
+      const int bx = (int)q.x / 510 - gx, by = (int)q.y / 510 - gy;
+      if (bx >= -1 && bx <= 1 && by >= -1 && by <= 1) {
+        if (cnt < kLaneCand) out[cnt] = (uint16_t)idx;
+        cnt++;
       }
     }
-    if (remaining < 0) {
-      if (cnt > kLaneCand) return false;
-      remaining = cnt;
-    }
-    if (best == 0xffffffffu) break;
-    float r = fmax_std(radius_of(T, newmass), rp);
-    if (r * r >= bestd2) {  // Ball::collides_with; can_eat(pellet) always holds for mass >= 25
-      out[ne++] = (uint16_t)((best - 1u) & 0xffffu);
+  }
+  if (cnt > kLaneCand) return false;
+  if (cnt == 0) return true;
+  // ascending key (insertion sort of at most kLaneCand entries; the keys are distinct: they carry the index)
+  for (int i = 1; i < cnt; i++) {
+    const uint16_t v = out[i];
+    const uint32_t kv = key_of(v);
+    int j = i - 1;
+    while (j >= 0 && key_of(out[j]) > kv) { out[j + 1] = out[j]; j--; }
+    out[j + 1] = v;
+  }
+  uint32_t newmass = mass;
+  for (int i = 0; i < cnt; i++) {
+    const uint16_t idx = out[i];
+    const float2 q = pel[idx];
+    const float d2 = sqr_dist(cx, cy, q.x, q.y);
+    const float r = fmax_std(radius_of(T, newmass), rp);
+    if (r * r >= d2) {  // Ball::collides_with; can_eat(pellet) always holds for mass >= 25
+      out[ne++] = idx;
       newmass = floor_mass(newmass + 1u);
     }
-    prev = best;
-    if (--remaining <= 0) break;
   }
   mass = newmass;
   return true;
