@@ -306,7 +306,9 @@ extern "C" int agarcl_batch_create(const agarcl_cfg* cfg, agarcl_batch** out) {
   b->obs_elems = (size_t)b->N * b->A * b->frames * b->C * b->G * b->G;
   b->obs_bytes = b->obs_elems * (cfg->obs_dtype == AGARCL_OBS_I16 ? 2 : 4);
   // spatial hash resolution: about 3 pellets per hash cell, 4..64 cells per side
-  int hg = (int)std::floor(std::sqrt((double)L.cap_pellets / 3.0));
+  double per_cell = 3.0;
+  if (const char* e = std::getenv("AGARCL_HASH_PER_CELL")) per_cell = std::atof(e);  // (A/B timing)
+  int hg = (int)std::floor(std::sqrt((double)L.cap_pellets / per_cell));
   b->HG = hg < 4 ? 4 : (hg > 64 ? 64 : hg);
   b->smem_per_warp = ag::make_smem_offsets(L, b->HG, b->so);
   if ((size_t)b->smem_per_warp + 2 * ag::kZeroTileBytes > 227 * 1024) {  // (room for one warp with both tiles at full size)
