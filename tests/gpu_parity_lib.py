@@ -110,7 +110,8 @@ def run_parity(cfg_kwargs, seeds, steps, p_feed=1 / 3, p_split=1 / 3, boost=None
         g_ram = ram_t.cpu().numpy() if ram else None
         for i, o in enumerate(oras):
             o.set_actions(dxdy[i], act[i])
-            o_rew, o_done, o_obs = o.step_with_ram() if ram else o.step(with_obs=want_obs and with_obs_in_step)
+            o_rew, o_done, o_obs = (o.step_with_ram(with_obs=want_obs and with_obs_in_step) if ram
+                                    else o.step(with_obs=want_obs and with_obs_in_step))
             if st % state_every == 0 or st == steps - 1:
                 gs = b.download_state(i)
                 d = compare_states(o.state, gs)

@@ -55,6 +55,25 @@ def test_cuda_matches_oracle_philox_2000_steps_configs1():
     print("philox 2000 steps x 8:", stats)
 
 
+# the parity statement holds over H = 2000 env-steps (8000 ticks) on EACH BASELINE config.  configs[1] runs its 2000
+# steps above (test_cuda_matches_oracle_philox_2000_steps_configs1, 8 instances, the bench's RNG mode); here the other four, two
+# instances each: rewards and dones every step, the whole state every 25, the observation (grid or ram records) every 100.
+H2000_CASES = {
+    "c1_single_agent": (dict(num_bots=0, num_viruses=0), dict()),
+    "c3_ram": (dict(num_bots=8, num_viruses=10), dict(ram=True, p_feed=0.0, p_split=0.0)),
+    "c4_multi_agent_split_eject": (dict(num_agents=4, num_bots=8, cap_foods=2048), dict(p_feed=0.3, p_split=0.3, boost=1000)),
+    "c5_large_arena": (dict(arena_size=2000, num_pellets=4000, num_viruses=50, cap_viruses=128), dict()),
+}
+
+
+@pytest.mark.parametrize("name", list(H2000_CASES))
+def test_cuda_matches_oracle_2000_steps_every_baseline_config(name):
+    cfg_kwargs, run_kwargs = H2000_CASES[name]
+    stats = run_parity(cfg_kwargs, seeds=[61, 62], steps=2000, obs_every=100, state_every=25, replay_len=1 << 18, **run_kwargs)
+    assert not stats["flags"], stats
+    print(name, stats)
+
+
 @pytest.mark.parametrize("name", list(LONG_CASES))
 def test_cuda_matches_oracle_long_horizon(name):
     cfg_kwargs, run_kwargs = LONG_CASES[name]

@@ -90,6 +90,20 @@ def test_long_horizon_configs1_steady_state(seed):
           "cells eaten", int(s.players["cells_eaten"].sum()))
 
 
+@pytest.mark.parametrize("name", ["c1_single_agent", "c4_multi_agent_split_eject", "c5_large_arena", "c3_roster"])
+def test_long_horizon_other_baseline_configs(name):
+    """H = 2000 env-steps on each BASELINE config -- configs[0], [3], [4] and the roster of [2] (its ram records are pinned
+    in tests/test_ram_obs.py); configs[1] runs 2500 steps above."""
+    ck, rk = {
+        "c1_single_agent": (dict(num_bots=0, num_viruses=0), dict()),
+        "c4_multi_agent_split_eject": (dict(num_agents=4, num_bots=8, cap_foods=2048), dict(p_feed=0.3, p_split=0.3, boost=1000)),
+        "c5_large_arena": (dict(arena_size=2000, num_pellets=4000, num_viruses=50, cap_viruses=128), dict()),
+        "c3_roster": (dict(num_bots=8, num_viruses=10), dict(p_feed=0.0, p_split=0.0)),
+    }[name]
+    s = lockstep(ck, seed=71, steps=2000, obs_every=100, state_every=25, trig_mode=1, replay_len=1 << 18, **rk)
+    assert int(s.hdr["flags"]) == 0, s.flag_names()
+
+
 def test_recombine_after_300_ticks():
     # a split cell pair merges once the (sim-time) recombine timer expires: 10 s = 300 ticks (Entities.hpp:183-193)
     s = lockstep(dict(num_agents=1, num_bots=0, num_viruses=0, arena_size=200, num_pellets=50), seed=5, steps=120,
