@@ -18,7 +18,7 @@ SYMBOLS = [
     "agarcl_batch_mirror", "agarcl_batch_sync_mirror", "agarcl_batch_step_mirror", "agarcl_batch_mirror_stats", "agarcl_batch_mirror_timing", "agarcl_batch_step_lists", "agarcl_batch_lists_expand",
     "agarcl_batch_download_state", "agarcl_batch_upload_state", "agarcl_batch_save_env_state", "agarcl_batch_load_env_state",
     "agarcl_snapshot_write", "agarcl_snapshot_read", "agarcl_batch_set_replay",
-    "agarcl_batch_render", "agarcl_batch_ram", "agarcl_batch_ram_host", "agarcl_batch_render_ram", "agarcl_batch_launches_per_step", "agarcl_batch_flags", "agarcl_selftest_std_sort", "agarcl_batch_set_timing", "agarcl_batch_get_timing", "agarcl_mt19937_draws",
+    "agarcl_batch_render", "agarcl_batch_ram", "agarcl_batch_ram_host", "agarcl_batch_render_ram", "agarcl_batch_launches_per_step", "agarcl_batch_flags", "agarcl_batch_costs", "agarcl_selftest_std_sort", "agarcl_batch_set_timing", "agarcl_batch_get_timing", "agarcl_mt19937_draws",
     "agarcl_last_error", "agarcl_version",
 ]
 
@@ -69,6 +69,7 @@ def lib():
         L.agarcl_batch_launches_per_step.argtypes = [_vp]
         L.agarcl_batch_flags.argtypes = [_vp, _vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32 * 32)]
         L.agarcl_selftest_std_sort.argtypes = [_vp, C.c_int32, _vp]
+        L.agarcl_batch_costs.argtypes = [_vp, _vp, _vp]
         L.agarcl_batch_set_timing.argtypes = [_vp, C.c_int]
         L.agarcl_batch_get_timing.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         L.agarcl_mt19937_draws.argtypes = [C.c_uint64, _vp, C.c_int32]

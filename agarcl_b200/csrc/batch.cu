@@ -156,6 +156,8 @@ static void fill_sim_params(const agarcl_batch* b, ag::SimParams& P) {
   P.obs_finish = 0; P.obs_G = b->G; P.obs_C = b->C;
   P.zero_chunks = 0;
   if (const char* e = std::getenv("AGARCL_ZERO_CHUNKS")) P.zero_chunks = std::atoi(e);
+  P.dyn_stripes = 1;
+  if (const char* e = std::getenv("AGARCL_DYNAMIC_STRIPES")) P.dyn_stripes = std::atoi(e);  // (A/B timing)
   P.tick_barrier = 6;  // bit mask of the alignment barriers of a tick (sim_kernel.cu, step_instance)
   if (const char* e = std::getenv("AGARCL_TICK_BARRIER")) P.tick_barrier = std::atoi(e);  // (A/B timing)
   P.align_group = ag::kMaxWarpsPerCta;  // the whole CTA (groups of 8 / 4 / 2 warps were slower: 1.78 / 1.97 / 2.16 vs 1.70 ms)
@@ -667,6 +669,15 @@ extern "C" int agarcl_batch_get_timing(agarcl_batch* b, double* sim_ms, double* 
 }
 
 extern "C" int agarcl_batch_launches_per_step(const agarcl_batch* b) { return b ? b->launches_last_step : 0; }
+
+extern "C" int agarcl_batch_costs(agarcl_batch* b, void* stream, uint32_t* out) {
+  if (!b || !out) return agarcl_set_error(AGARCL_ERR_INVALID, "null argument");
+  if (!b->d_cost) return agarcl_set_error(AGARCL_ERR_STATE, "this batch keeps no per-instance costs");
+  CK(cudaSetDevice(b->cfg.device));
+  CK(cudaMemcpyAsync(out, b->d_cost, sizeof(uint32_t) * (size_t)b->N, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return AGARCL_OK;
+}
 
 extern "C" int agarcl_selftest_std_sort(const float* ys, int32_t n, uint16_t* order_out) {
   if (n < 0 || n > 65535 || (n > 0 && (!ys || !order_out))) return agarcl_set_error(AGARCL_ERR_INVALID, "bad keys / count");

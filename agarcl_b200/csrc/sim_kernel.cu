@@ -131,6 +131,7 @@ static_assert(sizeof(ColdCtx) <= kColdCtxBytes - 16, "ColdCtx outgrew its shared
 // experiment builds only (tools/build_variant.sh with EXTRA=-DAGARCL_PHASE_TIMING): cycles per phase summed over all instance warps,
 // printed (running totals) by the first thread of every launch
 __device__ unsigned long long g_phase[32];
+__device__ unsigned int g_cta_cycles[256];  // lifetime of every CTA of the last launch (cycles / 1024)
 #define AG_PH(c, i) do { const long long t_ = clock64(); if ((c).lane == 0) atomicAdd(&g_phase[i], (unsigned long long)(t_ - (c).ph_t)); (c).ph_t = t_; } while (0)
 #else
 #define AG_PH(c, i) do { } while (0)
@@ -3029,6 +3030,9 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
     printf("PHASES");
     for (int i = 0; i < 28; i++) printf(" %llu", g_phase[i]);
     printf("\n");
+    printf("CTAS");
+    for (int i = 0; i < (int)gridDim.x && i < 256; i++) printf(" %u", g_cta_cycles[i]);
+    printf("\n");
   }
   const long long t_kernel0 = clock64();
 #endif
@@ -3063,10 +3067,33 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
     const uint32_t full = (uint32_t)P.N / per_round, rem = (uint32_t)P.N - full * per_round;
     const uint32_t wl = (rem + gridDim.x - 1u) / gridDim.x;  // stripe width of the last round
     const int bars_rest = __popc((unsigned)tb & 28u);  // barriers of a tick behind the pair solver
-    for (uint32_t r = 0; r <= full; r++) {
-      const uint32_t k = (r & 1u) ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
-      const uint32_t width = r < full ? nw : wl;
-      const uint32_t t = r * per_round + k * width + (uint32_t)warp;
+    // DYNAMIC STRIPES (default).  What a round costs a CTA cannot be predicted well enough from the last step (a rare collision
+    // sweep or a popped looking bot on a decision tick makes one CTA's round 50 % longer): with the static pairing the slowest
+    // CTA ran 20-35 % longer than the average one and the other SMs idled behind it.  So the stripes of 16 consecutive
+    // positions of the cost-sorted order are handed out by a ticket counter, most expensive first: a CTA that comes out of a
+    // round early takes the most expensive stripe that is left, one that was held up finds nothing left to take -- list
+    // scheduling on the ACTUAL round times.  (s_stripe lives in the spare word of warp 0's pool slot.)
+    const uint32_t n_stripes = ((uint32_t)P.N + nw - 1u) / nw;
+    volatile uint32_t* s_stripe = pool_slot(P, smem_raw, 0) + 3;
+#ifdef AGARCL_PHASE_TIMING
+    int rounds_done = 0;
+#endif
+    for (uint32_t r = 0; P.dyn_stripes || r <= full; r++) {
+      uint32_t k = (r & 1u) ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
+      uint32_t width = r < full ? nw : wl;
+      uint32_t t = r * per_round + k * width + (uint32_t)warp;
+      if (P.dyn_stripes) {
+        if (threadIdx.x == 0) *s_stripe = atomicAdd(P.tickets, 1u);
+        __syncthreads();
+        const uint32_t stripe = *s_stripe;
+        __syncthreads();  // (everybody has read it before thread 0 draws the next one)
+        if (stripe >= n_stripes) break;
+#ifdef AGARCL_PHASE_TIMING
+        rounds_done++;
+#endif
+        width = nw;
+        t = stripe * nw + (uint32_t)warp;
+      }
       if ((uint32_t)warp < width && t < (uint32_t)P.N) {
         const uint32_t inst = P.perm ? P.perm[t] : t;
         step_instance(P, smem_raw, P.inst_first + (int)inst, (int)t, warp, lane, mbar_phase, tb);
@@ -3086,7 +3113,12 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) k_step(const __grid_c
     }
 #ifdef AGARCL_PHASE_TIMING
     if (lane == 0) atomicAdd(&g_phase[0], (unsigned long long)(clock64() - t_kernel0));  // whole kernel, per warp
+    if (threadIdx.x == 0 && blockIdx.x < 256) g_cta_cycles[blockIdx.x] = (unsigned int)((clock64() - t_kernel0) >> 10) | ((unsigned int)rounds_done << 28);
 #endif
+    if (P.dyn_stripes && threadIdx.x == 0) {  // the last CTA to leave rewinds the ticket counter for the next launch
+      const uint32_t left = atomicAdd(P.tickets + 1, 1u);
+      if (left == gridDim.x - 1u) { P.tickets[0] = 0u; P.tickets[1] = 0u; }
+    }
     return;
   }
   while (true) {

@@ -112,6 +112,7 @@ struct SimParams {
   int32_t observe_cells, observe_others, observe_viruses, observe_pellets;
   int32_t tick_barrier;         // instruction-fetch alignment (step_instance), bit mask of the CTA barriers of a tick: 1 tick start, 2 around the
                                 // pooled pair solver, 4 before players_collision, 8 before move_foods, 16 before apply_removals; 0: free-running warps
+  int32_t dyn_stripes;          // aligned schedule: 1 = stripes handed out by the ticket counter (default), 0 = the static round-robin pairing
   int32_t align_group;          // warps per alignment group (a divisor-free choice: the last group of a CTA may be smaller)
   PackOut pk;                   // with obs_finish only
   int32_t inst_first;           // this launch steps instances [inst_first, inst_first + N) of the batch

@@ -316,6 +316,9 @@ int agarcl_batch_launches_per_step(const agarcl_batch* b);
  * AGARCL_FLAG bit `bit` set (either pointer may be NULL).  Synchronises `stream`.  The reference has no counterpart: its
  * containers grow without bound where this library has fixed capacities (BaseEnvironment.hpp / Engine.hpp vectors). */
 int agarcl_batch_flags(agarcl_batch* b, void* stream, uint32_t* or_all, uint32_t counts[32]);
+/* Diagnostics of the schedule: cycles every instance worked in the last step (what the cost-sorted schedule orders the next step by;
+ * waiting at the alignment barriers excluded).  out: HOST array of N entries.  Synchronises `stream`.  No reference counterpart. */
+int agarcl_batch_costs(agarcl_batch* b, void* stream, uint32_t* out);
 /* Self-test of the device's restatement of libstdc++'s std::sort (k_step's strip_std_sort; the reference sorts the strips of
  * PrecisionCollisionDetection::solve with it, agario/utils/collision_detection.hpp:29-31): sorts the indices 0..n-1 by the HOST keys
  * ys[n] on the current device and writes the resulting order to order_out[n].  n <= 65535.  tests/test_gpu_std_sort.py compares it
