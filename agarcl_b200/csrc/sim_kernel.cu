@@ -62,6 +62,7 @@ __device__ __forceinline__ Cell cell_load(const agarcl_cell* g) {
   c.rec = ldg_keep(reinterpret_cast<const uint32_t*>(g) + 8);
   return c;
 }
+constexpr int kEatUnknown = 0xff;    // premove_batch did not resolve the cell's pellets (no pellets / too many candidates for a lane)
 constexpr int kPremoveShadow = 16;  // cell slot of a premoved player's first result cell (players of up to 16 cells are premoved)
 // a premoved player's cell: position and velocities from the result slot, mass / id / recombine tick from the live cell
 __device__ __forceinline__ Cell cell_load_premoved(const agarcl_cell* g) {
@@ -596,7 +597,7 @@ __device__ __forceinline__ void move_cell(const SimParams& P, uint32_t& flags, C
 // One batch of the pair solver: up to 32 >> gshift players of one instance (state blob `blob`), one lane group each.
 // desc: w0 = gshift | players << 8, w1 / w2 = (player | cells << 8) of the groups, 16 bits each.  Returns the
 // players done as a bit mask (lo, hi) and ORs state flags into `flags`; everything else goes back to the cell arrays.
-__device__ void premove_batch(const SimParams& P, uint8_t* blob, uint32_t w0, uint32_t w1, uint32_t w2, int lane,
+__device__ void premove_batch(const SimParams& P, uint8_t* blob, uint8_t* owner_smem, bool eat, uint32_t w0, uint32_t w1, uint32_t w2, int lane,
                               uint32_t& done_lo, uint32_t& done_hi, uint32_t& flags) {
   const int gshift = (int)(w0 & 0xffu), count = (int)(w0 >> 8), gw = 1 << gshift;
   const int g = lane >> gshift, gl = lane & (gw - 1), gbase = g << gshift;
@@ -620,10 +621,29 @@ __device__ void premove_batch(const SimParams& P, uint8_t* blob, uint32_t w0, ui
   me = self_collisions_fn(me, radius_of(P.T, me.mass), gn, tx, ty, gbase, gl, gw, P.W);
   // the results go to the UPPER half of the player's cell slots (kPremoveShadow): the live cells stay as they were until the
   // player's own turn, which is what a looking bot earlier in the order must see on a decision tick (bot_chase reads cells)
+  // ... and so does what the cell eats: get_pellets_to_remove_and_increment_cells (Engine.hpp:976-1000) sees the pellets of the
+  // tick's start whoever is ticked before (they are removed behind the player loop, :221) and the cell where the solver left it,
+  // unless a virus gets in between (tick_player then scans again).  The scan runs against the OWNER's hash and pellet array in
+  // shared memory; the new mass, the count and up to kLaneCand indices travel in the unused words of the result slot.
+  uint32_t eat_mass = me.mass;
+  int eat_n = kEatUnknown;
+  uint16_t eat_idx[kLaneCand];
+#pragma unroll
+  for (int k = 0; k < kLaneCand; k++) eat_idx[k] = 0;
+  if (valid && eat) {
+    Ctx oc(P);  // (only P and the shared-memory carve-up of the owner are read)
+    oc.sm.base = owner_smem;
+    oc.sm.o = &P.so;
+    oc.lane = lane;
+    if (!lane_eat_pellets(oc, me.x, me.y, eat_mass, eat_n, eat_idx)) { eat_n = kEatUnknown; eat_mass = me.mass; }
+  }
   if (valid) {
     float4* r = reinterpret_cast<float4*>(cells + kPremoveShadow + gl);
     stg_keep(r, make_float4(me.x, me.y, me.vx, me.vy));
-    stg_keep(r + 1, make_float4(me.svx, me.svy, 0.0f, 0.0f));
+    stg_keep(r + 1, make_float4(me.svx, me.svy, __uint_as_float(eat_mass), __int_as_float(eat_n)));
+    static_assert(kLaneCand == 8, "eight 16-bit indices in the slot's last four words");
+    stg_keep(reinterpret_cast<int4*>(r + 2), make_int4((int)(eat_idx[0] | (uint32_t)eat_idx[1] << 16), (int)(eat_idx[2] | (uint32_t)eat_idx[3] << 16),
+                                                       (int)(eat_idx[4] | (uint32_t)eat_idx[5] << 16), (int)(eat_idx[6] | (uint32_t)eat_idx[7] << 16)));
   }
   const bool mark = have && gl == 0;
   done_lo |= __reduce_or_sync(AG_FULL, (mark && gp < 32) ? 1u << gp : 0u);
@@ -631,7 +651,8 @@ __device__ void premove_batch(const SimParams& P, uint8_t* blob, uint32_t w0, ui
 }
 
 // The warp's mailbox for the pooled pair solver (scratch that is dead before the player loop):
-// [0] batches  [1] [2] players done (lo, hi)  [3] state flags  [4] instance  [5] cycles spent on its batches  [8 + 4k ..] batch k
+// [0] batches  [1] [2] players done (lo, hi)  [3] state flags  [4] instance  [5] cycles spent on its batches  [6] pellet eating may be
+// resolved against this warp's hash  [8 + 4k ..] batch k
 constexpr int kMailHdr = 8, kMailBatches = 40;
 static_assert((kMailHdr + 4 * kMailBatches) * 4 <= kCandCap * 8 + (kPremCap * 2 + 15) / 16 * 16 + (kVremCap * 2 + 15) / 16 * 16,
               "the mailbox must fit into cand + prem + vrem: the lanes' speculation (lprem) may run before the pool's barrier");
@@ -722,6 +743,7 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
     volatile uint32_t* ps = pool_slot(P, smem_raw, warp);
     ps[0] = nb; ps[1] = 0u; ps[2] = 0u;
     mine[4] = c ? (uint32_t)c->cold().inst_local : 0u;
+    mine[6] = (c && c->n_pellets > 0 && c->hash_valid) ? 1u : 0u;  // the batches may resolve pellet eating against this warp's hash
     __threadfence_block();
     *pub = epoch;
   }
@@ -752,8 +774,8 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
     if (idx >= __shfl_sync(AG_FULL, cnt, owner)) continue;  // (another warp was quicker)
     const long long t0 = clock64();
     uint32_t lo = 0u, hi = 0u, fl = 0u;
-    premove_batch(P, P.state + (size_t)mb[4] * P.L.stride, mb[kMailHdr + 4 * idx], mb[kMailHdr + 4 * idx + 1], mb[kMailHdr + 4 * idx + 2],
-                  lane, lo, hi, fl);
+    premove_batch(P, P.state + (size_t)mb[4] * P.L.stride, smem_raw + P.tiles_bytes + (size_t)owner * P.smem_per_warp, mb[6] != 0u,
+                  mb[kMailHdr + 4 * idx], mb[kMailHdr + 4 * idx + 1], mb[kMailHdr + 4 * idx + 2], lane, lo, hi, fl);
     fl = __reduce_or_sync(AG_FULL, fl);
     if (lane == 0) {
       atomicOr(const_cast<uint32_t*>(mb + 1), lo);
@@ -959,7 +981,29 @@ __device__ void tick_player(Ctx& c, int p) {
     int ne = 0;
     uint32_t nm = me.mass;
     bool ok = true;
-    if (lane < n) ok = lane_eat_pellets(c, me.x, me.y, nm, ne, mine);
+    bool pooled = false;
+    if (premoved && viruses_eaten_inc == 0) {
+      // the pool has resolved this already (premove_batch), on the cells as the solver left them and the masses of the tick's
+      // start -- which is what they still are without a virus contact
+      int4 idx = make_int4(0, 0, 0, 0);
+      int pne = 0;
+      uint32_t pm = me.mass;
+      if (lane < n) {
+        const float4* r = reinterpret_cast<const float4*>(c.pcells(p) + kPremoveShadow + lane);
+        const float4 b = ldg_keep(r + 1);
+        idx = ldg_keep(reinterpret_cast<const int4*>(r + 2));
+        pm = __float_as_uint(b.z);
+        pne = __float_as_int(b.w);
+      }
+      if (__all_sync(AG_FULL, pne != kEatUnknown)) {
+        pooled = true;
+        ne = pne;
+        nm = pm;
+        mine[0] = (uint16_t)idx.x; mine[1] = (uint16_t)((uint32_t)idx.x >> 16); mine[2] = (uint16_t)idx.y; mine[3] = (uint16_t)((uint32_t)idx.y >> 16);
+        mine[4] = (uint16_t)idx.z; mine[5] = (uint16_t)((uint32_t)idx.z >> 16); mine[6] = (uint16_t)idx.w; mine[7] = (uint16_t)((uint32_t)idx.w >> 16);
+      }
+    }
+    if (!pooled && lane < n) ok = lane_eat_pellets(c, me.x, me.y, nm, ne, mine);
     if (__all_sync(AG_FULL, ok)) {
       int incl = ne;
 #pragma unroll
