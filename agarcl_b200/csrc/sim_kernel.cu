@@ -714,8 +714,9 @@ __device__ void premove_players(const SimParams& P, uint8_t* smem_raw, Ctx* c, i
           uint32_t w1 = 0u, w2 = 0u;  // (two scalars: an array indexed by g lives in local memory)
           int count = 0;
           for (int g = 0; g < per && todo; g++) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1u;
+            // the player with the most cells that is left: a batch costs its longest pair sequence, so the long ones go together
+            const int src = (int)(warp_max_u32(((todo >> lane) & 1u) ? ((uint32_t)np << 8 | (uint32_t)(31 - lane)) : 0u) & 0xffu) ^ 31;
+            todo &= ~(1u << src);
             const uint32_t pn = ((uint32_t)__shfl_sync(AG_FULL, p, src) | ((uint32_t)__shfl_sync(AG_FULL, np, src) << 8)) << ((g & 1) * 16);
             if (g < 2) w1 |= pn; else w2 |= pn;
             count++;
